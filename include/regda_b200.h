@@ -1,0 +1,151 @@
+/*
+ * regda_b200 -- C ABI of the B200-native RegDA self-training hot path.
+ *
+ * The reference (StuLiu/RegDA) is pure Python/PyTorch and has no FFI of its own; the
+ * "operator interface" it calls on this path is torch / torch_scatter.  Every entry point
+ * below names the reference call site (file:line under the reference tree) it replaces.
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - the caller owns every buffer (inputs, outputs, workspace); the library never
+ *    allocates, frees or keeps a pointer past return; inputs are const and never written;
+ *  - `stream` is a cudaStream_t passed as void*; kernels are launched on it and nothing
+ *    synchronises the host (safe inside CUDA-graph capture);
+ *  - return value: REGDA_OK or a REGDA_ERR_* code; regda_last_error() gives the text for
+ *    the calling thread;
+ *  - data-dependent domain errors (label / region id / probability out of range -- the
+ *    cases where the reference raises from one_hot / scatter / assert) cannot be known
+ *    without a sync, so kernels OR REGDA_FLAG_* bits into the caller's int32 `flags`
+ *    word (may be NULL); offending pixels are passed through unchanged.
+ *  - tensors are dense row-major with the shapes given; int64 labels / regions exactly as
+ *    the reference's LongTensors.
+ */
+#ifndef REGDA_B200_H
+#define REGDA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REGDA_ABI_VERSION 1
+
+#define REGDA_OK 0
+#define REGDA_ERR_INVALID_ARG 1
+#define REGDA_ERR_WORKSPACE 2
+#define REGDA_ERR_CUDA 3
+#define REGDA_ERR_UNSUPPORTED 4
+
+#define REGDA_FLAG_LABEL_RANGE 1  /* reference: RuntimeError from one_hot (local_region_homog.py:121) */
+#define REGDA_FLAG_REGION_RANGE 2 /* reference: RuntimeError from scatter index (local_region_homog.py:140) */
+#define REGDA_FLAG_PROB_RANGE 4   /* reference: AssertionError (pseudo_generation.py:71) */
+
+int regda_abi_version(void);
+const char *regda_last_error(void);
+/* 0: LRH auto, 1: force the generic (global-bin) path, 2: force the cluster path (error if it does not fit) */
+int regda_set_lrh_path(int mode);
+/* which path the last regda_lrh_forward on this thread took: 1 generic, 2 cluster; cluster size in *cluster */
+int regda_lrh_last_path(int *cluster);
+
+/* ---- Local Region Homogenizing ------------------------------------------------------
+ * Replaces Homogenizer.forward, regda/utils/local_region_homog.py:125-152 (incl. the
+ * torch_scatter.scatter(reduce='sum') at :140 and _index2onehot at :107-123).
+ * labels, regions, out: int64 [b][h*w].  region ids must lie in [0, region_bound);
+ * region_bound plays the role of the reference's batch-global `regions.max()+1`.
+ * percent is the Python double of the reference; it is compared as float32, as there. */
+size_t regda_lrh_workspace_bytes(int b, int64_t hw, int class_num, int64_t region_bound);
+int regda_lrh_forward(const int64_t *labels, const int64_t *regions, int64_t *out,
+                      int b, int64_t hw, int class_num, int64_t ignore_label, double percent,
+                      int64_t region_bound, int32_t *flags,
+                      void *workspace, size_t workspace_bytes, void *stream);
+/* max(regions)+1 (and a REGION_RANGE flag for negative ids) without leaving the device:
+ * bound_out is one int64.  Replaces the implicit index.max() inside scatter (:140). */
+int regda_region_bound(const int64_t *regions, int64_t n, int64_t *bound_out, int32_t *flags, void *stream);
+
+#if 0 /* PLANNED: moved out of this block as each kernel lands */
+/* ---- pseudo_selection ---------------------------------------------------------------
+ * Replaces regda/gast/pseudo_generation.py:59-93.  soft: float32 [b][c][hw];
+ * out: int64 [b][hw].  workspace: regda_select_workspace_bytes(b, c). */
+size_t regda_select_workspace_bytes(int b, int c);
+int regda_pseudo_select(const float *soft, int64_t *out, int b, int c, int64_t hw,
+                        double cutoff_top, double cutoff_low, int64_t ignore_label,
+                        int32_t *flags, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- Aligner.label_refine (label_t_sup=None, mode='all') -----------------------------
+ * Replaces regda/gast/alignment.py:194-265 with _pearson_dist :396-423, _softmax_T
+ * :283-286 and _logits_norm :288-298.
+ *   feat_nhwc   float32 [b][h][w][k]   (channels-last view of the reference's [b,k,h,w])
+ *   prototypes  float32 [c][k]
+ *   pred1/pred2 float32 [b][c][h][w]   (pred2 may be NULL: single-head form of :232-234)
+ *   soft_in/out float32 [b][c][H][W]
+ * workspace: regda_refine_workspace_bytes(b, c, h, w). */
+size_t regda_refine_workspace_bytes(int b, int c, int h, int w);
+int regda_pearson_dist(const float *rows, const float *prototypes, float *dist,
+                       int64_t n, int c, int k, void *stream);
+int regda_label_refine(const float *feat_nhwc, const float *prototypes,
+                       const float *pred1, const float *pred2,
+                       const float *soft_in, float *soft_out,
+                       int b, int c, int k, int h, int w, int H, int W, double temp,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- DownscaleLabel + prototype update ------------------------------------------------
+ * regda_downscale_label replaces DownscaleLabel.forward, alignment.py:466-481:
+ *   label int64 [b][H][W] -> out int64 [b][H/scale][W/scale].
+ * regda_class_sums replaces the one_hot x feature broadcast-sum of
+ *   _compute_local_prototypes (:313-320) and update_avg (:107-119):
+ *   feat_nhwc float32 [n][k], label_ds int64 [n] -> sums float32 [c][k], counts float32 [c]
+ *   (ACCUMULATED into sums/counts when accumulate != 0, which is update_avg's running sum).
+ * regda_prototype_ema replaces :319-325 + _ema :435-438 in place on `prototypes`. */
+int regda_downscale_label(const int64_t *label, int64_t *out, int b, int H, int W, int scale,
+                          int n_classes, int64_t ignore_label, double min_ratio,
+                          int32_t *flags, void *stream);
+size_t regda_class_sums_workspace_bytes(int64_t n, int c, int k);
+int regda_class_sums(const float *feat_nhwc, const int64_t *label_ds, float *sums, float *counts,
+                     int64_t n, int c, int k, int64_t ignore_label, int accumulate,
+                     void *workspace, size_t workspace_bytes, void *stream);
+int regda_prototype_ema(float *prototypes, const float *sums, const float *counts,
+                        int c, int k, double decay, void *stream);
+int regda_prototype_init_avg(float *prototypes, const float *sums, const float *counts,
+                             int c, int k, void *stream);
+
+/* ---- loss_calc + CrossEntropy --------------------------------------------------------
+ * Replaces regda/utils/tools.py:240-252 (bilinear align_corners=True upsample of each
+ * head) + regda/gast/balance.py:88-101 (per-pixel CE, ignore_index, mean over ALL pixels).
+ *   pred     float32 [b][c][h][w] low-resolution logits of ONE head
+ *   label    int64   [b][H][W]
+ *   loss     float32 [1]  : mean CE of this head (written, not accumulated)
+ *   dpred    float32 [b][c][h][w] : d(loss)/d(pred) * grad_scale  (may be NULL: forward only)
+ * workspace: regda_ce_workspace_bytes(b, h, w). Deterministic (fixed-order reductions). */
+size_t regda_ce_workspace_bytes(int b, int h, int w);
+int regda_ce_bilinear(const float *pred, const int64_t *label, float *loss, float *dpred,
+                      int b, int c, int h, int w, int H, int W, int64_t ignore_label,
+                      double grad_scale, const float *pixel_weight_by_class,
+                      int32_t *flags, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- ClassBalance counts (flag-gated --bcs/--bct, balance.py:35-53) ---------------------
+ * counts int64 [c] + n_valid int64 [1] written to counts_out[c+1]. */
+int regda_class_count(const int64_t *label, int64_t n, int c, int64_t ignore_label,
+                      int64_t *counts_out, int32_t *flags, void *stream);
+
+/* ---- clip_grad_norm_ + SGD(momentum, weight_decay) -------------------------------------
+ * Replaces tools/train_ssl_reg.py:239-241 over ONE flat fp32 parameter arena.
+ * regda_sumsq: partial sums of squares -> sumsq_out float32 [1] (deterministic two-stage).
+ * regda_sgd_step: coef = min(1, max_norm / (sqrt(sumsq)+1e-6)); g = coef*grad + wd*p;
+ *   buf = first_step ? g : momentum*buf + g; p -= lr*buf; optional bf16 shadow copy. */
+size_t regda_sumsq_workspace_bytes(int64_t n);
+int regda_sumsq(const float *x, int64_t n, float *sumsq_out, void *workspace, size_t workspace_bytes, void *stream);
+int regda_sgd_step(float *param, const float *grad, float *momentum_buf, void *param_bf16,
+                   int64_t n, const float *sumsq, double max_norm, double lr, double momentum,
+                   double weight_decay, int first_step, void *stream);
+/* ExponentialMovingAverage.update, regda/utils/ema.py:46-51 (opt-in; unused by the reference loop) */
+int regda_ema_update(float *shadow, const float *param, int64_t n, double decay, void *stream);
+
+#endif /* PLANNED */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REGDA_B200_H */

@@ -33,6 +33,28 @@ def lrh(labels, regions, class_num, ignore_label, percent):
     return torch.from_numpy(cbind.lrh(labels.cpu().numpy(), regions.cpu().numpy(), class_num, ignore_label, percent))
 
 
+def lrh_torch(labels, regions, class_num, ignore_label, percent):
+    """local_region_homog.py:107-152 restated op-for-op in torch (int64 one-hot counts,
+    scatter_add_ per image, float32 ratio test, gather, where).  This is the multi-threaded
+    CPU arm bench.py times as `--impl reference` (the C function above is the scalar checker);
+    tests/test_oracle_golden.py holds it to the same golden vectors."""
+    b = labels.shape[0]
+    lab = labels.reshape(b, -1)
+    reg = regions.reshape(b, -1)
+    code = torch.where(lab == ignore_label, torch.full_like(lab, class_num), lab)          # :118
+    onehot = F.one_hot(code, class_num + 1)[..., :class_num]                               # :121
+    n_reg = int(reg.max()) + 1                                                             # scatter's index.max()+1
+    counts = torch.zeros(b, n_reg, class_num, dtype=torch.int64)
+    counts.scatter_add_(1, reg.unsqueeze(-1).expand(-1, -1, class_num), onehot)            # :140
+    valid = counts.sum(-1)                                                                 # :141
+    best, arg = counts.max(-1)                                                             # :142 (first max)
+    ratio = best / (valid + 1e-5)                                                          # :143 float32
+    arg = torch.where(ratio < percent, torch.full_like(arg, ignore_label), arg)            # :144
+    out = torch.gather(arg, 1, reg)                                                        # :147
+    out = torch.where(reg == 0, torch.full_like(out, ignore_label), out)                   # :149
+    return torch.where(out == ignore_label, lab, out).view_as(labels)                      # :151
+
+
 def pseudo_select(soft, cutoff_top=0.8, cutoff_low=0.6, ignore_label=-1):
     """pseudo_generation.py:59-93 through the C oracle."""
     from . import cbind

@@ -129,3 +129,11 @@ def test_full_step_oracle_matches_reference_fixture():
             assert (r["hard"].numpy() != z["hard_0"]).mean() < 1e-3   # fp-threshold flips only
     torch.testing.assert_close(st.prototypes, t("proto_after"), rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(m.encoder.resnet.conv1.weight.detach(), t("conv1_after"), rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c["name"]) for c in CASES])
+def test_lrh_torch_port_bit_exact(case):
+    """the multi-threaded torch port timed by `bench.py --impl reference` is held to the same pins"""
+    out = so.lrh_torch(torch.from_numpy(case["labels"]), torch.from_numpy(case["regions"]),
+                       int(case["class_num"]), int(case["ignore"]), float(case["percent"]))
+    assert np.array_equal(out.numpy(), case["out"])
