@@ -17,7 +17,7 @@
  *  - data-dependent domain errors (label / region id / probability out of range -- the
  *    cases where the reference raises from one_hot / scatter / assert) cannot be known
  *    without a sync, so kernels OR REGDA_FLAG_* bits into the caller's int32 `flags`
- *    word (may be NULL); offending pixels are passed through unchanged.
+ *    word (may be NULL); the output at offending pixels is unspecified.
  *  - tensors are dense row-major with the shapes given; int64 labels / regions exactly as
  *    the reference's LongTensors.
  */
@@ -65,7 +65,6 @@ int regda_lrh_forward(const int64_t *labels, const int64_t *regions, int64_t *ou
  * bound_out is one int64.  Replaces the implicit index.max() inside scatter (:140). */
 int regda_region_bound(const int64_t *regions, int64_t n, int64_t *bound_out, int32_t *flags, void *stream);
 
-#if 0 /* PLANNED: moved out of this block as each kernel lands */
 /* ---- pseudo_selection ---------------------------------------------------------------
  * Replaces regda/gast/pseudo_generation.py:59-93.  soft: float32 [b][c][hw];
  * out: int64 [b][hw].  workspace: regda_select_workspace_bytes(b, c). */
@@ -81,15 +80,27 @@ int regda_pseudo_select(const float *soft, int64_t *out, int b, int c, int64_t h
  *   prototypes  float32 [c][k]
  *   pred1/pred2 float32 [b][c][h][w]   (pred2 may be NULL: single-head form of :232-234)
  *   soft_in/out float32 [b][c][H][W]
- * workspace: regda_refine_workspace_bytes(b, c, h, w). */
-size_t regda_refine_workspace_bytes(int b, int c, int h, int w);
-int regda_pearson_dist(const float *rows, const float *prototypes, float *dist,
-                       int64_t n, int c, int k, void *stream);
+ * regda_refine_select is the fused form used by the training step: label_refine followed
+ * by pseudo_selection (:218 of tools/train_ssl_reg.py) without materialising the refined
+ * [b,c,H,W] tensor; hard_out int64 [b][H][W].
+ * workspace: regda_refine_workspace_bytes(b, c, k, h, w) for both. */
+size_t regda_refine_workspace_bytes(int b, int c, int k, int h, int w);
 int regda_label_refine(const float *feat_nhwc, const float *prototypes,
                        const float *pred1, const float *pred2,
                        const float *soft_in, float *soft_out,
                        int b, int c, int k, int h, int w, int H, int W, double temp,
                        void *workspace, size_t workspace_bytes, void *stream);
+int regda_refine_select(const float *feat_nhwc, const float *prototypes,
+                        const float *pred1, const float *pred2,
+                        const float *soft_in, int64_t *hard_out,
+                        int b, int c, int k, int h, int w, int H, int W, double temp,
+                        double cutoff_top, double cutoff_low, int64_t ignore_label,
+                        void *workspace, size_t workspace_bytes, void *stream);
+/* _pearson_dist alone (alignment.py:396-423): rows float32 [n][k], prototypes [c][k] ->
+ * dist float32 [n][c].  workspace: regda_pearson_workspace_bytes(c, k). */
+size_t regda_pearson_workspace_bytes(int c, int k);
+int regda_pearson_dist(const float *rows, const float *prototypes, float *dist,
+                       int64_t n, int c, int k, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- DownscaleLabel + prototype update ------------------------------------------------
  * regda_downscale_label replaces DownscaleLabel.forward, alignment.py:466-481:
@@ -98,7 +109,8 @@ int regda_label_refine(const float *feat_nhwc, const float *prototypes,
  *   _compute_local_prototypes (:313-320) and update_avg (:107-119):
  *   feat_nhwc float32 [n][k], label_ds int64 [n] -> sums float32 [c][k], counts float32 [c]
  *   (ACCUMULATED into sums/counts when accumulate != 0, which is update_avg's running sum).
- * regda_prototype_ema replaces :319-325 + _ema :435-438 in place on `prototypes`. */
+ * regda_prototype_ema replaces :319-325 + _ema :435-438 in place on `prototypes`;
+ * regda_prototype_init_avg replaces init_avg :121-122. */
 int regda_downscale_label(const int64_t *label, int64_t *out, int b, int H, int W, int scale,
                           int n_classes, int64_t ignore_label, double min_ratio,
                           int32_t *flags, void *stream);
@@ -118,32 +130,35 @@ int regda_prototype_init_avg(float *prototypes, const float *sums, const float *
  *   label    int64   [b][H][W]
  *   loss     float32 [1]  : mean CE of this head (written, not accumulated)
  *   dpred    float32 [b][c][h][w] : d(loss)/d(pred) * grad_scale  (may be NULL: forward only)
- * workspace: regda_ce_workspace_bytes(b, h, w). Deterministic (fixed-order reductions). */
-size_t regda_ce_workspace_bytes(int b, int h, int w);
+ *   class_weight float32 [c] or NULL: ClassBalance per-class pixel weight (balance.py:30-33)
+ * workspace: regda_ce_workspace_bytes(b, h, H). */
+size_t regda_ce_workspace_bytes(int b, int h, int H);
 int regda_ce_bilinear(const float *pred, const int64_t *label, float *loss, float *dpred,
                       int b, int c, int h, int w, int H, int W, int64_t ignore_label,
-                      double grad_scale, const float *pixel_weight_by_class,
+                      double grad_scale, const float *class_weight,
                       int32_t *flags, void *workspace, size_t workspace_bytes, void *stream);
 
-/* ---- ClassBalance counts (flag-gated --bcs/--bct, balance.py:35-53) ---------------------
- * counts int64 [c] + n_valid int64 [1] written to counts_out[c+1]. */
+/* ---- ClassBalance counts (flag-gated --bcs/--bct, balance.py:43-66) ---------------------
+ * counts_out int64 [c+1]: per-class pixel counts, then the number of non-ignored pixels. */
 int regda_class_count(const int64_t *label, int64_t n, int c, int64_t ignore_label,
                       int64_t *counts_out, int32_t *flags, void *stream);
 
 /* ---- clip_grad_norm_ + SGD(momentum, weight_decay) -------------------------------------
  * Replaces tools/train_ssl_reg.py:239-241 over ONE flat fp32 parameter arena.
- * regda_sumsq: partial sums of squares -> sumsq_out float32 [1] (deterministic two-stage).
- * regda_sgd_step: coef = min(1, max_norm / (sqrt(sumsq)+1e-6)); g = coef*grad + wd*p;
- *   buf = first_step ? g : momentum*buf + g; p -= lr*buf; optional bf16 shadow copy. */
+ * regda_sumsq: sum of squares -> sumsq_out float32 [1] (fixed-order two-stage; accumulate != 0
+ *   adds to the value already there, for arenas split over several calls).
+ * regda_sgd_step: g = grad*grad_scale; coef = min(1, max_norm/(sqrt(sumsq)*grad_scale + 1e-6));
+ *   g = coef*g + wd*p;  buf = first_step ? g : momentum*buf + g;  p -= lr*buf;
+ *   optional bf16 shadow copy of p (param_bf16, may be NULL); sumsq NULL = no clipping. */
 size_t regda_sumsq_workspace_bytes(int64_t n);
-int regda_sumsq(const float *x, int64_t n, float *sumsq_out, void *workspace, size_t workspace_bytes, void *stream);
+int regda_sumsq(const float *x, int64_t n, float *sumsq_out, int accumulate,
+                void *workspace, size_t workspace_bytes, void *stream);
 int regda_sgd_step(float *param, const float *grad, float *momentum_buf, void *param_bf16,
-                   int64_t n, const float *sumsq, double max_norm, double lr, double momentum,
-                   double weight_decay, int first_step, void *stream);
+                   int64_t n, const float *sumsq, double max_norm, double grad_scale, double lr,
+                   double momentum, double weight_decay, int first_step, void *stream);
 /* ExponentialMovingAverage.update, regda/utils/ema.py:46-51 (opt-in; unused by the reference loop) */
 int regda_ema_update(float *shadow, const float *param, int64_t n, double decay, void *stream);
 
-#endif /* PLANNED */
 
 #ifdef __cplusplus
 }

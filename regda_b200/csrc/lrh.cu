@@ -111,16 +111,16 @@ lrh_cluster_kernel(const LrhArgs a, const int px_cta, const int nclusters) {
     const int tid = threadIdx.x, nthreads = blockDim.x;
 
     const int nwords = a.region_bound * CW;
+    const int rpc = ((a.region_bound + static_cast<int>(CL) - 1) / static_cast<int>(CL) + 15) & ~15;  // regions owned per CTA
     unsigned *bins = reinterpret_cast<unsigned *>(smem);
-    unsigned char *win = smem + static_cast<size_t>(nwords) * 4;
-    const size_t tile_off = (static_cast<size_t>(nwords) * 4 + a.region_bound + 15) & ~static_cast<size_t>(15);
+    unsigned char *win = smem + ((static_cast<size_t>(nwords) * 4 + 15) & ~static_cast<size_t>(15));
+    const size_t tile_off = ((static_cast<size_t>(nwords) * 4 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(rpc) * CL;
     uint4 *reg16 = reinterpret_cast<uint4 *>(smem + tile_off);                         // 8 x u16 per group
     uint2 *lab8 = reinterpret_cast<uint2 *>(smem + tile_off + static_cast<size_t>(px_cta) * 2);  // 8 x u8 per group
 
     const int start = min(a.hw, static_cast<int>(rank) * px_cta);
     const int end = min(a.hw, start + px_cta);
     const int ngroups = (end - start) / kGroupPx;
-    const int rpc = (a.region_bound + static_cast<int>(CL) - 1) / static_cast<int>(CL);
     const int r_lo = min(a.region_bound, static_cast<int>(rank) * rpc);
     const int r_hi = min(a.region_bound, r_lo + rpc);
     bool bad_label = false, bad_region = false;
@@ -163,6 +163,8 @@ lrh_cluster_kernel(const LrhArgs a, const int px_cta, const int nclusters) {
         cluster.sync();
 
         // ---- merge: the owner CTA of a region sums the CL partial bins over DSMEM ----------
+        // (winner bytes are written to the owner's OWN table; everyone pulls the slices after
+        // the sync with 16-byte DSMEM loads -- remote byte stores were the slow part.)
         for (int r = r_lo + tid; r < r_hi; r += nthreads) {
             unsigned tot[2 * CW];
 #pragma unroll
@@ -176,10 +178,22 @@ lrh_cluster_kernel(const LrhArgs a, const int px_cta, const int nclusters) {
                     tot[2 * w + 1] += v >> 16;
                 }
             }
-            const unsigned char wb = static_cast<unsigned char>(lrh_winner<2 * CW>(tot, a.class_num, a.percent, a.ignore_label));
-            for (unsigned j = 0; j < CL; ++j) cluster.map_shared_rank(win, j)[r] = wb;
+            win[r] = static_cast<unsigned char>(lrh_winner<2 * CW>(tot, a.class_num, a.percent, a.ignore_label));
         }
         cluster.sync();
+        {
+            // rpc is a multiple of 16 (see plan), so every owner slice is uint4-aligned
+            const int nvec = rpc / 16;
+            for (int i = tid; i < nvec * static_cast<int>(CL); i += nthreads) {
+                const unsigned j = static_cast<unsigned>(i / nvec);
+                if (j == rank) continue;
+                const int off = static_cast<int>(j) * rpc + (i - static_cast<int>(j) * nvec) * 16;
+                if (off >= a.region_bound) continue;
+                const uint4 v = *reinterpret_cast<const uint4 *>(cluster.map_shared_rank(win, j) + off);
+                *reinterpret_cast<uint4 *>(win + off) = v;
+            }
+        }
+        __syncthreads();
 
         // ---- pass 2: smem tile + winners -> HBM ------------------------------------------
         long long *out = a.out + static_cast<size_t>(img) * a.hw + start;
@@ -199,8 +213,204 @@ lrh_cluster_kernel(const LrhArgs a, const int px_cta, const int nclusters) {
             stg256_stream(out + g * kGroupPx, o0);
             stg256_stream(out + g * kGroupPx + 4, o1);
         }
-        // bins/win of this image are dead: every remote reader finished before the second
-        // cluster.sync, and remote writers of the next image wait for the next first sync.
+        // Remote CTAs may still be pulling this CTA's winner slice: the owner rewrites it only
+        // after the NEXT image's first cluster.sync, which every puller has passed by then.
+        // bins are re-zeroed at the top of the loop, but remote readers of the bins all
+        // finished before the second cluster.sync above.
+    }
+    if (bad_label) raise_flag(a.flags, REGDA_FLAG_LABEL_RANGE);
+    if (bad_region) raise_flag(a.flags, REGDA_FLAG_REGION_RANGE);
+}
+
+// ----------------------------------------------------------------------------------------
+// cluster path, fast variant: ignore_label == -1 (the value the training tools pass) and
+// class_num <= 14.  Same structure as lrh_cluster_kernel, ~4x fewer instructions per pixel:
+//   * labels are encoded as code = label + 1 (0 = ignored, 1..class_num = classes,
+//     class_num + 1 = "label == class_num"), validated in bulk (OR of the high words, max of
+//     the low words) instead of per element;
+//   * the loads of the next group are issued before the current group is histogrammed;
+//   * winners are stored as code (0 = keep the input label) with win[0] == 0, so region 0 and
+//     "did not pass" need no test of their own in pass 2.
+// ----------------------------------------------------------------------------------------
+struct alignas(32) u32x8 { unsigned v[8]; };
+__device__ __forceinline__ u32x8 ldg256_u32(const void *p) {
+    u32x8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg256_u32(void *p, const u32x8 &r) {
+    asm volatile("st.global.L1::no_allocate.v8.u32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+                 :: "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7]), "l"(p) : "memory");
+}
+
+template <int CW, typename AccT>
+__device__ __forceinline__ void flush_acc(unsigned *bins, unsigned region, AccT acc) {
+    // acc nibble k+1 = count of class k in the run (nibble 0 = ignored pixels: dropped)
+    if (region == 0u) return;                       // region 0 is never homogenised (:149)
+    unsigned *base = bins + region * CW;
+#pragma unroll
+    for (int w = 0; w < CW; ++w) {
+        const unsigned lo = static_cast<unsigned>(acc >> (8 * w + 4)) & 0xFu;
+        const unsigned hi = static_cast<unsigned>(acc >> (8 * w + 8)) & 0xFu;
+        const unsigned v = lo | (hi << 16);
+        if (v) atomicAdd(base + w, v);
+    }
+}
+
+template <int CW, typename AccT>
+__global__ void __launch_bounds__(512, 2)
+lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned CL = cluster.num_blocks();
+    const unsigned rank = cluster.block_rank();
+    const int cluster_id = blockIdx.x / CL;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+
+    const int nwords = a.region_bound * CW;
+    const int rpc = ((a.region_bound + static_cast<int>(CL) - 1) / static_cast<int>(CL) + 15) & ~15;
+    unsigned *bins = reinterpret_cast<unsigned *>(smem);
+    unsigned char *win = smem + ((static_cast<size_t>(nwords) * 4 + 15) & ~static_cast<size_t>(15));
+    const size_t tile_off = ((static_cast<size_t>(nwords) * 4 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(rpc) * CL;
+    uint4 *reg16 = reinterpret_cast<uint4 *>(smem + tile_off);
+    uint2 *lab8 = reinterpret_cast<uint2 *>(smem + tile_off + static_cast<size_t>(px_cta) * 2);
+
+    const int start = min(a.hw, static_cast<int>(rank) * px_cta);
+    const int end = min(a.hw, start + px_cta);
+    const int ngroups = (end - start) / kGroupPx;
+    const int r_lo = min(a.region_bound, static_cast<int>(rank) * rpc);
+    const int r_hi = min(a.region_bound, r_lo + rpc);
+    const unsigned max_code = static_cast<unsigned>(a.class_num) + 1u;
+    const unsigned bound = static_cast<unsigned>(a.region_bound);
+    bool bad_label = false, bad_region = false;
+
+    for (int img = cluster_id; img < a.b; img += nclusters) {
+        for (int i = tid; i < nwords; i += nthreads) bins[i] = 0u;
+        __syncthreads();
+
+        // ---- pass 1 ---------------------------------------------------------------------
+        const long long *lab = a.labels + static_cast<size_t>(img) * a.hw + start;
+        const long long *reg = a.regions + static_cast<size_t>(img) * a.hw + start;
+        u32x8 l0, l1, r0, r1;
+        int g = tid;
+        if (g < ngroups) {
+            l0 = ldg256_u32(lab + g * kGroupPx); l1 = ldg256_u32(lab + g * kGroupPx + 4);
+            r0 = ldg256_u32(reg + g * kGroupPx); r1 = ldg256_u32(reg + g * kGroupPx + 4);
+        }
+        while (g < ngroups) {
+            // code = label + 1 as a 64-bit add; valid iff the high word becomes 0 and low <= class_num + 1
+            unsigned cc[kGroupPx], rr[kGroupPx];
+            unsigned hi_or = 0u, lo_max = 0u, rhi_or = 0u, rlo_max = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                cc[k] = l0.v[2 * k] + 1u;
+                cc[k + 4] = l1.v[2 * k] + 1u;
+                hi_or |= l0.v[2 * k + 1] + (cc[k] == 0u ? 1u : 0u);
+                hi_or |= l1.v[2 * k + 1] + (cc[k + 4] == 0u ? 1u : 0u);
+                lo_max = max(lo_max, max(cc[k], cc[k + 4]));
+                rr[k] = r0.v[2 * k];
+                rr[k + 4] = r1.v[2 * k];
+                rhi_or |= r0.v[2 * k + 1] | r1.v[2 * k + 1];
+                rlo_max = max(rlo_max, max(rr[k], rr[k + 4]));
+            }
+            if (hi_or != 0u || lo_max > max_code) {            // rare: sanitise element-wise
+                bad_label = true;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (l0.v[2 * k + 1] + (cc[k] == 0u ? 1u : 0u) != 0u || cc[k] > max_code) cc[k] = 0u;
+                    if (l1.v[2 * k + 1] + (cc[k + 4] == 0u ? 1u : 0u) != 0u || cc[k + 4] > max_code) cc[k + 4] = 0u;
+                }
+            }
+            if (rhi_or != 0u || rlo_max >= bound) {
+                bad_region = true;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (r0.v[2 * k + 1] != 0u || rr[k] >= bound) rr[k] = 0u;
+                    if (r1.v[2 * k + 1] != 0u || rr[k + 4] >= bound) rr[k + 4] = 0u;
+                }
+            }
+            const int gn = g + nthreads;
+            const int cur = g;
+            g = gn;
+            if (gn < ngroups) {                                // next group's loads fly during the histogram
+                l0 = ldg256_u32(lab + gn * kGroupPx); l1 = ldg256_u32(lab + gn * kGroupPx + 4);
+                r0 = ldg256_u32(reg + gn * kGroupPx); r1 = ldg256_u32(reg + gn * kGroupPx + 4);
+            }
+            const unsigned p0 = rr[0] | (rr[1] << 16), p1 = rr[2] | (rr[3] << 16), p2 = rr[4] | (rr[5] << 16), p3 = rr[6] | (rr[7] << 16);
+            reg16[cur] = make_uint4(p0, p1, p2, p3);
+            lab8[cur] = make_uint2(cc[0] | (cc[1] << 8) | (cc[2] << 16) | (cc[3] << 24), cc[4] | (cc[5] << 8) | (cc[6] << 16) | (cc[7] << 24));
+            if (p0 == p1 && p2 == p3 && p0 == p2 && rr[0] == rr[1]) {   // one region over the 8 pixels
+                AccT acc = 0;
+#pragma unroll
+                for (int k = 0; k < kGroupPx; ++k) acc += static_cast<AccT>(1) << (4 * cc[k]);
+                flush_acc<CW, AccT>(bins, rr[0], acc);
+            } else {
+                unsigned curr = rr[0];
+                AccT acc = 0;
+#pragma unroll
+                for (int k = 0; k < kGroupPx; ++k) {
+                    if (rr[k] != curr) {
+                        flush_acc<CW, AccT>(bins, curr, acc);
+                        curr = rr[k];
+                        acc = 0;
+                    }
+                    acc += static_cast<AccT>(1) << (4 * cc[k]);
+                }
+                flush_acc<CW, AccT>(bins, curr, acc);
+            }
+        }
+        cluster.sync();
+
+        // ---- merge ----------------------------------------------------------------------
+        for (int r = r_lo + tid; r < r_hi; r += nthreads) {
+            unsigned tot[2 * CW];
+#pragma unroll
+            for (int c = 0; c < 2 * CW; ++c) tot[c] = 0u;
+            for (unsigned j = 0; j < CL; ++j) {
+                const unsigned *rb = cluster.map_shared_rank(bins, j) + r * CW;
+#pragma unroll
+                for (int w = 0; w < CW; ++w) {
+                    const unsigned v = rb[w];
+                    tot[2 * w] += v & 0xFFFFu;
+                    tot[2 * w + 1] += v >> 16;
+                }
+            }
+            const unsigned wv = lrh_winner<2 * CW>(tot, a.class_num, a.percent, a.ignore_label);
+            win[r] = static_cast<unsigned char>((wv == kWinNone || r == 0) ? 0u : wv + 1u);
+        }
+        cluster.sync();
+        {
+            const int nvec = rpc / 16;
+            for (int i = tid; i < nvec * static_cast<int>(CL); i += nthreads) {
+                const unsigned j = static_cast<unsigned>(i / nvec);
+                if (j == rank) continue;
+                const int off = static_cast<int>(j) * rpc + (i - static_cast<int>(j) * nvec) * 16;
+                if (off >= a.region_bound) continue;
+                *reinterpret_cast<uint4 *>(win + off) = *reinterpret_cast<const uint4 *>(cluster.map_shared_rank(win, j) + off);
+            }
+        }
+        __syncthreads();
+
+        // ---- pass 2 ---------------------------------------------------------------------
+        long long *out = a.out + static_cast<size_t>(img) * a.hw + start;
+        for (int g2 = tid; g2 < ngroups; g2 += nthreads) {
+            const uint4 rv = reg16[g2];
+            const uint2 lv = lab8[g2];
+            const unsigned rw[4] = {rv.x, rv.y, rv.z, rv.w};
+            u32x8 o0, o1;
+#pragma unroll
+            for (int k = 0; k < kGroupPx; ++k) {
+                const unsigned r = (k & 1) ? (rw[k >> 1] >> 16) : (rw[k >> 1] & 0xFFFFu);
+                const unsigned code = ((k < 4 ? lv.x : lv.y) >> ((k & 3) * 8)) & 0xFFu;
+                const unsigned wv = win[r];
+                const unsigned res = wv ? wv : code;          // code: 0 = ignore(-1), else class + 1
+                const unsigned lo = res - 1u, hi = res ? 0u : 0xFFFFFFFFu;
+                if (k < 4) { o0.v[2 * k] = lo; o0.v[2 * k + 1] = hi; } else { o1.v[2 * (k - 4)] = lo; o1.v[2 * (k - 4) + 1] = hi; }
+            }
+            stg256_u32(out + g2 * kGroupPx, o0);
+            stg256_u32(out + g2 * kGroupPx + 4, o1);
+        }
     }
     if (bad_label) raise_flag(a.flags, REGDA_FLAG_LABEL_RANGE);
     if (bad_region) raise_flag(a.flags, REGDA_FLAG_REGION_RANGE);
@@ -211,13 +421,14 @@ struct ClusterPlan {
     int cluster = 0;
     int px_cta = 0;
     int cw = 0;
+    int threads = 0;
     size_t smem = 0;
 };
 
-size_t cluster_smem_bytes(int region_bound, int cw, int px_cta) {
-    const size_t bins = static_cast<size_t>(region_bound) * cw * 4;
-    const size_t tile_off = (bins + region_bound + 15) & ~static_cast<size_t>(15);
-    return tile_off + static_cast<size_t>(px_cta) * 3;
+size_t cluster_smem_bytes(int region_bound, int cw, int px_cta, int cl) {
+    const size_t bins = (static_cast<size_t>(region_bound) * cw * 4 + 15) & ~static_cast<size_t>(15);
+    const size_t rpc = static_cast<size_t>(((region_bound + cl - 1) / cl + 15) & ~15);
+    return bins + rpc * cl + static_cast<size_t>(px_cta) * 3;
 }
 
 ClusterPlan plan_cluster(int b, int64_t hw, int class_num, int64_t region_bound) {
@@ -227,31 +438,33 @@ ClusterPlan plan_cluster(int b, int64_t hw, int class_num, int64_t region_bound)
     if (hw < kGroupPx || hw % kGroupPx != 0 || hw > (1ll << 30)) return p;
     p.cw = (class_num + 1) / 2;
     const size_t limit = static_cast<size_t>(max_optin_smem());
-    // small batches: spread one image over 16 SMs; otherwise the portable size 8 first
-    const int order_small[2] = {16, 8}, order_big[2] = {8, 16};
-    const int *order = (b * 8 <= sm_count() / 2) ? order_small : order_big;
-    for (int i = 0; i < 2; ++i) {
-        const int cl = order[i];
+    const size_t half = (limit + 1024) / 2 - 1024;             // two CTAs per SM (1 KB reserved each)
+    // Preference: two 512-thread CTAs per SM (their load / merge / store phases overlap), the
+    // portable cluster size first when the batch fills the GPU, 16 first for small batches.
+    const bool small = b * 8 <= sm_count() / 2;
+    const int order[4][2] = {{small ? 16 : 8, 2}, {small ? 8 : 16, 2}, {small ? 16 : 8, 1}, {small ? 8 : 16, 1}};
+    for (int i = 0; i < 4; ++i) {
+        const int cl = order[i][0], per_sm = order[i][1];
         int px = static_cast<int>((hw + cl - 1) / cl);
         px = (px + kGroupPx - 1) / kGroupPx * kGroupPx;
         if (px > 65535) continue;                              // u16 per-CTA counters
-        const size_t s = cluster_smem_bytes(static_cast<int>(region_bound), p.cw, px);
-        if (s > limit) continue;
+        const size_t s = cluster_smem_bytes(static_cast<int>(region_bound), p.cw, px, cl);
+        if (s > (per_sm == 2 ? half : limit)) continue;
+        const int groups = px / kGroupPx;
         p.ok = true; p.cluster = cl; p.px_cta = px; p.smem = s;
+        p.threads = groups >= 512 ? 512 : 256;   // 64 registers/thread: two such CTAs fill an SM's register file
         return p;
     }
     return p;
 }
 
-template <int CW>
-int launch_cluster(const LrhArgs &a, const ClusterPlan &p, cudaStream_t st, bool *launched) {
+template <typename Kern>
+int launch_cluster_kernel(Kern kern, const LrhArgs &a, const ClusterPlan &p, cudaStream_t st, bool *launched) {
     *launched = false;
-    auto kern = lrh_cluster_kernel<CW>;
     REGDA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
     if (p.cluster > 8) REGDA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    const int threads = (p.px_cta / kGroupPx >= 1024) ? 1024 : (p.px_cta / kGroupPx >= 512 ? 512 : 256);
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(threads);
+    cfg.blockDim = dim3(p.threads);
     cfg.dynamicSmemBytes = p.smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -273,6 +486,15 @@ int launch_cluster(const LrhArgs &a, const ClusterPlan &p, cudaStream_t st, bool
     REGDA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a, p.px_cta, nclusters));
     *launched = true;
     return REGDA_OK;
+}
+
+template <int CW>
+int launch_cluster(const LrhArgs &a, const ClusterPlan &p, cudaStream_t st, bool *launched) {
+    if (a.ignore_label == -1 && p.threads <= 512) {
+        if (a.class_num <= 6) return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned>, a, p, st, launched);
+        if (a.class_num <= 14) return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned long long>, a, p, st, launched);
+    }
+    return launch_cluster_kernel(lrh_cluster_kernel<CW>, a, p, st, launched);
 }
 
 // ----------------------------------------------------------------------------------------
