@@ -148,6 +148,8 @@ def bench_lrh(args, rank, world, local):
     n_regions = args.regions
     lab, reg = lrh_inputs(dev, n_regions, 2333 + rank)
     bound = int(reg.max()) + 1
+    if os.environ.get("REGDA_LRH_PATH"):
+        capi.check(capi.lib().regda_set_lrh_path(int(os.environ["REGDA_LRH_PATH"])))
     hom = Homogenizer(percent=0.5, class_num=6, ignore_label=-1, region_bound=bound, strict=False)
     npx = lab.numel()
 
@@ -267,10 +269,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank, world, local = dist_setup(args.gpus)
-    try:
-        from regda_b200 import step_bench
-    except ImportError:
-        step_bench = None
+    import bench_step as step_bench
     workload = args.workload or ("step" if step_bench is not None else "lrh")
 
     if args.impl == "reference":

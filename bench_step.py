@@ -1,0 +1,187 @@
+"""Benchmark harness of the self-training step (bench.py's default workload):
+BASELINE.json configs[1] -- st.regda.2potsdam, ResNet-101 DeepLab, bf16, 8 source + 8 target
+512x512 tiles per GPU, 6 classes.  Called by bench.py; see there for the JSON contract."""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import torch
+
+from regda_b200 import capi, synth
+
+CLASS_NUM, H, W, B = 6, 512, 512, 8
+FLOP_PER_IMG_FWD_BWD = 543.5e9       # 2 * 90.59 GMAC * 3 (R101, 512^2, C=6)
+MODEL_CFG = dict(backbone=dict(resnet_type="resnet101", output_stride=16, pretrained=False), multi_layer=True, cascade=False,
+                 use_ppm=True, ppm=dict(num_classes=CLASS_NUM, use_aux=False, fc_dim=2048), inchannels=2048,
+                 num_classes=CLASS_NUM, is_ins_norm=True)
+
+
+def build(device, world, resnet="resnet101", use_graph=True, n_regions=200, seed=2333, batch=B, hw=(H, W)):
+    from regda_b200.gast.alignment import Aligner
+    from regda_b200.models.Encoder import Deeplabv2
+    from regda_b200.trainer import GraphedStep, SelfTrainingStep
+    from regda_b200.utils.local_region_homog import Homogenizer
+    torch.manual_seed(seed)
+    cfg = dict(MODEL_CFG)
+    cfg["backbone"] = dict(cfg["backbone"], resnet_type=resnet)
+    model = Deeplabv2(cfg, compute_dtype=torch.bfloat16).to(device).train()
+    inputs = synth.step_inputs(batch, hw[0], hw[1], CLASS_NUM, n_regions, device=device, seed=seed)
+    images_s, label_s, images_t, soft_t, regs_t, proto = inputs
+    aligner = Aligner(None, 2048, CLASS_NUM, -1, 0.996, device=device)
+    aligner.prototypes = proto.clone()
+    bound = int(regs_t.max()) + 1
+    hom = Homogenizer(percent=0.5, class_num=CLASS_NUM, ignore_label=-1, region_bound=bound, strict=False)
+    step = SelfTrainingStep(model, aligner, hom, class_num=CLASS_NUM, ignore_label=-1, world_size=world)
+    tensors = [images_s, label_s, images_t, soft_t, regs_t]
+    runner = None
+    if use_graph:
+        runner = GraphedStep(step, tensors, lr=1e-2)
+    return model, step, runner, tensors
+
+
+def run(args, rank, world, local, pk, ClockSampler, barrier, max_over_ranks):
+    dev = torch.device("cuda", local)
+    use_graph = os.environ.get("REGDA_GRAPH", "1") != "0"
+    calls0 = capi.launch_count
+    model, step, runner, tensors = build(dev, world, use_graph=use_graph, seed=2333 + rank)
+    lr = 1e-2
+
+    def one_step(inp):
+        if runner is not None:
+            return runner(*inp, lr=lr)
+        return step(*inp, lr)
+
+    calls_per_step = None
+    for i in range(max(args.warmup, 3)):
+        c0 = capi.launch_count
+        out = one_step(tensors)
+        calls_per_step = capi.launch_count - c0
+    if runner is not None:
+        # kernels are replayed from the graph: the per-step count is what one eager pass issued during capture
+        c0 = capi.launch_count
+        step._step_impl(*tensors)
+        calls_per_step = capi.launch_count - c0
+    torch.cuda.synchronize()
+    loss0 = float(out["loss"])
+    assert loss0 == loss0 and abs(loss0) < 1e4, f"non-finite / diverged loss {loss0}"
+
+    sampler = ClockSampler(local)
+    barrier(world)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = one_step(tensors)
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    imgs = 2 * B * world
+    value = imgs / (ms * 1e-3)
+
+    # ---- e2e: pinned host inputs -> H2D every step (double-buffered on a copy stream) -> step -> loss D2H
+    host = [t.cpu().pin_memory() for t in tensors]
+    bufs = [[torch.empty_like(t) for t in tensors] for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def stage(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            for d, h in zip(bufs[slot], host):
+                d.copy_(h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    for s in range(2):
+        consumed[s].record()
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    n_e2e = max(3, min(args.steps, 10))
+
+    def e2e_loop(n):
+        stage(0)
+        for i in range(n):
+            slot = i & 1
+            if i + 1 < n:
+                stage(slot ^ 1)
+            torch.cuda.current_stream().wait_event(ready[slot])
+            o = one_step(bufs[slot])
+            consumed[slot].record()
+            loss_host.copy_(o["loss"].view(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()        # the trainer reads the loss every step
+        return float(loss_host[0])
+
+    e2e_loop(2)
+    barrier(world)
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    e2e_loop(n_e2e)
+    t1.record()
+    barrier(world)
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1), world) / n_e2e
+
+    if rank != 0:
+        return
+    from regda_b200.ops import conv as convmod
+    flops = FLOP_PER_IMG_FWD_BWD * 2 * B
+    ach = flops / (ms * 1e-3) / 1e12
+    line = {
+        "metric": "train images/sec (512x512, 6-class)", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "st.regda.2potsdam self-training step: ResNet-101 DeepLab (2 PPM heads), 8 source + 8 target 512x512 "
+                               "tiles per GPU, refine+select+LRH+prototype EMA+4 CE+backward+clip+SGD", "global_batch": imgs,
+                   "parallelism": f"dp{world}", "cuda_graph": use_graph, "conv_engine": convmod.ENGINE,
+                   "l2": "per-step working set (activations ~6 GB) far larger than L2"},
+        "e2e": {"value": round(imgs / (e2e_ms * 1e-3), 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(calls_per_step) * args.steps,
+        "roofline": {"bound": "tensor", "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": round(ach / pk["tf_sustained"], 4), "traffic": None, "peak_source": pk["source"] + " (sustained)",
+                     "kernel": "whole step (conv stacks dominate: 8.70 TFLOP algorithmic per 16-image step)"},
+        "clocks": clocks,
+        "conv_dispatch": dict(convmod.stats),
+        "loss_first": round(loss0, 4),
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_step_baseline(reps=2)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_step_baseline(reps=2, batch=2):
+    """The CPU arm: the torch fp32 port of the whole inner step (oracle/step_oracle.py, pinned to the
+    reference's golden vectors) with every host thread, on a bounded sample: `batch` source +
+    `batch` target 512x512 tiles (train-mode BatchNorm needs >= 2 images)."""
+    from oracle import step_oracle as so
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = so.DeeplabOracle("resnet101", CLASS_NUM)
+    images_s, label_s, images_t, soft_t, regs_t, proto = synth.step_inputs(batch, H, W, CLASS_NUM, 200, device="cpu")
+    st = so.StepState(model, proto)
+    so.inner_step(st, images_s, label_s, images_t, soft_t, regs_t, class_num=CLASS_NUM, lr=1e-2)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        so.inner_step(st, images_s, label_s, images_t, soft_t, regs_t, class_num=CLASS_NUM, lr=1e-2)
+    dt = (time.perf_counter() - t0) / reps
+    return dict(value=round(2 * batch / dt, 3), unit="images/s", cores=cores, kind="port",
+                sample=f"{batch}+{batch} tiles of 512x512 per step (of the 8+8), {reps} timed steps, torch fp32 port of the inner step",
+                ms_per_step=round(dt * 1e3, 1))
+
+
+def reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    r = cpu_step_baseline(reps=steps)
+    print(json.dumps({
+        "impl": "reference", "metric": "train images/sec (512x512, 6-class)", "value": r["value"], "unit": "images/s",
+        "n_gpus": world, "steps": steps, "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "st.regda.2potsdam self-training step: ResNet-101 DeepLab, 512x512 tiles, CPU port"},
+        "cpu_baseline": {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)

@@ -45,7 +45,8 @@ extern "C" {
 
 int regda_abi_version(void);
 const char *regda_last_error(void);
-/* 0: LRH auto, 1: force the generic (global-bin) path, 2: force the cluster path (error if it does not fit) */
+/* 0: LRH auto, 1: force the generic (global-bin) path, 2: force the cluster path (error if it does not
+ * fit), 3: cluster path with the loop-over-distinct-regions histogram (A/B switch for profiling) */
 int regda_set_lrh_path(int mode);
 /* which path the last regda_lrh_forward on this thread took: 1 generic, 2 cluster; cluster size in *cluster */
 int regda_lrh_last_path(int *cluster);
@@ -149,13 +150,16 @@ int regda_class_count(const int64_t *label, int64_t n, int c, int64_t ignore_lab
  *   adds to the value already there, for arenas split over several calls).
  * regda_sgd_step: g = grad*grad_scale; coef = min(1, max_norm/(sqrt(sumsq)*grad_scale + 1e-6));
  *   g = coef*g + wd*p;  buf = first_step ? g : momentum*buf + g;  p -= lr*buf;
- *   optional bf16 shadow copy of p (param_bf16, may be NULL); sumsq NULL = no clipping. */
+ *   optional bf16 shadow copy of p (param_bf16, may be NULL); sumsq NULL = no clipping;
+ *   lr_device (may be NULL) is a float32 device scalar that overrides `lr`, so a captured CUDA
+ *   graph can follow the learning-rate schedule (tools.py:199-207) without re-capture. */
 size_t regda_sumsq_workspace_bytes(int64_t n);
 int regda_sumsq(const float *x, int64_t n, float *sumsq_out, int accumulate,
                 void *workspace, size_t workspace_bytes, void *stream);
 int regda_sgd_step(float *param, const float *grad, float *momentum_buf, void *param_bf16,
                    int64_t n, const float *sumsq, double max_norm, double grad_scale, double lr,
-                   double momentum, double weight_decay, int first_step, void *stream);
+                   const float *lr_device, double momentum, double weight_decay, int first_step,
+                   void *stream);
 /* ExponentialMovingAverage.update, regda/utils/ema.py:46-51 (opt-in; unused by the reference loop) */
 int regda_ema_update(float *shadow, const float *param, int64_t n, double decay, void *stream);
 

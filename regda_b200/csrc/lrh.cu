@@ -244,21 +244,39 @@ __device__ __forceinline__ void stg256_u32(void *p, const u32x8 &r) {
                  :: "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7]), "l"(p) : "memory");
 }
 
-template <int CW, typename AccT>
-__device__ __forceinline__ void flush_acc(unsigned *bins, unsigned region, AccT acc) {
-    // acc nibble k+1 = count of class k in the run (nibble 0 = ignored pixels: dropped)
-    if (region == 0u) return;                       // region 0 is never homogenised (:149)
-    unsigned *base = bins + region * CW;
+// nibble accumulator -> the packed bin words of one region.  acc nibble 0 counts ignored pixels
+// (dropped), nibble k+1 counts class k (<= 8 per group).  32-bit form: classes 0..5 (+ the
+// "label == class_num" nibble 7, which is never a class and is masked out by the caller's CW).
+__device__ __forceinline__ void red_shared_add(unsigned saddr, unsigned v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
+}
+// `bins_s` is the 32-bit shared-window address of the bin table (no generic-address arithmetic per atomic)
+template <int CW>
+__device__ __forceinline__ void flush_acc(unsigned bins_s, unsigned region, unsigned acc) {
+    static_assert(CW <= 3, "32-bit nibble accumulator holds 6 classes");
+    const unsigned t = acc >> 4;
+    const unsigned ev = t & 0x0F0F0F0Fu;           // classes 0,2,4 in bytes 0,1,2
+    const unsigned od = (t >> 4) & 0x0F0F0F0Fu;    // classes 1,3,5 in bytes 0,1,2 ; byte 3 == 0
+    const unsigned base = bins_s + region * (CW * 4);
+#pragma unroll
+    for (int w = 0; w < CW; ++w) {
+        const unsigned v = __byte_perm(ev, od, (7u << 12) | ((4u + w) << 8) | (7u << 4) | static_cast<unsigned>(w));
+        if (v) red_shared_add(base + 4 * w, v);
+    }
+}
+template <int CW>
+__device__ __forceinline__ void flush_acc(unsigned bins_s, unsigned region, unsigned long long acc) {
+    const unsigned base = bins_s + region * (CW * 4);
 #pragma unroll
     for (int w = 0; w < CW; ++w) {
         const unsigned lo = static_cast<unsigned>(acc >> (8 * w + 4)) & 0xFu;
         const unsigned hi = static_cast<unsigned>(acc >> (8 * w + 8)) & 0xFu;
         const unsigned v = lo | (hi << 16);
-        if (v) atomicAdd(base + w, v);
+        if (v) red_shared_add(base + 4 * w, v);
     }
 }
 
-template <int CW, typename AccT>
+template <int CW, typename AccT, int HIST>
 __global__ void __launch_bounds__(512, 2)
 lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -283,6 +301,7 @@ lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters) {
     const int r_hi = min(a.region_bound, r_lo + rpc);
     const unsigned max_code = static_cast<unsigned>(a.class_num) + 1u;
     const unsigned bound = static_cast<unsigned>(a.region_bound);
+    const unsigned bins_s = static_cast<unsigned>(__cvta_generic_to_shared(bins));
     bool bad_label = false, bad_region = false;
 
     for (int img = cluster_id; img < a.b; img += nclusters) {
@@ -292,13 +311,9 @@ lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters) {
         // ---- pass 1 ---------------------------------------------------------------------
         const long long *lab = a.labels + static_cast<size_t>(img) * a.hw + start;
         const long long *reg = a.regions + static_cast<size_t>(img) * a.hw + start;
-        u32x8 l0, l1, r0, r1;
-        int g = tid;
-        if (g < ngroups) {
-            l0 = ldg256_u32(lab + g * kGroupPx); l1 = ldg256_u32(lab + g * kGroupPx + 4);
-            r0 = ldg256_u32(reg + g * kGroupPx); r1 = ldg256_u32(reg + g * kGroupPx + 4);
-        }
-        while (g < ngroups) {
+        for (int g = tid; g < ngroups; g += nthreads) {
+            const u32x8 l0 = ldg256_u32(lab + g * kGroupPx), l1 = ldg256_u32(lab + g * kGroupPx + 4);
+            const u32x8 r0 = ldg256_u32(reg + g * kGroupPx), r1 = ldg256_u32(reg + g * kGroupPx + 4);
             // code = label + 1 as a 64-bit add; valid iff the high word becomes 0 and low <= class_num + 1
             unsigned cc[kGroupPx], rr[kGroupPx];
             unsigned hi_or = 0u, lo_max = 0u, rhi_or = 0u, rlo_max = 0u;
@@ -330,34 +345,55 @@ lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters) {
                     if (r1.v[2 * k + 1] != 0u || rr[k + 4] >= bound) rr[k + 4] = 0u;
                 }
             }
-            const int gn = g + nthreads;
-            const int cur = g;
-            g = gn;
-            if (gn < ngroups) {                                // next group's loads fly during the histogram
-                l0 = ldg256_u32(lab + gn * kGroupPx); l1 = ldg256_u32(lab + gn * kGroupPx + 4);
-                r0 = ldg256_u32(reg + gn * kGroupPx); r1 = ldg256_u32(reg + gn * kGroupPx + 4);
-            }
-            const unsigned p0 = rr[0] | (rr[1] << 16), p1 = rr[2] | (rr[3] << 16), p2 = rr[4] | (rr[5] << 16), p3 = rr[6] | (rr[7] << 16);
-            reg16[cur] = make_uint4(p0, p1, p2, p3);
-            lab8[cur] = make_uint2(cc[0] | (cc[1] << 8) | (cc[2] << 16) | (cc[3] << 24), cc[4] | (cc[5] << 8) | (cc[6] << 16) | (cc[7] << 24));
-            if (p0 == p1 && p2 == p3 && p0 == p2 && rr[0] == rr[1]) {   // one region over the 8 pixels
-                AccT acc = 0;
+            reg16[g] = make_uint4(rr[0] | (rr[1] << 16), rr[2] | (rr[3] << 16), rr[4] | (rr[5] << 16), rr[6] | (rr[7] << 16));
+            lab8[g] = make_uint2(cc[0] | (cc[1] << 8) | (cc[2] << 16) | (cc[3] << 24), cc[4] | (cc[5] << 8) | (cc[6] << 16) | (cc[7] << 24));
+            if (HIST == 1) {
+                // Histogram, variant 1: loop over the DISTINCT regions of the 8 pixels (1-3 in
+                // practice; contiguity is irrelevant for counting).
+                AccT oh[kGroupPx];
 #pragma unroll
-                for (int k = 0; k < kGroupPx; ++k) acc += static_cast<AccT>(1) << (4 * cc[k]);
-                flush_acc<CW, AccT>(bins, rr[0], acc);
+                for (int k = 0; k < kGroupPx; ++k) oh[k] = static_cast<AccT>(1) << (4 * cc[k]);
+                unsigned rem = 0xFFu;
+                unsigned r = rr[0];
+                do {
+                    unsigned m = 0u;
+                    AccT acc = 0;
+#pragma unroll
+                    for (int k = 0; k < kGroupPx; ++k) {
+                        const bool e = rr[k] == r;
+                        m |= e ? (1u << k) : 0u;
+                        acc += e ? oh[k] : static_cast<AccT>(0);
+                    }
+                    if (r != 0u) flush_acc<CW>(bins_s, r, acc);
+                    rem &= ~m;
+                    unsigned nr = rr[7];
+#pragma unroll
+                    for (int k = 6; k >= 1; --k) nr = (rem & (1u << k)) ? rr[k] : nr;
+                    r = nr;
+                } while (rem != 0u);
             } else {
-                unsigned curr = rr[0];
-                AccT acc = 0;
+                // Histogram, variant 0: the common group is [first region x s][last region x (8-s)];
+                // both runs are accumulated without branches, anything else goes pixel by pixel.
+                const unsigned ra = rr[0], rb = rr[7];
+                unsigned in_a = 0u, in_b = 0u;
+                AccT acc_a = 0, acc_all = 0;
 #pragma unroll
                 for (int k = 0; k < kGroupPx; ++k) {
-                    if (rr[k] != curr) {
-                        flush_acc<CW, AccT>(bins, curr, acc);
-                        curr = rr[k];
-                        acc = 0;
-                    }
-                    acc += static_cast<AccT>(1) << (4 * cc[k]);
+                    const AccT one = static_cast<AccT>(1) << (4 * cc[k]);
+                    const bool ea = rr[k] == ra;
+                    in_a |= ea ? (1u << k) : 0u;
+                    in_b |= (rr[k] == rb) ? (1u << k) : 0u;
+                    acc_all += one;
+                    acc_a += ea ? one : static_cast<AccT>(0);
                 }
-                flush_acc<CW, AccT>(bins, curr, acc);
+                if (((in_a & (in_a + 1u)) == 0u) && ((in_a | in_b) == 0xFFu)) {
+                    if (ra != 0u) flush_acc<CW>(bins_s, ra, acc_a);
+                    if (rb != 0u && in_a != 0xFFu) flush_acc<CW>(bins_s, rb, static_cast<AccT>(acc_all - acc_a));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kGroupPx; ++k)
+                        if (rr[k] != 0u) flush_acc<CW>(bins_s, rr[k], static_cast<AccT>(static_cast<AccT>(1) << (4 * cc[k])));
+                }
             }
         }
         cluster.sync();
@@ -415,6 +451,10 @@ lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters) {
     if (bad_label) raise_flag(a.flags, REGDA_FLAG_LABEL_RANGE);
     if (bad_region) raise_flag(a.flags, REGDA_FLAG_REGION_RANGE);
 }
+
+thread_local int g_path_mode = 0;   // 0 auto, 1 generic, 2 cluster forced, 3 cluster with the loop histogram
+thread_local int g_last_path = 0;
+thread_local int g_last_cluster = 0;
 
 struct ClusterPlan {
     bool ok = false;
@@ -491,8 +531,13 @@ int launch_cluster_kernel(Kern kern, const LrhArgs &a, const ClusterPlan &p, cud
 template <int CW>
 int launch_cluster(const LrhArgs &a, const ClusterPlan &p, cudaStream_t st, bool *launched) {
     if (a.ignore_label == -1 && p.threads <= 512) {
-        if (a.class_num <= 6) return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned>, a, p, st, launched);
-        if (a.class_num <= 14) return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned long long>, a, p, st, launched);
+        if constexpr (CW <= 3) {
+            if (a.class_num <= 6) {
+                if (g_path_mode == 3) return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned, 1>, a, p, st, launched);
+                return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned, 0>, a, p, st, launched);
+            }
+        }
+        if (a.class_num <= 14) return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned long long, 1>, a, p, st, launched);
     }
     return launch_cluster_kernel(lrh_cluster_kernel<CW>, a, p, st, launched);
 }
@@ -586,9 +631,6 @@ region_bound_kernel(const long long *__restrict__ regions, long long n, long lon
     if (neg) raise_flag(flags, REGDA_FLAG_REGION_RANGE);
 }
 
-thread_local int g_path_mode = 0;
-thread_local int g_last_path = 0;
-thread_local int g_last_cluster = 0;
 
 size_t generic_workspace(int b, int class_num, int64_t region_bound) {
     const size_t cnt = align_up(static_cast<size_t>(b) * region_bound * class_num * 4, 256);
@@ -602,7 +644,7 @@ size_t generic_workspace(int b, int class_num, int64_t region_bound) {
 using namespace regda;
 
 extern "C" int regda_set_lrh_path(int mode) {
-    if (mode < 0 || mode > 2) return fail(REGDA_ERR_INVALID_ARG, "lrh path mode must be 0, 1 or 2");
+    if (mode < 0 || mode > 3) return fail(REGDA_ERR_INVALID_ARG, "lrh path mode must be 0..3");
     g_path_mode = mode;
     return REGDA_OK;
 }
@@ -659,7 +701,7 @@ extern "C" int regda_lrh_forward(const int64_t *labels, const int64_t *regions, 
             }
         }
     }
-    if (g_path_mode == 2) return fail(REGDA_ERR_UNSUPPORTED, "lrh: cluster path forced but shape/alignment does not fit it");
+    if (g_path_mode >= 2) return fail(REGDA_ERR_UNSUPPORTED, "lrh: cluster path forced but shape/alignment does not fit it");
 
     const size_t need = generic_workspace(b, class_num, region_bound);
     if (!workspace || workspace_bytes < need) return fail(REGDA_ERR_WORKSPACE, "lrh: workspace too small (%zu < %zu)", workspace_bytes, need);

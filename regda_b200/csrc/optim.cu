@@ -52,15 +52,16 @@ struct SgdArgs {
     float *buf;
     __nv_bfloat16 *shadow;
     const float *sumsq;
+    const float *lr_dev;
     long long n;
     float max_norm, lr, momentum, wd, grad_scale;
     int first_step;
 };
 
-__device__ __forceinline__ float sgd_one(float p, float g, float &b, float coef, const SgdArgs &a) {
+__device__ __forceinline__ float sgd_one(float p, float g, float &b, float coef, float lr, const SgdArgs &a) {
     g = g * coef + a.wd * p;                       // clip_grad_norm_ scaling, then weight decay (torch SGD: d_p += wd*p)
     b = a.first_step ? g : a.momentum * b + g;     // momentum buffer (dampening 0)
-    return p - a.lr * b;
+    return p - lr * b;
 }
 
 __global__ void __launch_bounds__(kOptThreads)
@@ -71,13 +72,14 @@ sgd_kernel(const SgdArgs a) {
         const float norm = sqrtf(a.sumsq[0]) * a.grad_scale;
         coef = a.grad_scale * fminf(1.0f, a.max_norm / (norm + 1e-6f));
     }
+    const float lr = a.lr_dev != nullptr ? a.lr_dev[0] : a.lr;
     const long long n4 = a.n / 4;
     for (long long i = static_cast<long long>(blockIdx.x) * kOptThreads + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * kOptThreads) {
         float4 p = reinterpret_cast<float4 *>(a.param)[i];
         const float4 g = reinterpret_cast<const float4 *>(a.grad)[i];
         float4 b = a.first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4 *>(a.buf)[i];
-        p.x = sgd_one(p.x, g.x, b.x, coef, a); p.y = sgd_one(p.y, g.y, b.y, coef, a);
-        p.z = sgd_one(p.z, g.z, b.z, coef, a); p.w = sgd_one(p.w, g.w, b.w, coef, a);
+        p.x = sgd_one(p.x, g.x, b.x, coef, lr, a); p.y = sgd_one(p.y, g.y, b.y, coef, lr, a);
+        p.z = sgd_one(p.z, g.z, b.z, coef, lr, a); p.w = sgd_one(p.w, g.w, b.w, coef, lr, a);
         reinterpret_cast<float4 *>(a.param)[i] = p;
         reinterpret_cast<float4 *>(a.buf)[i] = b;
         if (a.shadow != nullptr) {
@@ -90,7 +92,7 @@ sgd_kernel(const SgdArgs a) {
     if (blockIdx.x == 0 && threadIdx.x < a.n - n4 * 4) {
         const long long i = n4 * 4 + threadIdx.x;
         float b = a.first_step ? 0.f : a.buf[i];
-        const float p = sgd_one(a.param[i], a.grad[i], b, coef, a);
+        const float p = sgd_one(a.param[i], a.grad[i], b, coef, lr, a);
         a.param[i] = p; a.buf[i] = b;
         if (a.shadow != nullptr) a.shadow[i] = __float2bfloat16_rn(p);
     }
@@ -133,8 +135,8 @@ extern "C" int regda_sumsq(const float *x, int64_t n, float *sumsq_out, int accu
 }
 
 extern "C" int regda_sgd_step(float *param, const float *grad, float *momentum_buf, void *param_bf16, int64_t n,
-                              const float *sumsq, double max_norm, double grad_scale, double lr, double momentum,
-                              double weight_decay, int first_step, void *stream) {
+                              const float *sumsq, double max_norm, double grad_scale, double lr, const float *lr_device,
+                              double momentum, double weight_decay, int first_step, void *stream) {
     if (n < 0) return fail(REGDA_ERR_INVALID_ARG, "sgd_step: bad size");
     if (n == 0) return REGDA_OK;
     if (!param || !grad || !momentum_buf) return fail(REGDA_ERR_INVALID_ARG, "sgd_step: null pointer");
@@ -143,7 +145,7 @@ extern "C" int regda_sgd_step(float *param, const float *grad, float *momentum_b
     if (param_bf16 && (reinterpret_cast<uintptr_t>(param_bf16) & 7)) return fail(REGDA_ERR_INVALID_ARG, "sgd_step: bf16 shadow must be 8-byte aligned");
     SgdArgs a;
     a.param = param; a.grad = grad; a.buf = momentum_buf; a.shadow = static_cast<__nv_bfloat16 *>(param_bf16);
-    a.sumsq = sumsq; a.n = n; a.max_norm = static_cast<float>(max_norm); a.lr = static_cast<float>(lr);
+    a.sumsq = sumsq; a.lr_dev = lr_device; a.n = n; a.max_norm = static_cast<float>(max_norm); a.lr = static_cast<float>(lr);
     a.momentum = static_cast<float>(momentum); a.wd = static_cast<float>(weight_decay); a.grad_scale = static_cast<float>(grad_scale);
     a.first_step = first_step;
     sgd_kernel<<<opt_blocks(n), kOptThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);

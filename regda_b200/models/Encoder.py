@@ -1,0 +1,176 @@
+"""Deeplabv2 (ResNet OS16 + InstanceNorm + two PPM heads) -- drop-in for
+regda/models/Encoder.py:87-165 with regda/resnet.py:43-66,140-207 and regda/_resnets.py:72-212,
+for the configuration the self-training tools build (multi_layer=True, cascade=False,
+use_ppm=True, is_ins_norm=True; tools/train_ssl_reg.py:94-111).
+
+* state_dict keys and shapes are identical to the reference's (688 keys for ResNet-101), so
+  stage-2 checkpoints load with strict=True and checkpoints written here load in tools/eval.py;
+* train mode returns (x1, x2, feat) with x1/x2 float32 [b,C,h/16,w/16] and feat float32
+  [b,2048,h/16,w/16] (channels-last memory); eval mode returns the averaged softmax at input
+  resolution, as the reference does;
+* activations flow channels-last in `compute_dtype` (bf16 by default, float32 for parity
+  runs); every convolution goes through regda_b200.ops.conv.conv2d, which dispatches to the
+  hand-written tcgen05 implicit-GEMM kernels for the shapes they cover.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..ops.conv import Conv2d
+
+_DEPTHS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3)}
+
+
+class AttrDict(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def _merge(dst, src):
+    for k, v in src.items():
+        if isinstance(v, dict):
+            node = dst.get(k)
+            if not isinstance(node, dict):
+                node = AttrDict()
+            dst[k] = _merge(AttrDict(node), v)
+        else:
+            dst[k] = v
+    return dst
+
+
+class Bottleneck(nn.Module):
+    """_resnets.py:72-112 (stride on the 3x3, torchvision v1.5 style)."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=False):
+        super().__init__()
+        self.conv1 = Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = Conv2d(planes, planes, 3, stride=stride, padding=dilation, dilation=dilation, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.downsample = None
+        if downsample:
+            self.downsample = nn.Sequential(Conv2d(inplanes, planes * 4, 1, stride=stride, bias=False), nn.BatchNorm2d(planes * 4))
+
+    def forward(self, x):
+        out = F.relu(self.bn1(self.conv1(x)), inplace=True)
+        out = F.relu(self.bn2(self.conv2(out)), inplace=True)
+        out = self.bn3(self.conv3(out))
+        identity = x if self.downsample is None else self.downsample(x)
+        out += identity
+        return F.relu(out, inplace=True)
+
+
+class ResNet(nn.Module):
+    """_resnets.py:115-212 without avgpool/fc, after the output-stride-16 surgery of
+    resnet.py:62-63,192-207: layer4's stride-2 convs run at stride 1 (3x3: dilation 1) and the
+    other 3x3 convs of layer4 get dilation 2."""
+
+    def __init__(self, resnet_type="resnet101"):
+        super().__init__()
+        self.conv1 = Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        inplanes = 64
+        for li, (planes, nblk) in enumerate(zip((64, 128, 256, 512), _DEPTHS[resnet_type]), start=1):
+            blocks = []
+            for bi in range(nblk):
+                stride = 2 if (bi == 0 and li in (2, 3)) else 1
+                dil = 2 if (li == 4 and bi > 0) else 1
+                blocks.append(Bottleneck(inplanes, planes, stride, dil, downsample=(bi == 0)))
+                inplanes = planes * 4
+            setattr(self, f"layer{li}", nn.Sequential(*blocks))
+
+    def forward(self, x):
+        x = F.relu(self.bn1(self.conv1(x)), inplace=True)
+        x = F.max_pool2d(x, 3, 2, 1)
+        return self.layer4(self.layer3(self.layer2(self.layer1(x))))
+
+
+class ResNetEncoder(nn.Module):
+    """resnet.py:43-207: only the pieces that hold parameters / shape the forward."""
+
+    def __init__(self, config):
+        super().__init__()
+        rt = str(config.get("resnet_type", "resnet50")).lower()
+        if rt == "resnet":
+            rt = "resnet50"
+        if rt not in _DEPTHS:
+            raise ValueError(f"unsupported resnet_type {rt!r} (resnet50 / resnet101)")
+        if int(config.get("output_stride", 16)) != 16:
+            raise ValueError("only output_stride=16 is on the self-training path")
+        self.resnet = ResNet(rt)
+
+    def forward(self, x):
+        return self.resnet(x)
+
+
+class PPMBilinear(nn.Module):
+    """Encoder.py:8-65 (use_aux=False)."""
+
+    def __init__(self, num_classes=7, fc_dim=2048, use_aux=False, pool_scales=(1, 2, 3, 6), dropout=0.1):
+        super().__init__()
+        if use_aux:
+            raise NotImplementedError("use_aux=True is not used by the self-training tools")
+        self.ppm = nn.ModuleList([
+            nn.Sequential(nn.AdaptiveAvgPool2d(s), Conv2d(fc_dim, 512, 1, bias=False), nn.BatchNorm2d(512), nn.ReLU(inplace=True))
+            for s in pool_scales])
+        self.conv_last = nn.Sequential(
+            Conv2d(fc_dim + len(pool_scales) * 512, 512, 3, padding=1, bias=False), nn.BatchNorm2d(512), nn.ReLU(inplace=True),
+            nn.Dropout2d(dropout), Conv2d(512, num_classes, 1, bias=True))
+
+    def forward(self, conv_out):
+        size = conv_out.shape[-2:]
+        outs = [conv_out]
+        for branch in self.ppm:
+            outs.append(F.interpolate(branch(conv_out), size, mode="bilinear", align_corners=False))
+        return self.conv_last(torch.cat(outs, 1))
+
+
+class Deeplabv2(nn.Module):
+    def __init__(self, config, compute_dtype=torch.bfloat16):
+        super().__init__()
+        cfg = AttrDict(backbone=AttrDict(resnet_type="resnet50", output_stride=16, pretrained=False), multi_layer=False,
+                       cascade=False, use_ppm=False, ppm=AttrDict(num_classes=7, use_aux=False, fc_dim=2048),
+                       inchannels=2048, num_classes=7, is_ins_norm=False)
+        self._cfg = _merge(cfg, dict(config))
+        c = self._cfg
+        if not (c.multi_layer and not c.cascade and c.use_ppm):
+            raise NotImplementedError("regda_b200.Deeplabv2 implements the multi_layer / no-cascade / PPM form "
+                                      "that tools/train_ssl_reg.py:94-111 builds")
+        self.compute_dtype = compute_dtype
+        self.encoder = ResNetEncoder(c.backbone)
+        self.layer5 = PPMBilinear(**c.ppm)
+        self.layer6 = PPMBilinear(**c.ppm)
+        if c.is_ins_norm:
+            self.instance_norm = nn.InstanceNorm2d(c.inchannels)
+        self.to(memory_format=torch.channels_last)
+
+    @property
+    def config(self):
+        return self._cfg
+
+    def forward(self, x):
+        xin = x.to(self.compute_dtype).contiguous(memory_format=torch.channels_last)
+        feat = self.encoder(xin)
+        if self._cfg.is_ins_norm:
+            feat = self.instance_norm(feat.float())      # float32 statistics and output (feeds the Aligner)
+        else:
+            feat = feat.float()
+        fin = feat.to(self.compute_dtype)
+        x1 = self.layer5(fin).float()
+        x2 = self.layer6(fin).float()
+        if self.training:
+            return x1, x2, feat
+        x1 = F.interpolate(x1, x.shape[-2:], mode="bilinear", align_corners=True)
+        x2 = F.interpolate(x2, x.shape[-2:], mode="bilinear", align_corners=True)
+        return (x1.softmax(dim=1) + x2.softmax(dim=1)) / 2

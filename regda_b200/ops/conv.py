@@ -1,0 +1,105 @@
+"""Convolution front end of the model: `Conv2d` keeps the reference's parameter ABI
+(weight [O,I,kh,kw] float32, optional bias) and dispatches the arithmetic.
+
+Engines
+  tcgen05 : the hand-written sm_100a implicit-GEMM kernels (regda_b200/csrc/gemm_*.cu) --
+            bf16 operands, fp32 accumulation in tensor memory, TMA-fed.  Used for every
+            shape `tc.supports_*` accepts.
+  cudnn   : torch.nn.functional.conv2d (library call).  Baseline and float32 parity runs; also
+            the shapes the tcgen05 kernels do not cover yet (listed in DESIGN.md).
+Select with REGDA_CONV=auto|tcgen05|cudnn (auto: tcgen05 where supported).
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+ENGINE = os.environ.get("REGDA_CONV", "auto")
+stats = {"tcgen05_fprop": 0, "tcgen05_dgrad": 0, "tcgen05_wgrad": 0, "cudnn": 0}
+
+
+def set_engine(name: str):
+    global ENGINE
+    assert name in ("auto", "tcgen05", "cudnn")
+    ENGINE = name
+
+
+def _tc():
+    from . import tc
+    return tc
+
+
+class _ConvFn(torch.autograd.Function):
+    """x: channels-last bf16 [N,C,H,W]; weight: float32 master [O,I,kh,kw] (channels-last memory)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, padding, dilation):
+        tc = _tc()
+        w16 = tc.weight_shadow(weight)
+        ctx.save_for_backward(x, weight)
+        ctx.geom = (stride, padding, dilation)
+        stats["tcgen05_fprop"] += 1
+        return tc.fprop(x, w16, stride, padding, dilation)
+
+    @staticmethod
+    def backward(ctx, gy):
+        tc = _tc()
+        x, weight = ctx.saved_tensors
+        stride, padding, dilation = ctx.geom
+        gy = gy.contiguous(memory_format=torch.channels_last)
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            if tc.supports_dgrad(x.shape, weight.shape, stride, padding, dilation, x.dtype):
+                stats["tcgen05_dgrad"] += 1
+                gx = tc.dgrad(gy, tc.weight_shadow_t(weight), x.shape, stride, padding, dilation)
+            else:
+                stats["cudnn"] += 1
+                gx = torch.ops.aten.convolution_backward(gy, x, tc.weight_shadow(weight), None, [stride] * 2, [padding] * 2,
+                                                         [dilation] * 2, False, [0, 0], 1, [True, False, False])[0]
+        if ctx.needs_input_grad[1]:
+            if tc.supports_wgrad(x.shape, weight.shape, stride, padding, dilation, x.dtype):
+                stats["tcgen05_wgrad"] += 1
+                gw = tc.wgrad(gy, x, weight.shape, stride, padding, dilation)
+            else:
+                stats["cudnn"] += 1
+                gw = torch.ops.aten.convolution_backward(gy, x, tc.weight_shadow(weight), None, [stride] * 2, [padding] * 2,
+                                                         [dilation] * 2, False, [0, 0], 1, [False, True, False])[1].float()
+        return gx, gw, None, None, None
+
+
+class Conv2d(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, bias=True):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.padding, self.dilation = kernel_size, stride, padding, dilation
+        w = torch.empty(out_channels, in_channels, kernel_size, kernel_size)
+        nn.init.kaiming_normal_(w, mode="fan_out", nonlinearity="relu")          # _resnets.py:163
+        self.weight = nn.Parameter(w.contiguous(memory_format=torch.channels_last))
+        if bias:
+            bound = 1.0 / math.sqrt(in_channels * kernel_size * kernel_size)
+            self.bias = nn.Parameter(torch.empty(out_channels).uniform_(-bound, bound))
+        else:
+            self.register_parameter("bias", None)
+
+    def extra_repr(self):
+        return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "
+                f"padding={self.padding}, dilation={self.dilation}, bias={self.bias is not None}")
+
+    def forward(self, x):
+        use_tc = False
+        if ENGINE != "cudnn" and x.is_cuda and x.dtype == torch.bfloat16:
+            use_tc = _tc().supports_fprop(x.shape, self.weight.shape, self.stride, self.padding, self.dilation, x.dtype)
+            if ENGINE == "tcgen05" and not use_tc and os.environ.get("REGDA_CONV_STRICT"):
+                raise RuntimeError(f"no tcgen05 kernel for conv {tuple(x.shape)} x {tuple(self.weight.shape)}")
+        if use_tc:
+            y = _ConvFn.apply(x, self.weight, self.stride, self.padding, self.dilation)
+            if self.bias is not None:
+                y = y + self.bias.to(y.dtype).view(1, -1, 1, 1)
+            return y
+        stats["cudnn"] += 1
+        b = self.bias.to(x.dtype) if self.bias is not None else None
+        return F.conv2d(x, self.weight.to(x.dtype), b, self.stride, self.padding, self.dilation)

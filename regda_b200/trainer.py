@@ -1,0 +1,171 @@
+"""The self-training inner step (reference tools/train_ssl_reg.py:198-241) as one object.
+
+    step = SelfTrainingStep(model, aligner, homogenizer, ...)
+    out = step(images_s, label_s, images_t, soft_t, regs_t, lr)
+
+Per iteration, exactly what the reference loop does: two train-mode forwards (source, target:
+separate calls, so BatchNorm statistics are per domain batch), label_refine -> pseudo_selection
+(fused, regda_refine_select), Local Region Homogenizing, prototype EMA update, the four
+cross-entropy terms (fused bilinear-upsample CE), backward, clip_grad_norm_(32), SGD(0.9, 5e-4).
+
+B200-first choices: every parameter / gradient / momentum tensor is a view into one flat fp32
+arena, so gradient all-reduce is one NCCL call and clip + SGD are three kernel launches for the
+whole model; no host synchronisation anywhere inside the step (the reference has >= 3), which
+also makes the step capturable in a CUDA graph (`use_cuda_graph=True`).
+Data-parallel: one process per GPU, images sharded by rank, gradient arena all-reduced (mean)
+and prototype sums all-reduced (sum) so every rank keeps identical weights and prototypes.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import capi
+from .gast.balance import CrossEntropy
+from .utils.tools import loss_calc
+
+
+def _is_channels_last_4d(p):
+    return p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous()
+
+
+class ParamArena:
+    """All parameters of a module re-homed into one flat float32 buffer (plus gradient and
+    momentum buffers of the same layout).  Physical layouts are kept (conv weights stay
+    channels-last), so the flat order is the kernels' order."""
+
+    def __init__(self, module):
+        params = [p for p in module.parameters() if p.requires_grad]
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4          # 16-byte aligned segments
+        dev = params[0].device
+        self.numel = total
+        self.param = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.momentum = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.params = params
+        for p, o in zip(params, offs):
+            n = p.numel()
+
+            def view(buf):
+                seg = buf[o:o + n]
+                if _is_channels_last_4d(p):
+                    O, I, kh, kw = p.shape
+                    return seg.view(O, kh, kw, I).permute(0, 3, 1, 2)
+                return seg.view(p.shape)
+
+            v = view(self.param)
+            v.copy_(p.data)
+            p.data = v
+            p.grad = view(self.grad)
+        self.first_step = True
+        self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.lr_device = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def set_lr(self, lr):
+        """host float -> the device scalar the SGD kernel reads (graph-replay safe)."""
+        self.lr_device.fill_(float(lr))
+
+    def clip_and_sgd(self, max_norm=32.0, momentum=0.9, weight_decay=5e-4, grad_scale=1.0):
+        """clip_grad_norm_(max_norm) + SGD step over the whole arena (train_ssl_reg.py:239-241);
+        the learning rate is whatever set_lr() last wrote."""
+        ws = capi.workspace.get(capi.lib().regda_sumsq_workspace_bytes(self.numel), self.param.device)
+        capi.call("regda_sumsq", capi.ptr(self.grad), self.numel, capi.ptr(self._sumsq), 0, capi.ptr(ws), ws.numel(), capi.stream())
+        capi.call("regda_sgd_step", capi.ptr(self.param), capi.ptr(self.grad), capi.ptr(self.momentum), None, self.numel,
+                  capi.ptr(self._sumsq), float(max_norm), float(grad_scale), 0.0, capi.ptr(self.lr_device), float(momentum),
+                  float(weight_decay), int(self.first_step), capi.stream())
+        self.first_step = False
+
+    def grad_norm(self):
+        return self._sumsq.sqrt()
+
+
+class SelfTrainingStep:
+    def __init__(self, model, aligner, homogenizer, class_num=6, ignore_label=-1, cutoff_top=0.8, cutoff_low=0.6,
+                 refine_temp=2.0, sam_refine=True, refine_label=True, max_norm=32.0, momentum=0.9, weight_decay=5e-4,
+                 loss_fn_s=None, loss_fn_t=None, world_size=1, use_cuda_graph=False):
+        self.model, self.aligner, self.homogenizer = model, aligner, homogenizer
+        self.class_num, self.ignore_label = class_num, ignore_label
+        self.cutoff_top, self.cutoff_low, self.refine_temp = cutoff_top, cutoff_low, refine_temp
+        self.sam_refine, self.refine_label = sam_refine, refine_label
+        self.max_norm, self.momentum, self.weight_decay = max_norm, momentum, weight_decay
+        self.loss_fn_s = loss_fn_s or CrossEntropy(ignore_label=ignore_label)
+        self.loss_fn_t = loss_fn_t or CrossEntropy(ignore_label=ignore_label)
+        self.world_size = world_size
+        self.arena = ParamArena(model)
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._static = None
+        self._lr = torch.zeros((), dtype=torch.float64)
+
+    # ---- the step proper (no host sync inside) ------------------------------------------------
+    def _reduce_proto(self, sums, counts):
+        if self.world_size > 1:
+            dist.all_reduce(sums)
+            dist.all_reduce(counts)
+
+    def _step_impl(self, images_s, label_s, images_t, soft_t, regs_t):
+        m = self.model
+        self.arena.zero_grad()
+        pred_s1, pred_s2, feat_s = m(images_s)                                     # :210
+        pred_t1, pred_t2, feat_t = m(images_t)                                     # :212
+        with torch.no_grad():
+            if self.refine_label:
+                hard = self.aligner.refine_select(feat_t, [pred_t1, pred_t2], soft_t, self.refine_temp,
+                                                  self.cutoff_top, self.cutoff_low)   # :214-218
+            else:
+                from .gast.pseudo_generation import pseudo_selection
+                hard = pseudo_selection(soft_t, self.cutoff_top, self.cutoff_low, 'tensor', self.ignore_label, check=False)
+            if self.sam_refine:
+                hard = self.homogenizer(hard, regs_t.squeeze(1))                   # :223
+            self.aligner.update_prototype(feat_s, label_s, reduce_fn=self._reduce_proto)   # :225
+        loss_source = loss_calc([pred_s1, pred_s2], label_s, loss_fn=self.loss_fn_s, multi=True)   # :228
+        loss_target = loss_calc([pred_t1, pred_t2], hard, loss_fn=self.loss_fn_t, multi=True)      # :233
+        loss = loss_source + loss_target
+        loss.backward()                                                            # :238
+        if self.world_size > 1:
+            dist.all_reduce(self.arena.grad)                                       # mean over ranks via grad_scale
+        self.arena.clip_and_sgd(self.max_norm, self.momentum, self.weight_decay, 1.0 / self.world_size)   # :239-241
+        return loss.detach(), loss_source.detach(), loss_target.detach(), hard
+
+    def __call__(self, images_s, label_s, images_t, soft_t, regs_t, lr):
+        if not self.use_cuda_graph:
+            self.arena.set_lr(lr)
+            loss, ls, lt, hard = self._step_impl(images_s, label_s, images_t, soft_t, regs_t)
+            return dict(loss=loss, loss_source=ls, loss_target=lt, hard=hard, grad_norm=self.arena.grad_norm())
+        raise NotImplementedError("use GraphedStep for CUDA-graph replay")
+
+
+class GraphedStep:
+    """Captures SelfTrainingStep into a CUDA graph (fixed shapes).  The learning rate lives in a
+    device scalar, so the schedule is followed without re-capture."""
+
+    def __init__(self, step: SelfTrainingStep, example_inputs, lr=0.0, warmup=3):
+        self.step = step
+        self.static_in = [t.clone() for t in example_inputs]
+        step.arena.set_lr(lr)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                step._step_impl(*self.static_in)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = step._step_impl(*self.static_in)
+
+    def __call__(self, *inputs, lr=None):
+        if lr is not None:
+            self.step.arena.set_lr(lr)
+        for dst, src in zip(self.static_in, inputs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        loss, ls, lt, hard = self.out
+        return dict(loss=loss, loss_source=ls, loss_target=lt, hard=hard, grad_norm=self.step.arena.grad_norm())

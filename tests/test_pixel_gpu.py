@@ -221,7 +221,7 @@ def test_clip_and_sgd_match_torch(n):
         capi.call("regda_sumsq", capi.ptr(gr), n, capi.ptr(sumsq), 0, capi.ptr(ws), ws.numel(), capi.stream())
         assert abs(float(sumsq.sqrt()) - float(norm)) <= 1e-5 * float(norm)
         capi.call("regda_sgd_step", capi.ptr(p), capi.ptr(gr), capi.ptr(buf), capi.ptr(shadow), n, capi.ptr(sumsq), 32.0, 1.0,
-                  1e-2, 0.9, 5e-4, int(it == 0), capi.stream())
+                  1e-2, None, 0.9, 5e-4, int(it == 0), capi.stream())
         torch.testing.assert_close(p, ref_p.detach(), rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(shadow.float(), p.bfloat16().float(), rtol=0, atol=0)
 
