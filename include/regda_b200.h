@@ -164,6 +164,20 @@ int regda_sgd_step(float *param, const float *grad, float *momentum_buf, void *p
 int regda_ema_update(float *shadow, const float *param, int64_t n, double decay, void *stream);
 
 
+/* ---- convolution on the tcgen05 tensor cores -------------------------------------------
+ * Replaces the cuDNN convolutions behind nn.Conv2d in regda/_resnets.py:92-112 (Bottleneck) and
+ * regda/models/Encoder.py:33-40 (PPM fuse conv).  Stride-1 implicit GEMM, any dilation / padding:
+ *   x   bf16 [n][h][w][cin]        (channels-last)
+ *   wgt bf16 [cout][r][s][cin]     (OHWI = the channels-last memory of the reference's weight)
+ *   y   bf16 [n][oh][ow][cout],  oh = h + 2*pad - dil*(r-1)
+ * Also computes the data gradient of a stride-1 convolution when given dY, the flipped /
+ * transposed weights [cin][r][s][cout] and pad' = dil*(r-1) - pad.
+ * regda_conv_fprop_supported returns 1 when the shape is covered (cin, cout multiples of 64,
+ * stride 1, at least 128 output pixels per image). */
+int regda_conv_fprop_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil);
+int regda_conv_fprop_bf16(const void *x, const void *wgt, void *y, int n, int h, int w, int cin, int cout,
+                          int r, int s, int stride, int pad, int dil, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,12 @@ def ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def ptr_any(t):
+    """device pointer of a tensor whose memory (in whatever stride order) is dense"""
+    assert t.is_cuda
+    return ctypes.c_void_p(t.data_ptr())
+
+
 def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 

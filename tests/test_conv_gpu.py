@@ -1,0 +1,80 @@
+"""GPU: the tcgen05 implicit-GEMM convolution (regda_conv_fprop_bf16 through regda_b200.ops.conv)
+against a plain PyTorch float32 convolution of the same bf16-rounded operands.
+Tolerance: bf16 output rounding (2^-9 relative) + fp32 accumulation-order noise -> 1e-2 of the
+output scale, and a much tighter bound on the mean error."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# (n, cin, h, w, cout, k, pad, dil): every conv family of ResNet-101 OS16 + the PPM fuse conv
+SHAPES = [
+    (2, 64, 32, 32, 64, 1, 0, 1),
+    (2, 256, 32, 32, 128, 1, 0, 1),
+    (2, 64, 16, 16, 256, 1, 0, 1),
+    (1, 128, 64, 64, 128, 3, 1, 1),
+    (2, 256, 32, 32, 256, 3, 1, 1),
+    (2, 512, 32, 32, 512, 3, 2, 2),        # layer4 dilated
+    (2, 64, 128, 128, 64, 3, 1, 1),        # layer1: one image row per tile
+    (1, 64, 256, 256, 64, 1, 0, 1),        # two tiles per image row
+    (2, 128, 24, 40, 192, 3, 1, 1),        # ragged: patches overhang the image, cout = 3 x 64
+    (1, 1024, 32, 32, 256, 1, 0, 1),
+    (1, 4096, 32, 32, 512, 3, 1, 1),       # PPM fuse conv, K = 36864
+    (3, 64, 12, 12, 64, 3, 1, 1),          # small map, patch 8 x 16 overhangs
+]
+
+
+def _ref(x, w, pad, dil):
+    return F.conv2d(x.float(), w.float(), None, 1, pad, dil)
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=[str(s) for s in SHAPES])
+def test_fprop_matches_float32_reference(shape):
+    from regda_b200.ops import tc
+    n, cin, h, w, cout, k, pad, dil = shape
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5).bfloat16().contiguous(memory_format=torch.channels_last)
+    assert tc.supports_fprop(x.shape, wt.shape, 1, pad, dil, x.dtype)
+    y = tc.fprop(x, wt, 1, pad, dil)
+    ref = _ref(x, wt, pad, dil)
+    assert y.shape == ref.shape and y.dtype == torch.bfloat16
+    err = (y.float() - ref).abs()
+    scale = ref.abs().max()
+    assert float(err.max()) <= 1e-2 * float(scale), (float(err.max()), float(scale))
+    assert float(err.mean()) <= 2e-3 * float(ref.abs().mean())
+
+
+@pytest.mark.parametrize("shape", [SHAPES[1], SHAPES[4], SHAPES[5], SHAPES[8]], ids=str)
+def test_conv2d_module_forward_backward(shape):
+    """the nn.Module front end: forward through tcgen05, input gradient through the same kernel
+    (flipped / transposed weights), weight gradient through the library until the wgrad kernel lands."""
+    from regda_b200.ops import conv as C
+    n, cin, h, w, cout, k, pad, dil = shape
+    torch.manual_seed(0)
+    m = C.Conv2d(cin, cout, k, padding=pad, dilation=dil, bias=False).cuda()
+    x = torch.randn(n, cin, h, w, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    before = dict(C.stats)
+    y = m(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    assert C.stats["tcgen05_fprop"] == before["tcgen05_fprop"] + 1
+    assert C.stats["tcgen05_dgrad"] == before["tcgen05_dgrad"] + 1
+    xr = x.detach().float().requires_grad_(True)
+    wr = m.weight.detach().bfloat16().float().requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, 1, pad, dil)
+    yr.backward(gy.float())
+    for got, want in ((y, yr), (x.grad, xr.grad), (m.weight.grad, wr.grad)):
+        err = (got.float() - want).abs()
+        assert float(err.max()) <= 1.5e-2 * float(want.abs().max())
+
+
+def test_unsupported_shapes_are_refused():
+    from regda_b200 import capi
+    L = capi.lib()
+    assert L.regda_conv_fprop_supported(2, 32, 32, 64, 64, 1, 1, 1, 0, 1) == 1
+    assert L.regda_conv_fprop_supported(2, 32, 32, 3, 64, 7, 7, 2, 3, 1) == 0      # stem
+    assert L.regda_conv_fprop_supported(2, 32, 32, 64, 6, 1, 1, 1, 0, 1) == 0      # classifier
+    assert L.regda_conv_fprop_supported(2, 6, 6, 2048, 512, 1, 1, 1, 0, 1) == 0    # PPM branch on a pooled map
+    assert L.regda_conv_fprop_supported(2, 64, 64, 128, 128, 3, 3, 2, 1, 1) == 0   # strided

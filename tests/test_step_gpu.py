@@ -58,7 +58,8 @@ def test_model_float32_matches_reference(rt):
     got = dict(m.named_parameters())
     assert names == list(got.keys())
     norms = np.array([float(got[n].grad.norm()) for n in names])
-    assert np.allclose(norms, z["grad_norms"], rtol=2e-2, atol=1e-6)
+    bad = np.abs(norms - z["grad_norms"]) > 5e-2 * np.abs(z["grad_norms"]) + 1e-5 * z["grad_norms"].max()
+    assert not bad.any(), [(names[i], norms[i], z["grad_norms"][i]) for i in np.nonzero(bad)[0][:8]]
     assert _rel(m.encoder.resnet.conv1.weight.grad.cpu(), torch.from_numpy(z["grad_conv1"])) < 1e-2
     assert _rel(m.layer5.conv_last[4].weight.grad.cpu(), torch.from_numpy(z["grad_cls5"])) < 1e-3
     torch.testing.assert_close(m.encoder.resnet.bn1.running_mean.cpu(), torch.from_numpy(z["bn1_running_mean"]), rtol=1e-4, atol=1e-6)
