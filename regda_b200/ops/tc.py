@@ -66,7 +66,10 @@ def weight_shadow_t(weight):
 
 
 def _nhwc(t):
-    assert t.is_contiguous(memory_format=torch.channels_last), "tcgen05 convolutions take channels-last tensors"
+    """the tensor in channels-last memory (a copy only when the producer left it in another stride order,
+    e.g. the bilinear-upsampled PPM branches)"""
+    if not t.is_contiguous(memory_format=torch.channels_last):
+        t = t.contiguous(memory_format=torch.channels_last)
     return t
 
 
@@ -76,7 +79,8 @@ def fprop(x, w16, stride, padding, dilation):
     oh = h + 2 * padding - dilation * (r - 1)
     ow = w + 2 * padding - dilation * (s - 1)
     y = torch.empty((n, cout, oh, ow), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
-    capi.call("regda_conv_fprop_bf16", capi.ptr_any(_nhwc(x)), capi.ptr_any(_nhwc(w16)), capi.ptr_any(y), n, h, w, cin, cout, r, s,
+    x, w16 = _nhwc(x), _nhwc(w16)
+    capi.call("regda_conv_fprop_bf16", capi.ptr_any(x), capi.ptr_any(w16), capi.ptr_any(y), n, h, w, cin, cout, r, s,
               stride, padding, dilation, capi.stream())
     return y
 
