@@ -172,11 +172,64 @@ int regda_ema_update(float *shadow, const float *param, int64_t n, double decay,
  *   y   bf16 [n][oh][ow][cout],  oh = h + 2*pad - dil*(r-1)
  * Also computes the data gradient of a stride-1 convolution when given dY, the flipped /
  * transposed weights [cin][r][s][cout] and pad' = dil*(r-1) - pad.
+ * Stride 2 is handled through TMA element strides (every other input pixel is fetched).
  * regda_conv_fprop_supported returns 1 when the shape is covered (cin, cout multiples of 64,
- * stride 1, at least 128 output pixels per image). */
+ * stride 1 or 2, at least 128 output pixels per image). */
 int regda_conv_fprop_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil);
 int regda_conv_fprop_bf16(const void *x, const void *wgt, void *y, int n, int h, int w, int cin, int cout,
                           int r, int s, int stride, int pad, int dil, void *stream);
+
+/* Data gradient of a stride-1 convolution, reading the forward OHWI weights in place (MN-major B operand):
+ *   dy bf16 [n][oh][ow][cout], wgt bf16 [cout][r][s][cin] -> dx bf16 [n][h][w][cin]   (h, w, cin, cout, ... are the
+ *   FORWARD convolution's geometry). */
+int regda_conv_dgrad_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil);
+int regda_conv_dgrad_bf16(const void *dy, const void *wgt, void *dx, int n, int h, int w, int cin, int cout,
+                          int r, int s, int stride, int pad, int dil, void *stream);
+/* Weight gradient (stride 1 or 2), ACCUMULATED into dw fp32 [cout][r][s][cin] with global reductions:
+ *   dy bf16 [n][oh][ow][cout], x bf16 [n][h][w][cin]. */
+int regda_conv_wgrad_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil);
+int regda_conv_wgrad_bf16(const void *dy, const void *x, float *dw, int n, int h, int w, int cin, int cout,
+                          int r, int s, int stride, int pad, int dil, void *stream);
+
+/* ---- train-mode BatchNorm2d (+ residual add + ReLU) over channels-last bf16 -------------------
+ * Replaces nn.BatchNorm2d / F.relu / `out += identity` in regda/_resnets.py:92-112 and
+ * regda/models/Encoder.py:24-40.  y, residual (may be NULL), out: bf16 [npix][c];
+ * gamma/beta/running_*: float32 [c]; num_batches_tracked: int64 [1] (may be NULL).
+ *   out = relu?( gamma*(y-mean)*rstd + beta + residual ),  batch statistics in fp32 (biased variance for the
+ *   normalisation, unbiased for running_var, as torch).
+ * `groups` > 1 = that many independent statistics groups over equal contiguous pixel ranges: the source and target
+ * batches of one training step run through every layer as ONE tensor while BatchNorm keeps the reference's
+ * per-forward-call (per-domain) batch statistics; running statistics are updated once per group, in order.
+ * coef float32 [groups][4c] is written (scale, shift, mean, rstd) and must be kept for the backward call.
+ * Backward: dout, out (needed when relu), y -> dy (and dres = masked dout when dres != NULL);
+ * dgamma / dbeta float32 [c] are ACCUMULATED (+=). */
+int regda_bn_supported(int64_t npix, int c);
+size_t regda_bn_workspace_bytes(int c, int groups);
+int regda_bn_forward_bf16(const void *y, const void *residual, void *out, int64_t npix, int c, int groups,
+                          const float *gamma, const float *beta, float *running_mean, float *running_var,
+                          int64_t *num_batches_tracked, double eps, double momentum, int relu,
+                          float *coef, void *workspace, size_t workspace_bytes, void *stream);
+size_t regda_bn_backward_workspace_bytes(int c, int groups);
+int regda_bn_backward_bf16(const void *dout, const void *out, const void *y, void *dy, void *dres, int64_t npix, int c,
+                           int groups, const float *gamma, const float *coef, float *dgamma, float *dbeta, int relu,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- pyramid pooling front end of the PPM heads (regda/models/Encoder.py:43-52) -----------------
+ * scales_host: HOST array of nscales (<= 4) pool sizes, e.g. {1,2,3,6}; ncell = sum s^2; cells of scale k start
+ * at sum_{j<k} s_j^2, row-major.
+ *   regda_ppm_pool_fwd : AdaptiveAvgPool2d(s) for every scale in one pass: feat bf16 [b][h][w][c] -> pooled f32 [b][ncell][c]
+ *   regda_ppm_pool_bwd : dpooled f32 [b][ncell][c] -> dfeat bf16 [b][h][w][c]
+ *   regda_ppm_upcat_fwd: cat bf16 [b][h][w][c + nscales*cb] = concat(feat, bilinear(align_corners=False) of
+ *                        branch_k bf16 [b][s_k][s_k][cb])  (F.interpolate + torch.cat of Encoder.py:47-52)
+ *   regda_ppm_upcat_bwd: dcat -> dbranch_k f32 [b][s_k][s_k][cb] (written); d feat is dcat[..., :c] itself. */
+int regda_ppm_pool_fwd(const void *feat, float *pooled, int b, int h, int w, int c, const int *scales_host, int nscales,
+                       void *stream);
+int regda_ppm_pool_bwd(const float *dpooled, void *dfeat, int b, int h, int w, int c, const int *scales_host, int nscales,
+                       void *stream);
+int regda_ppm_upcat_fwd(const void *feat, const void *br0, const void *br1, const void *br2, const void *br3, void *cat,
+                        int b, int h, int w, int c, int cb, const int *scales_host, int nscales, void *stream);
+int regda_ppm_upcat_bwd(const void *dcat, float *dbr0, float *dbr1, float *dbr2, float *dbr3, int b, int h, int w, int c,
+                        int cb, const int *scales_host, int nscales, void *stream);
 
 #ifdef __cplusplus
 }

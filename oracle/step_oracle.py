@@ -289,7 +289,11 @@ def seeded_state_dict(model_or_keys, seed=2333):
     """Deterministic weights keyed by parameter *name* (so the reference, the oracle and
     the CUDA model can be filled identically on any host with this torch build).
     conv weights ~ N(0, sqrt(2/fan_out)) (the kaiming fan_out rule of _resnets.py:163),
-    BN gamma ~ U(0.5,1.5), beta ~ N(0,0.1), running_mean ~ N(0,0.1), running_var ~ U(0.5,1.5)."""
+    BN gamma ~ U(0.5,1.5), beta ~ N(0,0.1), running_mean ~ N(0,0.1), running_var ~ U(0.5,1.5); the last BatchNorm of
+    every bottleneck (bn3) gets gamma ~ U(0.05,0.25) -- the usual small-residual initialisation -- so that the
+    random network is well conditioned: with O(1) residual gains and the tiny batch-statistic sample counts of the
+    64x64 / 96x96 fixtures, float32 re-association noise is amplified to percents in the stem gradient, which says
+    nothing about kernel parity."""
     ref = model_or_keys.state_dict() if isinstance(model_or_keys, nn.Module) else model_or_keys
     out = OrderedDict()
     for name, t in ref.items():
@@ -302,6 +306,8 @@ def seeded_state_dict(model_or_keys, seed=2333):
         elif t.dim() == 4:
             fan_out = t.shape[0] * t.shape[2] * t.shape[3]
             out[name] = torch.randn(t.shape, generator=g) * math.sqrt(2.0 / fan_out)
+        elif name.endswith("bn3.weight"):
+            out[name] = torch.rand(t.shape, generator=g) * 0.2 + 0.05
         elif name.endswith("running_var") or (name.endswith("weight") and t.dim() == 1):
             out[name] = torch.rand(t.shape, generator=g) + 0.5
         else:

@@ -32,9 +32,10 @@ constexpr int kUmmaK = 16;
 constexpr int kThreads = 192;        // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 
 struct ConvGeom {
-    int n, h, w, cin, cout;          // input image, channels
+    int n, h, w, cin, cout;          // input image, reduction channels, output channels
     int oh, ow;                      // output image
-    int r, s, pad, dil;
+    int r, s, pad, dil, stride;
+    int flip;                        // dgrad: weight tap = taps-1-tap
     int bh, bw;                      // spatial patch of one M tile (bh*bw == 128)
     int tiles_h, tiles_w;            // patches per image
     int kc;                          // cin / 64
@@ -49,24 +50,10 @@ struct SmemLayout {
     static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 8;
 };
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn == nullptr) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-        else
-            (void)cudaGetLastError();
-    }
-    return fn;
-}
-
-template <int BLOCK_N, int STAGES>
+// B_MN = false: weights [cout][taps*cin] (K-major B tile, one 2-D box).  B_MN = true (dgrad): weights
+// [cin][taps][cout] read in place as an MN-major B tile: BLOCK_N/64 boxes of {64 cout, 1 tap, 64 cin}, i.e. 64
+// K-rows of 128 bytes each; descriptor LBO = 8 KB between the 64-wide N blocks, SBO = 1 KB between 8-row K groups.
+template <int BLOCK_N, int STAGES, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   __nv_bfloat16 *__restrict__ y, const ConvGeom g) {
@@ -119,15 +106,22 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 uint8_t *sa = smem + stage * L::kStageBytes;
                 uint8_t *sb = sa + L::kABytes;
                 mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes);
-                tma_load_4d(sa, &tmap_x, full_bar + stage, c0, ow0 + fs * g.dil - g.pad, oh0 + fr * g.dil - g.pad, img);
-                tma_load_2d(sb, &tmap_w, full_bar + stage, tap * g.cin + c0, n_blk * BLOCK_N);
+                tma_load_4d(sa, &tmap_x, full_bar + stage, c0, ow0 * g.stride + fs * g.dil - g.pad, oh0 * g.stride + fr * g.dil - g.pad, img);
+                if (B_MN) {
+                    const int wtap = g.flip ? g.r * g.s - 1 - tap : tap;
+#pragma unroll
+                    for (int i = 0; i < BLOCK_N / 64; ++i)
+                        tma_load_3d(sb + i * 8192, &tmap_w, full_bar + stage, n_blk * BLOCK_N + i * 64, wtap, c0);
+                } else {
+                    tma_load_2d(sb, &tmap_w, full_bar + stage, tap * g.cin + c0, n_blk * BLOCK_N);
+                }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, B_MN ? 1 : 0);
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < num_k; ++kb) {
@@ -136,11 +130,12 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
                 const uint32_t sb = sa + L::kABytes;
                 const uint64_t adesc = make_smem_desc(sa, 0, 1024);
-                const uint64_t bdesc = make_smem_desc(sb, 0, 1024);
+                const uint64_t bdesc = B_MN ? make_smem_desc(sb, 8192, 1024) : make_smem_desc(sb, 0, 1024);
 #pragma unroll
                 for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                    // advance the start address by k * 16 elements * 2 B = 32 B (>> 4 = 2) inside the swizzle span
-                    umma_bf16(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                    // K-major: advance the start address by 16 elements * 2 B = 32 B (>> 4 = 2) inside the swizzle span;
+                    // MN-major: by 16 K-rows * 128 B = 2048 B (>> 4 = 128)
+                    umma_bf16(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>((B_MN ? 128 : 2) * k), idesc,
                               (kb | k) != 0 ? 1u : 0u);
                 }
                 umma_commit(empty_bar + stage);          // frees the smem stage when these MMAs retire
@@ -187,38 +182,35 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 }
 
 int make_tmap_x(CUtensorMap *m, const void *x, const ConvGeom &g) {
-    EncodeTiledFn enc = encode_fn();
-    if (!enc) return fail(REGDA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(g.cin), static_cast<cuuint64_t>(g.w), static_cast<cuuint64_t>(g.h), static_cast<cuuint64_t>(g.n)};
-    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(g.cin) * 2, static_cast<cuuint64_t>(g.w) * g.cin * 2,
-                                   static_cast<cuuint64_t>(g.h) * g.w * g.cin * 2};
-    const cuuint32_t box[4] = {kBlockK, static_cast<cuuint32_t>(g.bw), static_cast<cuuint32_t>(g.bh), 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(x), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) return fail(REGDA_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed with %d", static_cast<int>(rc));
+    if (!encode_nhwc(m, x, g.n, g.h, g.w, g.cin, g.bw, g.bh, g.stride))
+        return REGDA_ERR_CUDA;   /* text set by encode_bf16_sw128 (activations) */
     return REGDA_OK;
 }
 
+// fprop weights: [cout][ktot] row-major, box {64 k, block_n}
 int make_tmap_w(CUtensorMap *m, const void *w, int cout, int ktot, int block_n) {
-    EncodeTiledFn enc = encode_fn();
-    if (!enc) return fail(REGDA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(cout)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ktot) * 2};
     const cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(block_n)};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(w), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) return fail(REGDA_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed with %d", static_cast<int>(rc));
+    if (!encode_bf16_sw128(m, w, 2, dims, strides, box, estr)) return REGDA_ERR_CUDA;   /* text set by encode_bf16_sw128 (weights) */
     return REGDA_OK;
 }
 
-template <int BLOCK_N, int STAGES>
+// dgrad weights in place: memory [red][taps][out] (the forward conv's OHWI), box {64 out, 1 tap, 64 red}
+int make_tmap_w_mn(CUtensorMap *m, const void *w, int red, int taps, int out) {
+    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(out), static_cast<cuuint64_t>(taps), static_cast<cuuint64_t>(red)};
+    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(out) * 2, static_cast<cuuint64_t>(taps) * out * 2};
+    const cuuint32_t box[3] = {64, 1, 64};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (!encode_bf16_sw128(m, w, 3, dims, strides, box, estr)) return REGDA_ERR_CUDA;   /* text set by encode_bf16_sw128 (weights, MN) */
+    return REGDA_OK;
+}
+
+template <int BLOCK_N, int STAGES, bool B_MN>
 int launch_fprop(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bfloat16 *y, const ConvGeom &g, cudaStream_t st) {
     using L = SmemLayout<BLOCK_N, STAGES>;
-    auto kern = conv_fprop_kernel<BLOCK_N, STAGES>;
+    auto kern = conv_fprop_kernel<BLOCK_N, STAGES, B_MN>;
     const int smem = L::kTotal + 1024;     // slack for the 1024-byte alignment of the dynamic segment
     REGDA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const dim3 grid(g.cout / BLOCK_N, g.n * g.tiles_h * g.tiles_w);
@@ -232,12 +224,27 @@ int launch_fprop(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bfloat16 *y,
 
 using namespace regda;
 
+namespace {
+int geom_init(ConvGeom &g, int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil) {
+    g.n = n; g.h = h; g.w = w; g.cin = cin; g.cout = cout; g.r = r; g.s = s; g.pad = pad; g.dil = dil; g.stride = stride; g.flip = 0;
+    g.oh = (h + 2 * pad - dil * (r - 1) - 1) / stride + 1;
+    g.ow = (w + 2 * pad - dil * (s - 1) - 1) / stride + 1;
+    int bw = 1;
+    while (bw * 2 <= g.ow && bw * 2 <= 128) bw *= 2;             // largest power of two <= min(ow, 128)
+    g.bw = bw; g.bh = kBlockM / bw;
+    g.tiles_w = (g.ow + g.bw - 1) / g.bw;
+    g.tiles_h = (g.oh + g.bh - 1) / g.bh;
+    g.kc = cin / kBlockK;
+    return REGDA_OK;
+}
+}  // namespace
+
 // 1 if (shape, alignment) is covered by the tcgen05 kernel
 extern "C" int regda_conv_fprop_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil) {
-    if (n < 1 || h < 1 || w < 1 || stride != 1 || r < 1 || s < 1 || r * s > 49 || dil < 1 || pad < 0) return 0;
+    if (n < 1 || h < 1 || w < 1 || stride < 1 || stride > 2 || r < 1 || s < 1 || r * s > 49 || dil < 1 || pad < 0) return 0;
     if (cin % 64 != 0 || cout % 64 != 0) return 0;
-    const int oh = h + 2 * pad - dil * (r - 1), ow = w + 2 * pad - dil * (s - 1);
-    if (oh < 1 || ow < 1) return 0;
+    if (h + 2 * pad < dil * (r - 1) + 1 || w + 2 * pad < dil * (s - 1) + 1) return 0;
+    const int oh = (h + 2 * pad - dil * (r - 1) - 1) / stride + 1, ow = (w + 2 * pad - dil * (s - 1) - 1) / stride + 1;
     if (static_cast<long long>(oh) * ow < 128) return 0;          // tiny maps (PPM branches) stay on the library path
     return 1;
 }
@@ -250,15 +257,8 @@ extern "C" int regda_conv_fprop_bf16(const void *x, const void *wgt, void *y, in
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wgt) | reinterpret_cast<uintptr_t>(y)) & 15)
         return fail(REGDA_ERR_INVALID_ARG, "conv_fprop: tensors must be 16-byte aligned");
     ConvGeom g;
-    g.n = n; g.h = h; g.w = w; g.cin = cin; g.cout = cout; g.r = r; g.s = s; g.pad = pad; g.dil = dil;
-    g.oh = h + 2 * pad - dil * (r - 1);
-    g.ow = w + 2 * pad - dil * (s - 1);
-    int bw = 1;
-    while (bw * 2 <= g.ow && bw * 2 <= 128) bw *= 2;             // largest power of two <= min(ow, 128)
-    g.bw = bw; g.bh = kBlockM / bw;
-    g.tiles_w = (g.ow + g.bw - 1) / g.bw;
-    g.tiles_h = (g.oh + g.bh - 1) / g.bh;
-    g.kc = cin / kBlockK;
+    geom_init(g, n, h, w, cin, cout, r, s, stride, pad, dil);
+    ensure_context(x);
     CUtensorMap tx, tw;
     int rc = make_tmap_x(&tx, x, g);
     if (rc) return rc;
@@ -267,9 +267,46 @@ extern "C" int regda_conv_fprop_bf16(const void *x, const void *wgt, void *y, in
     if (cout % 128 == 0) {
         rc = make_tmap_w(&tw, wgt, cout, r * s * cin, 128);
         if (rc) return rc;
-        return launch_fprop<128, 3>(tx, tw, yy, g, st);
+        return launch_fprop<128, 3, false>(tx, tw, yy, g, st);
     }
     rc = make_tmap_w(&tw, wgt, cout, r * s * cin, 64);
     if (rc) return rc;
-    return launch_fprop<64, 4>(tx, tw, yy, g, st);
+    return launch_fprop<64, 4, false>(tx, tw, yy, g, st);
+}
+
+// Data gradient of a stride-1 convolution, reading the forward weights IN PLACE:
+//   dx[n][h][w][cin] = sum_{r,s,co} dy[n][y + pad - r*dil][x + pad - s*dil][co] * wgt[co][r][s][cin]
+// dy bf16 [n][oh][ow][cout], wgt bf16 [cout][r][s][cin] (OHWI), dx bf16 [n][h][w][cin].
+extern "C" int regda_conv_dgrad_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil) {
+    if (stride != 1 || r != s) return 0;
+    const int pad2 = dil * (r - 1) - pad;
+    if (pad2 < 0) return 0;
+    const int oh = h + 2 * pad - dil * (r - 1), ow = w + 2 * pad - dil * (s - 1);
+    if (oh < 1 || ow < 1) return 0;
+    return regda_conv_fprop_supported(n, oh, ow, cout, cin, r, s, 1, pad2, dil);
+}
+
+extern "C" int regda_conv_dgrad_bf16(const void *dy, const void *wgt, void *dx, int n, int h, int w, int cin, int cout,
+                                     int r, int s, int stride, int pad, int dil, void *stream) {
+    if (!regda_conv_dgrad_supported(n, h, w, cin, cout, r, s, stride, pad, dil))
+        return fail(REGDA_ERR_UNSUPPORTED, "conv_dgrad: shape not covered by the tcgen05 kernel");
+    if (!dy || !wgt || !dx) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad: null pointer");
+    if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(wgt) | reinterpret_cast<uintptr_t>(dx)) & 15)
+        return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad: tensors must be 16-byte aligned");
+    const int oh = h + 2 * pad - dil * (r - 1), ow = w + 2 * pad - dil * (s - 1);
+    ConvGeom g;
+    // a stride-1 convolution of dy [n][oh][ow][cout] with reduction over cout, producing [n][h][w][cin]
+    geom_init(g, n, oh, ow, cout, cin, r, s, 1, dil * (r - 1) - pad, dil);
+    g.flip = 1;
+    if (g.oh != h || g.ow != w) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad: inconsistent geometry");
+    ensure_context(dy);
+    CUtensorMap tx, tw;
+    int rc = make_tmap_x(&tx, dy, g);
+    if (rc) return rc;
+    rc = make_tmap_w_mn(&tw, wgt, cout, r * s, cin);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    __nv_bfloat16 *out = static_cast<__nv_bfloat16 *>(dx);
+    if (cin % 128 == 0) return launch_fprop<128, 3, true>(tx, tw, out, g, st);
+    return launch_fprop<64, 4, true>(tx, tw, out, g, st);
 }

@@ -1,0 +1,221 @@
+// Weight gradient of a convolution on the tcgen05 tensor cores (sm_100a):
+//
+//   dW[co][r][s][ci] += sum_{n,oh,ow} dY[n,oh,ow,co] * X[n, oh*stride + r*dil - pad, ow*stride + s*dil - pad, ci]
+//
+// replaces cuDNN's convolution_backward (weight) behind nn.Conv2d in the reference's ResNet / PPM heads
+// (regda/_resnets.py:92-112, regda/models/Encoder.py:33-40).
+//
+// GEMM view: M = Cout, N = Cin, K = pixels, one GEMM per filter tap.  Pixels are the reduction dimension and the
+// channels are contiguous in NHWC memory, so BOTH operands are MN-major and are consumed straight from the
+// activation tensors: a K-block is a BH x BW patch of 64 output pixels of one image; the A tile is two 4-D TMA
+// boxes {64 co, BW, BH, 1} of dY, the B tile BLOCK_N/64 boxes {64 ci, BW, BH, 1} of X at the tap-shifted (and,
+// for stride 2, element-strided) coordinates -- halo / padding / patch overhang are TMA zero fill.  Each box
+// lands as 64 K-rows of 128 swizzled bytes; UMMA descriptors: LBO = 8 KB between 64-wide M/N blocks, SBO = 1 KB
+// between 8-row K groups, +2 KB start address per K=16 step.
+//
+// CTA = (128-cout tile, BLOCK_N-cin tile, tap, K split); fp32 accumulators in TMEM; the epilogue adds the tile
+// into the fp32 OHWI gradient with 16-byte global reductions (split-K partials and the two forward passes of a
+// training step accumulate in place).  Warp 0 = TMA, warp 1 = MMA issuer, warps 2-5 = epilogue.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace regda {
+namespace {
+
+using namespace tc;
+
+constexpr int kWgM = 128;            // cout tile
+constexpr int kWgK = 64;             // pixels per stage
+constexpr int kWgThreads = 192;
+
+struct WgradGeom {
+    int n, h, w, cin, cout, oh, ow;
+    int r, s, pad, dil, stride;
+    int bh, bw, tiles_h, tiles_w;    // 64-pixel patches of the OUTPUT image
+    int ksteps;                      // n * tiles_h * tiles_w
+    int splits, steps_per_split;
+    int n_tiles;                     // ceil(cin / BLOCK_N)
+};
+
+template <int BLOCK_N, int STAGES>
+struct WgSmem {
+    static constexpr int kABytes = kWgM * kWgK * 2;        // 16 KB: two 8 KB boxes
+    static constexpr int kBBytes = BLOCK_N * kWgK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 8;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kWgThreads, 2)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                  float *__restrict__ dw, const WgradGeom g) {
+    using L = WgSmem<BLOCK_N, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::kBarOffset);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *accum_bar = empty_bar + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int n_blk = blockIdx.x % g.n_tiles;             // cin tile
+    const int m_blk = blockIdx.x / g.n_tiles;             // cout tile
+    const int tap = blockIdx.y;
+    const int fr = tap / g.s, fs = tap - fr * g.s;
+    const int k_lo = blockIdx.z * g.steps_per_split;
+    const int k_hi = min(g.ksteps, k_lo + g.steps_per_split);
+    const int num_k = k_hi - k_lo;                        // >= 1 by construction
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_dy);
+        prefetch_tmap(&tmap_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, BLOCK_N);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int per_img = g.tiles_h * g.tiles_w;
+            for (int kb = k_lo; kb < k_hi; ++kb) {
+                const int img = kb / per_img;
+                const int t = kb - img * per_img;
+                const int th = t / g.tiles_w, tw = t - th * g.tiles_w;
+                const int oh0 = th * g.bh, ow0 = tw * g.bw;
+                mbar_wait(empty_bar + stage, phase ^ 1);
+                uint8_t *sa = smem + stage * L::kStageBytes;
+                uint8_t *sb = sa + L::kABytes;
+                mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes);
+#pragma unroll
+                for (int i = 0; i < kWgM / 64; ++i)
+                    tma_load_4d(sa + i * 8192, &tmap_dy, full_bar + stage, m_blk * kWgM + i * 64, ow0, oh0, img);
+                const int ix = ow0 * g.stride + fs * g.dil - g.pad, iy = oh0 * g.stride + fr * g.dil - g.pad;
+#pragma unroll
+                for (int i = 0; i < BLOCK_N / 64; ++i)
+                    tma_load_4d(sb + i * 8192, &tmap_x, full_bar + stage, n_blk * BLOCK_N + i * 64, ix, iy, img);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(kWgM, BLOCK_N, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(full_bar + stage, phase);
+                tc_fence_after_sync();
+                const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+                const uint32_t sb = sa + L::kABytes;
+                const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
+                const uint64_t bdesc = make_smem_desc(sb, 8192, 1024);
+#pragma unroll
+                for (int k = 0; k < kWgK / 16; ++k)
+                    umma_bf16(tmem_base, adesc + static_cast<uint64_t>(128 * k), bdesc + static_cast<uint64_t>(128 * k), idesc,
+                              (kb | k) != 0 ? 1u : 0u);
+                umma_commit(empty_bar + stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        // ===== epilogue: TMEM lane = cout row, 32 consecutive cin columns per load =====
+        const int q = warp & 3;
+        const int co = m_blk * kWgM + q * 32 + lane;
+        const int ci0 = n_blk * BLOCK_N;
+        float *dst = dw + (static_cast<size_t>(co) * (g.r * g.s) + tap) * g.cin + ci0;
+        mbar_wait(accum_bar, 0);
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
+            tmem_ld_wait();
+            if (co < g.cout && ci0 + c < g.cin) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    red_add_f32x4(dst + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                  __uint_as_float(v[j + 3]));
+            }
+        }
+        tc_fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, BLOCK_N);
+    }
+}
+
+template <int BLOCK_N, int STAGES>
+int launch_wgrad(const CUtensorMap &tdy, const CUtensorMap &tx, float *dw, const WgradGeom &g, cudaStream_t st) {
+    using L = WgSmem<BLOCK_N, STAGES>;
+    auto kern = conv_wgrad_kernel<BLOCK_N, STAGES>;
+    const int smem = L::kTotal + 1024;
+    REGDA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const dim3 grid(g.n_tiles * ((g.cout + kWgM - 1) / kWgM), g.r * g.s, g.splits);
+    kern<<<grid, kWgThreads, smem, st>>>(tdy, tx, dw, g);
+    REGDA_LAUNCH_CHECK();
+    return REGDA_OK;
+}
+
+}  // namespace
+}  // namespace regda
+
+using namespace regda;
+
+extern "C" int regda_conv_wgrad_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil) {
+    if (n < 1 || h < 1 || w < 1 || stride < 1 || stride > 2 || r < 1 || s < 1 || r * s > 49 || dil < 1 || pad < 0) return 0;
+    if (cin % 64 != 0 || cout % 64 != 0) return 0;
+    if (h + 2 * pad < dil * (r - 1) + 1 || w + 2 * pad < dil * (s - 1) + 1) return 0;
+    const int oh = (h + 2 * pad - dil * (r - 1) - 1) / stride + 1, ow = (w + 2 * pad - dil * (s - 1) - 1) / stride + 1;
+    if (static_cast<long long>(oh) * ow < 64) return 0;
+    return 1;
+}
+
+// dy bf16 [n][oh][ow][cout], x bf16 [n][h][w][cin], dw fp32 [cout][r][s][cin] (ACCUMULATED into)
+extern "C" int regda_conv_wgrad_bf16(const void *dy, const void *x, float *dw, int n, int h, int w, int cin, int cout,
+                                     int r, int s, int stride, int pad, int dil, void *stream) {
+    if (!regda_conv_wgrad_supported(n, h, w, cin, cout, r, s, stride, pad, dil))
+        return fail(REGDA_ERR_UNSUPPORTED, "conv_wgrad: shape not covered by the tcgen05 kernel");
+    if (!dy || !x || !dw) return fail(REGDA_ERR_INVALID_ARG, "conv_wgrad: null pointer");
+    if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dw)) & 15)
+        return fail(REGDA_ERR_INVALID_ARG, "conv_wgrad: tensors must be 16-byte aligned");
+    WgradGeom g;
+    g.n = n; g.h = h; g.w = w; g.cin = cin; g.cout = cout; g.r = r; g.s = s; g.pad = pad; g.dil = dil; g.stride = stride;
+    g.oh = (h + 2 * pad - dil * (r - 1) - 1) / stride + 1;
+    g.ow = (w + 2 * pad - dil * (s - 1) - 1) / stride + 1;
+    int bw = 1;
+    while (bw * 2 <= g.ow && bw * 2 <= kWgK) bw *= 2;
+    g.bw = bw; g.bh = kWgK / bw;
+    g.tiles_w = (g.ow + g.bw - 1) / g.bw;
+    g.tiles_h = (g.oh + g.bh - 1) / g.bh;
+    g.ksteps = n * g.tiles_h * g.tiles_w;
+    const int block_n = cin % 128 == 0 ? 128 : 64;
+    g.n_tiles = cin / block_n;
+    const int tiles = g.n_tiles * ((cout + kWgM - 1) / kWgM) * r * s;
+    // split K so that about two waves of CTAs exist, but keep >= 8 K-steps per CTA
+    int splits = (4 * sm_count() + tiles - 1) / tiles;
+    splits = std::max(1, std::min(splits, g.ksteps / 8));
+    g.steps_per_split = (g.ksteps + splits - 1) / splits;
+    g.splits = (g.ksteps + g.steps_per_split - 1) / g.steps_per_split;
+    ensure_context(dy);
+    CUtensorMap tdy, tx;
+    if (!encode_nhwc(&tdy, dy, n, g.oh, g.ow, cout, g.bw, g.bh, 1)) return REGDA_ERR_CUDA;   /* text set by encode_bf16_sw128 (dy) */
+    if (!encode_nhwc(&tx, x, n, h, w, cin, g.bw, g.bh, stride)) return REGDA_ERR_CUDA;   /* text set by encode_bf16_sw128 (x) */
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (block_n == 128) return launch_wgrad<128, 3>(tdy, tx, dw, g, st);
+    return launch_wgrad<64, 4>(tdy, tx, dw, g, st);
+}

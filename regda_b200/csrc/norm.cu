@@ -1,0 +1,365 @@
+// Train-mode BatchNorm2d over channels-last bf16 activations, fused with the residual add and ReLU
+// that follow it in the reference's Bottleneck / PPM blocks (regda/_resnets.py:92-112,
+// regda/models/Encoder.py:24-40), forward and backward.  Replaces the ATen batch_norm /
+// threshold / add kernels behind nn.BatchNorm2d, F.relu and `out += identity`.
+//
+// HBM-bound: every kernel streams [npix][C] bf16 rows with 16-byte accesses; a thread owns 8
+// consecutive channels for the whole launch (C divides 2048, so a 256-thread block covers
+// 2048/C whole pixels per step and the thread -> channel map never changes), which keeps the
+// per-channel coefficients / partial sums in registers.  Statistics are fp32.
+//
+//   forward : bn_stats (sum, sum of squares)  -> bn_finalize (mean, rstd, scale, shift, running stats)
+//             -> bn_apply  out = relu(y*scale + shift + residual)
+//   backward: bn_bwd_reduce (sum dz, sum dz*y with dz = dout masked by out > 0)
+//             -> bn_bwd_finalize (dgamma, dbeta accumulated into the gradient arena; coefficients)
+//             -> bn_bwd_apply  dy = g*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)),  dres = dz
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace regda {
+namespace {
+
+constexpr int kBnThreads = 256;
+constexpr int kBnSpan = kBnThreads * 8;     // elements one block covers per step
+
+struct alignas(16) bf16x8 { __nv_bfloat162 v[4]; };
+
+__device__ __forceinline__ bf16x8 ld8(const __nv_bfloat16 *p) { return *reinterpret_cast<const bf16x8 *>(p); }
+__device__ __forceinline__ bf16x8 ld8_stream(const __nv_bfloat16 *p) {
+    bf16x8 r;
+    uint4 u;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+    r = *reinterpret_cast<bf16x8 *>(&u);
+    return r;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16 *p, const bf16x8 &v) { *reinterpret_cast<bf16x8 *>(p) = v; }
+__device__ __forceinline__ void unpack(const bf16x8 &v, float (&f)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(v.v[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ bf16x8 pack(const float (&f)[8]) {
+    bf16x8 v;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return v;
+}
+
+// block-level reduction of per-thread channel-octet partials: threads t and t + C/8 (+ ...) own the same
+// channels.  `a`/`b` are the two 8-wide partial vectors; results are atomically added to ga / gb.
+__device__ __forceinline__ void block_channel_reduce(float (&a)[8], float (&b)[8], int c, float *__restrict__ ga,
+                                                     float *__restrict__ gb) {
+    __shared__ float sm[kBnThreads][17];
+    const int tid = threadIdx.x;
+    const int octs = c >> 3;                  // threads per pixel row
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sm[tid][i] = a[i]; sm[tid][8 + i] = b[i]; }
+    __syncthreads();
+    // 16 values per octet: thread `tid` < octs*16 sums value (tid & 15) of octet (tid >> 4) over the rows
+    for (int item = tid; item < octs * 16; item += kBnThreads) {
+        const int o = item >> 4, v = item & 15;
+        float s = 0.f;
+        for (int r = o; r < kBnThreads; r += octs) s += sm[r][v];
+        const int ch = o * 8 + (v & 7);
+        atomicAdd((v < 8 ? ga : gb) + ch, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBnThreads)
+bn_stats_kernel(const __nv_bfloat16 *__restrict__ y, long long total, int c, long long span_per_block,
+                float *__restrict__ gsum, float *__restrict__ gsq) {
+    // blockIdx.y = statistics group (a contiguous range of `total` elements); group g accumulates into gsum + 2*c*g
+    y += static_cast<long long>(blockIdx.y) * total;
+    gsum += 2 * c * blockIdx.y;
+    gsq += 2 * c * blockIdx.y;
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+    const long long lo = static_cast<long long>(blockIdx.x) * span_per_block;
+    const long long hi = min(total, lo + span_per_block);
+#pragma unroll 4
+    for (long long e = lo + static_cast<long long>(threadIdx.x) * 8; e < hi; e += kBnSpan) {
+        float f[8];
+        unpack(ld8_stream(y + e), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+    }
+    block_channel_reduce(s, q, c, gsum, gsq);
+}
+
+// per group g: stats[2c*g + 0..c) = sum, [.. c..2c) = sum of squares; coef[4c*g + ...]: [0..c) scale, [c..2c) shift,
+// [2c..3c) mean, [3c..4c) rstd.  Running statistics are updated once per group, in group order (= the reference's
+// sequence of forward calls: source batch, then target batch).
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float *__restrict__ stats, int c, int groups, float inv_n, float unbias, const float *__restrict__ gamma,
+                   const float *__restrict__ beta, float *__restrict__ running_mean, float *__restrict__ running_var,
+                   long long *__restrict__ num_batches, float eps, float momentum, float *__restrict__ coef) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch == 0 && num_batches != nullptr) *num_batches += groups;
+    if (ch >= c) return;
+    const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+    float rm = running_mean ? running_mean[ch] : 0.f, rv = running_var ? running_var[ch] : 0.f;
+    for (int grp = 0; grp < groups; ++grp) {
+        const float *st = stats + 2 * c * grp;
+        float *cf = coef + 4 * c * grp;
+        const float mean = st[ch] * inv_n;
+        const float var = fmaxf(fmaf(-mean, mean, st[c + ch] * inv_n), 0.f);
+        const float rstd = rsqrtf(var + eps);
+        const float scale = g * rstd;
+        cf[ch] = scale;
+        cf[c + ch] = fmaf(-mean, scale, b);
+        cf[2 * c + ch] = mean;
+        cf[3 * c + ch] = rstd;
+        rm = fmaf(momentum, mean - rm, rm);
+        rv = fmaf(momentum, var * unbias - rv, rv);
+    }
+    if (running_mean) running_mean[ch] = rm;
+    if (running_var) running_var[ch] = rv;
+}
+
+template <bool RELU, bool RES>
+__global__ void __launch_bounds__(kBnThreads)
+bn_apply_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__restrict__ res, __nv_bfloat16 *__restrict__ out,
+                long long total, int c, const float *__restrict__ coef) {
+    {   // blockIdx.y = statistics group
+        const long long off = static_cast<long long>(blockIdx.y) * total;
+        y += off; out += off;
+        if (RES) res += off;
+        coef += 4 * c * blockIdx.y;
+    }
+    const long long stride = static_cast<long long>(gridDim.x) * kBnSpan;
+    long long e = static_cast<long long>(blockIdx.x) * kBnSpan + static_cast<long long>(threadIdx.x) * 8;
+    if (e >= total) return;
+    const int ch = static_cast<int>(e % c);   // invariant: stride % c == 0
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc[i] = coef[ch + i]; sh[i] = coef[c + ch + i]; }
+    for (; e < total; e += stride) {
+        float f[8];
+        unpack(ld8_stream(y + e), f);
+        if (RES) {
+            float r[8];
+            unpack(ld8_stream(res + e), r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sh[i]) + r[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
+        }
+        if (RELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        st8(out + e, pack(f));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+template <bool RELU>
+__global__ void __launch_bounds__(kBnThreads)
+bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 *__restrict__ out, const __nv_bfloat16 *__restrict__ y,
+                     long long total, int c, long long span_per_block, float *__restrict__ gdz, float *__restrict__ gdzy) {
+    {
+        const long long off = static_cast<long long>(blockIdx.y) * total;
+        dout += off; y += off;
+        if (RELU) out += off;
+        gdz += 2 * c * blockIdx.y; gdzy += 2 * c * blockIdx.y;
+    }
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+    const long long lo = static_cast<long long>(blockIdx.x) * span_per_block;
+    const long long hi = min(total, lo + span_per_block);
+#pragma unroll 2
+    for (long long e = lo + static_cast<long long>(threadIdx.x) * 8; e < hi; e += kBnSpan) {
+        float d[8], v[8];
+        unpack(ld8_stream(dout + e), d);
+        unpack(ld8_stream(y + e), v);
+        if (RELU) {
+            float o[8];
+            unpack(ld8(out + e), o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += d[i]; q[i] = fmaf(d[i], v[i], q[i]); }
+    }
+    block_channel_reduce(s, q, c, gdz, gdzy);
+}
+
+// per group g: red[2c*g + 0..c) = sum dz, [.. c..2c) = sum dz*y.  bcoef[3c*g + ...]: [0..c) a = gamma*rstd, [c..2c) k1 = mean(dz),
+// [2c..3c) k2 = mean(dz*xhat)*rstd, so that dy = a * (dz - k1 - (y - mean) * k2).  dgamma / dbeta accumulate over the groups.
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float *__restrict__ red, int c, int groups, float inv_n, const float *__restrict__ gamma,
+                       const float *__restrict__ coef, float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ bcoef) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    const float g = gamma ? gamma[ch] : 1.f;
+    float dg = 0.f, db = 0.f;
+    for (int grp = 0; grp < groups; ++grp) {
+        const float *cf = coef + 4 * c * grp;
+        const float *rd = red + 2 * c * grp;
+        float *bc = bcoef + 3 * c * grp;
+        const float mean = cf[2 * c + ch], rstd = cf[3 * c + ch];
+        const float sdz = rd[ch];
+        const float sdzx = (rd[c + ch] - mean * sdz) * rstd;          // sum dz * xhat
+        dg += sdzx;
+        db += sdz;
+        bc[ch] = g * rstd;
+        bc[c + ch] = sdz * inv_n;
+        bc[2 * c + ch] = sdzx * inv_n * rstd;
+    }
+    if (dgamma) dgamma[ch] += dg;
+    if (dbeta) dbeta[ch] += db;
+}
+
+template <bool RELU, bool DRES>
+__global__ void __launch_bounds__(kBnThreads)
+bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 *__restrict__ out, const __nv_bfloat16 *__restrict__ y,
+                    __nv_bfloat16 *__restrict__ dy, __nv_bfloat16 *__restrict__ dres, long long total, int c,
+                    const float *__restrict__ coef, const float *__restrict__ bcoef) {
+    {
+        const long long off = static_cast<long long>(blockIdx.y) * total;
+        dout += off; y += off; dy += off;
+        if (RELU) out += off;
+        if (DRES) dres += off;
+        coef += 4 * c * blockIdx.y; bcoef += 3 * c * blockIdx.y;
+    }
+    const long long stride = static_cast<long long>(gridDim.x) * kBnSpan;
+    long long e = static_cast<long long>(blockIdx.x) * kBnSpan + static_cast<long long>(threadIdx.x) * 8;
+    if (e >= total) return;
+    const int ch = static_cast<int>(e % c);
+    float a[8], k1[8], k2[8], mu[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = bcoef[ch + i]; k1[i] = bcoef[c + ch + i]; k2[i] = bcoef[2 * c + ch + i]; mu[i] = coef[2 * c + ch + i];
+    }
+    for (; e < total; e += stride) {
+        float d[8], v[8];
+        unpack(ld8_stream(dout + e), d);
+        unpack(ld8_stream(y + e), v);
+        if (RELU) {
+            float o[8];
+            unpack(ld8_stream(out + e), o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+        }
+        if (DRES) st8(dres + e, pack(d));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = a[i] * (d[i] - k1[i] - (v[i] - mu[i]) * k2[i]);
+        st8(dy + e, pack(v));
+    }
+}
+
+bool bn_shape_ok(long long npix, int c) { return npix > 0 && c >= 8 && c % 8 == 0 && kBnSpan % c == 0; }
+
+int reduce_grid(long long total, int groups, long long *span) {
+    // whole steps of kBnSpan elements per block, about 4 blocks per SM over all groups
+    const long long steps = (total + kBnSpan - 1) / kBnSpan;
+    long long blocks = std::min<long long>(steps, std::max(1, 4 * sm_count() / groups));
+    const long long steps_per_block = (steps + blocks - 1) / blocks;
+    blocks = (steps + steps_per_block - 1) / steps_per_block;
+    *span = steps_per_block * kBnSpan;
+    return static_cast<int>(blocks);
+}
+
+int apply_grid(long long total, int groups) {
+    const long long steps = (total + kBnSpan - 1) / kBnSpan;
+    return static_cast<int>(std::min<long long>(steps, std::max(1, 8 * sm_count() / groups)));
+}
+
+}  // namespace
+}  // namespace regda
+
+using namespace regda;
+
+extern "C" int regda_bn_supported(int64_t npix, int c) { return bn_shape_ok(npix, c) ? 1 : 0; }
+
+// workspace (floats): stats [groups][2c]
+extern "C" size_t regda_bn_workspace_bytes(int c, int groups) { return static_cast<size_t>(2 * c) * std::max(groups, 1) * sizeof(float); }
+
+extern "C" int regda_bn_forward_bf16(const void *y, const void *residual, void *out, int64_t npix, int c, int groups,
+                                     const float *gamma, const float *beta, float *running_mean, float *running_var,
+                                     int64_t *num_batches_tracked, double eps, double momentum, int relu,
+                                     float *coef, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!bn_shape_ok(npix, c)) return fail(REGDA_ERR_UNSUPPORTED, "bn_forward: channels must divide 2048 and be a multiple of 8");
+    if (groups < 1 || npix % groups != 0) return fail(REGDA_ERR_INVALID_ARG, "bn_forward: groups must divide the pixel count");
+    if (!y || !out || !coef) return fail(REGDA_ERR_INVALID_ARG, "bn_forward: null pointer");
+    if (!workspace || workspace_bytes < regda_bn_workspace_bytes(c, groups)) return fail(REGDA_ERR_WORKSPACE, "bn_forward: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *stats = static_cast<float *>(workspace);
+    const long long gpix = npix / groups;
+    const long long total = gpix * c;                                   // elements per statistics group
+    REGDA_CUDA_CHECK(cudaMemsetAsync(stats, 0, static_cast<size_t>(2 * c) * groups * sizeof(float), st));
+    long long span = 0;
+    const int rg = reduce_grid(total, groups, &span);
+    const __nv_bfloat16 *yy = static_cast<const __nv_bfloat16 *>(y);
+    bn_stats_kernel<<<dim3(rg, groups), kBnThreads, 0, st>>>(yy, total, c, span, stats, stats + c);
+    REGDA_LAUNCH_CHECK();
+    const float n = static_cast<float>(gpix);
+    bn_finalize_kernel<<<(c + 255) / 256, 256, 0, st>>>(stats, c, groups, 1.f / n, gpix > 1 ? n / (n - 1.f) : 1.f, gamma, beta, running_mean,
+                                                         running_var, reinterpret_cast<long long *>(num_batches_tracked),
+                                                         static_cast<float>(eps), static_cast<float>(momentum), coef);
+    REGDA_LAUNCH_CHECK();
+    const dim3 ag(apply_grid(total, groups), groups);
+    const __nv_bfloat16 *rr = static_cast<const __nv_bfloat16 *>(residual);
+    __nv_bfloat16 *oo = static_cast<__nv_bfloat16 *>(out);
+    if (relu) {
+        if (rr) bn_apply_kernel<true, true><<<ag, kBnThreads, 0, st>>>(yy, rr, oo, total, c, coef);
+        else bn_apply_kernel<true, false><<<ag, kBnThreads, 0, st>>>(yy, rr, oo, total, c, coef);
+    } else {
+        if (rr) bn_apply_kernel<false, true><<<ag, kBnThreads, 0, st>>>(yy, rr, oo, total, c, coef);
+        else bn_apply_kernel<false, false><<<ag, kBnThreads, 0, st>>>(yy, rr, oo, total, c, coef);
+    }
+    REGDA_LAUNCH_CHECK();
+    return REGDA_OK;
+}
+
+// workspace (floats): red [groups][2c] + bcoef [groups][3c]
+extern "C" size_t regda_bn_backward_workspace_bytes(int c, int groups) { return static_cast<size_t>(5 * c) * std::max(groups, 1) * sizeof(float); }
+
+extern "C" int regda_bn_backward_bf16(const void *dout, const void *out, const void *y, void *dy, void *dres, int64_t npix, int c,
+                                      int groups, const float *gamma, const float *coef, float *dgamma, float *dbeta, int relu,
+                                      void *workspace, size_t workspace_bytes, void *stream) {
+    if (!bn_shape_ok(npix, c)) return fail(REGDA_ERR_UNSUPPORTED, "bn_backward: channels must divide 2048 and be a multiple of 8");
+    if (groups < 1 || npix % groups != 0) return fail(REGDA_ERR_INVALID_ARG, "bn_backward: groups must divide the pixel count");
+    if (!dout || !y || !dy || !coef || (relu && !out)) return fail(REGDA_ERR_INVALID_ARG, "bn_backward: null pointer");
+    if (!workspace || workspace_bytes < regda_bn_backward_workspace_bytes(c, groups)) return fail(REGDA_ERR_WORKSPACE, "bn_backward: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *red = static_cast<float *>(workspace);
+    float *bcoef = red + 2 * c * groups;
+    const long long gpix = npix / groups;
+    const long long total = gpix * c;
+    REGDA_CUDA_CHECK(cudaMemsetAsync(red, 0, static_cast<size_t>(2 * c) * groups * sizeof(float), st));
+    long long span = 0;
+    const int rg = reduce_grid(total, groups, &span);
+    const __nv_bfloat16 *dd = static_cast<const __nv_bfloat16 *>(dout);
+    const __nv_bfloat16 *oo = static_cast<const __nv_bfloat16 *>(out);
+    const __nv_bfloat16 *yy = static_cast<const __nv_bfloat16 *>(y);
+    if (relu) bn_bwd_reduce_kernel<true><<<dim3(rg, groups), kBnThreads, 0, st>>>(dd, oo, yy, total, c, span, red, red + c);
+    else bn_bwd_reduce_kernel<false><<<dim3(rg, groups), kBnThreads, 0, st>>>(dd, oo, yy, total, c, span, red, red + c);
+    REGDA_LAUNCH_CHECK();
+    bn_bwd_finalize_kernel<<<(c + 255) / 256, 256, 0, st>>>(red, c, groups, 1.f / static_cast<float>(gpix), gamma, coef, dgamma, dbeta, bcoef);
+    REGDA_LAUNCH_CHECK();
+    const dim3 ag(apply_grid(total, groups), groups);
+    __nv_bfloat16 *dyy = static_cast<__nv_bfloat16 *>(dy);
+    __nv_bfloat16 *dr = static_cast<__nv_bfloat16 *>(dres);
+    if (relu) {
+        if (dr) bn_bwd_apply_kernel<true, true><<<ag, kBnThreads, 0, st>>>(dd, oo, yy, dyy, dr, total, c, coef, bcoef);
+        else bn_bwd_apply_kernel<true, false><<<ag, kBnThreads, 0, st>>>(dd, oo, yy, dyy, dr, total, c, coef, bcoef);
+    } else {
+        if (dr) bn_bwd_apply_kernel<false, true><<<ag, kBnThreads, 0, st>>>(dd, oo, yy, dyy, dr, total, c, coef, bcoef);
+        else bn_bwd_apply_kernel<false, false><<<ag, kBnThreads, 0, st>>>(dd, oo, yy, dyy, dr, total, c, coef, bcoef);
+    }
+    REGDA_LAUNCH_CHECK();
+    return REGDA_OK;
+}

@@ -1,0 +1,298 @@
+// Pyramid pooling front end of the PPM heads (reference regda/models/Encoder.py:43-52): for every
+// pool scale s in (1,2,3,6), AdaptiveAvgPool2d(s) of the feature map and, after the tiny per-branch
+// 1x1 conv + BN + ReLU, bilinear upsampling (align_corners=False) back to the feature-map size and
+// concatenation with the feature map itself.  Replaces the ATen adaptive_avg_pool2d /
+// upsample_bilinear2d / cat kernels (34 % of the step's GPU time in the eager profile,
+// profiles/step_kernel_table_round1_cudnn_eager.txt) with four HBM-bound NHWC kernels:
+//
+//   ppm_pool_fwd   feat bf16 [b][h][w][c]            -> pooled f32 [b][ncell][c]   (ALL scales in one launch)
+//   ppm_pool_bwd   dpooled f32 [b][ncell][c]          -> dfeat  bf16 [b][h][w][c]
+//   ppm_upcat_fwd  feat + branch maps bf16 [b][s][s][cb] -> cat bf16 [b][h][w][c + nscale*cb]
+//   ppm_upcat_bwd  dcat -> dbranch f32 [b][s][s][cb] per scale   (d feat is the first c channels of dcat)
+//
+// ncell = sum s^2 (50 for (1,2,3,6)); cells of scale k start at off_k = sum_{j<k} s_j^2, row-major.
+// A thread owns 8 consecutive channels (16-byte accesses); one block per (image, feature-map row).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace regda {
+namespace {
+
+constexpr int kMaxScales = 4;
+struct PpmScales {
+    int n;
+    int s[kMaxScales];
+    int off[kMaxScales];
+    int ncell;
+};
+
+struct alignas(16) bf16x8 { __nv_bfloat162 v[4]; };
+__device__ __forceinline__ void unpack(const bf16x8 &v, float (&f)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(v.v[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ bf16x8 pack(const float (&f)[8]) {
+    bf16x8 v;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return v;
+}
+__device__ __forceinline__ void atomic_add8(float *p, const float (&f)[8], float w) {
+    atomicAdd(reinterpret_cast<float4 *>(p), make_float4(f[0] * w, f[1] * w, f[2] * w, f[3] * w));
+    atomicAdd(reinterpret_cast<float4 *>(p) + 1, make_float4(f[4] * w, f[5] * w, f[6] * w, f[7] * w));
+}
+
+// adaptive pooling window of output index i: [floor(i*n/s), ceil((i+1)*n/s))
+__device__ __forceinline__ int win_lo(int i, int n, int s) { return (i * n) / s; }
+__device__ __forceinline__ int win_hi(int i, int n, int s) { return ((i + 1) * n + s - 1) / s; }
+
+// grid (h, b), block c/8 threads (<= 1024; larger c loops)
+__global__ void __launch_bounds__(256)
+ppm_pool_fwd_kernel(const __nv_bfloat16 *__restrict__ feat, float *__restrict__ pooled, int h, int w, int c, const PpmScales sc) {
+    const int y = blockIdx.x, img = blockIdx.y;
+    const __nv_bfloat16 *row = feat + (static_cast<size_t>(img) * h + y) * w * c;
+    float *pimg = pooled + static_cast<size_t>(img) * sc.ncell * c;
+    for (int ch = threadIdx.x * 8; ch < c; ch += blockDim.x * 8) {
+        for (int k = 0; k < sc.n; ++k) {
+            const int s = sc.s[k];
+            // the row-cells this feature-map row belongs to (windows may overlap by one row)
+            const int i0 = (y * s) / h;
+            for (int j = 0; j < s; ++j) {
+                const int x0 = win_lo(j, w, s), x1 = win_hi(j, w, s);
+                float acc[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+                for (int x = x0; x < x1; ++x) {
+                    float f[8];
+                    unpack(*reinterpret_cast<const bf16x8 *>(row + static_cast<size_t>(x) * c + ch), f);
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) acc[t] += f[t];
+                }
+                for (int i = max(i0 - 1, 0); i <= min(i0 + 1, s - 1); ++i) {
+                    const int y0 = win_lo(i, h, s), y1 = win_hi(i, h, s);
+                    if (y < y0 || y >= y1) continue;
+                    const float wgt = 1.f / static_cast<float>((y1 - y0) * (x1 - x0));
+                    atomic_add8(pimg + static_cast<size_t>(sc.off[k] + i * s + j) * c + ch, acc, wgt);
+                }
+            }
+        }
+    }
+}
+
+// one thread per (pixel, channel octet)
+__global__ void __launch_bounds__(256)
+ppm_pool_bwd_kernel(const float *__restrict__ dpooled, __nv_bfloat16 *__restrict__ dfeat, int h, int w, int c, const PpmScales sc) {
+    const int y = blockIdx.x, img = blockIdx.y;
+    const float *pimg = dpooled + static_cast<size_t>(img) * sc.ncell * c;
+    __nv_bfloat16 *row = dfeat + (static_cast<size_t>(img) * h + y) * w * c;
+    const int octs = c >> 3;
+    for (int item = threadIdx.x; item < w * octs; item += blockDim.x) {
+        const int x = item / octs, ch = (item - x * octs) * 8;
+        float acc[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+        for (int k = 0; k < sc.n; ++k) {
+            const int s = sc.s[k];
+            const int i0 = (y * s) / h, j0 = (x * s) / w;
+            for (int i = max(i0 - 1, 0); i <= min(i0 + 1, s - 1); ++i) {
+                const int y0 = win_lo(i, h, s), y1 = win_hi(i, h, s);
+                if (y < y0 || y >= y1) continue;
+                for (int j = max(j0 - 1, 0); j <= min(j0 + 1, s - 1); ++j) {
+                    const int x0 = win_lo(j, w, s), x1 = win_hi(j, w, s);
+                    if (x < x0 || x >= x1) continue;
+                    const float wgt = 1.f / static_cast<float>((y1 - y0) * (x1 - x0));
+                    const float4 *p = reinterpret_cast<const float4 *>(pimg + static_cast<size_t>(sc.off[k] + i * s + j) * c + ch);
+                    const float4 a = p[0], b = p[1];
+                    acc[0] = fmaf(a.x, wgt, acc[0]); acc[1] = fmaf(a.y, wgt, acc[1]); acc[2] = fmaf(a.z, wgt, acc[2]); acc[3] = fmaf(a.w, wgt, acc[3]);
+                    acc[4] = fmaf(b.x, wgt, acc[4]); acc[5] = fmaf(b.y, wgt, acc[5]); acc[6] = fmaf(b.z, wgt, acc[6]); acc[7] = fmaf(b.w, wgt, acc[7]);
+                }
+            }
+        }
+        *reinterpret_cast<bf16x8 *>(row + static_cast<size_t>(x) * c + ch) = pack(acc);
+    }
+}
+
+// PyTorch's area_pixel_compute_source_index for align_corners=False: src = (dst + 0.5) * in/out - 0.5, clamped at 0
+__device__ __forceinline__ void bilinear_src(int dst, int in_size, int out_size, int &i0, int &i1, float &l1) {
+    const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
+    float src = (static_cast<float>(dst) + 0.5f) * scale - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    i0 = static_cast<int>(src);
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = src - static_cast<float>(i0);
+}
+
+struct BranchPtrs { const __nv_bfloat16 *p[kMaxScales]; };
+struct BranchGradPtrs { float *p[kMaxScales]; };
+
+// grid (h, b): cat[b][y][x][0..c) = feat, cat[.. c + k*cb + q] = bilinear(branch_k)[q]
+__global__ void __launch_bounds__(256)
+ppm_upcat_fwd_kernel(const __nv_bfloat16 *__restrict__ feat, const BranchPtrs br, __nv_bfloat16 *__restrict__ cat, int h, int w, int c,
+                     int cb, const PpmScales sc) {
+    const int y = blockIdx.x, img = blockIdx.y;
+    const int ctot = c + sc.n * cb;
+    const int octs = ctot >> 3;
+    const __nv_bfloat16 *frow = feat + (static_cast<size_t>(img) * h + y) * w * c;
+    __nv_bfloat16 *crow = cat + (static_cast<size_t>(img) * h + y) * w * ctot;
+    for (int item = threadIdx.x; item < w * octs; item += blockDim.x) {
+        const int x = item / octs, ch = (item - x * octs) * 8;
+        bf16x8 outv;
+        if (ch < c) {
+            outv = *reinterpret_cast<const bf16x8 *>(frow + static_cast<size_t>(x) * c + ch);
+        } else {
+            const int k = (ch - c) / cb, q = (ch - c) - k * cb;
+            const int s = sc.s[k];
+            int y0, y1, x0, x1;
+            float ly, lx;
+            bilinear_src(y, s, h, y0, y1, ly);
+            bilinear_src(x, s, w, x0, x1, lx);
+            const __nv_bfloat16 *b0 = br.p[k] + static_cast<size_t>(img) * s * s * cb + q;
+            float f00[8], f01[8], f10[8], f11[8], o[8];
+            unpack(*reinterpret_cast<const bf16x8 *>(b0 + static_cast<size_t>(y0 * s + x0) * cb), f00);
+            unpack(*reinterpret_cast<const bf16x8 *>(b0 + static_cast<size_t>(y0 * s + x1) * cb), f01);
+            unpack(*reinterpret_cast<const bf16x8 *>(b0 + static_cast<size_t>(y1 * s + x0) * cb), f10);
+            unpack(*reinterpret_cast<const bf16x8 *>(b0 + static_cast<size_t>(y1 * s + x1) * cb), f11);
+            const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) o[t] = w00 * f00[t] + w01 * f01[t] + w10 * f10[t] + w11 * f11[t];
+            outv = pack(o);
+        }
+        *reinterpret_cast<bf16x8 *>(crow + static_cast<size_t>(x) * ctot + ch) = outv;
+    }
+}
+
+// grid (h, b), one thread per (branch channel octet): for every source column j, the weighted sum of this row's
+// gradients that interpolate from column j, then atomically into the (up to two) source rows.
+__global__ void __launch_bounds__(256)
+ppm_upcat_bwd_kernel(const __nv_bfloat16 *__restrict__ dcat, const BranchGradPtrs dbr, int h, int w, int c, int cb, const PpmScales sc) {
+    const int y = blockIdx.x, img = blockIdx.y;
+    const int ctot = c + sc.n * cb;
+    const __nv_bfloat16 *drow = dcat + (static_cast<size_t>(img) * h + y) * w * ctot + c;
+    for (int ch = threadIdx.x * 8; ch < sc.n * cb; ch += blockDim.x * 8) {
+        const int k = ch / cb, q = ch - k * cb;
+        const int s = sc.s[k];
+        int y0, y1;
+        float ly;
+        bilinear_src(y, s, h, y0, y1, ly);
+        float *g = dbr.p[k] + static_cast<size_t>(img) * s * s * cb + q;
+        for (int j = 0; j < s; ++j) {
+            float acc[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+            // destination columns whose source index is in (j-1, j+1): conservative bounds, exact test inside
+            const float inv = static_cast<float>(w) / static_cast<float>(s);
+            const int xa = max(0, static_cast<int>(floorf((static_cast<float>(j) - 0.5f) * inv - 0.5f)) - 1);
+            const int xb = min(w - 1, static_cast<int>(ceilf((static_cast<float>(j) + 1.5f) * inv - 0.5f)) + 1);
+            for (int x = xa; x <= xb; ++x) {
+                int x0, x1;
+                float lx;
+                bilinear_src(x, s, w, x0, x1, lx);
+                float wgt = 0.f;
+                if (x0 == j) wgt += 1.f - lx;
+                if (x1 == j) wgt += lx;
+                if (wgt == 0.f) continue;
+                float f[8];
+                unpack(*reinterpret_cast<const bf16x8 *>(drow + static_cast<size_t>(x) * ctot + ch), f);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) acc[t] = fmaf(f[t], wgt, acc[t]);
+            }
+            if (y0 == y1) {
+                atomic_add8(g + static_cast<size_t>(y0 * s + j) * cb, acc, 1.f);
+            } else {
+                atomic_add8(g + static_cast<size_t>(y0 * s + j) * cb, acc, 1.f - ly);
+                atomic_add8(g + static_cast<size_t>(y1 * s + j) * cb, acc, ly);
+            }
+        }
+    }
+}
+
+int make_scales(const int *scales, int nscales, PpmScales *out) {
+    if (nscales < 1 || nscales > kMaxScales || !scales) return fail(REGDA_ERR_INVALID_ARG, "ppm: 1..4 pool scales");
+    out->n = nscales;
+    int off = 0;
+    for (int k = 0; k < kMaxScales; ++k) {
+        out->s[k] = k < nscales ? scales[k] : 1;
+        out->off[k] = off;
+        if (k < nscales) {
+            if (scales[k] < 1 || scales[k] > 64) return fail(REGDA_ERR_INVALID_ARG, "ppm: pool scale out of range");
+            off += scales[k] * scales[k];
+        }
+    }
+    out->ncell = off;
+    return REGDA_OK;
+}
+
+}  // namespace
+}  // namespace regda
+
+using namespace regda;
+
+extern "C" int regda_ppm_pool_fwd(const void *feat, float *pooled, int b, int h, int w, int c, const int *scales_host, int nscales,
+                                  void *stream) {
+    PpmScales sc;
+    const int rc = make_scales(scales_host, nscales, &sc);
+    if (rc) return rc;
+    if (!feat || !pooled || b < 1 || h < 1 || w < 1 || c < 8 || c % 8) return fail(REGDA_ERR_INVALID_ARG, "ppm_pool_fwd: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    REGDA_CUDA_CHECK(cudaMemsetAsync(pooled, 0, static_cast<size_t>(b) * sc.ncell * c * sizeof(float), st));
+    const int threads = std::min(256, (c / 8 + 31) / 32 * 32);
+    ppm_pool_fwd_kernel<<<dim3(h, b), threads, 0, st>>>(static_cast<const __nv_bfloat16 *>(feat), pooled, h, w, c, sc);
+    REGDA_LAUNCH_CHECK();
+    return REGDA_OK;
+}
+
+extern "C" int regda_ppm_pool_bwd(const float *dpooled, void *dfeat, int b, int h, int w, int c, const int *scales_host, int nscales,
+                                  void *stream) {
+    PpmScales sc;
+    const int rc = make_scales(scales_host, nscales, &sc);
+    if (rc) return rc;
+    if (!dpooled || !dfeat || b < 1 || h < 1 || w < 1 || c < 8 || c % 8) return fail(REGDA_ERR_INVALID_ARG, "ppm_pool_bwd: bad arguments");
+    ppm_pool_bwd_kernel<<<dim3(h, b), 256, 0, static_cast<cudaStream_t>(stream)>>>(dpooled, static_cast<__nv_bfloat16 *>(dfeat), h, w, c, sc);
+    REGDA_LAUNCH_CHECK();
+    return REGDA_OK;
+}
+
+extern "C" int regda_ppm_upcat_fwd(const void *feat, const void *br0, const void *br1, const void *br2, const void *br3, void *cat,
+                                   int b, int h, int w, int c, int cb, const int *scales_host, int nscales, void *stream) {
+    PpmScales sc;
+    const int rc = make_scales(scales_host, nscales, &sc);
+    if (rc) return rc;
+    if (!feat || !cat || b < 1 || h < 1 || w < 1 || c % 8 || cb % 8 || c < 8 || cb < 8) return fail(REGDA_ERR_INVALID_ARG, "ppm_upcat_fwd: bad arguments");
+    BranchPtrs bp;
+    const void *ps[4] = {br0, br1, br2, br3};
+    for (int k = 0; k < kMaxScales; ++k) {
+        bp.p[k] = static_cast<const __nv_bfloat16 *>(ps[k]);
+        if (k < nscales && !ps[k]) return fail(REGDA_ERR_INVALID_ARG, "ppm_upcat_fwd: null branch pointer");
+    }
+    ppm_upcat_fwd_kernel<<<dim3(h, b), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16 *>(feat), bp,
+                                                                                      static_cast<__nv_bfloat16 *>(cat), h, w, c, cb, sc);
+    REGDA_LAUNCH_CHECK();
+    return REGDA_OK;
+}
+
+extern "C" int regda_ppm_upcat_bwd(const void *dcat, float *dbr0, float *dbr1, float *dbr2, float *dbr3, int b, int h, int w, int c,
+                                   int cb, const int *scales_host, int nscales, void *stream) {
+    PpmScales sc;
+    const int rc = make_scales(scales_host, nscales, &sc);
+    if (rc) return rc;
+    if (!dcat || b < 1 || h < 1 || w < 1 || c % 8 || cb % 8 || c < 8 || cb < 8) return fail(REGDA_ERR_INVALID_ARG, "ppm_upcat_bwd: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    BranchGradPtrs gp;
+    float *ps[4] = {dbr0, dbr1, dbr2, dbr3};
+    for (int k = 0; k < kMaxScales; ++k) {
+        gp.p[k] = ps[k];
+        if (k < nscales) {
+            if (!ps[k]) return fail(REGDA_ERR_INVALID_ARG, "ppm_upcat_bwd: null branch gradient pointer");
+            REGDA_CUDA_CHECK(cudaMemsetAsync(ps[k], 0, static_cast<size_t>(b) * sc.s[k] * sc.s[k] * cb * sizeof(float), st));
+        }
+    }
+    const int threads = std::min(256, (nscales * cb / 8 + 31) / 32 * 32);
+    ppm_upcat_bwd_kernel<<<dim3(h, b), threads, 0, st>>>(static_cast<const __nv_bfloat16 *>(dcat), gp, h, w, c, cb, sc);
+    REGDA_LAUNCH_CHECK();
+    return REGDA_OK;
+}

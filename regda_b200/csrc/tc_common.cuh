@@ -45,6 +45,10 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
                      "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+                     "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
                      "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -110,6 +114,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_major
            (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// 16-byte fp32 reduction into global memory (RED.E.ADD.F32x4 on sm_90+)
+__device__ __forceinline__ void red_add_f32x4(float *p, float a, float b, float c, float d) {
+    atomicAdd(reinterpret_cast<float4 *>(p), make_float4(a, b, c, d));
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(
@@ -120,6 +129,82 @@ __device__ __forceinline__ bool elect_one() {
         "}"
         : "=r"(pred));
     return pred != 0;
+}
+
+// ---- host side: tensor-map encoding through the driver entry point (no -lcuda link dependency) ------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// cuTensorMapEncodeTiled needs a current driver context in the CALLING thread (CUDA_ERROR_INVALID_CONTEXT otherwise).
+// A fresh host thread -- e.g. PyTorch's autograd worker running a backward whose first CUDA action is one of our entry
+// points -- has none until a runtime call binds the primary context; bind the context of the device that owns `dev_ptr`.
+inline void ensure_context(const void *dev_ptr) {
+    typedef CUresult (*CtxGetCurrentFn)(CUcontext *);
+    static CtxGetCurrentFn get_current = nullptr;
+    static bool looked_up = false;
+    if (!looked_up) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            get_current = reinterpret_cast<CtxGetCurrentFn>(p);
+        else
+            (void)cudaGetLastError();
+        looked_up = true;
+    }
+    CUcontext ctx = nullptr;
+    if (get_current != nullptr && get_current(&ctx) == CUDA_SUCCESS && ctx != nullptr) return;
+    int dev = 0;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, dev_ptr) == cudaSuccess && at.type == cudaMemoryTypeDevice) dev = at.device;
+    else if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    (void)cudaSetDevice(dev);          // CUDA 12: initialises / binds the primary context for this thread
+    (void)cudaGetLastError();
+}
+
+// bf16 tensor map, 128-byte swizzle, zero fill out of bounds.  dims/box/estr innermost first; strides (bytes) for dims 1..rank-1.
+inline bool encode_bf16_sw128(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+                              const cuuint32_t *box, const cuuint32_t *estr) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return false;
+    }
+    const CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void *>(base), dims, strides,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled rc=%d base=%p rank=%d dims=[%llu,%llu,%llu,%llu] strides=[%llu,%llu,%llu] box=[%u,%u,%u,%u] estr=[%u,%u,%u,%u]",
+                  static_cast<int>(rc), base, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                  (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                  (unsigned long long)(rank > 1 ? strides[0] : 0), (unsigned long long)(rank > 2 ? strides[1] : 0),
+                  (unsigned long long)(rank > 3 ? strides[2] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0,
+                  estr[0], rank > 1 ? estr[1] : 0, rank > 2 ? estr[2] : 0, rank > 3 ? estr[3] : 0);
+        return false;
+    }
+    return true;
+}
+
+// NHWC activation map [n][h][w][c] with a {64 ch, bw, bh, 1}-pixel box sampled every `stride` pixels
+inline bool encode_nhwc(CUtensorMap *m, const void *base, int n, int h, int w, int c, int bw, int bh, int stride) {
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w) * c * 2, static_cast<cuuint64_t>(h) * w * c * 2};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw * stride), static_cast<cuuint32_t>(bh * stride), 1};
+    const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+    return encode_bf16_sw128(m, base, 4, dims, strides, box, estr);
 }
 
 }  // namespace tc

@@ -18,7 +18,37 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+import os
+
 from ..ops.conv import Conv2d
+from ..ops import norm as fnorm
+from ..ops import ppm as fppm
+
+FUSED = os.environ.get("REGDA_FUSED", "1") != "0"     # hand-written BN / PPM kernels for bf16 training forward+backward
+
+
+def set_fused(flag: bool):
+    global FUSED
+    FUSED = bool(flag)
+
+
+def _fused(x, bn):
+    return FUSED and fnorm.supported(x, bn)
+
+
+# number of BatchNorm statistics groups of the forward pass in flight: 1 for a plain model(x) call, 2 inside
+# Deeplabv2.forward_pair (source and target batch concatenated; see ops/norm.py)
+_GROUPS = 1
+
+
+def _bn(x, bn, residual=None, relu=False):
+    """relu?(bn(x) + residual) through the fused kernels when they apply, else through torch; honours _GROUPS"""
+    if _fused(x, bn):
+        return fnorm.bn_act(x, bn, residual=residual, relu=relu, groups=_GROUPS)
+    out = fnorm.bn_eager(x, bn, _GROUPS)
+    if residual is not None:
+        out = out + residual
+    return F.relu(out, inplace=True) if relu else out
 
 _DEPTHS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3)}
 
@@ -63,7 +93,13 @@ class Bottleneck(nn.Module):
             self.downsample = nn.Sequential(Conv2d(inplanes, planes * 4, 1, stride=stride, bias=False), nn.BatchNorm2d(planes * 4))
 
     def forward(self, x):
-        out = F.relu(self.bn1(self.conv1(x)), inplace=True)
+        y = self.conv1(x)
+        if _fused(y, self.bn1) or _GROUPS > 1:
+            out = _bn(y, self.bn1, relu=True)
+            out = _bn(self.conv2(out), self.bn2, relu=True)
+            identity = x if self.downsample is None else _bn(self.downsample[0](x), self.downsample[1])
+            return _bn(self.conv3(out), self.bn3, residual=identity, relu=True)
+        out = F.relu(self.bn1(y), inplace=True)
         out = F.relu(self.bn2(self.conv2(out)), inplace=True)
         out = self.bn3(self.conv3(out))
         identity = x if self.downsample is None else self.downsample(x)
@@ -91,7 +127,8 @@ class ResNet(nn.Module):
             setattr(self, f"layer{li}", nn.Sequential(*blocks))
 
     def forward(self, x):
-        x = F.relu(self.bn1(self.conv1(x)), inplace=True)
+        x = self.conv1(x)
+        x = _bn(x, self.bn1, relu=True)
         x = F.max_pool2d(x, 3, 2, 1)
         return self.layer4(self.layer3(self.layer2(self.layer1(x))))
 
@@ -121,6 +158,7 @@ class PPMBilinear(nn.Module):
         super().__init__()
         if use_aux:
             raise NotImplementedError("use_aux=True is not used by the self-training tools")
+        self.pool_scales = tuple(pool_scales)
         self.ppm = nn.ModuleList([
             nn.Sequential(nn.AdaptiveAvgPool2d(s), Conv2d(fc_dim, 512, 1, bias=False), nn.BatchNorm2d(512), nn.ReLU(inplace=True))
             for s in pool_scales])
@@ -128,12 +166,35 @@ class PPMBilinear(nn.Module):
             Conv2d(fc_dim + len(pool_scales) * 512, 512, 3, padding=1, bias=False), nn.BatchNorm2d(512), nn.ReLU(inplace=True),
             nn.Dropout2d(dropout), Conv2d(512, num_classes, 1, bias=True))
 
-    def forward(self, conv_out):
+    def fused_ok(self, conv_out):
+        return (FUSED and self.training and conv_out.is_cuda and conv_out.dtype == torch.bfloat16 and len(self.pool_scales) <= 4
+                and conv_out.shape[1] % 8 == 0 and self.ppm[0][1].out_channels % 8 == 0)
+
+    def forward(self, conv_out, pooled=None):
+        if self.fused_ok(conv_out):
+            # one-pass pyramid pooling (shared by both heads when the caller passes `pooled`), tiny per-branch
+            # 1x1 conv + BN + ReLU on the pooled maps, fused bilinear-upsample + concat, tcgen05 3x3 conv.
+            if pooled is None:
+                pooled = fppm.pool(conv_out, self.pool_scales)
+            b, c = conv_out.shape[:2]
+            branches, off = [], 0
+            for s, branch in zip(self.pool_scales, self.ppm):
+                p = pooled[:, off:off + s * s, :].reshape(b, s, s, c).permute(0, 3, 1, 2).to(conv_out.dtype)
+                off += s * s
+                branches.append(branch[3](fnorm.bn_eager(branch[1](p), branch[2], _GROUPS)))
+            cat = fppm.upsample_concat(conv_out, branches, self.pool_scales)
+            y = self.conv_last[0](cat)
+            bn = self.conv_last[1]
+            y = _bn(y, bn, relu=True)
+            return self.conv_last[4](self.conv_last[3](y))
         size = conv_out.shape[-2:]
         outs = [conv_out]
         for branch in self.ppm:
-            outs.append(F.interpolate(branch(conv_out), size, mode="bilinear", align_corners=False))
-        return self.conv_last(torch.cat(outs, 1))
+            t = branch[3](fnorm.bn_eager(branch[1](branch[0](conv_out)), branch[2], _GROUPS))
+            outs.append(F.interpolate(t, size, mode="bilinear", align_corners=False))
+        y = self.conv_last[0](torch.cat(outs, 1))
+        y = self.conv_last[2](fnorm.bn_eager(y, self.conv_last[1], _GROUPS))
+        return self.conv_last[4](self.conv_last[3](y))
 
 
 class Deeplabv2(nn.Module):
@@ -159,6 +220,20 @@ class Deeplabv2(nn.Module):
     def config(self):
         return self._cfg
 
+    def forward_pair(self, x_s, x_t):
+        """Train-mode forward of the source and the target batch as ONE tensor (tools/train_ssl_reg.py:210-212 makes two
+        calls): every convolution sees twice the rows, BatchNorm keeps one statistics group per domain, so the results
+        are those of two separate calls.  Returns ((x1_s, x2_s, feat_s), (x1_t, x2_t, feat_t))."""
+        global _GROUPS
+        assert self.training and x_s.shape == x_t.shape
+        b = x_s.shape[0]
+        _GROUPS = 2
+        try:
+            x1, x2, feat = self.forward(torch.cat([x_s, x_t], 0))
+        finally:
+            _GROUPS = 1
+        return (x1[:b], x2[:b], feat[:b]), (x1[b:], x2[b:], feat[b:])
+
     def forward(self, x):
         xin = x.to(self.compute_dtype).contiguous(memory_format=torch.channels_last)
         feat = self.encoder(xin)
@@ -167,8 +242,13 @@ class Deeplabv2(nn.Module):
         else:
             feat = feat.float()
         fin = feat.to(self.compute_dtype)
-        x1 = self.layer5(fin).float()
-        x2 = self.layer6(fin).float()
+        if self.layer5.fused_ok(fin) and self.layer5.pool_scales == self.layer6.pool_scales:
+            pooled = fppm.pool(fin, self.layer5.pool_scales)          # both heads pool the same feature map
+            x1 = self.layer5(fin, pooled).float()
+            x2 = self.layer6(fin, pooled).float()
+        else:
+            x1 = self.layer5(fin).float()
+            x2 = self.layer6(fin).float()
         if self.training:
             return x1, x2, feat
         x1 = F.interpolate(x1, x.shape[-2:], mode="bilinear", align_corners=True)

@@ -2,9 +2,9 @@
 (weight [O,I,kh,kw] float32, optional bias) and dispatches the arithmetic.
 
 Engines
-  tcgen05 : the hand-written sm_100a implicit-GEMM kernels (regda_b200/csrc/gemm_*.cu) --
-            bf16 operands, fp32 accumulation in tensor memory, TMA-fed.  Used for every
-            shape `tc.supports_*` accepts.
+  tcgen05 : the hand-written sm_100a implicit-GEMM kernels (regda_b200/csrc/conv_tc.cu fprop / dgrad,
+            conv_wgrad.cu) -- bf16 operands, fp32 accumulation in tensor memory, TMA-fed.  Used for
+            every shape `tc.supports_*` accepts ("tcgen05-fwd": forward only, library backward).
   cudnn   : torch.nn.functional.conv2d (library call).  Baseline and float32 parity runs; also
             the shapes the tcgen05 kernels do not cover yet (listed in DESIGN.md).
 Select with REGDA_CONV=auto|tcgen05|cudnn (auto: tcgen05 where supported).
@@ -24,7 +24,7 @@ stats = {"tcgen05_fprop": 0, "tcgen05_dgrad": 0, "tcgen05_wgrad": 0, "cudnn": 0}
 
 def set_engine(name: str):
     global ENGINE
-    assert name in ("auto", "tcgen05", "cudnn")
+    assert name in ("auto", "tcgen05", "tcgen05-fwd", "cudnn")
     ENGINE = name
 
 
@@ -34,13 +34,15 @@ def _tc():
 
 
 class _ConvFn(torch.autograd.Function):
-    """x: channels-last bf16 [N,C,H,W]; weight: float32 master [O,I,kh,kw] (channels-last memory)."""
+    """x: channels-last bf16 [N,C,H,W]; weight: float32 master [O,I,kh,kw] (channels-last memory).
+    The weight gradient is ACCUMULATED into weight.grad by the wgrad kernel (no autograd add)."""
 
     @staticmethod
     def forward(ctx, x, weight, stride, padding, dilation):
         tc = _tc()
         w16 = tc.weight_shadow(weight)
-        ctx.save_for_backward(x, weight)
+        ctx.save_for_backward(x, w16)
+        ctx.weight = weight
         ctx.geom = (stride, padding, dilation)
         stats["tcgen05_fprop"] += 1
         return tc.fprop(x, w16, stride, padding, dilation)
@@ -48,25 +50,28 @@ class _ConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         tc = _tc()
-        x, weight = ctx.saved_tensors
+        x, w16 = ctx.saved_tensors
+        weight = ctx.weight
         stride, padding, dilation = ctx.geom
         gy = gy.contiguous(memory_format=torch.channels_last)
         gx = gw = None
         if ctx.needs_input_grad[0]:
-            if tc.supports_dgrad(x.shape, weight.shape, stride, padding, dilation, x.dtype):
+            if ENGINE != "tcgen05-fwd" and tc.supports_dgrad(x.shape, weight.shape, stride, padding, dilation, x.dtype):
                 stats["tcgen05_dgrad"] += 1
-                gx = tc.dgrad(gy, tc.weight_shadow_t(weight), x.shape, stride, padding, dilation)
+                gx = tc.dgrad(gy, w16, x.shape, stride, padding, dilation)
             else:
                 stats["cudnn"] += 1
-                gx = torch.ops.aten.convolution_backward(gy, x, tc.weight_shadow(weight), None, [stride] * 2, [padding] * 2,
+                gx = torch.ops.aten.convolution_backward(gy, x, w16, None, [stride] * 2, [padding] * 2,
                                                          [dilation] * 2, False, [0, 0], 1, [True, False, False])[0]
         if ctx.needs_input_grad[1]:
-            if tc.supports_wgrad(x.shape, weight.shape, stride, padding, dilation, x.dtype):
+            if ENGINE != "tcgen05-fwd" and tc.supports_wgrad(x.shape, weight.shape, stride, padding, dilation, x.dtype):
                 stats["tcgen05_wgrad"] += 1
-                gw = tc.wgrad(gy, x, weight.shape, stride, padding, dilation)
+                if weight.grad is None:
+                    weight.grad = torch.zeros_like(weight)
+                tc.wgrad_accumulate(gy, x, weight.grad, stride, padding, dilation)
             else:
                 stats["cudnn"] += 1
-                gw = torch.ops.aten.convolution_backward(gy, x, tc.weight_shadow(weight), None, [stride] * 2, [padding] * 2,
+                gw = torch.ops.aten.convolution_backward(gy, x, w16, None, [stride] * 2, [padding] * 2,
                                                          [dilation] * 2, False, [0, 0], 1, [False, True, False])[1].float()
         return gx, gw, None, None, None
 
@@ -102,4 +107,8 @@ class Conv2d(nn.Module):
             return y
         stats["cudnn"] += 1
         b = self.bias.to(x.dtype) if self.bias is not None else None
-        return F.conv2d(x, self.weight.to(x.dtype), b, self.stride, self.padding, self.dilation)
+        w = self.weight if x.dtype == self.weight.dtype else (getattr(self.weight, "_bf16", None) if x.dtype == torch.bfloat16 and
+                                                             not torch.is_grad_enabled() else None)
+        if w is None:
+            w = self.weight.to(x.dtype)
+        return F.conv2d(x, w, b, self.stride, self.padding, self.dilation)

@@ -1,0 +1,89 @@
+"""Host side of the fused train-mode BatchNorm kernels (regda_b200/csrc/norm.cu).
+
+    out = bn_act(y, bn, residual=None, relu=True, groups=1)
+
+is `relu(bn(y) + residual)` of the reference's Bottleneck / PPM blocks (regda/_resnets.py:92-112,
+regda/models/Encoder.py:24-40) for a channels-last bf16 activation `y` and an nn.BatchNorm2d module
+`bn` in training mode: batch statistics in fp32, running statistics and num_batches_tracked updated
+in place (they are part of the checkpoint ABI), gradients of gamma / beta ACCUMULATED straight into
+`bn.weight.grad` / `bn.bias.grad` (views of the trainer's flat gradient arena).
+
+`groups` = G > 1 splits the batch into G equal consecutive parts with independent batch statistics:
+the source and the target batch of one training step travel through the network as ONE tensor
+(twice the rows per convolution launch, half the launches) while BatchNorm keeps the reference's
+per-forward-call statistics (tools/train_ssl_reg.py:210-212 calls the model once per domain);
+running statistics are updated once per group, in order, exactly like two consecutive calls.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import capi
+
+
+def supported(y, bn) -> bool:
+    if not (y.is_cuda and y.dtype == torch.bfloat16 and y.dim() == 4 and bn.training and bn.affine and bn.track_running_stats):
+        return False
+    n, c, h, w = y.shape
+    return bool(capi.lib().regda_bn_supported(n * h * w, c))
+
+
+def _cl(t):
+    return t if t.is_contiguous(memory_format=torch.channels_last) else t.contiguous(memory_format=torch.channels_last)
+
+
+def _grad_buffer(p):
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    return p.grad
+
+
+class _BnActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, residual, gamma, beta, bn, relu, groups):
+        y = _cl(y)
+        n, c, h, w = y.shape
+        npix = n * h * w
+        res = _cl(residual) if residual is not None else None
+        out = torch.empty_like(y)
+        assert n % groups == 0, "statistics groups must divide the batch"
+        coef = torch.empty(groups * 4 * c, dtype=torch.float32, device=y.device)
+        L = capi.lib()
+        ws = capi.workspace.get(L.regda_bn_workspace_bytes(c, groups), y.device)
+        capi.call("regda_bn_forward_bf16", capi.ptr_any(y), capi.ptr_any(res) if res is not None else None, capi.ptr_any(out), npix, c,
+                  groups, capi.ptr(gamma), capi.ptr(beta), capi.ptr(bn.running_mean), capi.ptr(bn.running_var),
+                  capi.ptr(bn.num_batches_tracked), float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1), int(relu),
+                  capi.ptr(coef), capi.ptr(ws), ws.numel(), capi.stream())
+        ctx.save_for_backward(y, out if relu else None, coef)
+        ctx.gamma, ctx.beta, ctx.relu, ctx.has_res, ctx.groups = gamma, beta, relu, residual is not None, groups
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, out, coef = ctx.saved_tensors
+        n, c, h, w = y.shape
+        dout = _cl(dout)
+        dy = torch.empty_like(y)
+        dres = torch.empty_like(y) if (ctx.has_res and ctx.needs_input_grad[1]) else None
+        gamma, beta = ctx.gamma, ctx.beta
+        dgamma = _grad_buffer(gamma) if gamma.requires_grad else None
+        dbeta = _grad_buffer(beta) if beta.requires_grad else None
+        L = capi.lib()
+        ws = capi.workspace.get(L.regda_bn_backward_workspace_bytes(c, ctx.groups), y.device)
+        capi.call("regda_bn_backward_bf16", capi.ptr_any(dout), capi.ptr_any(out) if out is not None else None, capi.ptr_any(y),
+                  capi.ptr_any(dy), capi.ptr_any(dres) if dres is not None else None, n * h * w, c, ctx.groups, capi.ptr(gamma), capi.ptr(coef),
+                  capi.ptr(dgamma) if dgamma is not None else None, capi.ptr(dbeta) if dbeta is not None else None, int(ctx.relu),
+                  capi.ptr(ws), ws.numel(), capi.stream())
+        # gamma / beta gradients were accumulated in place: nothing flows back through autograd for them
+        return dy, dres, None, None, None, None, None
+
+
+def bn_act(y, bn, residual=None, relu=True, groups=1):
+    return _BnActFn.apply(y, residual, bn.weight, bn.bias, bn, relu, groups)
+
+
+def bn_eager(x, bn, groups=1):
+    """nn.BatchNorm2d with the same statistics-group semantics, through torch (tiny maps, float32 parity mode)."""
+    if groups == 1 or not bn.training:
+        return bn(x)
+    return torch.cat([bn(part) for part in x.chunk(groups, dim=0)], dim=0)

@@ -39,12 +39,13 @@ class ParamArena:
         offs, total = [], 0
         for p in params:
             offs.append(total)
-            total += (p.numel() + 3) // 4 * 4          # 16-byte aligned segments
+            total += (p.numel() + 7) // 8 * 8          # segments 16-byte aligned in the bf16 shadow too (TMA base alignment)
         dev = params[0].device
         self.numel = total
         self.param = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.momentum = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.param_bf16 = torch.zeros(total, dtype=torch.bfloat16, device=dev)   # rewritten by the SGD kernel every step
         self.params = params
         for p, o in zip(params, offs):
             n = p.numel()
@@ -60,6 +61,8 @@ class ParamArena:
             v.copy_(p.data)
             p.data = v
             p.grad = view(self.grad)
+            p._bf16 = view(self.param_bf16)            # what the tcgen05 convolutions read (ops/tc.py weight_shadow)
+        self.param_bf16.copy_(self.param)
         self.first_step = True
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.lr_device = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -76,7 +79,7 @@ class ParamArena:
         the learning rate is whatever set_lr() last wrote."""
         ws = capi.workspace.get(capi.lib().regda_sumsq_workspace_bytes(self.numel), self.param.device)
         capi.call("regda_sumsq", capi.ptr(self.grad), self.numel, capi.ptr(self._sumsq), 0, capi.ptr(ws), ws.numel(), capi.stream())
-        capi.call("regda_sgd_step", capi.ptr(self.param), capi.ptr(self.grad), capi.ptr(self.momentum), None, self.numel,
+        capi.call("regda_sgd_step", capi.ptr(self.param), capi.ptr(self.grad), capi.ptr(self.momentum), capi.ptr(self.param_bf16), self.numel,
                   capi.ptr(self._sumsq), float(max_norm), float(grad_scale), 0.0, capi.ptr(self.lr_device), float(momentum),
                   float(weight_decay), int(self.first_step), capi.stream())
         self.first_step = False
@@ -88,7 +91,7 @@ class ParamArena:
 class SelfTrainingStep:
     def __init__(self, model, aligner, homogenizer, class_num=6, ignore_label=-1, cutoff_top=0.8, cutoff_low=0.6,
                  refine_temp=2.0, sam_refine=True, refine_label=True, max_norm=32.0, momentum=0.9, weight_decay=5e-4,
-                 loss_fn_s=None, loss_fn_t=None, world_size=1, use_cuda_graph=False):
+                 loss_fn_s=None, loss_fn_t=None, world_size=1, use_cuda_graph=False, pair_forward=True):
         self.model, self.aligner, self.homogenizer = model, aligner, homogenizer
         self.class_num, self.ignore_label = class_num, ignore_label
         self.cutoff_top, self.cutoff_low, self.refine_temp = cutoff_top, cutoff_low, refine_temp
@@ -97,6 +100,7 @@ class SelfTrainingStep:
         self.loss_fn_s = loss_fn_s or CrossEntropy(ignore_label=ignore_label)
         self.loss_fn_t = loss_fn_t or CrossEntropy(ignore_label=ignore_label)
         self.world_size = world_size
+        self.pair_forward = pair_forward and hasattr(model, "forward_pair")
         self.arena = ParamArena(model)
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
@@ -112,8 +116,12 @@ class SelfTrainingStep:
     def _step_impl(self, images_s, label_s, images_t, soft_t, regs_t):
         m = self.model
         self.arena.zero_grad()
-        pred_s1, pred_s2, feat_s = m(images_s)                                     # :210
-        pred_t1, pred_t2, feat_t = m(images_t)                                     # :212
+        if self.pair_forward and images_s.shape == images_t.shape:
+            # both domain batches through the network as one tensor, BatchNorm statistics per domain (models/Encoder.py)
+            (pred_s1, pred_s2, feat_s), (pred_t1, pred_t2, feat_t) = m.forward_pair(images_s, images_t)   # :210-212
+        else:
+            pred_s1, pred_s2, feat_s = m(images_s)                                 # :210
+            pred_t1, pred_t2, feat_t = m(images_t)                                 # :212
         with torch.no_grad():
             if self.refine_label:
                 hard = self.aligner.refine_select(feat_t, [pred_t1, pred_t2], soft_t, self.refine_temp,

@@ -48,8 +48,8 @@ def test_fprop_matches_float32_reference(shape):
 
 @pytest.mark.parametrize("shape", [SHAPES[1], SHAPES[4], SHAPES[5], SHAPES[8]], ids=str)
 def test_conv2d_module_forward_backward(shape):
-    """the nn.Module front end: forward through tcgen05, input gradient through the same kernel
-    (flipped / transposed weights), weight gradient through the library until the wgrad kernel lands."""
+    """the nn.Module front end: forward, input gradient (forward weights read in place as an MN-major operand)
+    and weight gradient (accumulated into weight.grad) all through the tcgen05 kernels."""
     from regda_b200.ops import conv as C
     n, cin, h, w, cout, k, pad, dil = shape
     torch.manual_seed(0)
@@ -61,6 +61,7 @@ def test_conv2d_module_forward_backward(shape):
     y.backward(gy)
     assert C.stats["tcgen05_fprop"] == before["tcgen05_fprop"] + 1
     assert C.stats["tcgen05_dgrad"] == before["tcgen05_dgrad"] + 1
+    assert C.stats["tcgen05_wgrad"] == before["tcgen05_wgrad"] + 1
     xr = x.detach().float().requires_grad_(True)
     wr = m.weight.detach().bfloat16().float().requires_grad_(True)
     yr = F.conv2d(xr, wr, None, 1, pad, dil)
@@ -77,4 +78,60 @@ def test_unsupported_shapes_are_refused():
     assert L.regda_conv_fprop_supported(2, 32, 32, 3, 64, 7, 7, 2, 3, 1) == 0      # stem
     assert L.regda_conv_fprop_supported(2, 32, 32, 64, 6, 1, 1, 1, 0, 1) == 0      # classifier
     assert L.regda_conv_fprop_supported(2, 6, 6, 2048, 512, 1, 1, 1, 0, 1) == 0    # PPM branch on a pooled map
-    assert L.regda_conv_fprop_supported(2, 64, 64, 128, 128, 3, 3, 2, 1, 1) == 0   # strided
+    assert L.regda_conv_fprop_supported(2, 64, 64, 128, 128, 3, 3, 2, 1, 1) == 1   # stride 2: TMA element strides
+    assert L.regda_conv_fprop_supported(2, 64, 64, 128, 128, 3, 3, 3, 1, 1) == 0   # stride 3
+    assert L.regda_conv_dgrad_supported(2, 64, 64, 128, 128, 3, 3, 2, 1, 1) == 0   # strided dgrad stays on the library
+
+
+# (n, cin, h, w, cout, k, stride, pad, dil)
+STRIDED = [
+    (2, 128, 64, 64, 128, 3, 2, 1, 1),     # layer2.0.conv2
+    (2, 256, 64, 64, 512, 1, 2, 0, 1),     # layer2.0.downsample
+    (1, 256, 32, 48, 256, 3, 2, 1, 1),     # ragged
+    (2, 64, 30, 30, 64, 3, 2, 1, 1),       # odd output size 15x15
+]
+
+
+@pytest.mark.parametrize("shape", STRIDED, ids=str)
+def test_strided_fprop_and_wgrad(shape):
+    from regda_b200.ops import tc
+    n, cin, h, w, cout, k, stride, pad, dil = shape
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5).bfloat16().contiguous(memory_format=torch.channels_last)
+    assert tc.supports_fprop(x.shape, wt.shape, stride, pad, dil, x.dtype)
+    y = tc.fprop(x, wt, stride, pad, dil)
+    xr, wr = x.float().requires_grad_(True), wt.float().requires_grad_(True)
+    ref = F.conv2d(xr, wr, None, stride, pad, dil)
+    assert y.shape == ref.shape
+    assert float((y.float() - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
+    gy = torch.randn(ref.shape, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    ref.backward(gy.float())
+    assert tc.supports_wgrad(x.shape, wt.shape, stride, pad, dil, x.dtype)
+    gw = torch.zeros(cout, cin, k, k, device="cuda").contiguous(memory_format=torch.channels_last)
+    tc.wgrad_accumulate(gy, x, gw, stride, pad, dil)
+    tc.wgrad_accumulate(gy, x, gw, stride, pad, dil)          # accumulates: second call doubles it
+    assert float((gw / 2 - wr.grad).abs().max()) <= 5e-3 * float(wr.grad.abs().max())
+
+
+WGRAD = [SHAPES[0], SHAPES[1], SHAPES[3], SHAPES[5], SHAPES[6], SHAPES[8], SHAPES[9], SHAPES[11], (2, 4096, 32, 32, 512, 3, 1, 1)]
+
+
+@pytest.mark.parametrize("shape", WGRAD, ids=str)
+def test_wgrad_and_dgrad_match_float32_reference(shape):
+    from regda_b200.ops import tc
+    n, cin, h, w, cout, k, pad, dil = shape
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5).bfloat16().contiguous(memory_format=torch.channels_last)
+    xr, wr = x.float().requires_grad_(True), wt.float().requires_grad_(True)
+    ref = F.conv2d(xr, wr, None, 1, pad, dil)
+    gy = torch.randn(ref.shape, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    ref.backward(gy.float())
+    assert tc.supports_wgrad(x.shape, wt.shape, 1, pad, dil, x.dtype)
+    gw = torch.zeros(cout, cin, k, k, device="cuda").contiguous(memory_format=torch.channels_last)
+    tc.wgrad_accumulate(gy, x, gw, 1, pad, dil)
+    assert float((gw - wr.grad).abs().max()) <= 5e-3 * float(wr.grad.abs().max())
+    assert tc.supports_dgrad(x.shape, wt.shape, 1, pad, dil, x.dtype)
+    gx = tc.dgrad(gy, wt, x.shape, 1, pad, dil)
+    assert float((gx.float() - xr.grad).abs().max()) <= 1e-2 * float(xr.grad.abs().max())
