@@ -19,6 +19,8 @@
 // bound / image size / alignment, 40 B/px worst case.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -278,7 +280,7 @@ __device__ __forceinline__ void flush_acc(unsigned bins_s, unsigned region, unsi
 
 template <int CW, typename AccT, int HIST>
 __global__ void __launch_bounds__(512, 2)
-lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters) {
+lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters, const int prefetch_iters) {
     extern __shared__ __align__(16) unsigned char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned CL = cluster.num_blocks();
@@ -289,8 +291,10 @@ lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters) {
     const int nwords = a.region_bound * CW;
     const int rpc = ((a.region_bound + static_cast<int>(CL) - 1) / static_cast<int>(CL) + 15) & ~15;
     unsigned *bins = reinterpret_cast<unsigned *>(smem);
-    unsigned char *win = smem + ((static_cast<size_t>(nwords) * 4 + 15) & ~static_cast<size_t>(15));
-    const size_t tile_off = ((static_cast<size_t>(nwords) * 4 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(rpc) * CL;
+    const size_t win_off = (static_cast<size_t>(nwords) * 4 + 15) & ~static_cast<size_t>(15);
+    unsigned char *win = smem + win_off;                                       // winner code of EVERY region (rpc * CL bytes)
+    unsigned *acc = reinterpret_cast<unsigned *>(smem + win_off + static_cast<size_t>(rpc) * CL);   // cluster-wide counts of OWN regions
+    const size_t tile_off = win_off + static_cast<size_t>(rpc) * CL + static_cast<size_t>(rpc) * (2 * CW) * 4;
     uint4 *reg16 = reinterpret_cast<uint4 *>(smem + tile_off);
     uint2 *lab8 = reinterpret_cast<uint2 *>(smem + tile_off + static_cast<size_t>(px_cta) * 2);
 
@@ -299,14 +303,18 @@ lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters) {
     const int ngroups = (end - start) / kGroupPx;
     const int r_lo = min(a.region_bound, static_cast<int>(rank) * rpc);
     const int r_hi = min(a.region_bound, r_lo + rpc);
+    for (int i = tid; i < rpc * 2 * CW; i += nthreads) acc[i] = 0u;          // re-zeroed by the owner after every use
+    for (int i = tid; i < nwords; i += nthreads) bins[i] = 0u;                // re-zeroed by the push phase
+    cluster.sync();                                                            // nobody pushes into an un-zeroed table
     const unsigned max_code = static_cast<unsigned>(a.class_num) + 1u;
     const unsigned bound = static_cast<unsigned>(a.region_bound);
     const unsigned bins_s = static_cast<unsigned>(__cvta_generic_to_shared(bins));
     bool bad_label = false, bad_region = false;
 
     for (int img = cluster_id; img < a.b; img += nclusters) {
-        for (int i = tid; i < nwords; i += nthreads) bins[i] = 0u;
-        __syncthreads();
+        // (bins are zero here: zeroed before the loop and again by the push phase of the previous image, and every
+        //  thread re-enters pass 1 with the groups it just finished in pass 2 -- no barrier between the two, so the
+        //  stores of one image and the loads of the next overlap)
 
         // ---- pass 1 ---------------------------------------------------------------------
         const long long *lab = a.labels + static_cast<size_t>(img) * a.hw + start;
@@ -372,61 +380,98 @@ lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters) {
                     r = nr;
                 } while (rem != 0u);
             } else {
-                // Histogram, variant 0: the common group is [first region x s][last region x (8-s)];
-                // both runs are accumulated without branches, anything else goes pixel by pixel.
+                // Histogram, variant 0: counting does not care where in the group a region's pixels sit, so a group
+                // with at most THREE distinct regions (first pixel's, last pixel's, one more) is accumulated without
+                // branches on the pixel position; only >= 4 regions in 8 pixels go pixel by pixel.  (A warp executes
+                // the union of its threads' paths, so the rare path must be rare per WARP, not per thread.)
                 const unsigned ra = rr[0], rb = rr[7];
                 unsigned in_a = 0u, in_b = 0u;
-                AccT acc_a = 0, acc_all = 0;
+                AccT acc_a = 0, acc_b = 0, acc_all = 0;
 #pragma unroll
                 for (int k = 0; k < kGroupPx; ++k) {
                     const AccT one = static_cast<AccT>(1) << (4 * cc[k]);
                     const bool ea = rr[k] == ra;
+                    const bool eb = !ea && rr[k] == rb;
                     in_a |= ea ? (1u << k) : 0u;
-                    in_b |= (rr[k] == rb) ? (1u << k) : 0u;
+                    in_b |= eb ? (1u << k) : 0u;
                     acc_all += one;
                     acc_a += ea ? one : static_cast<AccT>(0);
+                    acc_b += eb ? one : static_cast<AccT>(0);
                 }
-                if (((in_a & (in_a + 1u)) == 0u) && ((in_a | in_b) == 0xFFu)) {
+                const unsigned rest = ~(in_a | in_b) & 0xFFu;
+                if (rest == 0u) {
                     if (ra != 0u) flush_acc<CW>(bins_s, ra, acc_a);
-                    if (rb != 0u && in_a != 0xFFu) flush_acc<CW>(bins_s, rb, static_cast<AccT>(acc_all - acc_a));
+                    if (rb != 0u && in_b != 0u) flush_acc<CW>(bins_s, rb, acc_b);
                 } else {
+                    unsigned rm = rr[6];                       // first pixel that is in neither run (pixels 0 and 7 never are)
 #pragma unroll
-                    for (int k = 0; k < kGroupPx; ++k)
-                        if (rr[k] != 0u) flush_acc<CW>(bins_s, rr[k], static_cast<AccT>(static_cast<AccT>(1) << (4 * cc[k])));
+                    for (int k = 5; k >= 1; --k) rm = (rest & (1u << k)) ? rr[k] : rm;
+                    unsigned in_m = 0u;
+#pragma unroll
+                    for (int k = 1; k < kGroupPx - 1; ++k) in_m |= (rr[k] == rm) ? (1u << k) : 0u;
+                    if ((rest & ~in_m) == 0u) {
+                        if (ra != 0u) flush_acc<CW>(bins_s, ra, acc_a);
+                        if (rb != 0u && in_b != 0u) flush_acc<CW>(bins_s, rb, acc_b);
+                        if (rm != 0u) flush_acc<CW>(bins_s, rm, static_cast<AccT>(acc_all - acc_a - acc_b));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kGroupPx; ++k)
+                            if (rr[k] != 0u) flush_acc<CW>(bins_s, rr[k], static_cast<AccT>(static_cast<AccT>(1) << (4 * cc[k])));
+                    }
                 }
-            }
-        }
-        cluster.sync();
-
-        // ---- merge ----------------------------------------------------------------------
-        for (int r = r_lo + tid; r < r_hi; r += nthreads) {
-            unsigned tot[2 * CW];
-#pragma unroll
-            for (int c = 0; c < 2 * CW; ++c) tot[c] = 0u;
-            for (unsigned j = 0; j < CL; ++j) {
-                const unsigned *rb = cluster.map_shared_rank(bins, j) + r * CW;
-#pragma unroll
-                for (int w = 0; w < CW; ++w) {
-                    const unsigned v = rb[w];
-                    tot[2 * w] += v & 0xFFFFu;
-                    tot[2 * w + 1] += v >> 16;
-                }
-            }
-            const unsigned wv = lrh_winner<2 * CW>(tot, a.class_num, a.percent, a.ignore_label);
-            win[r] = static_cast<unsigned char>((wv == kWinNone || r == 0) ? 0u : wv + 1u);
-        }
-        cluster.sync();
-        {
-            const int nvec = rpc / 16;
-            for (int i = tid; i < nvec * static_cast<int>(CL); i += nthreads) {
-                const unsigned j = static_cast<unsigned>(i / nvec);
-                if (j == rank) continue;
-                const int off = static_cast<int>(j) * rpc + (i - static_cast<int>(j) * nvec) * 16;
-                if (off >= a.region_bound) continue;
-                *reinterpret_cast<uint4 *>(win + off) = *reinterpret_cast<const uint4 *>(cluster.map_shared_rank(win, j) + off);
             }
         }
         __syncthreads();
+
+        // ---- merge: PUSH.  Every CTA adds its non-zero packed bins to the owner CTA's 32-bit table with remote
+        // shared-memory reductions (fire and forget: no DSMEM load round trips on the critical path), the owner
+        // applies the exact float32 test locally and pushes 16-byte slices of winner codes to all CTAs. ----------
+        for (int i = tid; i < nwords; i += nthreads) {
+            const unsigned v = bins[i];
+            if (v == 0u) continue;
+            bins[i] = 0u;                                                    // ready for the next image
+            const int r = i / CW, w = i - r * CW;
+            const int owner = r / rpc;
+            unsigned *dst = cluster.map_shared_rank(acc, owner) + (r - owner * rpc) * (2 * CW) + 2 * w;
+            if (v & 0xFFFFu) atomicAdd(dst, v & 0xFFFFu);
+            if (v >> 16) atomicAdd(dst + 1, v >> 16);
+        }
+        {   // keep HBM busy across the two cluster barriers: pull the head of the next image's slice into L2
+            const int nimg = img + nclusters;
+            if (nimg < a.b) {
+                const char *nl = reinterpret_cast<const char *>(a.labels + static_cast<size_t>(nimg) * a.hw + start);
+                const char *nr = reinterpret_cast<const char *>(a.regions + static_cast<size_t>(nimg) * a.hw + start);
+                const size_t bytes = static_cast<size_t>(end - start) * 8;
+                for (int it = 0; it < prefetch_iters; ++it) {
+                    const size_t off = (static_cast<size_t>(it) * nthreads + tid) * 128;
+                    if (off < bytes) {
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(nl + off));
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(nr + off));
+                    }
+                }
+            }
+        }
+        cluster.sync();
+        for (int r = r_lo + tid; r < r_hi; r += nthreads) {
+            unsigned *ar = acc + (r - r_lo) * (2 * CW);
+            unsigned tot[2 * CW];
+#pragma unroll
+            for (int c = 0; c < 2 * CW; ++c) { tot[c] = ar[c]; ar[c] = 0u; }
+            const unsigned wv = lrh_winner<2 * CW>(tot, a.class_num, a.percent, a.ignore_label);
+            win[r] = static_cast<unsigned char>((wv == kWinNone || r == 0) ? 0u : wv + 1u);
+        }
+        __syncthreads();
+        {
+            const int nvec = rpc / 16;                                         // own slice, in 16-byte vectors
+            const uint4 *own = reinterpret_cast<const uint4 *>(win + static_cast<size_t>(rank) * rpc);
+            for (int i = tid; i < nvec * static_cast<int>(CL); i += nthreads) {
+                const unsigned j = static_cast<unsigned>(i / nvec);
+                const int vi = i - static_cast<int>(j) * nvec;
+                if (j == rank || static_cast<int>(rank) * rpc + vi * 16 >= a.region_bound) continue;
+                reinterpret_cast<uint4 *>(cluster.map_shared_rank(win, j) + static_cast<size_t>(rank) * rpc)[vi] = own[vi];
+            }
+        }
+        cluster.sync();
 
         // ---- pass 2 ---------------------------------------------------------------------
         long long *out = a.out + static_cast<size_t>(img) * a.hw + start;
@@ -462,44 +507,59 @@ struct ClusterPlan {
     int px_cta = 0;
     int cw = 0;
     int threads = 0;
+    int prefetch = 0;
     size_t smem = 0;
 };
+
+int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
 
 size_t cluster_smem_bytes(int region_bound, int cw, int px_cta, int cl) {
     const size_t bins = (static_cast<size_t>(region_bound) * cw * 4 + 15) & ~static_cast<size_t>(15);
     const size_t rpc = static_cast<size_t>(((region_bound + cl - 1) / cl + 15) & ~15);
-    return bins + rpc * cl + static_cast<size_t>(px_cta) * 3;
+    // packed local bins + winner bytes of all regions + 32-bit cluster-wide counts of the owned regions + 3 B/px tile
+    return bins + rpc * cl + rpc * (2 * cw) * 4 + static_cast<size_t>(px_cta) * 3;
 }
 
-ClusterPlan plan_cluster(int b, int64_t hw, int class_num, int64_t region_bound) {
+ClusterPlan plan_cluster(int b, int64_t hw, int class_num, int64_t region_bound, bool allow_single) {
     ClusterPlan p;
     if (class_num < 1 || class_num > kMaxFastClasses) return p;
     if (region_bound < 1 || region_bound > 65536) return p;   // u16 region ids in the smem tile
     if (hw < kGroupPx || hw % kGroupPx != 0 || hw > (1ll << 30)) return p;
     p.cw = (class_num + 1) / 2;
     const size_t limit = static_cast<size_t>(max_optin_smem());
-    const size_t half = (limit + 1024) / 2 - 1024;             // two CTAs per SM (1 KB reserved each)
-    // Preference: two 512-thread CTAs per SM (their load / merge / store phases overlap), the
-    // portable cluster size first when the batch fills the GPU, 16 first for small batches.
-    const bool small = b * 8 <= sm_count() / 2;
-    const int order[4][2] = {{small ? 16 : 8, 2}, {small ? 8 : 16, 2}, {small ? 16 : 8, 1}, {small ? 8 : 16, 1}};
-    for (int i = 0; i < 4; ++i) {
+    // Candidates (cluster size, CTAs per SM): several CTAs per SM in different phases (load / merge barriers / store)
+    // are what keeps HBM busy.  One CTA per SM is only taken when the path is forced: the 3-kernel global-bin path
+    // is faster there (measured: 5000 regions/tile, 27 % vs 40 % of the HBM roofline).
+    // Tuning knobs (profiling only): REGDA_LRH_CLUSTER, REGDA_LRH_PER_SM, REGDA_LRH_THREADS, REGDA_LRH_PREFETCH.
+    // small bin tables: 16-CTA clusters measured faster (50 regions/tile: 72.8 % vs 69.8 % of the HBM roofline)
+    const bool small = b * 8 <= sm_count() / 2 || region_bound <= 256;
+    int order[6][2] = {{small ? 16 : 8, 2}, {small ? 8 : 16, 2}, {16, 3}, {small ? 16 : 8, 1}, {small ? 8 : 16, 1}, {0, 0}};
+    int ncand = allow_single ? 5 : 3;
+    const int fc = env_int("REGDA_LRH_CLUSTER", 0), fp = env_int("REGDA_LRH_PER_SM", 0);
+    if (fc > 0 && fp > 0) { order[0][0] = fc; order[0][1] = fp; ncand = 1; }
+    for (int i = 0; i < ncand; ++i) {
         const int cl = order[i][0], per_sm = order[i][1];
         int px = static_cast<int>((hw + cl - 1) / cl);
         px = (px + kGroupPx - 1) / kGroupPx * kGroupPx;
         if (px > 65535) continue;                              // u16 per-CTA counters
         const size_t s = cluster_smem_bytes(static_cast<int>(region_bound), p.cw, px, cl);
-        if (s > (per_sm == 2 ? half : limit)) continue;
+        if (s > (limit + 1024) / per_sm - 1024) continue;      // per_sm CTAs per SM (1 KB reserved each)
         const int groups = px / kGroupPx;
         p.ok = true; p.cluster = cl; p.px_cta = px; p.smem = s;
-        p.threads = groups >= 512 ? 512 : 256;   // 64 registers/thread: two such CTAs fill an SM's register file
+        // 64 registers/thread: 1024 threads per SM fill the register file
+        p.threads = per_sm == 3 ? 256 : (groups >= 512 ? 512 : 256);
+        p.threads = env_int("REGDA_LRH_THREADS", p.threads);
+        p.prefetch = env_int("REGDA_LRH_PREFETCH", 0);
         return p;
     }
     return p;
 }
 
-template <typename Kern>
-int launch_cluster_kernel(Kern kern, const LrhArgs &a, const ClusterPlan &p, cudaStream_t st, bool *launched) {
+template <typename Kern, typename... Extra>
+int launch_cluster_kernel(Kern kern, const LrhArgs &a, const ClusterPlan &p, cudaStream_t st, bool *launched, Extra... extra) {
     *launched = false;
     REGDA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
     if (p.cluster > 8) REGDA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -523,7 +583,7 @@ int launch_cluster_kernel(Kern kern, const LrhArgs &a, const ClusterPlan &p, cud
     }
     const int nclusters = a.b < max_clusters ? a.b : max_clusters;
     cfg.gridDim = dim3(p.cluster * nclusters);
-    REGDA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a, p.px_cta, nclusters));
+    REGDA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a, p.px_cta, nclusters, extra...));
     *launched = true;
     return REGDA_OK;
 }
@@ -533,11 +593,11 @@ int launch_cluster(const LrhArgs &a, const ClusterPlan &p, cudaStream_t st, bool
     if (a.ignore_label == -1 && p.threads <= 512) {
         if constexpr (CW <= 3) {
             if (a.class_num <= 6) {
-                if (g_path_mode == 3) return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned, 1>, a, p, st, launched);
-                return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned, 0>, a, p, st, launched);
+                if (g_path_mode == 3) return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned, 1>, a, p, st, launched, p.prefetch);
+                return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned, 0>, a, p, st, launched, p.prefetch);
             }
         }
-        if (a.class_num <= 14) return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned long long, 1>, a, p, st, launched);
+        if (a.class_num <= 14) return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned long long, 1>, a, p, st, launched, p.prefetch);
     }
     return launch_cluster_kernel(lrh_cluster_kernel<CW>, a, p, st, launched);
 }
@@ -679,7 +739,7 @@ extern "C" int regda_lrh_forward(const int64_t *labels, const int64_t *regions, 
     const bool aligned = (reinterpret_cast<uintptr_t>(labels) % 32 == 0) && (reinterpret_cast<uintptr_t>(regions) % 32 == 0) &&
                          (reinterpret_cast<uintptr_t>(out) % 32 == 0) && (hw % 4 == 0);
     if (g_path_mode != 1 && aligned) {
-        const ClusterPlan p = plan_cluster(b, hw, class_num, region_bound);
+        const ClusterPlan p = plan_cluster(b, hw, class_num, region_bound, g_path_mode >= 2);
         if (p.ok) {
             bool launched = false;
             int rc = REGDA_OK;

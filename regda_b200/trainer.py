@@ -91,7 +91,7 @@ class ParamArena:
 class SelfTrainingStep:
     def __init__(self, model, aligner, homogenizer, class_num=6, ignore_label=-1, cutoff_top=0.8, cutoff_low=0.6,
                  refine_temp=2.0, sam_refine=True, refine_label=True, max_norm=32.0, momentum=0.9, weight_decay=5e-4,
-                 loss_fn_s=None, loss_fn_t=None, world_size=1, use_cuda_graph=False, pair_forward=True):
+                 loss_fn_s=None, loss_fn_t=None, world_size=1, use_cuda_graph=False, pair_forward=None):
         self.model, self.aligner, self.homogenizer = model, aligner, homogenizer
         self.class_num, self.ignore_label = class_num, ignore_label
         self.cutoff_top, self.cutoff_low, self.refine_temp = cutoff_top, cutoff_low, refine_temp
@@ -100,7 +100,12 @@ class SelfTrainingStep:
         self.loss_fn_s = loss_fn_s or CrossEntropy(ignore_label=ignore_label)
         self.loss_fn_t = loss_fn_t or CrossEntropy(ignore_label=ignore_label)
         self.world_size = world_size
-        self.pair_forward = pair_forward and hasattr(model, "forward_pair")
+        # paired forward (both domain batches as one tensor, per-domain BatchNorm groups) is the bf16 performance mode;
+        # the float32 parity mode mirrors the reference's two model calls so that the library picks the same
+        # convolution algorithms the golden vectors were produced with
+        if pair_forward is None:
+            pair_forward = getattr(model, "compute_dtype", None) == torch.bfloat16
+        self.pair_forward = bool(pair_forward) and hasattr(model, "forward_pair")
         self.arena = ParamArena(model)
         self.use_cuda_graph = use_cuda_graph
         self._graph = None

@@ -14,6 +14,15 @@ def _cl(t):
     return t.contiguous(memory_format=torch.channels_last)
 
 
+def _close_most(got, want, tol, frac=2e-3):
+    """like _close, but a fraction `frac` of the elements may be off (a ReLU mask bit that flips where the bf16
+    pre-activation rounds to +-0 changes that element's gradient by the full incoming value)"""
+    err = (got.float() - want.float()).abs()
+    scale = float(want.float().abs().max())
+    bad = float((err > tol * scale + 1e-6).float().mean())
+    assert bad <= frac, (bad, float(err.max()), scale)
+
+
 def _close(got, want, tol):
     err = float((got.float() - want.float()).abs().max())
     scale = float(want.float().abs().max())
@@ -193,8 +202,8 @@ def test_bn_statistics_groups_equal_separate_calls():
     # the fp32 statistics are accumulated with atomics (order differs between launches): outputs may differ by one
     # bf16 ulp, and a ReLU mask bit may flip where the pre-activation rounds to +-0
     _close(oc, torch.cat([oa, ob]), 8e-3)
-    _close(ycat.grad, torch.cat([ins[0].grad, ins[1].grad]), 1e-2)
-    _close(rcat.grad, torch.cat([ins[2].grad, ins[3].grad]), 1e-2)
+    _close_most(ycat.grad, torch.cat([ins[0].grad, ins[1].grad]), 1e-2)
+    _close_most(rcat.grad, torch.cat([ins[2].grad, ins[3].grad]), 1e-2)
     _close(bn2.running_mean, bn1.running_mean, 1e-5)
     _close(bn2.running_var, bn1.running_var, 1e-5)
     _close(bn2.weight.grad, bn1.weight.grad, 1e-3)
@@ -202,40 +211,69 @@ def test_bn_statistics_groups_equal_separate_calls():
     assert int(bn2.num_batches_tracked) == 2 == int(bn1.num_batches_tracked)
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["float32", "bf16"])
-def test_forward_pair_equals_two_forward_calls(dtype):
-    """Deeplabv2.forward_pair(xs, xt) == (model(xs), model(xt)): logits, features, parameter gradients, BN buffers."""
+def _pair_run(dtype, pair, xs, xt):
     from oracle import step_oracle as so
     from regda_b200.models import Encoder as E
     cfg = dict(backbone=dict(resnet_type="resnet50", output_stride=16, pretrained=False), multi_layer=True, cascade=False, use_ppm=True,
                ppm=dict(num_classes=6, use_aux=False, fc_dim=2048), inchannels=2048, num_classes=6, is_ins_norm=True)
+    m = E.Deeplabv2(cfg, compute_dtype=dtype)
+    m.load_state_dict(so.seeded_state_dict(m, 2333), strict=True)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout2d):
+            mod.p = 0.0
+    m = m.cuda().train()
+    if dtype == torch.float64:
+        m = m.double()
+    if pair:
+        (a1, a2, fa), (b1, b2, fb) = m.forward_pair(xs, xt)
+    else:
+        a1, a2, fa = m(xs)
+        b1, b2, fb = m(xt)
+    (a1.square().mean() + a2.mean() + b1.square().mean() - 0.5 * b2.mean()).backward()   # no exactly-cancelling terms
+    return dict(out=[t.detach().double() for t in (a1, a2, fa, b1, b2, fb)],
+                g={n: p.grad.double().clone() for n, p in m.named_parameters()},
+                rm=m.encoder.resnet.layer2[0].bn1.running_mean.clone(), rv=m.layer5.conv_last[1].running_var.clone())
+
+
+def test_forward_pair_equals_two_forward_calls_float64():
+    """Deeplabv2.forward_pair(xs, xt) == (model(xs), model(xt)) -- logits, features, parameter gradients, BN buffers --
+    in float64, where the library has exact algorithms for every batch size: pins the LOGIC (statistics groups,
+    slicing, running-stat order) at 1e-6."""
+    torch.manual_seed(1)
+    xs = torch.randn(2, 3, 64, 64, device="cuda").clamp(max=1.0)
+    xt = (torch.randn(2, 3, 64, 64, device="cuda") * 0.7 + 0.3).clamp(max=1.0)
+    sep, par = _pair_run(torch.float64, False, xs, xt), _pair_run(torch.float64, True, xs, xt)
+    for a, b in zip(sep["out"], par["out"]):
+        _close(b, a, 1e-5)
+    _close(par["rm"], sep["rm"], 1e-6)
+    _close(par["rv"], sep["rv"], 1e-6)
+    gmax = max(float(v.norm()) for v in sep["g"].values())
+    worst = max(float((par["g"][n] - sep["g"][n]).norm() / (sep["g"][n].norm() + 1e-6 * gmax)) for n in sep["g"])
+    assert worst < 1e-4, worst
+
+
+def test_forward_pair_bf16_is_as_accurate_as_two_calls():
+    """The bf16 hand-written path, paired vs two calls, both measured against the float32 two-call model (the random
+    50-layer network amplifies one-ulp differences, so pair-vs-separate is compared through their distance to the
+    float32 anchor): the paired forward may not be further from float32 than 1.3x the two-call forward."""
     torch.manual_seed(1)
     xs = torch.randn(2, 3, 256, 256, device="cuda").clamp(max=1.0)
     xt = (torch.randn(2, 3, 256, 256, device="cuda") * 0.7 + 0.3).clamp(max=1.0)
-    res = []
-    for pair in (False, True):
-        m = E.Deeplabv2(cfg, compute_dtype=dtype)
-        m.load_state_dict(so.seeded_state_dict(m, 2333), strict=True)
-        for mod in m.modules():
-            if isinstance(mod, torch.nn.Dropout2d):
-                mod.p = 0.0
-        m = m.cuda().train()
-        if pair:
-            (a1, a2, fa), (b1, b2, fb) = m.forward_pair(xs, xt)
-        else:
-            a1, a2, fa = m(xs)
-            b1, b2, fb = m(xt)
-        (a1.square().mean() + a2.mean() + b1.square().mean() - b2.mean()).backward()
-        res.append(dict(out=[t.detach() for t in (a1, a2, fa, b1, b2, fb)],
-                        g={n: p.grad.float().clone() for n, p in m.named_parameters()},
-                        rm=m.encoder.resnet.layer2[0].bn1.running_mean.clone(), rv=m.layer5.conv_last[1].running_var.clone()))
-    # float32: the library may pick different algorithms for batch 2 and batch 4; bf16: one-ulp differences from the
-    # atomics' summation order are amplified by the random 50-layer network (the same spread two runs of the SAME
-    # configuration show), so the bf16 bar is statistical
-    tol = 1e-3 if dtype == torch.float32 else 0.12
-    for a, b in zip(res[0]["out"], res[1]["out"]):
-        _close(b, a, tol)
-    _close(res[1]["rm"], res[0]["rm"], tol)
-    _close(res[1]["rv"], res[0]["rv"], tol)
-    worst = max(float((res[1]["g"][n] - res[0]["g"][n]).norm() / (res[0]["g"][n].norm() + 1e-12)) for n in res[0]["g"])
-    assert worst < (5e-3 if dtype == torch.float32 else 0.4), worst
+    ref, sep, par = _pair_run(torch.float32, False, xs, xt), _pair_run(torch.bfloat16, False, xs, xt), _pair_run(torch.bfloat16, True, xs, xt)
+
+    def oerr(r):
+        return [float((a - b).abs().max() / b.abs().max()) for a, b in zip(r["out"], ref["out"])]
+
+    for ep, es in zip(oerr(par), oerr(sep)):
+        assert ep <= 1.3 * es + 5e-3, (ep, es)
+    gmax = max(float(v.norm()) for v in ref["g"].values())
+
+    def gdev(r):
+        return sorted(float((r["g"][n] - ref["g"][n]).norm() / (ref["g"][n].norm() + 1e-6 * gmax)) for n in ref["g"])
+
+    dp, ds = gdev(par), gdev(sep)
+    for q in (0.5, 0.9):
+        i = int(q * len(dp))
+        assert dp[i] <= 1.3 * ds[i] + 1e-2, (q, dp[i], ds[i])
+    _close(par["rm"], sep["rm"], 2e-2)
+    _close(par["rv"], sep["rv"], 2e-2)
