@@ -234,7 +234,7 @@ def reference_lrh(args, rank, world):
     if rank != 0:
         return
     steps, warm = args.steps, max(args.warmup, 1)
-    tiles = 16
+    tiles = int(os.environ.get("REGDA_REF_LRH_TILES", "16"))
     from oracle import step_oracle as so
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)

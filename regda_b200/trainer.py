@@ -20,7 +20,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from . import capi
+from . import capi, parallel
 from .gast.balance import CrossEntropy
 from .utils.tools import loss_calc
 
@@ -70,6 +70,11 @@ class ParamArena:
     def zero_grad(self):
         self.grad.zero_()
 
+    def sync_shadow(self):
+        """refresh the bf16 shadow after the fp32 parameters were written from outside the SGD kernel
+        (load_state_dict, broadcast)"""
+        self.param_bf16.copy_(self.param)
+
     def set_lr(self, lr):
         """host float -> the device scalar the SGD kernel reads (graph-replay safe)."""
         self.lr_device.fill_(float(lr))
@@ -107,6 +112,12 @@ class SelfTrainingStep:
             pair_forward = getattr(model, "compute_dtype", None) == torch.bfloat16
         self.pair_forward = bool(pair_forward) and hasattr(model, "forward_pair")
         self.arena = ParamArena(model)
+        if world_size > 1:
+            # every rank trains the same weights: start from rank 0's (model construction may have been seeded per rank)
+            parallel.broadcast_parameters(self.arena.param)
+            self.arena.sync_shadow()
+            for buf in model.buffers():
+                parallel.broadcast_parameters(buf)
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
         self._static = None
@@ -115,8 +126,7 @@ class SelfTrainingStep:
     # ---- the step proper (no host sync inside) ------------------------------------------------
     def _reduce_proto(self, sums, counts):
         if self.world_size > 1:
-            dist.all_reduce(sums)
-            dist.all_reduce(counts)
+            parallel.allreduce_sum_(sums, counts)
 
     def _step_impl(self, images_s, label_s, images_t, soft_t, regs_t):
         m = self.model
@@ -142,7 +152,7 @@ class SelfTrainingStep:
         loss = loss_source + loss_target
         loss.backward()                                                            # :238
         if self.world_size > 1:
-            dist.all_reduce(self.arena.grad)                                       # mean over ranks via grad_scale
+            parallel.allreduce_sum_(self.arena.grad)                               # mean over ranks via grad_scale
         self.arena.clip_and_sgd(self.max_norm, self.momentum, self.weight_decay, 1.0 / self.world_size)   # :239-241
         return loss.detach(), loss_source.detach(), loss_target.detach(), hard
 
