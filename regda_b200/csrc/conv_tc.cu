@@ -18,6 +18,9 @@
 //     (tcgen05.ld -> bf16 -> global), STAGES-deep mbarrier ring between producer and MMA.
 // The same kernel computes the data gradient of a stride-1 convolution when it is given dY and
 // the flipped / transposed weights (host side prepares them).
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -181,6 +184,201 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks the tile list (N tile fastest, so CTAs running side by side share the
+// activation patch in L2); the TMA / MMA / epilogue warps each loop over the tiles on their own, coupled only by
+// mbarriers: the shared-memory ring keeps streaming across tile boundaries and TWO accumulators in tensor memory
+// (2 x BLOCK_N columns) let the epilogue of tile i drain while the MMAs of tile i+1 run.  Barrier / TMEM /
+// tensor-map set-up is paid once per SM instead of once per tile, which is what the many small-K convolutions
+// of layer3 (K = 256 .. 2304, 4-36 k-blocks per tile) are bound by.  BLOCK_N = 256 halves the L2->SM bytes per
+// flop of the 128 x 128 tile.
+// ---------------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int STAGES>
+struct PersistSmem {
+    static constexpr int kABytes = kBlockM * kBlockK * 2;
+    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kNumBars = 2 * STAGES + 4;          // full, empty, tmem_full[2], tmem_empty[2]
+    static constexpr int kTotal = kBarOffset + kNumBars * 8 + 8;
+};
+
+// STATS: the epilogue also accumulates the per-channel sum and sum of squares of the (bf16-rounded) outputs --
+// the train-mode BatchNorm statistics of the layer that follows -- into stats[group][2][cout] with one fp32
+// atomic per channel per warp per tile (warp-transposing butterfly: 31 shuffles per quantity per 32 channels),
+// which removes BatchNorm's own pass over the activation.  group = image / imgs_per_group.
+template <int BLOCK_N, int STAGES, bool B_MN, bool STATS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                       __nv_bfloat16 *__restrict__ y, const ConvGeom g, const int n_tiles_n, const int num_tiles,
+                       float *__restrict__ stats, const int imgs_per_group) {
+    using L = PersistSmem<BLOCK_N, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::kBarOffset);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tfull_bar = empty_bar + STAGES;                // [2] accumulator ready for the epilogue
+    uint64_t *tempty_bar = tfull_bar + 2;                    // [2] accumulator drained (4 epilogue warps arrive)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_k = g.r * g.s * g.kc;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 4); }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int n_blk = t % n_tiles_n;
+                int m_blk = t / n_tiles_n;
+                const int tw = m_blk % g.tiles_w; m_blk /= g.tiles_w;
+                const int th = m_blk % g.tiles_h;
+                const int img = m_blk / g.tiles_h;
+                const int ix0 = tw * g.bw * g.stride - g.pad, iy0 = th * g.bh * g.stride - g.pad;
+                int tap = 0, fr = 0, fs = 0, c0 = 0;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    uint8_t *sa = smem + stage * L::kStageBytes;
+                    uint8_t *sb = sa + L::kABytes;
+                    mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes);
+                    tma_load_4d(sa, &tmap_x, full_bar + stage, c0, ix0 + fs * g.dil, iy0 + fr * g.dil, img);
+                    if (B_MN) {
+                        const int wtap = g.flip ? g.r * g.s - 1 - tap : tap;
+#pragma unroll
+                        for (int i = 0; i < BLOCK_N / 64; ++i)
+                            tma_load_3d(sb + i * 8192, &tmap_w, full_bar + stage, n_blk * BLOCK_N + i * 64, wtap, c0);
+                    } else {
+                        tma_load_2d(sb, &tmap_w, full_bar + stage, tap * g.cin + c0, n_blk * BLOCK_N);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    c0 += kBlockK;
+                    if (c0 == g.cin) { c0 = 0; ++tap; if (++fs == g.s) { fs = 0; ++fr; } }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, B_MN ? 1 : 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                mbar_wait(tempty_bar + acc, acc_phase ^ 1);           // epilogue has drained this accumulator
+                tc_fence_after_sync();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(full_bar + stage, phase);
+                    tc_fence_after_sync();
+                    const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+                    const uint32_t sb = sa + L::kABytes;
+                    const uint64_t adesc = make_smem_desc(sa, 0, 1024);
+                    const uint64_t bdesc = B_MN ? make_smem_desc(sb, 8192, 1024) : make_smem_desc(sb, 0, 1024);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_bf16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>((B_MN ? 128 : 2) * k), idesc,
+                                  (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(empty_bar + stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar + acc);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> bf16 -> global (NHWC) =====
+        const int q = warp & 3;                                        // TMEM lane quadrant of this warp
+        const int row = q * 32 + lane;
+        const int ph = row / g.bw, pw = row - ph * g.bw;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int n_blk = t % n_tiles_n;
+            int m_blk = t / n_tiles_n;
+            const int tw = m_blk % g.tiles_w; m_blk /= g.tiles_w;
+            const int th = m_blk % g.tiles_h;
+            const int img = m_blk / g.tiles_h;
+            const int oh = th * g.bh + ph, ow = tw * g.bw + pw;
+            const bool valid = oh < g.oh && ow < g.ow;
+            __nv_bfloat16 *dst = y + ((static_cast<size_t>(img) * g.oh + oh) * g.ow + ow) * g.cout + static_cast<size_t>(n_blk) * BLOCK_N;
+            mbar_wait(tfull_bar + acc, acc_phase);
+            tc_fence_after_sync();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+                tmem_ld_wait();
+                uint32_t pkd[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                    pkd[j >> 1] = *reinterpret_cast<uint32_t *>(&b);
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<uint4 *>(dst + c + 2 * j) = make_uint4(pkd[j], pkd[j + 1], pkd[j + 2], pkd[j + 3]);
+                }
+                if (STATS) {
+                    // statistics of what BatchNorm will read back: the bf16-rounded values; rows outside the image count 0
+                    float a[32], b2[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&pkd[j >> 1]));
+                        a[j] = valid ? f.x : 0.f; a[j + 1] = valid ? f.y : 0.f;
+                        b2[j] = a[j] * a[j]; b2[j + 1] = a[j + 1] * a[j + 1];
+                    }
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int j = 0; j < off; ++j) {
+                            const float sa_ = up ? a[j] : a[j + off], ka = up ? a[j + off] : a[j];
+                            const float sb_ = up ? b2[j] : b2[j + off], kb_ = up ? b2[j + off] : b2[j];
+                            a[j] = ka + __shfl_xor_sync(0xffffffffu, sa_, off);
+                            b2[j] = kb_ + __shfl_xor_sync(0xffffffffu, sb_, off);
+                        }
+                    }
+                    // lane L now holds the warp totals of channel c + L
+                    float *sp = stats + static_cast<size_t>(img / imgs_per_group) * 2 * g.cout + static_cast<size_t>(n_blk) * BLOCK_N + c + lane;
+                    atomicAdd(sp, a[0]);
+                    atomicAdd(sp + g.cout, b2[0]);
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar + acc);            // this warp's quadrant of the accumulator is free
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 2 * BLOCK_N);
+    }
+}
+
 int make_tmap_x(CUtensorMap *m, const void *x, const ConvGeom &g) {
     if (!encode_nhwc(m, x, g.n, g.h, g.w, g.cin, g.bw, g.bh, g.stride))
         return REGDA_ERR_CUDA;   /* text set by encode_bf16_sw128 (activations) */
@@ -217,6 +415,61 @@ int launch_fprop(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bfloat16 *y,
     kern<<<grid, kThreads, smem, st>>>(tx, tw, y, g);
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
+}
+
+template <int BLOCK_N, int STAGES, bool B_MN, bool STATS>
+int launch_persistent_impl(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bfloat16 *y, const ConvGeom &g, cudaStream_t st,
+                           float *stats, int imgs_per_group) {
+    using L = PersistSmem<BLOCK_N, STAGES>;
+    auto kern = conv_persistent_kernel<BLOCK_N, STAGES, B_MN, STATS>;
+    const int smem = L::kTotal + 1024;
+    REGDA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int n_tiles_n = g.cout / BLOCK_N;
+    const int num_tiles = n_tiles_n * g.n * g.tiles_h * g.tiles_w;
+    const int grid = std::min(num_tiles, sm_count());
+    kern<<<grid, kThreads, smem, st>>>(tx, tw, y, g, n_tiles_n, num_tiles, stats, imgs_per_group);
+    REGDA_LAUNCH_CHECK();
+    return REGDA_OK;
+}
+
+template <int BLOCK_N, int STAGES, bool B_MN>
+int launch_persistent(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bfloat16 *y, const ConvGeom &g, cudaStream_t st,
+                      float *stats, int imgs_per_group) {
+    if (!B_MN && stats != nullptr) return launch_persistent_impl<BLOCK_N, STAGES, false, true>(tx, tw, y, g, st, stats, imgs_per_group);
+    return launch_persistent_impl<BLOCK_N, STAGES, B_MN, false>(tx, tw, y, g, st, nullptr, 1);
+}
+
+// Tile shape policy.  REGDA_CONV_KERNEL=classic selects the one-tile-per-CTA kernel (A/B comparisons).
+bool use_persistent() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("REGDA_CONV_KERNEL");
+        v = (e && strcmp(e, "classic") == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
+
+template <bool B_MN>
+int launch_conv(const void *act, const void *wgt, __nv_bfloat16 *out, const ConvGeom &g, int taps, cudaStream_t st,
+                float *stats = nullptr, int imgs_per_group = 1) {
+    // g.cin = reduction channels, g.cout = output channels of THIS GEMM (already swapped for dgrad)
+    CUtensorMap tx, tw;
+    int rc = make_tmap_x(&tx, act, g);
+    if (rc) return rc;
+    const long long m_tiles = static_cast<long long>(g.n) * g.tiles_h * g.tiles_w;
+    int block_n = 64;
+    if (g.cout % 256 == 0 && use_persistent() && m_tiles * (g.cout / 256) >= sm_count() / 2) block_n = 256;
+    else if (g.cout % 128 == 0) block_n = 128;
+    rc = B_MN ? make_tmap_w_mn(&tw, wgt, g.cin, taps, g.cout) : make_tmap_w(&tw, wgt, g.cout, taps * g.cin, block_n);
+    if (rc) return rc;
+    if (use_persistent()) {
+        if (block_n == 256) return launch_persistent<256, 4, B_MN>(tx, tw, out, g, st, stats, imgs_per_group);
+        if (block_n == 128) return launch_persistent<128, 6, B_MN>(tx, tw, out, g, st, stats, imgs_per_group);
+        return launch_persistent<64, 8, B_MN>(tx, tw, out, g, st, stats, imgs_per_group);
+    }
+    if (stats != nullptr) return fail(REGDA_ERR_UNSUPPORTED, "conv_fprop: fused BatchNorm statistics need the persistent kernel");
+    if (block_n == 128) return launch_fprop<128, 3, B_MN>(tx, tw, out, g, st);
+    return launch_fprop<64, 4, B_MN>(tx, tw, out, g, st);
 }
 
 }  // namespace
@@ -259,19 +512,27 @@ extern "C" int regda_conv_fprop_bf16(const void *x, const void *wgt, void *y, in
     ConvGeom g;
     geom_init(g, n, h, w, cin, cout, r, s, stride, pad, dil);
     ensure_context(x);
-    CUtensorMap tx, tw;
-    int rc = make_tmap_x(&tx, x, g);
-    if (rc) return rc;
+    return launch_conv<false>(x, wgt, static_cast<__nv_bfloat16 *>(y), g, r * s, static_cast<cudaStream_t>(stream));
+}
+
+// Forward convolution that also produces the train-mode BatchNorm statistics of its output:
+// bn_stats float32 [groups][2][cout] = per-group per-channel (sum, sum of squares) over the group's n/groups images,
+// written (zeroed here first).  Feed it to regda_bn_forward_bf16(..., have_stats = 1).
+extern "C" int regda_conv_fprop_stats_bf16(const void *x, const void *wgt, void *y, int n, int h, int w, int cin, int cout,
+                                           int r, int s, int stride, int pad, int dil, float *bn_stats, int groups, void *stream) {
+    if (!regda_conv_fprop_supported(n, h, w, cin, cout, r, s, stride, pad, dil))
+        return fail(REGDA_ERR_UNSUPPORTED, "conv_fprop: shape not covered by the tcgen05 kernel");
+    if (!x || !wgt || !y || !bn_stats) return fail(REGDA_ERR_INVALID_ARG, "conv_fprop_stats: null pointer");
+    if (groups < 1 || n % groups != 0) return fail(REGDA_ERR_INVALID_ARG, "conv_fprop_stats: groups must divide the batch");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wgt) | reinterpret_cast<uintptr_t>(y)) & 15)
+        return fail(REGDA_ERR_INVALID_ARG, "conv_fprop: tensors must be 16-byte aligned");
+    if (!use_persistent()) return fail(REGDA_ERR_UNSUPPORTED, "conv_fprop_stats: needs the persistent kernel");
+    ConvGeom g;
+    geom_init(g, n, h, w, cin, cout, r, s, stride, pad, dil);
+    ensure_context(x);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    __nv_bfloat16 *yy = static_cast<__nv_bfloat16 *>(y);
-    if (cout % 128 == 0) {
-        rc = make_tmap_w(&tw, wgt, cout, r * s * cin, 128);
-        if (rc) return rc;
-        return launch_fprop<128, 3, false>(tx, tw, yy, g, st);
-    }
-    rc = make_tmap_w(&tw, wgt, cout, r * s * cin, 64);
-    if (rc) return rc;
-    return launch_fprop<64, 4, false>(tx, tw, yy, g, st);
+    REGDA_CUDA_CHECK(cudaMemsetAsync(bn_stats, 0, static_cast<size_t>(groups) * 2 * cout * sizeof(float), st));
+    return launch_conv<false>(x, wgt, static_cast<__nv_bfloat16 *>(y), g, r * s, st, bn_stats, n / groups);
 }
 
 // Data gradient of a stride-1 convolution, reading the forward weights IN PLACE:
@@ -300,13 +561,5 @@ extern "C" int regda_conv_dgrad_bf16(const void *dy, const void *wgt, void *dx, 
     g.flip = 1;
     if (g.oh != h || g.ow != w) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad: inconsistent geometry");
     ensure_context(dy);
-    CUtensorMap tx, tw;
-    int rc = make_tmap_x(&tx, dy, g);
-    if (rc) return rc;
-    rc = make_tmap_w_mn(&tw, wgt, cout, r * s, cin);
-    if (rc) return rc;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    __nv_bfloat16 *out = static_cast<__nv_bfloat16 *>(dx);
-    if (cin % 128 == 0) return launch_fprop<128, 3, true>(tx, tw, out, g, st);
-    return launch_fprop<64, 4, true>(tx, tw, out, g, st);
+    return launch_conv<true>(dy, wgt, static_cast<__nv_bfloat16 *>(dx), g, r * s, static_cast<cudaStream_t>(stream));
 }

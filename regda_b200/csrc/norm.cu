@@ -290,21 +290,26 @@ extern "C" size_t regda_bn_workspace_bytes(int c, int groups) { return static_ca
 extern "C" int regda_bn_forward_bf16(const void *y, const void *residual, void *out, int64_t npix, int c, int groups,
                                      const float *gamma, const float *beta, float *running_mean, float *running_var,
                                      int64_t *num_batches_tracked, double eps, double momentum, int relu,
-                                     float *coef, void *workspace, size_t workspace_bytes, void *stream) {
+                                     float *coef, const float *ready_stats, void *workspace, size_t workspace_bytes, void *stream) {
     if (!bn_shape_ok(npix, c)) return fail(REGDA_ERR_UNSUPPORTED, "bn_forward: channels must divide 2048 and be a multiple of 8");
     if (groups < 1 || npix % groups != 0) return fail(REGDA_ERR_INVALID_ARG, "bn_forward: groups must divide the pixel count");
     if (!y || !out || !coef) return fail(REGDA_ERR_INVALID_ARG, "bn_forward: null pointer");
-    if (!workspace || workspace_bytes < regda_bn_workspace_bytes(c, groups)) return fail(REGDA_ERR_WORKSPACE, "bn_forward: workspace too small");
+    if (!ready_stats && (!workspace || workspace_bytes < regda_bn_workspace_bytes(c, groups)))
+        return fail(REGDA_ERR_WORKSPACE, "bn_forward: workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    float *stats = static_cast<float *>(workspace);
     const long long gpix = npix / groups;
     const long long total = gpix * c;                                   // elements per statistics group
-    REGDA_CUDA_CHECK(cudaMemsetAsync(stats, 0, static_cast<size_t>(2 * c) * groups * sizeof(float), st));
-    long long span = 0;
-    const int rg = reduce_grid(total, groups, &span);
     const __nv_bfloat16 *yy = static_cast<const __nv_bfloat16 *>(y);
-    bn_stats_kernel<<<dim3(rg, groups), kBnThreads, 0, st>>>(yy, total, c, span, stats, stats + c);
-    REGDA_LAUNCH_CHECK();
+    const float *stats = ready_stats;                                    // [groups][2][c] from the producing convolution's epilogue
+    if (stats == nullptr) {
+        float *ws = static_cast<float *>(workspace);
+        REGDA_CUDA_CHECK(cudaMemsetAsync(ws, 0, static_cast<size_t>(2 * c) * groups * sizeof(float), st));
+        long long span = 0;
+        const int rg = reduce_grid(total, groups, &span);
+        bn_stats_kernel<<<dim3(rg, groups), kBnThreads, 0, st>>>(yy, total, c, span, ws, ws + c);
+        REGDA_LAUNCH_CHECK();
+        stats = ws;
+    }
     const float n = static_cast<float>(gpix);
     bn_finalize_kernel<<<(c + 255) / 256, 256, 0, st>>>(stats, c, groups, 1.f / n, gpix > 1 ? n / (n - 1.f) : 1.f, gamma, beta, running_mean,
                                                          running_var, reinterpret_cast<long long *>(num_batches_tracked),

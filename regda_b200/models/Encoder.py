@@ -41,6 +41,17 @@ def _fused(x, bn):
 _GROUPS = 1
 
 
+def _conv_bn(conv, bn, x, residual=None, relu=False):
+    """relu?(bn(conv(x)) + residual); on the hand-written path the BatchNorm statistics come out of the convolution
+    kernel's epilogue, so BatchNorm makes one pass (apply) instead of two over the activation"""
+    if FUSED and bn.training and x.is_cuda and x.dtype == torch.bfloat16:
+        y, st = conv.forward_with_bn_stats(x, _GROUPS)
+        if st is not None and fnorm.supported(y, bn):
+            return fnorm.bn_act(y, bn, residual=residual, relu=relu, groups=_GROUPS, stats=st)
+        return _bn(y, bn, residual, relu)
+    return _bn(conv(x), bn, residual, relu)
+
+
 def _bn(x, bn, residual=None, relu=False):
     """relu?(bn(x) + residual) through the fused kernels when they apply, else through torch; honours _GROUPS"""
     if _fused(x, bn):
@@ -93,12 +104,12 @@ class Bottleneck(nn.Module):
             self.downsample = nn.Sequential(Conv2d(inplanes, planes * 4, 1, stride=stride, bias=False), nn.BatchNorm2d(planes * 4))
 
     def forward(self, x):
+        if (FUSED and self.training and x.is_cuda and x.dtype == torch.bfloat16) or _GROUPS > 1:
+            out = _conv_bn(self.conv1, self.bn1, x, relu=True)
+            out = _conv_bn(self.conv2, self.bn2, out, relu=True)
+            identity = x if self.downsample is None else _conv_bn(self.downsample[0], self.downsample[1], x)
+            return _conv_bn(self.conv3, self.bn3, out, residual=identity, relu=True)
         y = self.conv1(x)
-        if _fused(y, self.bn1) or _GROUPS > 1:
-            out = _bn(y, self.bn1, relu=True)
-            out = _bn(self.conv2(out), self.bn2, relu=True)
-            identity = x if self.downsample is None else _bn(self.downsample[0](x), self.downsample[1])
-            return _bn(self.conv3(out), self.bn3, residual=identity, relu=True)
         out = F.relu(self.bn1(y), inplace=True)
         out = F.relu(self.bn2(self.conv2(out)), inplace=True)
         out = self.bn3(self.conv3(out))
@@ -183,9 +194,7 @@ class PPMBilinear(nn.Module):
                 off += s * s
                 branches.append(branch[3](fnorm.bn_eager(branch[1](p), branch[2], _GROUPS)))
             cat = fppm.upsample_concat(conv_out, branches, self.pool_scales)
-            y = self.conv_last[0](cat)
-            bn = self.conv_last[1]
-            y = _bn(y, bn, relu=True)
+            y = _conv_bn(self.conv_last[0], self.conv_last[1], cat, relu=True)
             return self.conv_last[4](self.conv_last[3](y))
         size = conv_out.shape[-2:]
         outs = [conv_out]

@@ -19,6 +19,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 ENGINE = os.environ.get("REGDA_CONV", "auto")
+FUSE_BN_STATS = os.environ.get("REGDA_FUSE_BN_STATS", "1") != "0" and os.environ.get("REGDA_CONV_KERNEL", "") != "classic"
 stats = {"tcgen05_fprop": 0, "tcgen05_dgrad": 0, "tcgen05_wgrad": 0, "cudnn": 0}
 
 
@@ -38,17 +39,21 @@ class _ConvFn(torch.autograd.Function):
     The weight gradient is ACCUMULATED into weight.grad by the wgrad kernel (no autograd add)."""
 
     @staticmethod
-    def forward(ctx, x, weight, stride, padding, dilation):
+    def forward(ctx, x, weight, stride, padding, dilation, stats_groups=None):
         tc = _tc()
         w16 = tc.weight_shadow(weight)
         ctx.save_for_backward(x, w16)
         ctx.weight = weight
         ctx.geom = (stride, padding, dilation)
         stats["tcgen05_fprop"] += 1
-        return tc.fprop(x, w16, stride, padding, dilation)
+        if stats_groups is None:
+            return tc.fprop(x, w16, stride, padding, dilation)
+        y, bn_stats = tc.fprop(x, w16, stride, padding, dilation, stats_groups)
+        ctx.mark_non_differentiable(bn_stats)
+        return y, bn_stats
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, *unused):
         tc = _tc()
         x, w16 = ctx.saved_tensors
         weight = ctx.weight
@@ -73,7 +78,7 @@ class _ConvFn(torch.autograd.Function):
                 stats["cudnn"] += 1
                 gw = torch.ops.aten.convolution_backward(gy, x, w16, None, [stride] * 2, [padding] * 2,
                                                          [dilation] * 2, False, [0, 0], 1, [False, True, False])[1].float()
-        return gx, gw, None, None, None
+        return gx, gw, None, None, None, None
 
 
 class Conv2d(nn.Module):
@@ -93,6 +98,14 @@ class Conv2d(nn.Module):
     def extra_repr(self):
         return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "
                 f"padding={self.padding}, dilation={self.dilation}, bias={self.bias is not None}")
+
+    def forward_with_bn_stats(self, x, groups):
+        """(y, stats): the convolution plus the BatchNorm statistics of its output from the kernel's epilogue, or
+        (y, None) when this shape / engine does not run on the tcgen05 kernel."""
+        if (ENGINE != "cudnn" and self.bias is None and x.is_cuda and x.dtype == torch.bfloat16 and FUSE_BN_STATS
+                and _tc().supports_fprop(x.shape, self.weight.shape, self.stride, self.padding, self.dilation, x.dtype)):
+            return _ConvFn.apply(x, self.weight, self.stride, self.padding, self.dilation, groups)
+        return self.forward(x), None
 
     def forward(self, x):
         use_tc = False

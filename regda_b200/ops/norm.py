@@ -40,7 +40,7 @@ def _grad_buffer(p):
 
 class _BnActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y, residual, gamma, beta, bn, relu, groups):
+    def forward(ctx, y, residual, gamma, beta, bn, relu, groups, ready_stats):
         y = _cl(y)
         n, c, h, w = y.shape
         npix = n * h * w
@@ -50,10 +50,12 @@ class _BnActFn(torch.autograd.Function):
         coef = torch.empty(groups * 4 * c, dtype=torch.float32, device=y.device)
         L = capi.lib()
         ws = capi.workspace.get(L.regda_bn_workspace_bytes(c, groups), y.device)
+        if ready_stats is not None:
+            assert ready_stats.shape == (groups, 2, c) and ready_stats.dtype == torch.float32
         capi.call("regda_bn_forward_bf16", capi.ptr_any(y), capi.ptr_any(res) if res is not None else None, capi.ptr_any(out), npix, c,
                   groups, capi.ptr(gamma), capi.ptr(beta), capi.ptr(bn.running_mean), capi.ptr(bn.running_var),
                   capi.ptr(bn.num_batches_tracked), float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1), int(relu),
-                  capi.ptr(coef), capi.ptr(ws), ws.numel(), capi.stream())
+                  capi.ptr(coef), capi.ptr(ready_stats) if ready_stats is not None else None, capi.ptr(ws), ws.numel(), capi.stream())
         ctx.save_for_backward(y, out if relu else None, coef)
         ctx.gamma, ctx.beta, ctx.relu, ctx.has_res, ctx.groups = gamma, beta, relu, residual is not None, groups
         return out
@@ -75,11 +77,12 @@ class _BnActFn(torch.autograd.Function):
                   capi.ptr(dgamma) if dgamma is not None else None, capi.ptr(dbeta) if dbeta is not None else None, int(ctx.relu),
                   capi.ptr(ws), ws.numel(), capi.stream())
         # gamma / beta gradients were accumulated in place: nothing flows back through autograd for them
-        return dy, dres, None, None, None, None, None
+        return dy, dres, None, None, None, None, None, None
 
 
-def bn_act(y, bn, residual=None, relu=True, groups=1):
-    return _BnActFn.apply(y, residual, bn.weight, bn.bias, bn, relu, groups)
+def bn_act(y, bn, residual=None, relu=True, groups=1, stats=None):
+    """stats: the [groups][2][c] sums produced by the convolution's epilogue (ops/tc.py fprop(..., stats_groups)), if any"""
+    return _BnActFn.apply(y, residual, bn.weight, bn.bias, bn, relu, groups, stats)
 
 
 def bn_eager(x, bn, groups=1):

