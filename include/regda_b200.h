@@ -220,6 +220,11 @@ int regda_bn_backward_bf16(const void *dout, const void *out, const void *y, voi
                            int groups, const float *gamma, const float *coef, float *dgamma, float *dbeta, int relu,
                            void *workspace, size_t workspace_bytes, void *stream);
 
+/* MaxPool2d(3, stride 2, padding 1) over channels-last bf16 (regda/_resnets.py:153): x [n][h][w][c] -> y [n][oh][ow][c],
+ * oh = (h-1)/2+1.  Backward recomputes the arg-max (first maximum in window order, as ATen) from x and y. */
+int regda_maxpool3s2_fwd_bf16(const void *x, void *y, int n, int h, int w, int c, void *stream);
+int regda_maxpool3s2_bwd_bf16(const void *x, const void *y, const void *dy, void *dx, int n, int h, int w, int c, void *stream);
+
 /* ---- pyramid pooling front end of the PPM heads (regda/models/Encoder.py:43-52) -----------------
  * scales_host: HOST array of nscales (<= 4) pool sizes, e.g. {1,2,3,6}; ncell = sum s^2; cells of scale k start
  * at sum_{j<k} s_j^2, row-major.

@@ -84,34 +84,54 @@ ppm_pool_fwd_kernel(const __nv_bfloat16 *__restrict__ feat, float *__restrict__ 
     }
 }
 
-// one thread per (pixel, channel octet)
+// grid (h, b, c / kPoolBwdChunk): for one feature-map row y and a 512-channel chunk, phase 1 folds the (at most two) row
+// cells of every scale that contain y into per-column vectors R[column cell][channel] (12 x 512 floats in shared memory,
+// 1/area included), phase 2 writes each pixel as the sum of the <= 2 column vectors per scale that contain x.
+constexpr int kPoolBwdChunk = 512;
+constexpr int kMaxColCells = 16;           // sum of the pool scales (1+2+3+6 = 12)
 __global__ void __launch_bounds__(256)
 ppm_pool_bwd_kernel(const float *__restrict__ dpooled, __nv_bfloat16 *__restrict__ dfeat, int h, int w, int c, const PpmScales sc) {
-    const int y = blockIdx.x, img = blockIdx.y;
-    const float *pimg = dpooled + static_cast<size_t>(img) * sc.ncell * c;
-    __nv_bfloat16 *row = dfeat + (static_cast<size_t>(img) * h + y) * w * c;
-    const int octs = c >> 3;
+    __shared__ float R[kMaxColCells][kPoolBwdChunk];
+    const int y = blockIdx.x, img = blockIdx.y, c0 = blockIdx.z * kPoolBwdChunk;
+    const int cw = min(kPoolBwdChunk, c - c0);
+    const float *pimg = dpooled + static_cast<size_t>(img) * sc.ncell * c + c0;
+    int col = 0;
+    for (int k = 0; k < sc.n; ++k) {
+        const int s = sc.s[k];
+        const int i0 = (y * s) / h;
+        for (int j = 0; j < s; ++j, ++col) {
+            const int x0 = win_lo(j, w, s), x1 = win_hi(j, w, s);
+            for (int ch = threadIdx.x; ch < cw; ch += blockDim.x) {
+                float acc = 0.f;
+                for (int i = max(i0 - 1, 0); i <= min(i0 + 1, s - 1); ++i) {
+                    const int y0 = win_lo(i, h, s), y1 = win_hi(i, h, s);
+                    if (y < y0 || y >= y1) continue;
+                    acc += pimg[static_cast<size_t>(sc.off[k] + i * s + j) * c + ch] / static_cast<float>((y1 - y0) * (x1 - x0));
+                }
+                R[col][ch] = acc;
+            }
+        }
+    }
+    __syncthreads();
+    __nv_bfloat16 *row = dfeat + (static_cast<size_t>(img) * h + y) * w * c + c0;
+    const int octs = cw >> 3;
     for (int item = threadIdx.x; item < w * octs; item += blockDim.x) {
         const int x = item / octs, ch = (item - x * octs) * 8;
         float acc[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+        int base = 0;
         for (int k = 0; k < sc.n; ++k) {
             const int s = sc.s[k];
-            const int i0 = (y * s) / h, j0 = (x * s) / w;
-            for (int i = max(i0 - 1, 0); i <= min(i0 + 1, s - 1); ++i) {
-                const int y0 = win_lo(i, h, s), y1 = win_hi(i, h, s);
-                if (y < y0 || y >= y1) continue;
-                for (int j = max(j0 - 1, 0); j <= min(j0 + 1, s - 1); ++j) {
-                    const int x0 = win_lo(j, w, s), x1 = win_hi(j, w, s);
-                    if (x < x0 || x >= x1) continue;
-                    const float wgt = 1.f / static_cast<float>((y1 - y0) * (x1 - x0));
-                    const float4 *p = reinterpret_cast<const float4 *>(pimg + static_cast<size_t>(sc.off[k] + i * s + j) * c + ch);
-                    const float4 a = p[0], b = p[1];
-                    acc[0] = fmaf(a.x, wgt, acc[0]); acc[1] = fmaf(a.y, wgt, acc[1]); acc[2] = fmaf(a.z, wgt, acc[2]); acc[3] = fmaf(a.w, wgt, acc[3]);
-                    acc[4] = fmaf(b.x, wgt, acc[4]); acc[5] = fmaf(b.y, wgt, acc[5]); acc[6] = fmaf(b.z, wgt, acc[6]); acc[7] = fmaf(b.w, wgt, acc[7]);
-                }
+            const int j0 = (x * s) / w;
+            for (int j = max(j0 - 1, 0); j <= min(j0 + 1, s - 1); ++j) {
+                if (x < win_lo(j, w, s) || x >= win_hi(j, w, s)) continue;
+                const float4 a = *reinterpret_cast<const float4 *>(&R[base + j][ch]);
+                const float4 b = *reinterpret_cast<const float4 *>(&R[base + j][ch + 4]);
+                acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+                acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
             }
+            base += s;
         }
         *reinterpret_cast<bf16x8 *>(row + static_cast<size_t>(x) * c + ch) = pack(acc);
     }
@@ -130,39 +150,50 @@ __device__ __forceinline__ void bilinear_src(int dst, int in_size, int out_size,
 struct BranchPtrs { const __nv_bfloat16 *p[kMaxScales]; };
 struct BranchGradPtrs { float *p[kMaxScales]; };
 
-// grid (h, b): cat[b][y][x][0..c) = feat, cat[.. c + k*cb + q] = bilinear(branch_k)[q]
+// grid (h, b, 1 + nscales): segment 0 copies the feature row into cat[..., 0..c); segment 1+k writes
+// cat[..., c + k*cb + q] = bilinear(branch_k)[q] (the row's two source rows and weights are block-uniform)
 __global__ void __launch_bounds__(256)
 ppm_upcat_fwd_kernel(const __nv_bfloat16 *__restrict__ feat, const BranchPtrs br, __nv_bfloat16 *__restrict__ cat, int h, int w, int c,
                      int cb, const PpmScales sc) {
-    const int y = blockIdx.x, img = blockIdx.y;
+    const int y = blockIdx.x, img = blockIdx.y, seg = blockIdx.z;
     const int ctot = c + sc.n * cb;
-    const int octs = ctot >> 3;
-    const __nv_bfloat16 *frow = feat + (static_cast<size_t>(img) * h + y) * w * c;
     __nv_bfloat16 *crow = cat + (static_cast<size_t>(img) * h + y) * w * ctot;
-    for (int item = threadIdx.x; item < w * octs; item += blockDim.x) {
-        const int x = item / octs, ch = (item - x * octs) * 8;
-        bf16x8 outv;
-        if (ch < c) {
-            outv = *reinterpret_cast<const bf16x8 *>(frow + static_cast<size_t>(x) * c + ch);
-        } else {
-            const int k = (ch - c) / cb, q = (ch - c) - k * cb;
-            const int s = sc.s[k];
-            int y0, y1, x0, x1;
-            float ly, lx;
-            bilinear_src(y, s, h, y0, y1, ly);
-            bilinear_src(x, s, w, x0, x1, lx);
-            const __nv_bfloat16 *b0 = br.p[k] + static_cast<size_t>(img) * s * s * cb + q;
-            float f00[8], f01[8], f10[8], f11[8], o[8];
-            unpack(*reinterpret_cast<const bf16x8 *>(b0 + static_cast<size_t>(y0 * s + x0) * cb), f00);
-            unpack(*reinterpret_cast<const bf16x8 *>(b0 + static_cast<size_t>(y0 * s + x1) * cb), f01);
-            unpack(*reinterpret_cast<const bf16x8 *>(b0 + static_cast<size_t>(y1 * s + x0) * cb), f10);
-            unpack(*reinterpret_cast<const bf16x8 *>(b0 + static_cast<size_t>(y1 * s + x1) * cb), f11);
-            const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-#pragma unroll
-            for (int t = 0; t < 8; ++t) o[t] = w00 * f00[t] + w01 * f01[t] + w10 * f10[t] + w11 * f11[t];
-            outv = pack(o);
+    if (seg == 0) {
+        const __nv_bfloat16 *frow = feat + (static_cast<size_t>(img) * h + y) * w * c;
+        const int octs = c >> 3;
+        for (int item = threadIdx.x; item < w * octs; item += blockDim.x) {
+            const int x = item / octs, ch = (item - x * octs) * 8;
+            *reinterpret_cast<bf16x8 *>(crow + static_cast<size_t>(x) * ctot + ch) =
+                *reinterpret_cast<const bf16x8 *>(frow + static_cast<size_t>(x) * c + ch);
         }
-        *reinterpret_cast<bf16x8 *>(crow + static_cast<size_t>(x) * ctot + ch) = outv;
+        return;
+    }
+    const int k = seg - 1;
+    int s = sc.s[0];
+    const __nv_bfloat16 *bp = br.p[0];
+    if (k == 1) { s = sc.s[1]; bp = br.p[1]; }
+    if (k == 2) { s = sc.s[2]; bp = br.p[2]; }
+    if (k == 3) { s = sc.s[3]; bp = br.p[3]; }
+    int y0, y1;
+    float ly;
+    bilinear_src(y, s, h, y0, y1, ly);
+    const __nv_bfloat16 *r0 = bp + (static_cast<size_t>(img) * s + y0) * s * cb;
+    const __nv_bfloat16 *r1 = bp + (static_cast<size_t>(img) * s + y1) * s * cb;
+    const int octs = cb >> 3;
+    for (int item = threadIdx.x; item < w * octs; item += blockDim.x) {
+        const int x = item / octs, q = (item - x * octs) * 8;
+        int x0, x1;
+        float lx;
+        bilinear_src(x, s, w, x0, x1, lx);
+        float f00[8], f01[8], f10[8], f11[8], o[8];
+        unpack(*reinterpret_cast<const bf16x8 *>(r0 + static_cast<size_t>(x0) * cb + q), f00);
+        unpack(*reinterpret_cast<const bf16x8 *>(r0 + static_cast<size_t>(x1) * cb + q), f01);
+        unpack(*reinterpret_cast<const bf16x8 *>(r1 + static_cast<size_t>(x0) * cb + q), f10);
+        unpack(*reinterpret_cast<const bf16x8 *>(r1 + static_cast<size_t>(x1) * cb + q), f11);
+        const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = w00 * f00[t] + w01 * f01[t] + w10 * f10[t] + w11 * f11[t];
+        *reinterpret_cast<bf16x8 *>(crow + static_cast<size_t>(x) * ctot + c + k * cb + q) = pack(o);
     }
 }
 
@@ -252,7 +283,11 @@ extern "C" int regda_ppm_pool_bwd(const float *dpooled, void *dfeat, int b, int 
     const int rc = make_scales(scales_host, nscales, &sc);
     if (rc) return rc;
     if (!dpooled || !dfeat || b < 1 || h < 1 || w < 1 || c < 8 || c % 8) return fail(REGDA_ERR_INVALID_ARG, "ppm_pool_bwd: bad arguments");
-    ppm_pool_bwd_kernel<<<dim3(h, b), 256, 0, static_cast<cudaStream_t>(stream)>>>(dpooled, static_cast<__nv_bfloat16 *>(dfeat), h, w, c, sc);
+    int cols = 0;
+    for (int k = 0; k < sc.n; ++k) cols += sc.s[k];
+    if (cols > kMaxColCells) return fail(REGDA_ERR_UNSUPPORTED, "ppm_pool_bwd: pool scales sum to more than 16");
+    ppm_pool_bwd_kernel<<<dim3(h, b, (c + kPoolBwdChunk - 1) / kPoolBwdChunk), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        dpooled, static_cast<__nv_bfloat16 *>(dfeat), h, w, c, sc);
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
 }
@@ -269,7 +304,7 @@ extern "C" int regda_ppm_upcat_fwd(const void *feat, const void *br0, const void
         bp.p[k] = static_cast<const __nv_bfloat16 *>(ps[k]);
         if (k < nscales && !ps[k]) return fail(REGDA_ERR_INVALID_ARG, "ppm_upcat_fwd: null branch pointer");
     }
-    ppm_upcat_fwd_kernel<<<dim3(h, b), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16 *>(feat), bp,
+    ppm_upcat_fwd_kernel<<<dim3(h, b, 1 + nscales), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16 *>(feat), bp,
                                                                                       static_cast<__nv_bfloat16 *>(cat), h, w, c, cb, sc);
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;

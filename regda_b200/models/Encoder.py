@@ -140,7 +140,7 @@ class ResNet(nn.Module):
     def forward(self, x):
         x = self.conv1(x)
         x = _bn(x, self.bn1, relu=True)
-        x = F.max_pool2d(x, 3, 2, 1)
+        x = fnorm.max_pool3s2(x) if FUSED else F.max_pool2d(x, 3, 2, 1)
         return self.layer4(self.layer3(self.layer2(self.layer1(x))))
 
 
@@ -246,11 +246,17 @@ class Deeplabv2(nn.Module):
     def forward(self, x):
         xin = x.to(self.compute_dtype).contiguous(memory_format=torch.channels_last)
         feat = self.encoder(xin)
-        if self._cfg.is_ins_norm:
-            feat = self.instance_norm(feat.float())      # float32 statistics and output (feeds the Aligner)
+        if self._cfg.is_ins_norm and FUSED and self.training and fnorm.instance_norm_supported(feat):
+            # hand-written path: per-image statistics groups of the BatchNorm kernels, bf16 in / bf16 out; the Aligner's
+            # float32 feature view is one conversion of the result
+            fin = fnorm.instance_norm(feat, self.instance_norm.eps)
+            feat = fin.float()
         else:
-            feat = feat.float()
-        fin = feat.to(self.compute_dtype)
+            if self._cfg.is_ins_norm:
+                feat = self.instance_norm(feat.float())      # float32 statistics and output (feeds the Aligner)
+            else:
+                feat = feat.float()
+            fin = feat.to(self.compute_dtype)
         if self.layer5.fused_ok(fin) and self.layer5.pool_scales == self.layer6.pool_scales:
             pooled = fppm.pool(fin, self.layer5.pool_scales)          # both heads pool the same feature map
             x1 = self.layer5(fin, pooled).float()

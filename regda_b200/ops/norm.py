@@ -90,3 +90,70 @@ def bn_eager(x, bn, groups=1):
     if groups == 1 or not bn.training:
         return bn(x)
     return torch.cat([bn(part) for part in x.chunk(groups, dim=0)], dim=0)
+
+
+class _MaxPool3s2Fn(torch.autograd.Function):
+    """F.max_pool2d(x, 3, 2, 1) for channels-last bf16 (the stem pool, regda/_resnets.py:153)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _cl(x)
+        n, c, h, w = x.shape
+        y = torch.empty((n, c, (h - 1) // 2 + 1, (w - 1) // 2 + 1), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        capi.call("regda_maxpool3s2_fwd_bf16", capi.ptr_any(x), capi.ptr_any(y), n, h, w, c, capi.stream())
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        n, c, h, w = x.shape
+        dy = _cl(dy)
+        dx = torch.empty_like(x)
+        capi.call("regda_maxpool3s2_bwd_bf16", capi.ptr_any(x), capi.ptr_any(y), capi.ptr_any(dy), capi.ptr_any(dx), n, h, w, c, capi.stream())
+        return dx
+
+
+def max_pool3s2(x):
+    if x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] % 8 == 0:
+        return _MaxPool3s2Fn.apply(x)
+    return torch.nn.functional.max_pool2d(x, 3, 2, 1)
+
+
+class _InstanceNormFn(torch.autograd.Function):
+    """nn.InstanceNorm2d(C) (no affine, no running statistics; regda/models/Encoder.py:118-123) on channels-last bf16:
+    BatchNorm with one statistics group per image and gamma = 1, beta = 0 -- the same three kernels."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        x = _cl(x)
+        n, c, h, w = x.shape
+        out = torch.empty_like(x)
+        coef = torch.empty(n * 4 * c, dtype=torch.float32, device=x.device)
+        ws = capi.workspace.get(capi.lib().regda_bn_workspace_bytes(c, n), x.device)
+        capi.call("regda_bn_forward_bf16", capi.ptr_any(x), None, capi.ptr_any(out), n * h * w, c, n, None, None, None, None, None,
+                  float(eps), 0.0, 0, capi.ptr(coef), None, capi.ptr(ws), ws.numel(), capi.stream())
+        ctx.save_for_backward(x, coef)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, coef = ctx.saved_tensors
+        n, c, h, w = x.shape
+        dout = _cl(dout)
+        dx = torch.empty_like(x)
+        ws = capi.workspace.get(capi.lib().regda_bn_backward_workspace_bytes(c, n), x.device)
+        capi.call("regda_bn_backward_bf16", capi.ptr_any(dout), None, capi.ptr_any(x), capi.ptr_any(dx), None, n * h * w, c, n, None,
+                  capi.ptr(coef), None, None, 0, capi.ptr(ws), ws.numel(), capi.stream())
+        return dx, None
+
+
+def instance_norm(x, eps=1e-5):
+    return _InstanceNormFn.apply(x, eps)
+
+
+def instance_norm_supported(x):
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4):
+        return False
+    n, c, h, w = x.shape
+    return bool(capi.lib().regda_bn_supported(h * w, c))

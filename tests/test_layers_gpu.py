@@ -277,3 +277,35 @@ def test_forward_pair_bf16_is_as_accurate_as_two_calls():
         assert dp[i] <= 1.3 * ds[i] + 1e-2, (q, dp[i], ds[i])
     _close(par["rm"], sep["rm"], 6e-2)
     _close(par["rv"], sep["rv"], 6e-2)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 32, 32), (1, 64, 17, 23), (2, 128, 9, 8)], ids=str)
+def test_maxpool3s2_matches_torch(shape):
+    from regda_b200.ops import norm
+    g = torch.Generator(device="cuda").manual_seed(5)
+    # post-ReLU-like input: many exact zeros, so window ties (first maximum wins) are exercised
+    x = _cl(torch.relu(torch.randn(shape, device="cuda", generator=g)).bfloat16()).requires_grad_(True)
+    y = norm.max_pool3s2(x)
+    xr = x.detach().clone().requires_grad_(True)
+    yr = F.max_pool2d(xr, 3, 2, 1)
+    assert torch.equal(y, yr)
+    gy = _cl(torch.randn(yr.shape, device="cuda", generator=g).bfloat16())
+    y.backward(gy)
+    yr.backward(gy)
+    _close(x.grad, xr.grad, 1e-2)          # sums of up to four bf16 gradients: rounding order only
+
+
+@pytest.mark.parametrize("shape", [(4, 2048, 16, 16), (2, 256, 8, 8), (3, 512, 7, 9)], ids=str)
+def test_instance_norm_matches_torch(shape):
+    from regda_b200.ops import norm
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = _cl((torch.randn(shape, device="cuda", generator=g) * 1.5 + 0.5).bfloat16()).requires_grad_(True)
+    assert norm.instance_norm_supported(x)
+    y = norm.instance_norm(x, 1e-5)
+    xr = x.detach().float().requires_grad_(True)
+    yr = F.instance_norm(xr, eps=1e-5)
+    _close(y, yr, 1e-2)
+    gy = _cl(torch.randn(shape, device="cuda", generator=g).bfloat16())
+    y.backward(gy)
+    yr.backward(gy.float())
+    _close(x.grad, xr.grad, 1.5e-2)
