@@ -16,6 +16,9 @@
 // CTA = (128-cout tile, BLOCK_N-cin tile, tap, K split); fp32 accumulators in TMEM; the epilogue adds the tile
 // into the fp32 OHWI gradient with 16-byte global reductions (split-K partials and the two forward passes of a
 // training step accumulate in place).  Warp 0 = TMA, warp 1 = MMA issuer, warps 2-5 = epilogue.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -159,6 +162,178 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM loops over the work items (cout tile, cin tile, tap, K split), ordered so that
+// CTAs running side by side work on the SAME pixel range and tap (the dY / X patches are shared through L2); two
+// accumulators in tensor memory let the fp32 reduction of item i into the gradient overlap the MMAs of item i+1;
+// BLOCK_N = 256 cin per tile halves the L2->SM bytes per flop of the 128 x 128 tile.
+// ---------------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int STAGES>
+struct WgPersistSmem {
+    static constexpr int kABytes = kWgM * kWgK * 2;
+    static constexpr int kBBytes = BLOCK_N * kWgK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 8;
+};
+
+struct WgItem { int m_blk, n_blk, tap, k_lo, k_hi; };
+
+__device__ __forceinline__ WgItem wg_decode(int item, const WgradGeom &g, int m_tiles) {
+    WgItem it;
+    it.n_blk = item % g.n_tiles; item /= g.n_tiles;
+    it.m_blk = item % m_tiles; item /= m_tiles;
+    const int taps = g.r * g.s;
+    it.tap = item % taps;
+    const int split = item / taps;
+    it.k_lo = split * g.steps_per_split;
+    it.k_hi = min(g.ksteps, it.k_lo + g.steps_per_split);
+    return it;
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                             float *__restrict__ dw, const WgradGeom g, const int m_tiles, const int num_items) {
+    using L = WgPersistSmem<BLOCK_N, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::kBarOffset);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tfull_bar = empty_bar + STAGES;
+    uint64_t *tempty_bar = tfull_bar + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_dy);
+        prefetch_tmap(&tmap_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 4); }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int per_img = g.tiles_h * g.tiles_w;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const WgItem it = wg_decode(item, g, m_tiles);
+                const int fr = it.tap / g.s, fs = it.tap - fr * g.s;
+                for (int kb = it.k_lo; kb < it.k_hi; ++kb) {
+                    const int img = kb / per_img;
+                    const int t = kb - img * per_img;
+                    const int th = t / g.tiles_w, tw = t - th * g.tiles_w;
+                    const int oh0 = th * g.bh, ow0 = tw * g.bw;
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    uint8_t *sa = smem + stage * L::kStageBytes;
+                    uint8_t *sb = sa + L::kABytes;
+                    mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes);
+#pragma unroll
+                    for (int i = 0; i < kWgM / 64; ++i)
+                        tma_load_4d(sa + i * 8192, &tmap_dy, full_bar + stage, it.m_blk * kWgM + i * 64, ow0, oh0, img);
+                    const int ix = ow0 * g.stride + fs * g.dil - g.pad, iy = oh0 * g.stride + fr * g.dil - g.pad;
+#pragma unroll
+                    for (int i = 0; i < BLOCK_N / 64; ++i)
+                        tma_load_4d(sb + i * 8192, &tmap_x, full_bar + stage, it.n_blk * BLOCK_N + i * 64, ix, iy, img);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(kWgM, BLOCK_N, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const WgItem it = wg_decode(item, g, m_tiles);
+                const int num_k = it.k_hi - it.k_lo;
+                mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+                tc_fence_after_sync();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(full_bar + stage, phase);
+                    tc_fence_after_sync();
+                    const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+                    const uint32_t sb = sa + L::kABytes;
+                    const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
+                    const uint64_t bdesc = make_smem_desc(sb, 8192, 1024);
+#pragma unroll
+                    for (int k = 0; k < kWgK / 16; ++k)
+                        umma_bf16(tmem_d, adesc + static_cast<uint64_t>(128 * k), bdesc + static_cast<uint64_t>(128 * k), idesc,
+                                  (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(empty_bar + stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar + acc);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            const WgItem it = wg_decode(item, g, m_tiles);
+            const int co = it.m_blk * kWgM + q * 32 + lane;
+            const int ci0 = it.n_blk * BLOCK_N;
+            float *dst = dw + (static_cast<size_t>(co) * (g.r * g.s) + it.tap) * g.cin + ci0;
+            mbar_wait(tfull_bar + acc, acc_phase);
+            tc_fence_after_sync();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+                tmem_ld_wait();
+                if (co < g.cout && it.k_hi > it.k_lo) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        red_add_f32x4(dst + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                      __uint_as_float(v[j + 3]));
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar + acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 2 * BLOCK_N);
+    }
+}
+
+template <int BLOCK_N, int STAGES>
+int launch_wgrad_persistent(const CUtensorMap &tdy, const CUtensorMap &tx, float *dw, const WgradGeom &g, cudaStream_t st) {
+    using L = WgPersistSmem<BLOCK_N, STAGES>;
+    auto kern = conv_wgrad_persistent_kernel<BLOCK_N, STAGES>;
+    const int smem = L::kTotal + 1024;
+    REGDA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int m_tiles = (g.cout + kWgM - 1) / kWgM;
+    const int num_items = g.n_tiles * m_tiles * g.r * g.s * g.splits;
+    const int grid = std::min(num_items, sm_count());
+    kern<<<grid, kWgThreads, smem, st>>>(tdy, tx, dw, g, m_tiles, num_items);
+    REGDA_LAUNCH_CHECK();
+    return REGDA_OK;
+}
+
 template <int BLOCK_N, int STAGES>
 int launch_wgrad(const CUtensorMap &tdy, const CUtensorMap &tx, float *dw, const WgradGeom &g, cudaStream_t st) {
     using L = WgSmem<BLOCK_N, STAGES>;
@@ -203,11 +378,13 @@ extern "C" int regda_conv_wgrad_bf16(const void *dy, const void *x, float *dw, i
     g.tiles_w = (g.ow + g.bw - 1) / g.bw;
     g.tiles_h = (g.oh + g.bh - 1) / g.bh;
     g.ksteps = n * g.tiles_h * g.tiles_w;
-    const int block_n = cin % 128 == 0 ? 128 : 64;
+    const char *kenv = getenv("REGDA_CONV_KERNEL");
+    const bool persistent = !(kenv && strcmp(kenv, "classic") == 0);
+    const int block_n = (persistent && cin % 256 == 0) ? 256 : (cin % 128 == 0 ? 128 : 64);
     g.n_tiles = cin / block_n;
     const int tiles = g.n_tiles * ((cout + kWgM - 1) / kWgM) * r * s;
-    // split K so that about two waves of CTAs exist, but keep >= 8 K-steps per CTA
-    int splits = (4 * sm_count() + tiles - 1) / tiles;
+    // split K so that every SM gets work (persistent: ~2 items per SM; classic: ~4 CTAs per SM), >= 8 K-steps per item
+    int splits = ((persistent ? 2 : 4) * sm_count() + tiles - 1) / tiles;
     splits = std::max(1, std::min(splits, g.ksteps / 8));
     g.steps_per_split = (g.ksteps + splits - 1) / splits;
     g.splits = (g.ksteps + g.steps_per_split - 1) / g.steps_per_split;
@@ -216,6 +393,11 @@ extern "C" int regda_conv_wgrad_bf16(const void *dy, const void *x, float *dw, i
     if (!encode_nhwc(&tdy, dy, n, g.oh, g.ow, cout, g.bw, g.bh, 1)) return REGDA_ERR_CUDA;   /* text set by encode_bf16_sw128 (dy) */
     if (!encode_nhwc(&tx, x, n, h, w, cin, g.bw, g.bh, stride)) return REGDA_ERR_CUDA;   /* text set by encode_bf16_sw128 (x) */
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (persistent) {
+        if (block_n == 256) return launch_wgrad_persistent<256, 4>(tdy, tx, dw, g, st);
+        if (block_n == 128) return launch_wgrad_persistent<128, 6>(tdy, tx, dw, g, st);
+        return launch_wgrad_persistent<64, 8>(tdy, tx, dw, g, st);
+    }
     if (block_n == 128) return launch_wgrad<128, 3>(tdy, tx, dw, g, st);
     return launch_wgrad<64, 4>(tdy, tx, dw, g, st);
 }
