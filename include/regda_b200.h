@@ -179,9 +179,10 @@ int regda_conv_fprop_supported(int n, int h, int w, int cin, int cout, int r, in
 int regda_conv_fprop_bf16(const void *x, const void *wgt, void *y, int n, int h, int w, int cin, int cout,
                           int r, int s, int stride, int pad, int dil, void *stream);
 /* same, and the epilogue also accumulates the train-mode BatchNorm statistics of y: bn_stats float32
- * [groups][2][cout] (per-group per-channel sum and sum of squares of the bf16 outputs; zeroed inside). */
+ * [groups][2][cout] (per-group per-channel sum and sum of squares of the bf16 outputs; zeroed inside unless
+ * stats_zeroed != 0, i.e. the caller hands out slices of a pool it zeroes once per step). */
 int regda_conv_fprop_stats_bf16(const void *x, const void *wgt, void *y, int n, int h, int w, int cin, int cout,
-                                int r, int s, int stride, int pad, int dil, float *bn_stats, int groups, void *stream);
+                                int r, int s, int stride, int pad, int dil, float *bn_stats, int groups, int stats_zeroed, void *stream);
 
 /* Data gradient of a stride-1 convolution, reading the forward OHWI weights in place (MN-major B operand):
  *   dy bf16 [n][oh][ow][cout], wgt bf16 [cout][r][s][cin] -> dx bf16 [n][h][w][cin]   (h, w, cin, cout, ... are the
@@ -204,21 +205,21 @@ int regda_conv_wgrad_bf16(const void *dy, const void *x, float *dw, int n, int h
  * `groups` > 1 = that many independent statistics groups over equal contiguous pixel ranges: the source and target
  * batches of one training step run through every layer as ONE tensor while BatchNorm keeps the reference's
  * per-forward-call (per-domain) batch statistics; running statistics are updated once per group, in order.
- * coef float32 [groups][4c] is written (scale, shift, mean, rstd) and must be kept for the backward call.
- * ready_stats (may be NULL): float32 [groups][2][c] sums / sums of squares already produced by the epilogue of
- * regda_conv_fprop_stats_bf16 -- the statistics pass over y is skipped.
+ * No separate "finalize" launches: the apply kernels derive mean / rstd / scale / shift of their channels from the sums.
  * Backward: dout, out (needed when relu), y -> dy (and dres = masked dout when dres != NULL);
  * dgamma / dbeta float32 [c] are ACCUMULATED (+=). */
 int regda_bn_supported(int64_t npix, int c);
-size_t regda_bn_workspace_bytes(int c, int groups);
+/* stats float32 [groups][2][c]: per-group per-channel sum and sum of squares of y.  have_stats != 0: already produced by
+ * regda_conv_fprop_stats_bf16 (the statistics pass over y is skipped); otherwise computed here into `stats` (zeroed first
+ * unless stats_zeroed != 0).  Keep `stats` for the backward call. */
 int regda_bn_forward_bf16(const void *y, const void *residual, void *out, int64_t npix, int c, int groups,
                           const float *gamma, const float *beta, float *running_mean, float *running_var,
                           int64_t *num_batches_tracked, double eps, double momentum, int relu,
-                          float *coef, const float *ready_stats, void *workspace, size_t workspace_bytes, void *stream);
-size_t regda_bn_backward_workspace_bytes(int c, int groups);
+                          float *stats, int have_stats, int stats_zeroed, void *stream);
+/* red float32 [groups][2][c]: scratch for the two backward reductions (zeroed here unless red_zeroed != 0). */
 int regda_bn_backward_bf16(const void *dout, const void *out, const void *y, void *dy, void *dres, int64_t npix, int c,
-                           int groups, const float *gamma, const float *coef, float *dgamma, float *dbeta, int relu,
-                           void *workspace, size_t workspace_bytes, void *stream);
+                           int groups, const float *gamma, const float *stats, double eps, float *dgamma, float *dbeta,
+                           int relu, float *red, int red_zeroed, void *stream);
 
 /* MaxPool2d(3, stride 2, padding 1) over channels-last bf16 (regda/_resnets.py:153): x [n][h][w][c] -> y [n][oh][ow][c],
  * oh = (h-1)/2+1.  Backward recomputes the arg-max (first maximum in window order, as ATen) from x and y. */

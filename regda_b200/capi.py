@@ -128,3 +128,44 @@ class Workspace:
 
 
 workspace = Workspace()
+
+
+class ZeroPool:
+    """Pre-zeroed float32 scratch for the many small accumulators of a step (BatchNorm sums, backward reductions):
+    the trainer zeroes ONE buffer per step (`reset()`, a single memset node in the captured graph) and the ops take
+    consecutive slices instead of issuing one tiny memset each.  Outside an armed step `take` returns (tensor, False)
+    and the callee zeroes it itself."""
+
+    def __init__(self, nfloats=8 << 20):
+        self.nfloats = nfloats
+        self._buf = {}
+        self._off = 0
+        self._armed = False
+
+    def reset(self, device):
+        key = torch.device(device).index or 0
+        b = self._buf.get(key)
+        if b is None:
+            b = self._buf[key] = torch.empty(self.nfloats, dtype=torch.float32, device=device)
+        b.zero_()
+        self._off = 0
+        self._armed = True
+
+    def disarm(self):
+        self._armed = False
+
+    def take(self, shape, device):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        key = torch.device(device).index or 0
+        b = self._buf.get(key)
+        n4 = (n + 3) // 4 * 4
+        if self._armed and b is not None and self._off + n4 <= self.nfloats:
+            t = b[self._off:self._off + n].view(shape)
+            self._off += n4
+            return t, True
+        return torch.empty(shape, dtype=torch.float32, device=device), False
+
+
+zero_pool = ZeroPool()

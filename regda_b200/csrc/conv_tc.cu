@@ -519,7 +519,8 @@ extern "C" int regda_conv_fprop_bf16(const void *x, const void *wgt, void *y, in
 // bn_stats float32 [groups][2][cout] = per-group per-channel (sum, sum of squares) over the group's n/groups images,
 // written (zeroed here first).  Feed it to regda_bn_forward_bf16(..., have_stats = 1).
 extern "C" int regda_conv_fprop_stats_bf16(const void *x, const void *wgt, void *y, int n, int h, int w, int cin, int cout,
-                                           int r, int s, int stride, int pad, int dil, float *bn_stats, int groups, void *stream) {
+                                           int r, int s, int stride, int pad, int dil, float *bn_stats, int groups, int stats_zeroed,
+                                           void *stream) {
     if (!regda_conv_fprop_supported(n, h, w, cin, cout, r, s, stride, pad, dil))
         return fail(REGDA_ERR_UNSUPPORTED, "conv_fprop: shape not covered by the tcgen05 kernel");
     if (!x || !wgt || !y || !bn_stats) return fail(REGDA_ERR_INVALID_ARG, "conv_fprop_stats: null pointer");
@@ -531,7 +532,7 @@ extern "C" int regda_conv_fprop_stats_bf16(const void *x, const void *wgt, void 
     geom_init(g, n, h, w, cin, cout, r, s, stride, pad, dil);
     ensure_context(x);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    REGDA_CUDA_CHECK(cudaMemsetAsync(bn_stats, 0, static_cast<size_t>(groups) * 2 * cout * sizeof(float), st));
+    if (!stats_zeroed) REGDA_CUDA_CHECK(cudaMemsetAsync(bn_stats, 0, static_cast<size_t>(groups) * 2 * cout * sizeof(float), st));
     return launch_conv<false>(x, wgt, static_cast<__nv_bfloat16 *>(y), g, r * s, st, bn_stats, n / groups);
 }
 

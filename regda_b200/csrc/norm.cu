@@ -8,11 +8,10 @@
 // 2048/C whole pixels per step and the thread -> channel map never changes), which keeps the
 // per-channel coefficients / partial sums in registers.  Statistics are fp32.
 //
-//   forward : bn_stats (sum, sum of squares)  -> bn_finalize (mean, rstd, scale, shift, running stats)
-//             -> bn_apply  out = relu(y*scale + shift + residual)
+//   forward : [bn_stats (sum, sum of squares) unless the producing convolution's epilogue already made them]
+//             -> bn_apply  out = relu(y*scale + shift + residual)   (constants derived in-kernel, running stats by block 0)
 //   backward: bn_bwd_reduce (sum dz, sum dz*y with dz = dout masked by out > 0)
-//             -> bn_bwd_finalize (dgamma, dbeta accumulated into the gradient arena; coefficients)
-//             -> bn_bwd_apply  dy = g*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)),  dres = dz
+//             -> bn_bwd_apply  dy = g*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)),  dres = dz,  dgamma/dbeta by block 0
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -94,45 +93,46 @@ bn_stats_kernel(const __nv_bfloat16 *__restrict__ y, long long total, int c, lon
     block_channel_reduce(s, q, c, gsum, gsq);
 }
 
-// per group g: stats[2c*g + 0..c) = sum, [.. c..2c) = sum of squares; coef[4c*g + ...]: [0..c) scale, [c..2c) shift,
-// [2c..3c) mean, [3c..4c) rstd.  Running statistics are updated once per group, in group order (= the reference's
-// sequence of forward calls: source batch, then target batch).
-__global__ void __launch_bounds__(256)
-bn_finalize_kernel(const float *__restrict__ stats, int c, int groups, float inv_n, float unbias, const float *__restrict__ gamma,
-                   const float *__restrict__ beta, float *__restrict__ running_mean, float *__restrict__ running_var,
-                   long long *__restrict__ num_batches, float eps, float momentum, float *__restrict__ coef) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch == 0 && num_batches != nullptr) *num_batches += groups;
-    if (ch >= c) return;
-    const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
-    float rm = running_mean ? running_mean[ch] : 0.f, rv = running_var ? running_var[ch] : 0.f;
-    for (int grp = 0; grp < groups; ++grp) {
-        const float *st = stats + 2 * c * grp;
-        float *cf = coef + 4 * c * grp;
-        const float mean = st[ch] * inv_n;
-        const float var = fmaxf(fmaf(-mean, mean, st[c + ch] * inv_n), 0.f);
-        const float rstd = rsqrtf(var + eps);
-        const float scale = g * rstd;
-        cf[ch] = scale;
-        cf[c + ch] = fmaf(-mean, scale, b);
-        cf[2 * c + ch] = mean;
-        cf[3 * c + ch] = rstd;
-        rm = fmaf(momentum, mean - rm, rm);
-        rv = fmaf(momentum, var * unbias - rv, rv);
-    }
-    if (running_mean) running_mean[ch] = rm;
-    if (running_var) running_var[ch] = rv;
+// per-channel normalisation constants from the group's sums: mean, rstd (biased variance, as torch normalises)
+__device__ __forceinline__ void bn_moments(const float *__restrict__ st, int c, int ch, float inv_n, float eps, float &mean, float &rstd,
+                                           float &var) {
+    mean = st[ch] * inv_n;
+    var = fmaxf(fmaf(-mean, mean, st[c + ch] * inv_n), 0.f);
+    rstd = rsqrtf(var + eps);
 }
 
+// out = relu?(gamma*(y-mean)*rstd + beta + res).  stats [groups][2][c] are the per-group sums / sums of squares (from the
+// producing convolution's epilogue or from bn_stats_kernel); every thread derives the constants of its 8 channels itself
+// (no separate "finalize" launch), and block (0,0) updates the running statistics once per group, in group order
+// (= the reference's sequence of forward calls: source batch, then target batch).
 template <bool RELU, bool RES>
 __global__ void __launch_bounds__(kBnThreads)
 bn_apply_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__restrict__ res, __nv_bfloat16 *__restrict__ out,
-                long long total, int c, const float *__restrict__ coef) {
+                long long total, int c, const float *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta,
+                float inv_n, float unbias, float eps, float momentum, float *__restrict__ running_mean, float *__restrict__ running_var,
+                long long *__restrict__ num_batches) {
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        const int groups = gridDim.y;
+        if (threadIdx.x == 0 && num_batches != nullptr) *num_batches += groups;
+        if (running_mean != nullptr && running_var != nullptr) {
+            for (int ch = threadIdx.x; ch < c; ch += kBnThreads) {
+                float rm = running_mean[ch], rv = running_var[ch];
+                for (int grp = 0; grp < groups; ++grp) {
+                    float mean, rstd, var;
+                    bn_moments(stats + 2 * c * grp, c, ch, inv_n, eps, mean, rstd, var);
+                    rm = fmaf(momentum, mean - rm, rm);
+                    rv = fmaf(momentum, var * unbias - rv, rv);
+                }
+                running_mean[ch] = rm;
+                running_var[ch] = rv;
+            }
+        }
+    }
     {   // blockIdx.y = statistics group
         const long long off = static_cast<long long>(blockIdx.y) * total;
         y += off; out += off;
         if (RES) res += off;
-        coef += 4 * c * blockIdx.y;
+        stats += 2 * c * blockIdx.y;
     }
     const long long stride = static_cast<long long>(gridDim.x) * kBnSpan;
     long long e = static_cast<long long>(blockIdx.x) * kBnSpan + static_cast<long long>(threadIdx.x) * 8;
@@ -140,7 +140,13 @@ bn_apply_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__rest
     const int ch = static_cast<int>(e % c);   // invariant: stride % c == 0
     float sc[8], sh[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { sc[i] = coef[ch + i]; sh[i] = coef[c + ch + i]; }
+    for (int i = 0; i < 8; ++i) {
+        float mean, rstd, var;
+        bn_moments(stats, c, ch + i, inv_n, eps, mean, rstd, var);
+        const float g = gamma ? gamma[ch + i] : 1.f, b = beta ? beta[ch + i] : 0.f;
+        sc[i] = g * rstd;
+        sh[i] = fmaf(-mean, sc[i], b);
+    }
     for (; e < total; e += stride) {
         float f[8];
         unpack(ld8_stream(y + e), f);
@@ -196,43 +202,35 @@ bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16
     block_channel_reduce(s, q, c, gdz, gdzy);
 }
 
-// per group g: red[2c*g + 0..c) = sum dz, [.. c..2c) = sum dz*y.  bcoef[3c*g + ...]: [0..c) a = gamma*rstd, [c..2c) k1 = mean(dz),
-// [2c..3c) k2 = mean(dz*xhat)*rstd, so that dy = a * (dz - k1 - (y - mean) * k2).  dgamma / dbeta accumulate over the groups.
-__global__ void __launch_bounds__(256)
-bn_bwd_finalize_kernel(const float *__restrict__ red, int c, int groups, float inv_n, const float *__restrict__ gamma,
-                       const float *__restrict__ coef, float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ bcoef) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= c) return;
-    const float g = gamma ? gamma[ch] : 1.f;
-    float dg = 0.f, db = 0.f;
-    for (int grp = 0; grp < groups; ++grp) {
-        const float *cf = coef + 4 * c * grp;
-        const float *rd = red + 2 * c * grp;
-        float *bc = bcoef + 3 * c * grp;
-        const float mean = cf[2 * c + ch], rstd = cf[3 * c + ch];
-        const float sdz = rd[ch];
-        const float sdzx = (rd[c + ch] - mean * sdz) * rstd;          // sum dz * xhat
-        dg += sdzx;
-        db += sdz;
-        bc[ch] = g * rstd;
-        bc[c + ch] = sdz * inv_n;
-        bc[2 * c + ch] = sdzx * inv_n * rstd;
-    }
-    if (dgamma) dgamma[ch] += dg;
-    if (dbeta) dbeta[ch] += db;
-}
-
+// dy = a * (dz - k1 - (y - mean) * k2) with a = gamma*rstd, k1 = mean(dz), k2 = mean(dz*xhat)*rstd, all derived per thread from
+// red [groups][2][c] (sum dz, sum dz*y) and the forward stats; dres = dz.  Block (0,0) accumulates dgamma / dbeta over the groups.
 template <bool RELU, bool DRES>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 *__restrict__ out, const __nv_bfloat16 *__restrict__ y,
                     __nv_bfloat16 *__restrict__ dy, __nv_bfloat16 *__restrict__ dres, long long total, int c,
-                    const float *__restrict__ coef, const float *__restrict__ bcoef) {
+                    const float *__restrict__ stats, const float *__restrict__ red, const float *__restrict__ gamma, float inv_n, float eps,
+                    float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (dgamma != nullptr || dbeta != nullptr)) {
+        const int groups = gridDim.y;
+        for (int ch = threadIdx.x; ch < c; ch += kBnThreads) {
+            float dg = 0.f, db = 0.f;
+            for (int grp = 0; grp < groups; ++grp) {
+                float mean, rstd, var;
+                bn_moments(stats + 2 * c * grp, c, ch, inv_n, eps, mean, rstd, var);
+                const float sdz = red[2 * c * grp + ch];
+                dg += (red[2 * c * grp + c + ch] - mean * sdz) * rstd;
+                db += sdz;
+            }
+            if (dgamma) dgamma[ch] += dg;
+            if (dbeta) dbeta[ch] += db;
+        }
+    }
     {
         const long long off = static_cast<long long>(blockIdx.y) * total;
         dout += off; y += off; dy += off;
         if (RELU) out += off;
         if (DRES) dres += off;
-        coef += 4 * c * blockIdx.y; bcoef += 3 * c * blockIdx.y;
+        stats += 2 * c * blockIdx.y; red += 2 * c * blockIdx.y;
     }
     const long long stride = static_cast<long long>(gridDim.x) * kBnSpan;
     long long e = static_cast<long long>(blockIdx.x) * kBnSpan + static_cast<long long>(threadIdx.x) * 8;
@@ -241,7 +239,13 @@ bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 
     float a[8], k1[8], k2[8], mu[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        a[i] = bcoef[ch + i]; k1[i] = bcoef[c + ch + i]; k2[i] = bcoef[2 * c + ch + i]; mu[i] = coef[2 * c + ch + i];
+        float rstd, var;
+        bn_moments(stats, c, ch + i, inv_n, eps, mu[i], rstd, var);
+        const float sdz = red[ch + i];
+        const float sdzx = (red[c + ch + i] - mu[i] * sdz) * rstd;        // sum dz * xhat
+        a[i] = (gamma ? gamma[ch + i] : 1.f) * rstd;
+        k1[i] = sdz * inv_n;
+        k2[i] = sdzx * inv_n * rstd;
     }
     for (; e < total; e += stride) {
         float d[8], v[8];
@@ -284,67 +288,49 @@ using namespace regda;
 
 extern "C" int regda_bn_supported(int64_t npix, int c) { return bn_shape_ok(npix, c) ? 1 : 0; }
 
-// workspace (floats): stats [groups][2c]
-extern "C" size_t regda_bn_workspace_bytes(int c, int groups) { return static_cast<size_t>(2 * c) * std::max(groups, 1) * sizeof(float); }
-
 extern "C" int regda_bn_forward_bf16(const void *y, const void *residual, void *out, int64_t npix, int c, int groups,
                                      const float *gamma, const float *beta, float *running_mean, float *running_var,
                                      int64_t *num_batches_tracked, double eps, double momentum, int relu,
-                                     float *coef, const float *ready_stats, void *workspace, size_t workspace_bytes, void *stream) {
+                                     float *stats, int have_stats, int stats_zeroed, void *stream) {
     if (!bn_shape_ok(npix, c)) return fail(REGDA_ERR_UNSUPPORTED, "bn_forward: channels must divide 2048 and be a multiple of 8");
     if (groups < 1 || npix % groups != 0) return fail(REGDA_ERR_INVALID_ARG, "bn_forward: groups must divide the pixel count");
-    if (!y || !out || !coef) return fail(REGDA_ERR_INVALID_ARG, "bn_forward: null pointer");
-    if (!ready_stats && (!workspace || workspace_bytes < regda_bn_workspace_bytes(c, groups)))
-        return fail(REGDA_ERR_WORKSPACE, "bn_forward: workspace too small");
+    if (!y || !out || !stats) return fail(REGDA_ERR_INVALID_ARG, "bn_forward: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long gpix = npix / groups;
     const long long total = gpix * c;                                   // elements per statistics group
     const __nv_bfloat16 *yy = static_cast<const __nv_bfloat16 *>(y);
-    const float *stats = ready_stats;                                    // [groups][2][c] from the producing convolution's epilogue
-    if (stats == nullptr) {
-        float *ws = static_cast<float *>(workspace);
-        REGDA_CUDA_CHECK(cudaMemsetAsync(ws, 0, static_cast<size_t>(2 * c) * groups * sizeof(float), st));
+    if (!have_stats) {
+        if (!stats_zeroed) REGDA_CUDA_CHECK(cudaMemsetAsync(stats, 0, static_cast<size_t>(2 * c) * groups * sizeof(float), st));
         long long span = 0;
         const int rg = reduce_grid(total, groups, &span);
-        bn_stats_kernel<<<dim3(rg, groups), kBnThreads, 0, st>>>(yy, total, c, span, ws, ws + c);
+        bn_stats_kernel<<<dim3(rg, groups), kBnThreads, 0, st>>>(yy, total, c, span, stats, stats + c);
         REGDA_LAUNCH_CHECK();
-        stats = ws;
     }
     const float n = static_cast<float>(gpix);
-    bn_finalize_kernel<<<(c + 255) / 256, 256, 0, st>>>(stats, c, groups, 1.f / n, gpix > 1 ? n / (n - 1.f) : 1.f, gamma, beta, running_mean,
-                                                         running_var, reinterpret_cast<long long *>(num_batches_tracked),
-                                                         static_cast<float>(eps), static_cast<float>(momentum), coef);
-    REGDA_LAUNCH_CHECK();
+    const float inv_n = 1.f / n, unbias = gpix > 1 ? n / (n - 1.f) : 1.f, e = static_cast<float>(eps), mom = static_cast<float>(momentum);
+    long long *nbt = reinterpret_cast<long long *>(num_batches_tracked);
     const dim3 ag(apply_grid(total, groups), groups);
     const __nv_bfloat16 *rr = static_cast<const __nv_bfloat16 *>(residual);
     __nv_bfloat16 *oo = static_cast<__nv_bfloat16 *>(out);
-    if (relu) {
-        if (rr) bn_apply_kernel<true, true><<<ag, kBnThreads, 0, st>>>(yy, rr, oo, total, c, coef);
-        else bn_apply_kernel<true, false><<<ag, kBnThreads, 0, st>>>(yy, rr, oo, total, c, coef);
-    } else {
-        if (rr) bn_apply_kernel<false, true><<<ag, kBnThreads, 0, st>>>(yy, rr, oo, total, c, coef);
-        else bn_apply_kernel<false, false><<<ag, kBnThreads, 0, st>>>(yy, rr, oo, total, c, coef);
-    }
+#define REGDA_BN_APPLY(R, S) bn_apply_kernel<R, S><<<ag, kBnThreads, 0, st>>>(yy, rr, oo, total, c, stats, gamma, beta, inv_n, unbias, e, mom, \
+                                                                             running_mean, running_var, nbt)
+    if (relu) { if (rr) REGDA_BN_APPLY(true, true); else REGDA_BN_APPLY(true, false); }
+    else { if (rr) REGDA_BN_APPLY(false, true); else REGDA_BN_APPLY(false, false); }
+#undef REGDA_BN_APPLY
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
 }
 
-// workspace (floats): red [groups][2c] + bcoef [groups][3c]
-extern "C" size_t regda_bn_backward_workspace_bytes(int c, int groups) { return static_cast<size_t>(5 * c) * std::max(groups, 1) * sizeof(float); }
-
 extern "C" int regda_bn_backward_bf16(const void *dout, const void *out, const void *y, void *dy, void *dres, int64_t npix, int c,
-                                      int groups, const float *gamma, const float *coef, float *dgamma, float *dbeta, int relu,
-                                      void *workspace, size_t workspace_bytes, void *stream) {
+                                      int groups, const float *gamma, const float *stats, double eps, float *dgamma, float *dbeta,
+                                      int relu, float *red, int red_zeroed, void *stream) {
     if (!bn_shape_ok(npix, c)) return fail(REGDA_ERR_UNSUPPORTED, "bn_backward: channels must divide 2048 and be a multiple of 8");
     if (groups < 1 || npix % groups != 0) return fail(REGDA_ERR_INVALID_ARG, "bn_backward: groups must divide the pixel count");
-    if (!dout || !y || !dy || !coef || (relu && !out)) return fail(REGDA_ERR_INVALID_ARG, "bn_backward: null pointer");
-    if (!workspace || workspace_bytes < regda_bn_backward_workspace_bytes(c, groups)) return fail(REGDA_ERR_WORKSPACE, "bn_backward: workspace too small");
+    if (!dout || !y || !dy || !stats || !red || (relu && !out)) return fail(REGDA_ERR_INVALID_ARG, "bn_backward: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    float *red = static_cast<float *>(workspace);
-    float *bcoef = red + 2 * c * groups;
     const long long gpix = npix / groups;
     const long long total = gpix * c;
-    REGDA_CUDA_CHECK(cudaMemsetAsync(red, 0, static_cast<size_t>(2 * c) * groups * sizeof(float), st));
+    if (!red_zeroed) REGDA_CUDA_CHECK(cudaMemsetAsync(red, 0, static_cast<size_t>(2 * c) * groups * sizeof(float), st));
     long long span = 0;
     const int rg = reduce_grid(total, groups, &span);
     const __nv_bfloat16 *dd = static_cast<const __nv_bfloat16 *>(dout);
@@ -353,18 +339,14 @@ extern "C" int regda_bn_backward_bf16(const void *dout, const void *out, const v
     if (relu) bn_bwd_reduce_kernel<true><<<dim3(rg, groups), kBnThreads, 0, st>>>(dd, oo, yy, total, c, span, red, red + c);
     else bn_bwd_reduce_kernel<false><<<dim3(rg, groups), kBnThreads, 0, st>>>(dd, oo, yy, total, c, span, red, red + c);
     REGDA_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<(c + 255) / 256, 256, 0, st>>>(red, c, groups, 1.f / static_cast<float>(gpix), gamma, coef, dgamma, dbeta, bcoef);
-    REGDA_LAUNCH_CHECK();
+    const float inv_n = 1.f / static_cast<float>(gpix), e = static_cast<float>(eps);
     const dim3 ag(apply_grid(total, groups), groups);
     __nv_bfloat16 *dyy = static_cast<__nv_bfloat16 *>(dy);
     __nv_bfloat16 *dr = static_cast<__nv_bfloat16 *>(dres);
-    if (relu) {
-        if (dr) bn_bwd_apply_kernel<true, true><<<ag, kBnThreads, 0, st>>>(dd, oo, yy, dyy, dr, total, c, coef, bcoef);
-        else bn_bwd_apply_kernel<true, false><<<ag, kBnThreads, 0, st>>>(dd, oo, yy, dyy, dr, total, c, coef, bcoef);
-    } else {
-        if (dr) bn_bwd_apply_kernel<false, true><<<ag, kBnThreads, 0, st>>>(dd, oo, yy, dyy, dr, total, c, coef, bcoef);
-        else bn_bwd_apply_kernel<false, false><<<ag, kBnThreads, 0, st>>>(dd, oo, yy, dyy, dr, total, c, coef, bcoef);
-    }
+#define REGDA_BN_BWD(R, D) bn_bwd_apply_kernel<R, D><<<ag, kBnThreads, 0, st>>>(dd, oo, yy, dyy, dr, total, c, stats, red, gamma, inv_n, e, dgamma, dbeta)
+    if (relu) { if (dr) REGDA_BN_BWD(true, true); else REGDA_BN_BWD(true, false); }
+    else { if (dr) REGDA_BN_BWD(false, true); else REGDA_BN_BWD(false, false); }
+#undef REGDA_BN_BWD
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
 }

@@ -47,22 +47,23 @@ class _BnActFn(torch.autograd.Function):
         res = _cl(residual) if residual is not None else None
         out = torch.empty_like(y)
         assert n % groups == 0, "statistics groups must divide the batch"
-        coef = torch.empty(groups * 4 * c, dtype=torch.float32, device=y.device)
-        L = capi.lib()
-        ws = capi.workspace.get(L.regda_bn_workspace_bytes(c, groups), y.device)
         if ready_stats is not None:
             assert ready_stats.shape == (groups, 2, c) and ready_stats.dtype == torch.float32
+            stats, have, zeroed = ready_stats, 1, True
+        else:
+            stats, zeroed = capi.zero_pool.take((groups, 2, c), y.device)
+            have = 0
         capi.call("regda_bn_forward_bf16", capi.ptr_any(y), capi.ptr_any(res) if res is not None else None, capi.ptr_any(out), npix, c,
                   groups, capi.ptr(gamma), capi.ptr(beta), capi.ptr(bn.running_mean), capi.ptr(bn.running_var),
                   capi.ptr(bn.num_batches_tracked), float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1), int(relu),
-                  capi.ptr(coef), capi.ptr(ready_stats) if ready_stats is not None else None, capi.ptr(ws), ws.numel(), capi.stream())
-        ctx.save_for_backward(y, out if relu else None, coef)
-        ctx.gamma, ctx.beta, ctx.relu, ctx.has_res, ctx.groups = gamma, beta, relu, residual is not None, groups
+                  capi.ptr_any(stats), have, int(zeroed), capi.stream())
+        ctx.save_for_backward(y, out if relu else None, stats)
+        ctx.gamma, ctx.beta, ctx.relu, ctx.has_res, ctx.groups, ctx.eps = gamma, beta, relu, residual is not None, groups, float(bn.eps)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        y, out, coef = ctx.saved_tensors
+        y, out, stats = ctx.saved_tensors
         n, c, h, w = y.shape
         dout = _cl(dout)
         dy = torch.empty_like(y)
@@ -70,12 +71,11 @@ class _BnActFn(torch.autograd.Function):
         gamma, beta = ctx.gamma, ctx.beta
         dgamma = _grad_buffer(gamma) if gamma.requires_grad else None
         dbeta = _grad_buffer(beta) if beta.requires_grad else None
-        L = capi.lib()
-        ws = capi.workspace.get(L.regda_bn_backward_workspace_bytes(c, ctx.groups), y.device)
+        red, zeroed = capi.zero_pool.take((ctx.groups, 2, c), y.device)
         capi.call("regda_bn_backward_bf16", capi.ptr_any(dout), capi.ptr_any(out) if out is not None else None, capi.ptr_any(y),
-                  capi.ptr_any(dy), capi.ptr_any(dres) if dres is not None else None, n * h * w, c, ctx.groups, capi.ptr(gamma), capi.ptr(coef),
-                  capi.ptr(dgamma) if dgamma is not None else None, capi.ptr(dbeta) if dbeta is not None else None, int(ctx.relu),
-                  capi.ptr(ws), ws.numel(), capi.stream())
+                  capi.ptr_any(dy), capi.ptr_any(dres) if dres is not None else None, n * h * w, c, ctx.groups, capi.ptr(gamma),
+                  capi.ptr_any(stats), ctx.eps, capi.ptr(dgamma) if dgamma is not None else None,
+                  capi.ptr(dbeta) if dbeta is not None else None, int(ctx.relu), capi.ptr_any(red), int(zeroed), capi.stream())
         # gamma / beta gradients were accumulated in place: nothing flows back through autograd for them
         return dy, dres, None, None, None, None, None, None
 
@@ -122,29 +122,29 @@ def max_pool3s2(x):
 
 class _InstanceNormFn(torch.autograd.Function):
     """nn.InstanceNorm2d(C) (no affine, no running statistics; regda/models/Encoder.py:118-123) on channels-last bf16:
-    BatchNorm with one statistics group per image and gamma = 1, beta = 0 -- the same three kernels."""
+    BatchNorm with one statistics group per image and gamma = 1, beta = 0 -- the same kernels."""
 
     @staticmethod
     def forward(ctx, x, eps):
         x = _cl(x)
         n, c, h, w = x.shape
         out = torch.empty_like(x)
-        coef = torch.empty(n * 4 * c, dtype=torch.float32, device=x.device)
-        ws = capi.workspace.get(capi.lib().regda_bn_workspace_bytes(c, n), x.device)
+        stats, zeroed = capi.zero_pool.take((n, 2, c), x.device)
         capi.call("regda_bn_forward_bf16", capi.ptr_any(x), None, capi.ptr_any(out), n * h * w, c, n, None, None, None, None, None,
-                  float(eps), 0.0, 0, capi.ptr(coef), None, capi.ptr(ws), ws.numel(), capi.stream())
-        ctx.save_for_backward(x, coef)
+                  float(eps), 0.0, 0, capi.ptr_any(stats), 0, int(zeroed), capi.stream())
+        ctx.save_for_backward(x, stats)
+        ctx.eps = float(eps)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, coef = ctx.saved_tensors
+        x, stats = ctx.saved_tensors
         n, c, h, w = x.shape
         dout = _cl(dout)
         dx = torch.empty_like(x)
-        ws = capi.workspace.get(capi.lib().regda_bn_backward_workspace_bytes(c, n), x.device)
+        red, zeroed = capi.zero_pool.take((n, 2, c), x.device)
         capi.call("regda_bn_backward_bf16", capi.ptr_any(dout), None, capi.ptr_any(x), capi.ptr_any(dx), None, n * h * w, c, n, None,
-                  capi.ptr(coef), None, None, 0, capi.ptr(ws), ws.numel(), capi.stream())
+                  capi.ptr_any(stats), ctx.eps, None, None, 0, capi.ptr_any(red), int(zeroed), capi.stream())
         return dx, None
 
 

@@ -78,9 +78,9 @@ def fprop(x, w16, stride, padding, dilation, stats_groups=None):
         capi.call("regda_conv_fprop_bf16", capi.ptr_any(x), capi.ptr_any(w16), capi.ptr_any(y), n, h, w, cin, cout, r, s,
                   stride, padding, dilation, capi.stream())
         return y
-    stats = torch.empty((stats_groups, 2, cout), dtype=torch.float32, device=x.device)
+    stats, zeroed = capi.zero_pool.take((stats_groups, 2, cout), x.device)
     capi.call("regda_conv_fprop_stats_bf16", capi.ptr_any(x), capi.ptr_any(w16), capi.ptr_any(y), n, h, w, cin, cout, r, s,
-              stride, padding, dilation, capi.ptr(stats), stats_groups, capi.stream())
+              stride, padding, dilation, capi.ptr_any(stats), stats_groups, int(zeroed), capi.stream())
     return y, stats
 
 

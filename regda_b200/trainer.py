@@ -131,6 +131,7 @@ class SelfTrainingStep:
     def _step_impl(self, images_s, label_s, images_t, soft_t, regs_t):
         m = self.model
         self.arena.zero_grad()
+        capi.zero_pool.reset(self.arena.param.device)      # one memset for every small accumulator of the step
         if self.pair_forward and images_s.shape == images_t.shape:
             # both domain batches through the network as one tensor, BatchNorm statistics per domain (models/Encoder.py)
             (pred_s1, pred_s2, feat_s), (pred_t1, pred_t2, feat_t) = m.forward_pair(images_s, images_t)   # :210-212
@@ -154,6 +155,7 @@ class SelfTrainingStep:
         if self.world_size > 1:
             parallel.allreduce_sum_(self.arena.grad)                               # mean over ranks via grad_scale
         self.arena.clip_and_sgd(self.max_norm, self.momentum, self.weight_decay, 1.0 / self.world_size)   # :239-241
+        capi.zero_pool.disarm()
         return loss.detach(), loss_source.detach(), loss_target.detach(), hard
 
     def __call__(self, images_s, label_s, images_t, soft_t, regs_t, lr):
