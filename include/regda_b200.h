@@ -186,10 +186,11 @@ int regda_conv_fprop_stats_bf16(const void *x, const void *wgt, void *y, int n, 
 
 /* Data gradient of a stride-1 convolution, reading the forward OHWI weights in place (MN-major B operand):
  *   dy bf16 [n][oh][ow][cout], wgt bf16 [cout][r][s][cin] -> dx bf16 [n][h][w][cin]   (h, w, cin, cout, ... are the
- *   FORWARD convolution's geometry). */
+ *   FORWARD convolution's geometry).  addend (may be NULL): bf16 [n][h][w][cin] added in the epilogue, dx = dgrad + addend --
+ *   the gradient of a residual branch that also reads x (`out += identity`, regda/_resnets.py:108) joins here. */
 int regda_conv_dgrad_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil);
 int regda_conv_dgrad_bf16(const void *dy, const void *wgt, void *dx, int n, int h, int w, int cin, int cout,
-                          int r, int s, int stride, int pad, int dil, void *stream);
+                          int r, int s, int stride, int pad, int dil, const void *addend, void *stream);
 /* Weight gradient (stride 1 or 2), ACCUMULATED into dw fp32 [cout][r][s][cin] with global reductions:
  *   dy bf16 [n][oh][ow][cout], x bf16 [n][h][w][cin]. */
 int regda_conv_wgrad_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil);
@@ -222,9 +223,10 @@ int regda_bn_backward_bf16(const void *dout, const void *out, const void *y, voi
                            int relu, float *red, int red_zeroed, void *stream);
 
 /* MaxPool2d(3, stride 2, padding 1) over channels-last bf16 (regda/_resnets.py:153): x [n][h][w][c] -> y [n][oh][ow][c],
- * oh = (h-1)/2+1.  Backward recomputes the arg-max (first maximum in window order, as ATen) from x and y. */
-int regda_maxpool3s2_fwd_bf16(const void *x, void *y, int n, int h, int w, int c, void *stream);
-int regda_maxpool3s2_bwd_bf16(const void *x, const void *y, const void *dy, void *dx, int n, int h, int w, int c, void *stream);
+ * oh = (h-1)/2+1; argmax_u8 (may be NULL for inference) [n][oh][ow][c] receives the position 0..8 of the first maximum
+ * inside each window, which is all the backward needs. */
+int regda_maxpool3s2_fwd_bf16(const void *x, void *y, void *argmax_u8, int n, int h, int w, int c, void *stream);
+int regda_maxpool3s2_bwd_bf16(const void *argmax_u8, const void *dy, void *dx, int n, int h, int w, int c, void *stream);
 
 /* ---- pyramid pooling front end of the PPM heads (regda/models/Encoder.py:43-52) -----------------
  * scales_host: HOST array of nscales (<= 4) pool sizes, e.g. {1,2,3,6}; ncell = sum s^2; cells of scale k start

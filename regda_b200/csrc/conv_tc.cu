@@ -211,7 +211,7 @@ template <int BLOCK_N, int STAGES, bool B_MN, bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                        __nv_bfloat16 *__restrict__ y, const ConvGeom g, const int n_tiles_n, const int num_tiles,
-                       float *__restrict__ stats, const int imgs_per_group) {
+                       float *__restrict__ stats, const int imgs_per_group, const __nv_bfloat16 *__restrict__ addend) {
     using L = PersistSmem<BLOCK_N, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -328,6 +328,21 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                 uint32_t v[32];
                 tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
                 tmem_ld_wait();
+                if (addend != nullptr && valid) {
+                    // y = conv + addend (the residual branch's gradient joins the data gradient here instead of in a separate add pass)
+                    const uint4 *ap = reinterpret_cast<const uint4 *>(addend + (dst - y) + c);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const uint4 u = ap[q4];
+                        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w4[e]));
+                            v[q4 * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[q4 * 8 + 2 * e]) + f.x);
+                            v[q4 * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(v[q4 * 8 + 2 * e + 1]) + f.y);
+                        }
+                    }
+                }
                 uint32_t pkd[16];
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
@@ -419,7 +434,7 @@ int launch_fprop(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bfloat16 *y,
 
 template <int BLOCK_N, int STAGES, bool B_MN, bool STATS>
 int launch_persistent_impl(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bfloat16 *y, const ConvGeom &g, cudaStream_t st,
-                           float *stats, int imgs_per_group) {
+                           float *stats, int imgs_per_group, const __nv_bfloat16 *addend) {
     using L = PersistSmem<BLOCK_N, STAGES>;
     auto kern = conv_persistent_kernel<BLOCK_N, STAGES, B_MN, STATS>;
     const int smem = L::kTotal + 1024;
@@ -427,16 +442,16 @@ int launch_persistent_impl(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bf
     const int n_tiles_n = g.cout / BLOCK_N;
     const int num_tiles = n_tiles_n * g.n * g.tiles_h * g.tiles_w;
     const int grid = std::min(num_tiles, sm_count());
-    kern<<<grid, kThreads, smem, st>>>(tx, tw, y, g, n_tiles_n, num_tiles, stats, imgs_per_group);
+    kern<<<grid, kThreads, smem, st>>>(tx, tw, y, g, n_tiles_n, num_tiles, stats, imgs_per_group, addend);
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
 }
 
 template <int BLOCK_N, int STAGES, bool B_MN>
 int launch_persistent(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bfloat16 *y, const ConvGeom &g, cudaStream_t st,
-                      float *stats, int imgs_per_group) {
-    if (!B_MN && stats != nullptr) return launch_persistent_impl<BLOCK_N, STAGES, false, true>(tx, tw, y, g, st, stats, imgs_per_group);
-    return launch_persistent_impl<BLOCK_N, STAGES, B_MN, false>(tx, tw, y, g, st, nullptr, 1);
+                      float *stats, int imgs_per_group, const __nv_bfloat16 *addend) {
+    if (!B_MN && stats != nullptr) return launch_persistent_impl<BLOCK_N, STAGES, false, true>(tx, tw, y, g, st, stats, imgs_per_group, addend);
+    return launch_persistent_impl<BLOCK_N, STAGES, B_MN, false>(tx, tw, y, g, st, nullptr, 1, addend);
 }
 
 // Tile shape policy.  REGDA_CONV_KERNEL=classic selects the one-tile-per-CTA kernel (A/B comparisons).
@@ -451,7 +466,7 @@ bool use_persistent() {
 
 template <bool B_MN>
 int launch_conv(const void *act, const void *wgt, __nv_bfloat16 *out, const ConvGeom &g, int taps, cudaStream_t st,
-                float *stats = nullptr, int imgs_per_group = 1) {
+                float *stats = nullptr, int imgs_per_group = 1, const __nv_bfloat16 *addend = nullptr) {
     // g.cin = reduction channels, g.cout = output channels of THIS GEMM (already swapped for dgrad)
     CUtensorMap tx, tw;
     int rc = make_tmap_x(&tx, act, g);
@@ -463,11 +478,12 @@ int launch_conv(const void *act, const void *wgt, __nv_bfloat16 *out, const Conv
     rc = B_MN ? make_tmap_w_mn(&tw, wgt, g.cin, taps, g.cout) : make_tmap_w(&tw, wgt, g.cout, taps * g.cin, block_n);
     if (rc) return rc;
     if (use_persistent()) {
-        if (block_n == 256) return launch_persistent<256, 4, B_MN>(tx, tw, out, g, st, stats, imgs_per_group);
-        if (block_n == 128) return launch_persistent<128, 6, B_MN>(tx, tw, out, g, st, stats, imgs_per_group);
-        return launch_persistent<64, 8, B_MN>(tx, tw, out, g, st, stats, imgs_per_group);
+        if (block_n == 256) return launch_persistent<256, 4, B_MN>(tx, tw, out, g, st, stats, imgs_per_group, addend);
+        if (block_n == 128) return launch_persistent<128, 6, B_MN>(tx, tw, out, g, st, stats, imgs_per_group, addend);
+        return launch_persistent<64, 8, B_MN>(tx, tw, out, g, st, stats, imgs_per_group, addend);
     }
-    if (stats != nullptr) return fail(REGDA_ERR_UNSUPPORTED, "conv_fprop: fused BatchNorm statistics need the persistent kernel");
+    if (stats != nullptr || addend != nullptr)
+        return fail(REGDA_ERR_UNSUPPORTED, "conv: fused BatchNorm statistics / addend need the persistent kernel");
     if (block_n == 128) return launch_fprop<128, 3, B_MN>(tx, tw, out, g, st);
     return launch_fprop<64, 4, B_MN>(tx, tw, out, g, st);
 }
@@ -549,7 +565,7 @@ extern "C" int regda_conv_dgrad_supported(int n, int h, int w, int cin, int cout
 }
 
 extern "C" int regda_conv_dgrad_bf16(const void *dy, const void *wgt, void *dx, int n, int h, int w, int cin, int cout,
-                                     int r, int s, int stride, int pad, int dil, void *stream) {
+                                     int r, int s, int stride, int pad, int dil, const void *addend, void *stream) {
     if (!regda_conv_dgrad_supported(n, h, w, cin, cout, r, s, stride, pad, dil))
         return fail(REGDA_ERR_UNSUPPORTED, "conv_dgrad: shape not covered by the tcgen05 kernel");
     if (!dy || !wgt || !dx) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad: null pointer");
@@ -562,5 +578,7 @@ extern "C" int regda_conv_dgrad_bf16(const void *dy, const void *wgt, void *dx, 
     g.flip = 1;
     if (g.oh != h || g.ow != w) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad: inconsistent geometry");
     ensure_context(dy);
-    return launch_conv<true>(dy, wgt, static_cast<__nv_bfloat16 *>(dx), g, r * s, static_cast<cudaStream_t>(stream));
+    if (addend != nullptr && (reinterpret_cast<uintptr_t>(addend) & 15)) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad: addend must be 16-byte aligned");
+    return launch_conv<true>(dy, wgt, static_cast<__nv_bfloat16 *>(dx), g, r * s, static_cast<cudaStream_t>(stream), nullptr, 1,
+                             static_cast<const __nv_bfloat16 *>(addend));
 }

@@ -354,15 +354,16 @@ extern "C" int regda_bn_backward_bf16(const void *dout, const void *out, const v
 // ---------------------------------------------------------------------------------------------------------
 // MaxPool2d(kernel 3, stride 2, padding 1) over channels-last bf16 (the stem pool, regda/_resnets.py:153),
 // forward and backward.  HBM-bound streaming kernels, a thread owns 8 channels of one output (forward) or
-// input (backward) pixel.  The backward recomputes the arg-max from x (first maximum in window order, the
-// order ATen uses) instead of storing int64 indices: dx[p] = sum over the <= 4 windows containing p of
-// dy[window] where p is that window's arg-max.
+// input (backward) pixel.  The forward records the arg-max position inside the window as ONE byte per output
+// element (first maximum in window order, the order ATen uses; ATen stores int64 indices): dx[p] = sum over the
+// <= 4 windows containing p of dy[window] where p is that window's arg-max.
 // ---------------------------------------------------------------------------------------------------------
 namespace regda {
 namespace {
 
 __global__ void __launch_bounds__(256)
-maxpool3s2_fwd_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restrict__ y, int n, int h, int w, int c, int oh, int ow) {
+maxpool3s2_fwd_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restrict__ y, unsigned char *__restrict__ arg, int n, int h, int w,
+                      int c, int oh, int ow) {
     const int octs = c >> 3;
     const long long total = static_cast<long long>(n) * oh * ow * octs;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -372,8 +373,9 @@ maxpool3s2_fwd_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__rest
         const int oy = static_cast<int>(p % oh);
         const int img = static_cast<int>(p / oh);
         float m[8];
+        unsigned am[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) m[t] = -INFINITY;
+        for (int t = 0; t < 8; ++t) { m[t] = -INFINITY; am[t] = 0u; }
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
             const int iy = oy * 2 - 1 + dy;
@@ -385,16 +387,25 @@ maxpool3s2_fwd_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__rest
                 float f[8];
                 unpack(ld8(x + ((static_cast<long long>(img) * h + iy) * w + ix) * c + o * 8), f);
 #pragma unroll
-                for (int t = 0; t < 8; ++t) m[t] = fmaxf(m[t], f[t]);
+                for (int t = 0; t < 8; ++t)
+                    if (f[t] > m[t]) { m[t] = f[t]; am[t] = static_cast<unsigned>(dy * 3 + dx); }      // first maximum wins, as ATen
             }
         }
-        st8(y + ((static_cast<long long>(img) * oh + oy) * ow + ox) * c + o * 8, pack(m));
+        const long long q = ((static_cast<long long>(img) * oh + oy) * ow + ox) * c + o * 8;
+        st8(y + q, pack(m));
+        if (arg != nullptr) {
+            uint2 pk;
+            pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+            pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+            *reinterpret_cast<uint2 *>(arg + q) = pk;
+        }
     }
 }
 
+// one thread per (input pixel, 8 channels): the <= 4 windows containing the pixel, one byte compare each
 __global__ void __launch_bounds__(256)
-maxpool3s2_bwd_kernel(const __nv_bfloat16 *__restrict__ x, const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__restrict__ dy,
-                      __nv_bfloat16 *__restrict__ dx, int n, int h, int w, int c, int oh, int ow) {
+maxpool3s2_bwd_kernel(const unsigned char *__restrict__ arg, const __nv_bfloat16 *__restrict__ dy, __nv_bfloat16 *__restrict__ dx, int n, int h,
+                      int w, int c, int oh, int ow) {
     const int octs = c >> 3;
     const long long total = static_cast<long long>(n) * h * w * octs;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -403,35 +414,23 @@ maxpool3s2_bwd_kernel(const __nv_bfloat16 *__restrict__ x, const __nv_bfloat16 *
         const int ix = static_cast<int>(p % w); p /= w;
         const int iy = static_cast<int>(p % h);
         const int img = static_cast<int>(p / h);
-        float xv[8], acc[8];
-        unpack(ld8_stream(x + i * 8), xv);
+        float acc[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) acc[t] = 0.f;
-        // output windows that contain (iy, ix): oy in [ceil((iy-1)/2), floor((iy+1)/2)]
         const int oy0 = max(0, iy >> 1), oy1 = min(oh - 1, (iy + 1) >> 1);
         const int ox0 = max(0, ix >> 1), ox1 = min(ow - 1, (ix + 1) >> 1);
         for (int oy = oy0; oy <= oy1; ++oy) {
             for (int ox = ox0; ox <= ox1; ++ox) {
+                const unsigned pos = static_cast<unsigned>((iy - (oy * 2 - 1)) * 3 + (ix - (ox * 2 - 1)));      // my index in that window
                 const long long q = ((static_cast<long long>(img) * oh + oy) * ow + ox) * c + o * 8;
-                float yv[8], gv[8];
-                unpack(ld8(y + q), yv);
+                const uint2 av = *reinterpret_cast<const uint2 *>(arg + q);
+                float gv[8];
                 unpack(ld8(dy + q), gv);
-                // is (iy, ix) the FIRST position of this window (row-major) that attains the maximum?
-                bool first[8];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) first[t] = xv[t] == yv[t];
-                for (int wy = oy * 2 - 1; wy <= iy; ++wy) {
-                    if (wy < 0) continue;
-                    const int wx_end = (wy == iy) ? ix - 1 : min(w - 1, ox * 2 + 1);
-                    for (int wx = max(0, ox * 2 - 1); wx <= wx_end; ++wx) {
-                        float e[8];
-                        unpack(ld8(x + ((static_cast<long long>(img) * h + wy) * w + wx) * c + o * 8), e);
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) first[t] = first[t] && !(e[t] == yv[t]);
-                    }
+                for (int t = 0; t < 8; ++t) {
+                    const unsigned a = ((t < 4 ? av.x : av.y) >> ((t & 3) * 8)) & 0xFFu;
+                    acc[t] += a == pos ? gv[t] : 0.f;
                 }
-#pragma unroll
-                for (int t = 0; t < 8; ++t) acc[t] += first[t] ? gv[t] : 0.f;
             }
         }
         st8(dx + i * 8, pack(acc));
@@ -441,25 +440,25 @@ maxpool3s2_bwd_kernel(const __nv_bfloat16 *__restrict__ x, const __nv_bfloat16 *
 }  // namespace
 }  // namespace regda
 
-extern "C" int regda_maxpool3s2_fwd_bf16(const void *x, void *y, int n, int h, int w, int c, void *stream) {
+extern "C" int regda_maxpool3s2_fwd_bf16(const void *x, void *y, void *argmax_u8, int n, int h, int w, int c, void *stream) {
     if (!x || !y || n < 1 || h < 1 || w < 1 || c < 8 || c % 8) return fail(REGDA_ERR_INVALID_ARG, "maxpool_fwd: bad arguments");
     const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
     const long long total = static_cast<long long>(n) * oh * ow * (c / 8);
     const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 16ll * sm_count()));
-    maxpool3s2_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16 *>(x),
-                                                                                    static_cast<__nv_bfloat16 *>(y), n, h, w, c, oh, ow);
+    maxpool3s2_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16 *>(x), static_cast<__nv_bfloat16 *>(y),
+                                                                                    static_cast<unsigned char *>(argmax_u8), n, h, w, c, oh, ow);
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
 }
 
-extern "C" int regda_maxpool3s2_bwd_bf16(const void *x, const void *y, const void *dy, void *dx, int n, int h, int w, int c, void *stream) {
-    if (!x || !y || !dy || !dx || n < 1 || h < 1 || w < 1 || c < 8 || c % 8) return fail(REGDA_ERR_INVALID_ARG, "maxpool_bwd: bad arguments");
+extern "C" int regda_maxpool3s2_bwd_bf16(const void *argmax_u8, const void *dy, void *dx, int n, int h, int w, int c, void *stream) {
+    if (!argmax_u8 || !dy || !dx || n < 1 || h < 1 || w < 1 || c < 8 || c % 8) return fail(REGDA_ERR_INVALID_ARG, "maxpool_bwd: bad arguments");
     const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
     const long long total = static_cast<long long>(n) * h * w * (c / 8);
     const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 16ll * sm_count()));
-    maxpool3s2_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16 *>(x), static_cast<const __nv_bfloat16 *>(y), static_cast<const __nv_bfloat16 *>(dy),
-        static_cast<__nv_bfloat16 *>(dx), n, h, w, c, oh, ow);
+    maxpool3s2_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const unsigned char *>(argmax_u8),
+                                                                                    static_cast<const __nv_bfloat16 *>(dy), static_cast<__nv_bfloat16 *>(dx),
+                                                                                    n, h, w, c, oh, ow);
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
 }

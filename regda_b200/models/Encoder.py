@@ -41,15 +41,20 @@ def _fused(x, bn):
 _GROUPS = 1
 
 
-def _conv_bn(conv, bn, x, residual=None, relu=False):
+def _conv_bn(conv, bn, x, residual=None, relu=False, tap=False):
     """relu?(bn(conv(x)) + residual); on the hand-written path the BatchNorm statistics come out of the convolution
-    kernel's epilogue, so BatchNorm makes one pass (apply) instead of two over the activation"""
+    kernel's epilogue, so BatchNorm makes one pass (apply) instead of two over the activation.  tap=True returns
+    (out, x_tap): x_tap is x for a residual branch, routed so that its gradient is added inside the dgrad kernel."""
     if FUSED and bn.training and x.is_cuda and x.dtype == torch.bfloat16:
-        y, st = conv.forward_with_bn_stats(x, _GROUPS)
+        res = conv.forward_with_bn_stats(x, _GROUPS, tap)
+        y, st = res[0], res[1]
         if st is not None and fnorm.supported(y, bn):
-            return fnorm.bn_act(y, bn, residual=residual, relu=relu, groups=_GROUPS, stats=st)
-        return _bn(y, bn, residual, relu)
-    return _bn(conv(x), bn, residual, relu)
+            out = fnorm.bn_act(y, bn, residual=residual, relu=relu, groups=_GROUPS, stats=st)
+        else:
+            out = _bn(y, bn, residual, relu)
+        return (out, res[2]) if tap else out
+    out = _bn(conv(x), bn, residual, relu)
+    return (out, x) if tap else out
 
 
 def _bn(x, bn, residual=None, relu=False):
@@ -105,9 +110,12 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         if (FUSED and self.training and x.is_cuda and x.dtype == torch.bfloat16) or _GROUPS > 1:
-            out = _conv_bn(self.conv1, self.bn1, x, relu=True)
+            if self.downsample is None:
+                out, identity = _conv_bn(self.conv1, self.bn1, x, relu=True, tap=True)
+            else:
+                out = _conv_bn(self.conv1, self.bn1, x, relu=True)
+                identity = _conv_bn(self.downsample[0], self.downsample[1], x)
             out = _conv_bn(self.conv2, self.bn2, out, relu=True)
-            identity = x if self.downsample is None else _conv_bn(self.downsample[0], self.downsample[1], x)
             return _conv_bn(self.conv3, self.bn3, out, residual=identity, relu=True)
         y = self.conv1(x)
         out = F.relu(self.bn1(y), inplace=True)

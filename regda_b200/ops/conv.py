@@ -39,35 +39,50 @@ class _ConvFn(torch.autograd.Function):
     The weight gradient is ACCUMULATED into weight.grad by the wgrad kernel (no autograd add)."""
 
     @staticmethod
-    def forward(ctx, x, weight, stride, padding, dilation, stats_groups=None):
+    def forward(ctx, x, weight, stride, padding, dilation, stats_groups=None, tap=False):
+        """returns y [, bn_stats] [, x_tap].  x_tap (tap=True) is x itself handed back as a second consumer handle: a
+        residual branch that reads the same x goes through it, so this node's backward receives that branch's gradient and
+        the dgrad kernel adds it in its epilogue (dx = dgrad(dy) + d_tap) instead of autograd launching an add."""
         tc = _tc()
         w16 = tc.weight_shadow(weight)
         ctx.save_for_backward(x, w16)
         ctx.weight = weight
         ctx.geom = (stride, padding, dilation)
+        ctx.has_stats, ctx.tap = stats_groups is not None, tap
         stats["tcgen05_fprop"] += 1
+        outs = []
         if stats_groups is None:
-            return tc.fprop(x, w16, stride, padding, dilation)
-        y, bn_stats = tc.fprop(x, w16, stride, padding, dilation, stats_groups)
-        ctx.mark_non_differentiable(bn_stats)
-        return y, bn_stats
+            outs.append(tc.fprop(x, w16, stride, padding, dilation))
+        else:
+            y, bn_stats = tc.fprop(x, w16, stride, padding, dilation, stats_groups)
+            ctx.mark_non_differentiable(bn_stats)
+            outs += [y, bn_stats]
+        if tap:
+            outs.append(x.view_as(x))
+        return outs[0] if len(outs) == 1 else tuple(outs)
 
     @staticmethod
-    def backward(ctx, gy, *unused):
+    def backward(ctx, gy, *rest):
         tc = _tc()
         x, w16 = ctx.saved_tensors
         weight = ctx.weight
         stride, padding, dilation = ctx.geom
         gy = gy.contiguous(memory_format=torch.channels_last)
+        g_tap = rest[-1] if ctx.tap else None
         gx = gw = None
         if ctx.needs_input_grad[0]:
             if ENGINE != "tcgen05-fwd" and tc.supports_dgrad(x.shape, weight.shape, stride, padding, dilation, x.dtype):
                 stats["tcgen05_dgrad"] += 1
-                gx = tc.dgrad(gy, w16, x.shape, stride, padding, dilation)
+                fuse = g_tap is not None and g_tap.dtype == torch.bfloat16 and FUSE_BN_STATS
+                gx = tc.dgrad(gy, w16, x.shape, stride, padding, dilation, addend=g_tap if fuse else None)
+                if g_tap is not None and not fuse:
+                    gx = gx + g_tap
             else:
                 stats["cudnn"] += 1
                 gx = torch.ops.aten.convolution_backward(gy, x, w16, None, [stride] * 2, [padding] * 2,
                                                          [dilation] * 2, False, [0, 0], 1, [True, False, False])[0]
+                if g_tap is not None:
+                    gx = gx + g_tap
         if ctx.needs_input_grad[1]:
             if ENGINE != "tcgen05-fwd" and tc.supports_wgrad(x.shape, weight.shape, stride, padding, dilation, x.dtype):
                 stats["tcgen05_wgrad"] += 1
@@ -78,7 +93,7 @@ class _ConvFn(torch.autograd.Function):
                 stats["cudnn"] += 1
                 gw = torch.ops.aten.convolution_backward(gy, x, w16, None, [stride] * 2, [padding] * 2,
                                                          [dilation] * 2, False, [0, 0], 1, [False, True, False])[1].float()
-        return gx, gw, None, None, None, None
+        return gx, gw, None, None, None, None, None
 
 
 class Conv2d(nn.Module):
@@ -99,13 +114,14 @@ class Conv2d(nn.Module):
         return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "
                 f"padding={self.padding}, dilation={self.dilation}, bias={self.bias is not None}")
 
-    def forward_with_bn_stats(self, x, groups):
-        """(y, stats): the convolution plus the BatchNorm statistics of its output from the kernel's epilogue, or
-        (y, None) when this shape / engine does not run on the tcgen05 kernel."""
+    def forward_with_bn_stats(self, x, groups, tap=False):
+        """(y, stats[, x_tap]): the convolution plus the BatchNorm statistics of its output from the kernel's epilogue
+        (stats is None when this shape / engine does not run on the tcgen05 kernel); with tap=True also the handle a
+        residual branch should read x through (see _ConvFn.forward)."""
         if (ENGINE != "cudnn" and self.bias is None and x.is_cuda and x.dtype == torch.bfloat16 and FUSE_BN_STATS
                 and _tc().supports_fprop(x.shape, self.weight.shape, self.stride, self.padding, self.dilation, x.dtype)):
-            return _ConvFn.apply(x, self.weight, self.stride, self.padding, self.dilation, groups)
-        return self.forward(x), None
+            return _ConvFn.apply(x, self.weight, self.stride, self.padding, self.dilation, groups, tap)
+        return (self.forward(x), None, x) if tap else (self.forward(x), None)
 
     def forward(self, x):
         use_tc = False

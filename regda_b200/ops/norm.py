@@ -100,17 +100,19 @@ class _MaxPool3s2Fn(torch.autograd.Function):
         x = _cl(x)
         n, c, h, w = x.shape
         y = torch.empty((n, c, (h - 1) // 2 + 1, (w - 1) // 2 + 1), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
-        capi.call("regda_maxpool3s2_fwd_bf16", capi.ptr_any(x), capi.ptr_any(y), n, h, w, c, capi.stream())
-        ctx.save_for_backward(x, y)
+        arg = torch.empty(y.shape, dtype=torch.uint8, device=x.device, memory_format=torch.channels_last)
+        capi.call("regda_maxpool3s2_fwd_bf16", capi.ptr_any(x), capi.ptr_any(y), capi.ptr_any(arg), n, h, w, c, capi.stream())
+        ctx.save_for_backward(arg)
+        ctx.xshape = (n, c, h, w)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y = ctx.saved_tensors
-        n, c, h, w = x.shape
+        (arg,) = ctx.saved_tensors
+        n, c, h, w = ctx.xshape
         dy = _cl(dy)
-        dx = torch.empty_like(x)
-        capi.call("regda_maxpool3s2_bwd_bf16", capi.ptr_any(x), capi.ptr_any(y), capi.ptr_any(dy), capi.ptr_any(dx), n, h, w, c, capi.stream())
+        dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+        capi.call("regda_maxpool3s2_bwd_bf16", capi.ptr_any(arg), capi.ptr_any(dy), capi.ptr_any(dx), n, h, w, c, capi.stream())
         return dx
 
 

@@ -84,14 +84,18 @@ def fprop(x, w16, stride, padding, dilation, stats_groups=None):
     return y, stats
 
 
-def dgrad(gy, w16, xshape, stride, padding, dilation):
-    """dX from dY and the forward weights [O,I,kh,kw] (bf16, channels-last)."""
+def dgrad(gy, w16, xshape, stride, padding, dilation, addend=None):
+    """dX from dY and the forward weights [O,I,kh,kw] (bf16, channels-last); `addend` (same shape as x) is added in the
+    kernel's epilogue."""
     n, cin, h, w = xshape
     cout, _, r, s = w16.shape
     gx = torch.empty((n, cin, h, w), dtype=torch.bfloat16, device=gy.device, memory_format=torch.channels_last)
     gy, w16 = _nhwc(gy), _nhwc(w16)
+    if addend is not None:
+        assert tuple(addend.shape) == tuple(xshape) and addend.dtype == torch.bfloat16
+        addend = _nhwc(addend)
     capi.call("regda_conv_dgrad_bf16", capi.ptr_any(gy), capi.ptr_any(w16), capi.ptr_any(gx), n, h, w, cin, cout, r, s,
-              stride, padding, dilation, capi.stream())
+              stride, padding, dilation, capi.ptr_any(addend) if addend is not None else None, capi.stream())
     return gx
 
 

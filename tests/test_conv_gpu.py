@@ -135,3 +135,25 @@ def test_wgrad_and_dgrad_match_float32_reference(shape):
     assert tc.supports_dgrad(x.shape, wt.shape, 1, pad, dil, x.dtype)
     gx = tc.dgrad(gy, wt, x.shape, 1, pad, dil)
     assert float((gx.float() - xr.grad).abs().max()) <= 1e-2 * float(xr.grad.abs().max())
+
+
+def test_conv_tap_adds_the_residual_gradient_in_the_dgrad_epilogue():
+    """y, stats, x_tap = conv(x, tap=True): the gradient arriving through x_tap (the residual branch) is added inside the
+    dgrad kernel; statistics from the epilogue equal the sums of the bf16 outputs."""
+    from regda_b200.ops import conv as C
+    torch.manual_seed(2)
+    m = C.Conv2d(256, 128, 3, padding=1, bias=False).cuda()
+    x = torch.randn(4, 256, 32, 32, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y, st, xt = m.forward_with_bn_stats(x, 2, tap=True)
+    assert st is not None and st.shape == (2, 2, 128)
+    yf = y.float()
+    want = torch.stack([torch.stack([yf[:2].sum((0, 2, 3)), yf[:2].square().sum((0, 2, 3))]), torch.stack([yf[2:].sum((0, 2, 3)), yf[2:].square().sum((0, 2, 3))])])
+    assert float((st - want).abs().max()) <= 2e-3 * float(want.abs().max())
+    gy = torch.randn_like(y)
+    gt = torch.randn_like(x)
+    torch.autograd.backward([y, xt], [gy, gt])
+    xr = x.detach().float().requires_grad_(True)
+    wr = m.weight.detach().bfloat16().float()
+    yr = F.conv2d(xr, wr, None, 1, 1, 1)
+    torch.autograd.backward([yr, xr * 1.0], [gy.float(), gt.float()])
+    assert float((x.grad.float() - xr.grad).abs().max()) <= 1.5e-2 * float(xr.grad.abs().max())
