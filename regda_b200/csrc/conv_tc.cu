@@ -32,7 +32,9 @@ using namespace tc;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;          // bf16: 128 bytes = one swizzle span
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 192;        // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kThreads = 192;        // classic kernel: warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kPersistThreads = 320; // persistent kernel: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane
+                                     // quadrant, each draining half of the accumulator's columns)
 
 struct ConvGeom {
     int n, h, w, cin, cout;          // input image, reduction channels, output channels
@@ -208,7 +210,7 @@ struct PersistSmem {
 // atomic per channel per warp per tile (warp-transposing butterfly: 31 shuffles per quantity per 32 channels),
 // which removes BatchNorm's own pass over the activation.  group = image / imgs_per_group.
 template <int BLOCK_N, int STAGES, bool B_MN, bool STATS>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kPersistThreads, 1)
 conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                        __nv_bfloat16 *__restrict__ y, const ConvGeom g, const int n_tiles_n, const int num_tiles,
                        float *__restrict__ stats, const int imgs_per_group, const __nv_bfloat16 *__restrict__ addend) {
@@ -231,7 +233,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 8); }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -307,6 +309,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     } else {
         // ===== epilogue: TMEM -> registers -> bf16 -> global (NHWC) =====
         const int q = warp & 3;                                        // TMEM lane quadrant of this warp
+        const int col_lo = ((warp - 2) >> 2) * (BLOCK_N / 2), col_hi = col_lo + BLOCK_N / 2;    // this warp's half of the columns
         const int row = q * 32 + lane;
         const int ph = row / g.bw, pw = row - ph * g.bw;
         int acc = 0;
@@ -320,27 +323,38 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             const int oh = th * g.bh + ph, ow = tw * g.bw + pw;
             const bool valid = oh < g.oh && ow < g.ow;
             __nv_bfloat16 *dst = y + ((static_cast<size_t>(img) * g.oh + oh) * g.ow + ow) * g.cout + static_cast<size_t>(n_blk) * BLOCK_N;
+            // the addend (if any) does not depend on the accumulator: its first chunk is requested before waiting for the
+            // MMAs, and chunk c+1 while chunk c is converted and stored, so its latency stays off the epilogue's critical path
+            const bool has_add = addend != nullptr && valid;
+            const uint4 *ap = reinterpret_cast<const uint4 *>(addend + (dst - y) + col_lo);
+            uint4 cur[4], nxt[4];
+            if (has_add) {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) cur[q4] = __ldg(ap + q4);
+            }
             mbar_wait(tfull_bar + acc, acc_phase);
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 32) {
+            for (int c = col_lo; c < col_hi; c += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+                if (has_add && c + 32 < col_hi) {
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) nxt[q4] = __ldg(ap + (c + 32 - col_lo) / 8 + q4);
+                }
                 tmem_ld_wait();
-                if (addend != nullptr && valid) {
-                    // y = conv + addend (the residual branch's gradient joins the data gradient here instead of in a separate add pass)
-                    const uint4 *ap = reinterpret_cast<const uint4 *>(addend + (dst - y) + c);
+                if (has_add) {
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
-                        const uint4 u = ap[q4];
-                        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+                        const uint32_t w4[4] = {cur[q4].x, cur[q4].y, cur[q4].z, cur[q4].w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w4[e]));
                             v[q4 * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[q4 * 8 + 2 * e]) + f.x);
                             v[q4 * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(v[q4 * 8 + 2 * e + 1]) + f.y);
                         }
+                        cur[q4] = nxt[q4];
                     }
                 }
                 uint32_t pkd[16];
@@ -442,7 +456,7 @@ int launch_persistent_impl(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bf
     const int n_tiles_n = g.cout / BLOCK_N;
     const int num_tiles = n_tiles_n * g.n * g.tiles_h * g.tiles_w;
     const int grid = std::min(num_tiles, sm_count());
-    kern<<<grid, kThreads, smem, st>>>(tx, tw, y, g, n_tiles_n, num_tiles, stats, imgs_per_group, addend);
+    kern<<<grid, kPersistThreads, smem, st>>>(tx, tw, y, g, n_tiles_n, num_tiles, stats, imgs_per_group, addend);
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
 }

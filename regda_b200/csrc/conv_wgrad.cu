@@ -191,8 +191,10 @@ __device__ __forceinline__ WgItem wg_decode(int item, const WgradGeom &g, int m_
     return it;
 }
 
+constexpr int kWgPersistThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant, half the columns each)
+
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(kWgThreads, 1)
+__global__ void __launch_bounds__(kWgPersistThreads, 1)
 conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                              float *__restrict__ dw, const WgradGeom g, const int m_tiles, const int num_items) {
     using L = WgPersistSmem<BLOCK_N, STAGES>;
@@ -213,7 +215,7 @@ conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const 
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 8); }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -284,6 +286,7 @@ conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const 
         }
     } else {
         const int q = warp & 3;
+        const int col_lo = ((warp - 2) >> 2) * (BLOCK_N / 2), col_hi = col_lo + BLOCK_N / 2;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -295,7 +298,7 @@ conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const 
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 32) {
+            for (int c = col_lo; c < col_hi; c += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
                 tmem_ld_wait();
@@ -329,7 +332,7 @@ int launch_wgrad_persistent(const CUtensorMap &tdy, const CUtensorMap &tx, float
     const int m_tiles = (g.cout + kWgM - 1) / kWgM;
     const int num_items = g.n_tiles * m_tiles * g.r * g.s * g.splits;
     const int grid = std::min(num_items, sm_count());
-    kern<<<grid, kWgThreads, smem, st>>>(tdy, tx, dw, g, m_tiles, num_items);
+    kern<<<grid, kWgPersistThreads, smem, st>>>(tdy, tx, dw, g, m_tiles, num_items);
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
 }
