@@ -49,6 +49,7 @@ class _ConvFn(torch.autograd.Function):
         ctx.weight = weight
         ctx.geom = (stride, padding, dilation)
         ctx.has_stats, ctx.tap = stats_groups is not None, tap
+        ctx.set_materialize_grads(False)        # no zero-filled gradient tensors for the statistics / unused tap outputs
         stats["tcgen05_fprop"] += 1
         outs = []
         if stats_groups is None:
@@ -67,8 +68,10 @@ class _ConvFn(torch.autograd.Function):
         x, w16 = ctx.saved_tensors
         weight = ctx.weight
         stride, padding, dilation = ctx.geom
-        gy = gy.contiguous(memory_format=torch.channels_last)
         g_tap = rest[-1] if ctx.tap else None
+        if gy is None:                           # only the tap branch carried a gradient
+            return g_tap, None, None, None, None, None, None
+        gy = gy.contiguous(memory_format=torch.channels_last)
         gx = gw = None
         if ctx.needs_input_grad[0]:
             if ENGINE != "tcgen05-fwd" and tc.supports_dgrad(x.shape, weight.shape, stride, padding, dilation, x.dtype):
