@@ -200,7 +200,9 @@ struct PersistSmem {
     static constexpr int kABytes = kBlockM * kBlockK * 2;
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kEpiWarps = BLOCK_N >= 128 ? 8 : 4; // TMA-store epilogue: warps that drain the accumulator
+    static constexpr int kStoreOffset = STAGES * kStageBytes; // 4 KB per epilogue warp: one 32-row x 64-channel bf16 box
+    static constexpr int kBarOffset = kStoreOffset + 8 * 4096;
     static constexpr int kNumBars = 2 * STAGES + 4;          // full, empty, tmem_full[2], tmem_empty[2]
     static constexpr int kTotal = kBarOffset + kNumBars * 8 + 8;
 };
@@ -209,9 +211,15 @@ struct PersistSmem {
 // the train-mode BatchNorm statistics of the layer that follows -- into stats[group][2][cout] with one fp32
 // atomic per channel per warp per tile (warp-transposing butterfly: 31 shuffles per quantity per 32 channels),
 // which removes BatchNorm's own pass over the activation.  group = image / imgs_per_group.
-template <int BLOCK_N, int STAGES, bool B_MN, bool STATS>
+//
+// TMA_EPI: the epilogue stages each warp's 32 pixels x 64 channels in 128B-swizzled shared memory and writes it with ONE
+// TMA store (full 128-byte lines; the box is clipped at the image border) instead of 16-byte-per-lane scattered stores
+// (32 distinct lines per store instruction); the BatchNorm statistics are then column sums read back from the staged
+// tile (32 conflict-free LDS per lane for 2 channels) instead of a 31-shuffle warp transpose per quantity.
+template <int BLOCK_N, int STAGES, bool B_MN, bool STATS, bool TMA_EPI>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                       const __grid_constant__ CUtensorMap tmap_y,
                        __nv_bfloat16 *__restrict__ y, const ConvGeom g, const int n_tiles_n, const int num_tiles,
                        float *__restrict__ stats, const int imgs_per_group, const __nv_bfloat16 *__restrict__ addend) {
     using L = PersistSmem<BLOCK_N, STAGES>;
@@ -230,10 +238,11 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_x);
         prefetch_tmap(&tmap_w);
+        if (TMA_EPI) prefetch_tmap(&tmap_y);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, TMA_EPI ? L::kEpiWarps : 8); }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -305,6 +314,151 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                 umma_commit(tfull_bar + acc);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+        }
+    } else if (TMA_EPI) {
+        // ===== epilogue: TMEM -> registers -> bf16 -> swizzled shared memory -> TMA store (NHWC) =====
+        constexpr int kCols = BLOCK_N >= 128 ? BLOCK_N / 2 : BLOCK_N;   // columns per warp: 128 / 64 / 64
+        const int wq = warp - 2;
+        const int q = warp & 3;                                        // TMEM lane quadrant of this warp
+        if (wq < L::kEpiWarps) {
+            const int col_lo = (BLOCK_N >= 128 ? (wq >> 2) : 0) * kCols;
+            const int row = q * 32 + lane;
+            const int ph = row / g.bw, pw = row - ph * g.bw;
+            // the warp's 32 rows are one box {64 ch, min(bw,32) px, 32/min(bw,32) rows}: its origin inside the patch
+            const int bph0 = (q * 32) / g.bw, bpw0 = (q * 32) - bph0 * g.bw;
+            const uint32_t stage_s = smem_u32(smem + L::kStoreOffset + wq * 4096);
+            const uint32_t my_row_s = stage_s + static_cast<uint32_t>(lane) * 128u;
+            const uint32_t sw = static_cast<uint32_t>(lane & 7);
+            // BatchNorm statistics stay in registers across the tiles of this CTA for as long as (channel block, statistics
+            // group) does not change -- with a tile stride of gridDim.x that is most of the walk -- and are flushed with
+            // one coalesced fp32 reduction per 32 channels; per-tile atomics on the same few hundred addresses from every
+            // CTA would serialise in L2.
+            constexpr int kChunks = kCols / 64;
+            float sacc[kChunks][4];
+#pragma unroll
+            for (int i = 0; i < kChunks; ++i) sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f;
+            int stat_key = -1;
+            auto flush_stats = [&](int key) {
+                float *base = stats + static_cast<size_t>(key & 0xffff) * 2 * g.cout + static_cast<size_t>(key >> 16) * BLOCK_N + col_lo;
+#pragma unroll
+                for (int i = 0; i < kChunks; ++i) {
+                    // lane L holds channels 2L, 2L+1 of the chunk; hand lane L channels L and 32 + L instead
+                    const int src = lane >> 1;
+                    const bool odd = (lane & 1) != 0;
+#pragma unroll
+                    for (int qn = 0; qn < 2; ++qn) {
+                        const float e = sacc[i][2 * qn], o = sacc[i][2 * qn + 1];
+                        const float lo_e = __shfl_sync(0xffffffffu, e, src), lo_o = __shfl_sync(0xffffffffu, o, src);
+                        const float hi_e = __shfl_sync(0xffffffffu, e, 16 + src), hi_o = __shfl_sync(0xffffffffu, o, 16 + src);
+                        float *dstp = base + qn * g.cout + i * 64 + lane;
+                        atomicAdd(dstp, odd ? lo_o : lo_e);
+                        atomicAdd(dstp + 32, odd ? hi_o : hi_e);
+                    }
+                    sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f;
+                }
+            };
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int n_blk = t % n_tiles_n;
+                int m_blk = t / n_tiles_n;
+                const int tw = m_blk % g.tiles_w; m_blk /= g.tiles_w;
+                const int th = m_blk % g.tiles_h;
+                const int img = m_blk / g.tiles_h;
+                const int oh = th * g.bh + ph, ow = tw * g.bw + pw;
+                const bool valid = oh < g.oh && ow < g.ow;
+                if (STATS) {
+                    const int key = (n_blk << 16) | (img / imgs_per_group);
+                    if (key != stat_key) {
+                        if (stat_key >= 0) flush_stats(stat_key);
+                        stat_key = key;
+                    }
+                }
+                const size_t pix_off = ((static_cast<size_t>(img) * g.oh + oh) * g.ow + ow) * g.cout + static_cast<size_t>(n_blk) * BLOCK_N;
+                const bool has_add = addend != nullptr && valid;
+                const uint4 *ap = reinterpret_cast<const uint4 *>(addend + pix_off + col_lo);
+                uint4 cur[4], nxt[4];
+                if (has_add) {
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) cur[q4] = __ldg(ap + q4);
+                }
+                mbar_wait(tfull_bar + acc, acc_phase);
+                tc_fence_after_sync();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+#pragma unroll
+                for (int c64 = 0; c64 < kCols; c64 += 64) {
+#pragma unroll
+                    for (int hseg = 0; hseg < 2; ++hseg) {
+                        const int c = col_lo + c64 + hseg * 32;
+                        uint32_t v[32];
+                        tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+                        if (has_add && c + 32 < col_lo + kCols) {
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; ++q4) nxt[q4] = __ldg(ap + (c + 32 - col_lo) / 8 + q4);
+                        }
+                        tmem_ld_wait();
+                        if (c + 32 == col_lo + kCols) {
+                            // the accumulator has been read completely: hand it back to the MMA warp before the stores
+                            tc_fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(tempty_bar + acc);
+                        }
+                        if (has_add) {
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; ++q4) {
+                                const uint32_t w4[4] = {cur[q4].x, cur[q4].y, cur[q4].z, cur[q4].w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w4[e]));
+                                    v[q4 * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[q4 * 8 + 2 * e]) + f.x);
+                                    v[q4 * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(v[q4 * 8 + 2 * e + 1]) + f.y);
+                                }
+                                cur[q4] = nxt[q4];
+                            }
+                        }
+                        uint32_t pkd[16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            // rows outside the image are stored as zeros (the TMA store clips them; the statistics must not see them)
+                            __nv_bfloat162 b = __floats2bfloat162_rn(valid ? __uint_as_float(v[j]) : 0.f, valid ? __uint_as_float(v[j + 1]) : 0.f);
+                            pkd[j >> 1] = *reinterpret_cast<uint32_t *>(&b);
+                        }
+                        if (hseg == 0) {
+                            // the previous TMA store of this warp must have finished reading the staging buffer
+                            if (lane == 0) bulk_wait_read0();
+                            __syncwarp();
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t chunk = static_cast<uint32_t>(hseg * 4 + j) ^ sw;       // 128B swizzle: 16-byte chunk ^ (row & 7)
+                            st_shared_v4(my_row_s + (chunk << 4), pkd[4 * j], pkd[4 * j + 1], pkd[4 * j + 2], pkd[4 * j + 3]);
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d(&tmap_y, smem + L::kStoreOffset + wq * 4096, n_blk * BLOCK_N + col_lo + c64, tw * g.bw + bpw0, th * g.bh + bph0, img);
+                        bulk_commit();
+                    }
+                    if (STATS) {
+                        // lane L sums channels 2L, 2L+1 of this 64-channel chunk over the warp's 32 rows (bf16-rounded values,
+                        // i.e. what BatchNorm will read back); word L of row r sits in 16-byte chunk (L/4) ^ (r & 7)
+                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                        const uint32_t lchunk = static_cast<uint32_t>(lane >> 2), lword = static_cast<uint32_t>(lane & 3) << 2;
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) {
+                            const uint32_t wv = ld_shared_u32(stage_s + static_cast<uint32_t>(r) * 128u + ((lchunk ^ static_cast<uint32_t>(r & 7)) << 4) + lword);
+                            const float f0 = __uint_as_float(wv << 16), f1 = __uint_as_float(wv & 0xffff0000u);
+                            s0 += f0; s1 += f1;
+                            q0 = fmaf(f0, f0, q0); q1 = fmaf(f1, f1, q1);
+                        }
+                        sacc[c64 / 64][0] += s0; sacc[c64 / 64][1] += s1; sacc[c64 / 64][2] += q0; sacc[c64 / 64][3] += q1;
+                    }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (STATS && stat_key >= 0) flush_stats(stat_key);
+            if (lane == 0) bulk_wait_read0();          // shared memory must outlive the last TMA store's reads
         }
     } else {
         // ===== epilogue: TMEM -> registers -> bf16 -> global (NHWC) =====
@@ -446,17 +600,30 @@ int launch_fprop(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bfloat16 *y,
     return REGDA_OK;
 }
 
-template <int BLOCK_N, int STAGES, bool B_MN, bool STATS>
+// REGDA_CONV_EPILOGUE=direct selects the per-lane global-store epilogue (A/B comparisons); default: TMA store
+bool use_tma_epilogue() {
+    const char *e = getenv("REGDA_CONV_EPILOGUE");
+    return !(e && strcmp(e, "direct") == 0);
+}
+
+template <int BLOCK_N, int STAGES, bool B_MN, bool STATS, bool TMA_EPI>
 int launch_persistent_impl(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bfloat16 *y, const ConvGeom &g, cudaStream_t st,
                            float *stats, int imgs_per_group, const __nv_bfloat16 *addend) {
     using L = PersistSmem<BLOCK_N, STAGES>;
-    auto kern = conv_persistent_kernel<BLOCK_N, STAGES, B_MN, STATS>;
+    auto kern = conv_persistent_kernel<BLOCK_N, STAGES, B_MN, STATS, TMA_EPI>;
     const int smem = L::kTotal + 1024;
+    static_assert(L::kTotal + 1024 <= 232448, "persistent conv kernel: shared memory over the 227 KB limit");
     REGDA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int n_tiles_n = g.cout / BLOCK_N;
     const int num_tiles = n_tiles_n * g.n * g.tiles_h * g.tiles_w;
     const int grid = std::min(num_tiles, sm_count());
-    kern<<<grid, kPersistThreads, smem, st>>>(tx, tw, y, g, n_tiles_n, num_tiles, stats, imgs_per_group, addend);
+    CUtensorMap ty = tx;          // unused by the direct epilogue
+    if (TMA_EPI) {
+        // output map [n][oh][ow][cout]; box = one epilogue warp's 32 pixels x 64 channels
+        const int sbw = std::min(g.bw, 32), sbh = 32 / sbw;
+        if (!encode_nhwc(&ty, y, g.n, g.oh, g.ow, g.cout, sbw, sbh, 1)) return REGDA_ERR_CUDA;
+    }
+    kern<<<grid, kPersistThreads, smem, st>>>(tx, tw, ty, y, g, n_tiles_n, num_tiles, stats, imgs_per_group, addend);
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
 }
@@ -464,8 +631,12 @@ int launch_persistent_impl(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bf
 template <int BLOCK_N, int STAGES, bool B_MN>
 int launch_persistent(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bfloat16 *y, const ConvGeom &g, cudaStream_t st,
                       float *stats, int imgs_per_group, const __nv_bfloat16 *addend) {
-    if (!B_MN && stats != nullptr) return launch_persistent_impl<BLOCK_N, STAGES, false, true>(tx, tw, y, g, st, stats, imgs_per_group, addend);
-    return launch_persistent_impl<BLOCK_N, STAGES, B_MN, false>(tx, tw, y, g, st, nullptr, 1, addend);
+    if (use_tma_epilogue()) {
+        if (!B_MN && stats != nullptr) return launch_persistent_impl<BLOCK_N, STAGES, false, true, true>(tx, tw, y, g, st, stats, imgs_per_group, addend);
+        return launch_persistent_impl<BLOCK_N, STAGES, B_MN, false, true>(tx, tw, y, g, st, nullptr, 1, addend);
+    }
+    if (!B_MN && stats != nullptr) return launch_persistent_impl<BLOCK_N, STAGES, false, true, false>(tx, tw, y, g, st, stats, imgs_per_group, addend);
+    return launch_persistent_impl<BLOCK_N, STAGES, B_MN, false, false>(tx, tw, y, g, st, nullptr, 1, addend);
 }
 
 // Tile shape policy.  REGDA_CONV_KERNEL=classic selects the one-tile-per-CTA kernel (A/B comparisons).

@@ -55,6 +55,28 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m
                  : "memory");
 }
 
+// TMA store (shared -> global, bulk-group completion); out-of-bounds parts of the box are not written
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, const void *smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::
+                     "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// TMA reduce-store: global[box] += shared[box] (element-wise add performed at L2)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *m, const void *smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::
+                     "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory source (the buffer may be rewritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+
 // ---- tcgen05 ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
@@ -193,6 +215,28 @@ inline bool encode_bf16_sw128(CUtensorMap *m, const void *base, int rank, const 
                   (unsigned long long)(rank > 1 ? strides[0] : 0), (unsigned long long)(rank > 2 ? strides[1] : 0),
                   (unsigned long long)(rank > 3 ? strides[2] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0,
                   estr[0], rank > 1 ? estr[1] : 0, rank > 2 ? estr[2] : 0, rank > 3 ? estr[3] : 0);
+        return false;
+    }
+    return true;
+}
+
+// float32 2-D map [rows][cols] (row-major) with a {32 cols, box_rows} box, 128-byte swizzle: the staging layout of the
+// weight-gradient epilogue's TMA reduce-stores
+inline bool encode_f32_2d_sw128(CUtensorMap *m, const void *base, long long rows, long long cols, int box_rows) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return false;
+    }
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 4};
+    const cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(f32 2d) rc=%d base=%p rows=%lld cols=%lld", static_cast<int>(rc), base, rows, cols);
         return false;
     }
     return true;

@@ -21,9 +21,26 @@ SHAPES = [
 ]
 
 
+GRAPH_INNER = 0      # --graph N: time N back-to-back launches replayed from a CUDA graph (no host launch floor, warm L2)
+
+
 def timeit(fn, flush, reps=10):
     for _ in range(3):
         fn()
+    if GRAPH_INNER > 0:
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for _ in range(GRAPH_INNER):
+                fn()
+        gr.replay()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) / GRAPH_INNER)
+        ts.sort()
+        return ts[len(ts) // 2]
     ts = []
     for _ in range(reps):
         flush.zero_()
@@ -40,7 +57,11 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--wgrad", action="store_true", help="time the weight-gradient kernel instead of fprop")
     ap.add_argument("--dgrad", action="store_true", help="time the data-gradient kernel instead of fprop")
+    ap.add_argument("--stats", action="store_true", help="fprop with the fused BatchNorm statistics epilogue (2 groups), as the step runs it")
+    ap.add_argument("--graph", type=int, default=0, help="time N launches replayed from one CUDA graph")
     a = ap.parse_args()
+    global GRAPH_INNER
+    GRAPH_INNER = a.graph
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     tot = {"tc": 0.0, "lib": 0.0, "flop": 0.0}
     for name, cnt, cin, hw, cout, k, pad, dil in SHAPES:
@@ -59,7 +80,7 @@ def main():
                 t_tc = timeit(lambda: tc.dgrad(gy, w, x.shape, 1, pad, dil), flush)
             t_lib = timeit(lambda: torch.ops.aten.convolution_backward(gy, x, w, None, [1, 1], [pad, pad], [dil, dil], False, [0, 0], 1, mask), flush)
         else:
-            t_tc = timeit(lambda: tc.fprop(x, w, 1, pad, dil), flush)
+            t_tc = timeit(lambda: tc.fprop(x, w, 1, pad, dil, 2 if a.stats else None), flush)
             t_lib = timeit(lambda: F.conv2d(x, w, None, 1, pad, dil), flush)
         tot["tc"] += cnt * t_tc; tot["lib"] += cnt * t_lib; tot["flop"] += cnt * flop
         print(f"{name:12s} x{cnt:2d} M={a.n*hw*hw:6d} N={cout:4d} K={cin*k*k:5d}  tcgen05 {t_tc*1e3:8.1f} us {flop/t_tc/1e9:7.1f} TF/s | "

@@ -21,7 +21,7 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(2):
         step(*tensors, 1e-2)
     torch.cuda.synchronize()
-tab = prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90)
+tab = prof.key_averages().table(sort_by="cuda_time_total", row_limit=90, max_name_column_width=150)
 os.makedirs(os.path.dirname(a.out), exist_ok=True)
 open(a.out, "w").write(tab)
 print(tab[-6000:])

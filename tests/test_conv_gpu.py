@@ -157,3 +157,32 @@ def test_conv_tap_adds_the_residual_gradient_in_the_dgrad_epilogue():
     yr = F.conv2d(xr, wr, None, 1, 1, 1)
     torch.autograd.backward([yr, xr * 1.0], [gy.float(), gt.float()])
     assert float((x.grad.float() - xr.grad).abs().max()) <= 1.5e-2 * float(xr.grad.abs().max())
+
+
+@pytest.mark.parametrize("epilogue", ["tma", "direct"])
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[2], SHAPES[4], SHAPES[8], SHAPES[11], (4, 256, 32, 32, 1024, 1, 0, 1),
+                                   (2, 128, 5, 40, 128, 3, 1, 1)], ids=str)
+def test_fused_bn_statistics_and_both_epilogues(shape, epilogue, monkeypatch):
+    """The conv epilogue's per-group per-channel (sum, sum of squares) equal those of the bf16 output it wrote, for the
+    TMA-store epilogue and the per-lane-store epilogue, and both epilogues write the same output bits."""
+    from regda_b200.ops import tc
+    monkeypatch.setenv("REGDA_CONV_EPILOGUE", epilogue)
+    n, cin, h, w, cout, k, pad, dil = shape
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5).bfloat16().contiguous(memory_format=torch.channels_last)
+    groups = 2 if n % 2 == 0 else 1
+    y, st = tc.fprop(x, wt, 1, pad, dil, groups)
+    y_plain = tc.fprop(x, wt, 1, pad, dil)
+    assert torch.equal(y, y_plain)
+    monkeypatch.setenv("REGDA_CONV_EPILOGUE", "direct" if epilogue == "tma" else "tma")
+    assert torch.equal(y, tc.fprop(x, wt, 1, pad, dil))
+    ref = _ref(x, wt, pad, dil)
+    assert float((y.float() - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
+    yf = y.float().reshape(groups, n // groups, cout, -1)
+    want_sum = yf.sum(dim=(1, 3))
+    want_sq = (yf * yf).sum(dim=(1, 3))
+    assert st.shape == (groups, 2, cout)
+    cnt = (n // groups) * y.shape[2] * y.shape[3]
+    assert torch.allclose(st[:, 0], want_sum, rtol=1e-4, atol=1e-4 * cnt ** 0.5 * float(yf.abs().max()))
+    assert torch.allclose(st[:, 1], want_sq, rtol=1e-4, atol=1e-3)
