@@ -173,7 +173,8 @@ struct WgPersistSmem {
     static constexpr int kABytes = kWgM * kWgK * 2;
     static constexpr int kBBytes = BLOCK_N * kWgK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kStoreOffset = STAGES * kStageBytes;     // 4 KB per epilogue warp: one 32 cout x 32 cin fp32 box
+    static constexpr int kBarOffset = kStoreOffset + 8 * 4096;
     static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 8;
 };
 
@@ -193,9 +194,13 @@ __device__ __forceinline__ WgItem wg_decode(int item, const WgradGeom &g, int m_
 
 constexpr int kWgPersistThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant, half the columns each)
 
-template <int BLOCK_N, int STAGES>
+// TMA_EPI: each epilogue warp stages 32 cout rows x 32 cin columns of fp32 in 128B-swizzled shared memory and adds the box
+// to the gradient with ONE TMA reduce-store (cp.reduce.async.bulk.tensor .add: whole 128-byte lines, reduced in L2)
+// instead of 16-byte-per-lane red.global instructions that touch 32 different lines each.
+template <int BLOCK_N, int STAGES, bool TMA_EPI>
 __global__ void __launch_bounds__(kWgPersistThreads, 1)
 conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                             const __grid_constant__ CUtensorMap tmap_dw,
                              float *__restrict__ dw, const WgradGeom g, const int m_tiles, const int num_items) {
     using L = WgPersistSmem<BLOCK_N, STAGES>;
     extern __shared__ uint8_t smem_raw[];
@@ -212,6 +217,7 @@ conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_dy);
         prefetch_tmap(&tmap_x);
+        if (TMA_EPI) prefetch_tmap(&tmap_dw);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
@@ -284,6 +290,49 @@ conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const 
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
+    } else if (TMA_EPI) {
+        const int q = warp & 3;
+        const int col_lo = ((warp - 2) >> 2) * (BLOCK_N / 2), col_hi = col_lo + BLOCK_N / 2;
+        uint8_t *stage_p = smem + L::kStoreOffset + (warp - 2) * 4096;
+        const uint32_t my_row_s = smem_u32(stage_p) + static_cast<uint32_t>(lane) * 128u;
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            const WgItem it = wg_decode(item, g, m_tiles);
+            const int row0 = it.m_blk * kWgM + q * 32;                                   // first cout row of this warp's box
+            const int colbase = it.tap * g.cin + it.n_blk * BLOCK_N;                     // column in the [cout][taps*cin] matrix
+            const bool live = it.k_hi > it.k_lo && row0 < g.cout;
+            mbar_wait(tfull_bar + acc, acc_phase);
+            tc_fence_after_sync();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+#pragma unroll 1
+            for (int c = col_lo; c < col_hi; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+                tmem_ld_wait();
+                if (c + 32 == col_hi) {
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar + acc);      // accumulator read completely: MMAs of item i+2 may start
+                }
+                if (live) {
+                    if (lane == 0) bulk_wait_read0();                  // previous reduce-store has read the staging buffer
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        st_shared_v4(my_row_s + ((static_cast<uint32_t>(j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_reduce_add_2d(&tmap_dw, stage_p, colbase + c, row0);
+                        bulk_commit();
+                    }
+                }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (lane == 0) bulk_wait_read0();
     } else {
         const int q = warp & 3;
         const int col_lo = ((warp - 2) >> 2) * (BLOCK_N / 2), col_hi = col_lo + BLOCK_N / 2;
@@ -323,18 +372,28 @@ conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const 
     }
 }
 
-template <int BLOCK_N, int STAGES>
-int launch_wgrad_persistent(const CUtensorMap &tdy, const CUtensorMap &tx, float *dw, const WgradGeom &g, cudaStream_t st) {
+template <int BLOCK_N, int STAGES, bool TMA_EPI>
+int launch_wgrad_persistent_impl(const CUtensorMap &tdy, const CUtensorMap &tx, float *dw, const WgradGeom &g, cudaStream_t st) {
     using L = WgPersistSmem<BLOCK_N, STAGES>;
-    auto kern = conv_wgrad_persistent_kernel<BLOCK_N, STAGES>;
+    auto kern = conv_wgrad_persistent_kernel<BLOCK_N, STAGES, TMA_EPI>;
     const int smem = L::kTotal + 1024;
+    static_assert(L::kTotal + 1024 <= 232448, "persistent wgrad kernel: shared memory over the 227 KB limit");
+    CUtensorMap tdw = tdy;        // unused by the direct epilogue
+    if (TMA_EPI && !encode_f32_2d_sw128(&tdw, dw, g.cout, static_cast<long long>(g.r) * g.s * g.cin, 32)) return REGDA_ERR_CUDA;
     REGDA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int m_tiles = (g.cout + kWgM - 1) / kWgM;
     const int num_items = g.n_tiles * m_tiles * g.r * g.s * g.splits;
     const int grid = std::min(num_items, sm_count());
-    kern<<<grid, kWgPersistThreads, smem, st>>>(tdy, tx, dw, g, m_tiles, num_items);
+    kern<<<grid, kWgPersistThreads, smem, st>>>(tdy, tx, tdw, dw, g, m_tiles, num_items);
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+int launch_wgrad_persistent(const CUtensorMap &tdy, const CUtensorMap &tx, float *dw, const WgradGeom &g, cudaStream_t st) {
+    const char *e = getenv("REGDA_CONV_EPILOGUE");          // "direct": per-lane red.global epilogue (A/B comparisons)
+    if (e && strcmp(e, "direct") == 0) return launch_wgrad_persistent_impl<BLOCK_N, STAGES, false>(tdy, tx, dw, g, st);
+    return launch_wgrad_persistent_impl<BLOCK_N, STAGES, true>(tdy, tx, dw, g, st);
 }
 
 template <int BLOCK_N, int STAGES>

@@ -117,9 +117,11 @@ def test_strided_fprop_and_wgrad(shape):
 WGRAD = [SHAPES[0], SHAPES[1], SHAPES[3], SHAPES[5], SHAPES[6], SHAPES[8], SHAPES[9], SHAPES[11], (2, 4096, 32, 32, 512, 3, 1, 1)]
 
 
+@pytest.mark.parametrize("epilogue", ["tma", "direct"])
 @pytest.mark.parametrize("shape", WGRAD, ids=str)
-def test_wgrad_and_dgrad_match_float32_reference(shape):
+def test_wgrad_and_dgrad_match_float32_reference(shape, epilogue, monkeypatch):
     from regda_b200.ops import tc
+    monkeypatch.setenv("REGDA_CONV_EPILOGUE", epilogue)
     n, cin, h, w, cout, k, pad, dil = shape
     g = torch.Generator(device="cuda").manual_seed(5)
     x = torch.randn(n, cin, h, w, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
