@@ -218,9 +218,11 @@ int regda_bn_forward_bf16(const void *y, const void *residual, void *out, int64_
                           int64_t *num_batches_tracked, double eps, double momentum, int relu,
                           float *stats, int have_stats, int stats_zeroed, void *stream);
 /* red float32 [groups][2][c]: scratch for the two backward reductions (zeroed here unless red_zeroed != 0). */
+/* ReLU mask: from `out` (out > 0) when it is given; with relu != 0, out == NULL and dres == NULL (no residual) the mask is
+ * recomputed from y, gamma, beta and stats exactly as the forward computed the output, so `out` is not read at all. */
 int regda_bn_backward_bf16(const void *dout, const void *out, const void *y, void *dy, void *dres, int64_t npix, int c,
-                           int groups, const float *gamma, const float *stats, double eps, float *dgamma, float *dbeta,
-                           int relu, float *red, int red_zeroed, void *stream);
+                           int groups, const float *gamma, const float *beta, const float *stats, double eps, float *dgamma,
+                           float *dbeta, int relu, float *red, int red_zeroed, void *stream);
 
 /* MaxPool2d(3, stride 2, padding 1) over channels-last bf16 (regda/_resnets.py:153): x [n][h][w][c] -> y [n][oh][ow][c],
  * oh = (h-1)/2+1; argmax_u8 (may be NULL for inference) [n][oh][ow][c] receives the position 0..8 of the first maximum

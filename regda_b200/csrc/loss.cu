@@ -7,8 +7,11 @@
 // One block per (image, strip of ceil(H/h) full-resolution rows): such a strip touches at most
 // three low-resolution rows, which are staged in shared memory.  A thread walks one column
 // of the strip, accumulating the row-direction part of the transposed interpolation in
-// registers; the column-direction part goes through shared-memory atomics (2-3 per pixel
-// instead of 4c), then one global atomicAdd per touched low-resolution element.
+// registers and parking it in shared memory ([3][c][W]); the column-direction part is then a
+// GATHER: one thread per staged low-resolution element sums the ~2*W/w columns whose
+// interpolation footprint covers it, in a fixed order (no shared-memory float atomics: those
+// compile to compare-and-swap loops that serialise 16-way on the ~W/w columns sharing a
+// target), then one global atomicAdd per touched low-resolution element.
 #include <algorithm>
 
 #include "common.cuh"
@@ -41,12 +44,11 @@ ce_bilinear_kernel(const CeArgs a) {
     const int nrow = min(3, a.h - ylo);
     const int plane = a.h * a.w;
     float *lo = sm;                        // [3][c][w] staged logits
-    float *acc = sm + 3 * a.c * a.w;       // [3][c][w] gradient accumulators
+    float *gcol = sm + 3 * a.c * a.w;      // [3][c][W] per-column gradient (row direction already applied)
     const float *pimg = a.pred + static_cast<size_t>(img) * a.c * plane;
     for (int i = threadIdx.x; i < 3 * a.c * a.w; i += kCeThreads) {
         const int r = i / (a.c * a.w), rem = i - r * a.c * a.w, j = rem / a.w, x = rem - j * a.w;
         lo[i] = r < nrow ? pimg[static_cast<size_t>(j) * plane + (ylo + r) * a.w + x] : 0.f;
-        acc[i] = 0.f;
     }
     __syncthreads();
 
@@ -108,11 +110,7 @@ ce_bilinear_kernel(const CeArgs a) {
             for (int r = 0; r < 3; ++r)
 #pragma unroll
                 for (int j = 0; j < CMAX; ++j)
-                    if (j < a.c && g[r][j] != 0.f) {
-                        float *row = acc + (r * a.c + j) * a.w;
-                        atomicAdd(row + x0, wx0 * g[r][j]);
-                        if (wx1 != 0.f) atomicAdd(row + x1, wx1 * g[r][j]);
-                    }
+                    if (j < a.c) gcol[(r * a.c + j) * a.W + X] = g[r][j];
         }
     }
     if (bad) raise_flag(a.flags, REGDA_FLAG_LABEL_RANGE);
@@ -127,10 +125,28 @@ ce_bilinear_kernel(const CeArgs a) {
         a.partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
     }
     if (a.dpred != nullptr) {
+        // (the __syncthreads above also ordered the gcol stores)  Column X feeds low-resolution column x0(X) with weight
+        // wx0 and x0(X)+1 with wx1, x0 / wx1 computed exactly as in the forward part; the columns that can reach x lie
+        // within (x-1)/sx .. (x+1)/sx, scanned with one column of slack on each side.
         float *dimg = a.dpred + static_cast<size_t>(img) * a.c * plane;
+        const float inv_sx = a.sx > 0.f ? 1.0f / a.sx : 0.f;
         for (int i = threadIdx.x; i < nrow * a.c * a.w; i += kCeThreads) {
             const int r = i / (a.c * a.w), rem = i - r * a.c * a.w, j = rem / a.w, x = rem - j * a.w;
-            const float v = acc[i];
+            int Xlo = 0, Xhi = a.W - 1;
+            if (a.sx > 0.f) {
+                Xlo = max(0, static_cast<int>(static_cast<float>(x - 1) * inv_sx) - 1);
+                Xhi = min(a.W - 1, static_cast<int>(static_cast<float>(x + 1) * inv_sx) + 2);
+            }
+            const float *gr = gcol + (r * a.c + j) * a.W;
+            float v = 0.f;
+            for (int X = Xlo; X <= Xhi; ++X) {
+                const float fx = a.sx * static_cast<float>(X);
+                const int x0 = static_cast<int>(fx);
+                const float wx1 = fx - static_cast<float>(x0);
+                const bool inner = x0 < a.w - 1;             // at the last column x1 == x0: both weights land on x0
+                const float wgt = (x0 == x ? (inner ? 1.0f - wx1 : 1.0f) : 0.f) + ((x0 + 1 == x && inner) ? wx1 : 0.f);
+                v = fmaf(wgt, gr[X], v);
+            }
             if (v != 0.f) atomicAdd(dimg + static_cast<size_t>(j) * plane + (ylo + r) * a.w + x, v * a.gscale);
         }
     }
@@ -203,7 +219,7 @@ extern "C" int regda_ce_bilinear(const float *pred, const int64_t *label, float 
     if (!pred || !label) return fail(REGDA_ERR_INVALID_ARG, "ce_bilinear: null pointer");
     const size_t need = regda_ce_workspace_bytes(b, h, H);
     if (!workspace || workspace_bytes < need) return fail(REGDA_ERR_WORKSPACE, "ce_bilinear: workspace too small");
-    const size_t smem = static_cast<size_t>(6) * c * w * 4;
+    const size_t smem = static_cast<size_t>(3) * c * (w + W) * 4;      // staged logits [3][c][w] + per-column gradients [3][c][W]
     if (smem > 200 * 1024) return fail(REGDA_ERR_UNSUPPORTED, "ce_bilinear: low-resolution row too wide for shared memory");
     CeArgs a;
     a.pred = pred; a.label = reinterpret_cast<const long long *>(label); a.dpred = dpred;

@@ -183,31 +183,51 @@ bn_apply_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__rest
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-template <bool RELU>
+// RELU: 0 = no ReLU, 1 = mask from the saved output (out > 0), 2 = mask recomputed from y exactly as the forward computed
+// it (fmaf(y, gamma*rstd, beta - mean*gamma*rstd) > 0; only valid without a residual) -- saves reading `out` (2 of 6 B/element)
+template <int RELU>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 *__restrict__ out, const __nv_bfloat16 *__restrict__ y,
-                     long long total, int c, long long span_per_block, float *__restrict__ gdz, float *__restrict__ gdzy) {
+                     long long total, int c, long long span_per_block, float *__restrict__ gdz, float *__restrict__ gdzy,
+                     const float *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta, float inv_n, float eps) {
     {
         const long long off = static_cast<long long>(blockIdx.y) * total;
         dout += off; y += off;
-        if (RELU) out += off;
+        if (RELU == 1) out += off;
         gdz += 2 * c * blockIdx.y; gdzy += 2 * c * blockIdx.y;
+        stats += 2 * c * blockIdx.y;
     }
     float s[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
     const long long lo = static_cast<long long>(blockIdx.x) * span_per_block;
     const long long hi = min(total, lo + span_per_block);
+    float sc[8], sh[8];
+    if (RELU == 2) {
+        const int ch = static_cast<int>((lo + static_cast<long long>(threadIdx.x) * 8) % c);      // invariant: kBnSpan % c == 0
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float mean, rstd, var;
+            bn_moments(stats, c, ch + i, inv_n, eps, mean, rstd, var);
+            const float g = gamma ? gamma[ch + i] : 1.f, b = beta ? beta[ch + i] : 0.f;
+            sc[i] = g * rstd;
+            sh[i] = fmaf(-mean, sc[i], b);
+        }
+    }
 #pragma unroll 2
     for (long long e = lo + static_cast<long long>(threadIdx.x) * 8; e < hi; e += kBnSpan) {
         float d[8], v[8];
         unpack(ld8_stream(dout + e), d);
         unpack(ld8_stream(y + e), v);
-        if (RELU) {
+        if (RELU == 1) {
             float o[8];
             unpack(ld8(out + e), o);
 #pragma unroll
             for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+        }
+        if (RELU == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = fmaf(v[i], sc[i], sh[i]) > 0.f ? d[i] : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s[i] += d[i]; q[i] = fmaf(d[i], v[i], q[i]); }
@@ -217,12 +237,12 @@ bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16
 
 // dy = a * (dz - k1 - (y - mean) * k2) with a = gamma*rstd, k1 = mean(dz), k2 = mean(dz*xhat)*rstd, all derived per thread from
 // red [groups][2][c] (sum dz, sum dz*y) and the forward stats; dres = dz.  Block (0,0) accumulates dgamma / dbeta over the groups.
-template <bool RELU, bool DRES>
+template <int RELU, bool DRES>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 *__restrict__ out, const __nv_bfloat16 *__restrict__ y,
                     __nv_bfloat16 *__restrict__ dy, __nv_bfloat16 *__restrict__ dres, long long total, int c,
                     const float *__restrict__ stats, const float *__restrict__ red, const float *__restrict__ gamma, float inv_n, float eps,
-                    float *__restrict__ dgamma, float *__restrict__ dbeta) {
+                    float *__restrict__ dgamma, float *__restrict__ dbeta, const float *__restrict__ beta) {
     if (blockIdx.x == 0 && blockIdx.y == 0 && (dgamma != nullptr || dbeta != nullptr)) {
         const int groups = gridDim.y;
         for (int ch = threadIdx.x; ch < c; ch += kBnThreads) {
@@ -241,7 +261,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 
     {
         const long long off = static_cast<long long>(blockIdx.y) * total;
         dout += off; y += off; dy += off;
-        if (RELU) out += off;
+        if (RELU == 1) out += off;
         if (DRES) dres += off;
         stats += 2 * c * blockIdx.y; red += 2 * c * blockIdx.y;
     }
@@ -249,7 +269,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 
     long long e = static_cast<long long>(blockIdx.x) * kBnSpan + static_cast<long long>(threadIdx.x) * 8;
     if (e >= total) return;
     const int ch = static_cast<int>(e % c);
-    float a[8], k1[8], k2[8], mu[8];
+    float a[8], k1[8], k2[8], mu[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         float rstd, var;
@@ -259,16 +279,17 @@ bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 
         a[i] = (gamma ? gamma[ch + i] : 1.f) * rstd;
         k1[i] = sdz * inv_n;
         k2[i] = sdzx * inv_n * rstd;
+        sh[i] = RELU == 2 ? fmaf(-mu[i], a[i], beta ? beta[ch + i] : 0.f) : 0.f;     // forward shift (a = forward scale)
     }
     for (; e < total; e += 2 * stride) {
         const long long e2 = e + stride;
         const bool two = e2 < total;
         bf16x8 d0 = ld8_stream(dout + e), v0 = ld8_stream(y + e), o0 = d0, d1 = d0, v1 = v0, o1 = d0;
-        if (RELU) o0 = ld8_stream(out + e);
+        if (RELU == 1) o0 = ld8_stream(out + e);
         if (two) {
             d1 = ld8_stream(dout + e2);
             v1 = ld8_stream(y + e2);
-            if (RELU) o1 = ld8_stream(out + e2);
+            if (RELU == 1) o1 = ld8_stream(out + e2);
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -276,11 +297,15 @@ bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 
             float d[8], v[8];
             unpack(h ? d1 : d0, d);
             unpack(h ? v1 : v0, v);
-            if (RELU) {
+            if (RELU == 1) {
                 float o[8];
                 unpack(h ? o1 : o0, o);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+            }
+            if (RELU == 2) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d[i] = fmaf(v[i], a[i], sh[i]) > 0.f ? d[i] : 0.f;
             }
             const long long pos = h ? e2 : e;
             if (DRES) st8(dres + pos, pack(d));
@@ -349,11 +374,13 @@ extern "C" int regda_bn_forward_bf16(const void *y, const void *residual, void *
 }
 
 extern "C" int regda_bn_backward_bf16(const void *dout, const void *out, const void *y, void *dy, void *dres, int64_t npix, int c,
-                                      int groups, const float *gamma, const float *stats, double eps, float *dgamma, float *dbeta,
-                                      int relu, float *red, int red_zeroed, void *stream) {
+                                      int groups, const float *gamma, const float *beta, const float *stats, double eps, float *dgamma,
+                                      float *dbeta, int relu, float *red, int red_zeroed, void *stream) {
     if (!bn_shape_ok(npix, c)) return fail(REGDA_ERR_UNSUPPORTED, "bn_backward: channels must divide 2048 and be a multiple of 8");
     if (groups < 1 || npix % groups != 0) return fail(REGDA_ERR_INVALID_ARG, "bn_backward: groups must divide the pixel count");
-    if (!dout || !y || !dy || !stats || !red || (relu && !out)) return fail(REGDA_ERR_INVALID_ARG, "bn_backward: null pointer");
+    if (!dout || !y || !dy || !stats || !red) return fail(REGDA_ERR_INVALID_ARG, "bn_backward: null pointer");
+    if (relu && !out && dres) return fail(REGDA_ERR_INVALID_ARG, "bn_backward: a residual layer needs the saved output for its ReLU mask");
+    const int rmode = !relu ? 0 : (out ? 1 : 2);      // 2: mask recomputed from y (no residual)
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long gpix = npix / groups;
     const long long total = gpix * c;
@@ -363,16 +390,18 @@ extern "C" int regda_bn_backward_bf16(const void *dout, const void *out, const v
     const __nv_bfloat16 *dd = static_cast<const __nv_bfloat16 *>(dout);
     const __nv_bfloat16 *oo = static_cast<const __nv_bfloat16 *>(out);
     const __nv_bfloat16 *yy = static_cast<const __nv_bfloat16 *>(y);
-    if (relu) bn_bwd_reduce_kernel<true><<<dim3(rg, groups), kBnThreads, 0, st>>>(dd, oo, yy, total, c, span, red, red + c);
-    else bn_bwd_reduce_kernel<false><<<dim3(rg, groups), kBnThreads, 0, st>>>(dd, oo, yy, total, c, span, red, red + c);
-    REGDA_LAUNCH_CHECK();
     const float inv_n = 1.f / static_cast<float>(gpix), e = static_cast<float>(eps);
+#define REGDA_BN_RED(R) bn_bwd_reduce_kernel<R><<<dim3(rg, groups), kBnThreads, 0, st>>>(dd, oo, yy, total, c, span, red, red + c, stats, gamma, beta, inv_n, e)
+    if (rmode == 0) REGDA_BN_RED(0); else if (rmode == 1) REGDA_BN_RED(1); else REGDA_BN_RED(2);
+#undef REGDA_BN_RED
+    REGDA_LAUNCH_CHECK();
     const dim3 ag(apply_grid(total, groups), groups);
     __nv_bfloat16 *dyy = static_cast<__nv_bfloat16 *>(dy);
     __nv_bfloat16 *dr = static_cast<__nv_bfloat16 *>(dres);
-#define REGDA_BN_BWD(R, D) bn_bwd_apply_kernel<R, D><<<ag, kBnThreads, 0, st>>>(dd, oo, yy, dyy, dr, total, c, stats, red, gamma, inv_n, e, dgamma, dbeta)
-    if (relu) { if (dr) REGDA_BN_BWD(true, true); else REGDA_BN_BWD(true, false); }
-    else { if (dr) REGDA_BN_BWD(false, true); else REGDA_BN_BWD(false, false); }
+#define REGDA_BN_BWD(R, D) bn_bwd_apply_kernel<R, D><<<ag, kBnThreads, 0, st>>>(dd, oo, yy, dyy, dr, total, c, stats, red, gamma, inv_n, e, dgamma, dbeta, beta)
+    if (rmode == 2) REGDA_BN_BWD(2, false);
+    else if (rmode == 1) { if (dr) REGDA_BN_BWD(1, true); else REGDA_BN_BWD(1, false); }
+    else { if (dr) REGDA_BN_BWD(0, true); else REGDA_BN_BWD(0, false); }
 #undef REGDA_BN_BWD
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;

@@ -57,7 +57,9 @@ class _BnActFn(torch.autograd.Function):
                   groups, capi.ptr(gamma), capi.ptr(beta), capi.ptr(bn.running_mean), capi.ptr(bn.running_var),
                   capi.ptr(bn.num_batches_tracked), float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1), int(relu),
                   capi.ptr_any(stats), have, int(zeroed), capi.stream())
-        ctx.save_for_backward(y, out if relu else None, stats)
+        # the backward recomputes the ReLU mask of a residual-free layer from y (bit-identical to this forward), so the
+        # output is only kept where a residual entered it
+        ctx.save_for_backward(y, out if (relu and residual is not None) else None, stats)
         ctx.gamma, ctx.beta, ctx.relu, ctx.has_res, ctx.groups, ctx.eps = gamma, beta, relu, residual is not None, groups, float(bn.eps)
         return out
 
@@ -74,7 +76,7 @@ class _BnActFn(torch.autograd.Function):
         red, zeroed = capi.zero_pool.take((ctx.groups, 2, c), y.device)
         capi.call("regda_bn_backward_bf16", capi.ptr_any(dout), capi.ptr_any(out) if out is not None else None, capi.ptr_any(y),
                   capi.ptr_any(dy), capi.ptr_any(dres) if dres is not None else None, n * h * w, c, ctx.groups, capi.ptr(gamma),
-                  capi.ptr_any(stats), ctx.eps, capi.ptr(dgamma) if dgamma is not None else None,
+                  capi.ptr(beta), capi.ptr_any(stats), ctx.eps, capi.ptr(dgamma) if dgamma is not None else None,
                   capi.ptr(dbeta) if dbeta is not None else None, int(ctx.relu), capi.ptr_any(red), int(zeroed), capi.stream())
         # gamma / beta gradients were accumulated in place: nothing flows back through autograd for them
         return dy, dres, None, None, None, None, None, None
@@ -146,7 +148,7 @@ class _InstanceNormFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         red, zeroed = capi.zero_pool.take((n, 2, c), x.device)
         capi.call("regda_bn_backward_bf16", capi.ptr_any(dout), None, capi.ptr_any(x), capi.ptr_any(dx), None, n * h * w, c, n, None,
-                  capi.ptr_any(stats), ctx.eps, None, None, 0, capi.ptr_any(red), int(zeroed), capi.stream())
+                  None, capi.ptr_any(stats), ctx.eps, None, None, 0, capi.ptr_any(red), int(zeroed), capi.stream())
         return dx, None
 
 
