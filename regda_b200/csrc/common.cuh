@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "regda_b200.h"
 
@@ -32,6 +33,39 @@ int max_optin_smem();
             return ::regda::fail(REGDA_ERR_CUDA, "kernel launch failed: %s (%s:%d)",        \
                                  cudaGetErrorString(_e), __FILE__, __LINE__);               \
     } while (0)
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// A kernel that calls pdl_trigger() at its start lets the NEXT kernel of the stream be scheduled while this one is still
+// running; that kernel runs its prologue (barrier / tensor-memory / descriptor set-up) and then blocks in pdl_wait() until
+// this grid has completed and its memory is visible.  Rule for every PDL-launched kernel: NO global-memory access before
+// pdl_wait().  REGDA_PDL=0 launches them as plain stream-ordered kernels (both intrinsics are then no-ops).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// REGDA_PDL: 0 = off, 1 = kernels of level 1 (the tensor-core kernels, which have a real prologue to overlap), 2 = all
+inline int pdl_level() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("REGDA_PDL");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+template <int LEVEL = 1, typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_level() >= LEVEL ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -235,6 +235,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     const int lane = threadIdx.x & 31;
     const int num_k = g.r * g.s * g.kc;
 
+    pdl_trigger();          // the next kernel's prologue may overlap this kernel (it blocks in its own pdl_wait)
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_x);
         prefetch_tmap(&tmap_w);
@@ -251,6 +252,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();             // everything above touched only shared / tensor memory; global memory from here on
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -623,8 +625,7 @@ int launch_persistent_impl(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bf
         const int sbw = std::min(g.bw, 32), sbh = 32 / sbw;
         if (!encode_nhwc(&ty, y, g.n, g.oh, g.ow, g.cout, sbw, sbh, 1)) return REGDA_ERR_CUDA;
     }
-    kern<<<grid, kPersistThreads, smem, st>>>(tx, tw, ty, y, g, n_tiles_n, num_tiles, stats, imgs_per_group, addend);
-    REGDA_LAUNCH_CHECK();
+    REGDA_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kPersistThreads), smem, st, tx, tw, ty, y, g, n_tiles_n, num_tiles, stats, imgs_per_group, addend));
     return REGDA_OK;
 }
 

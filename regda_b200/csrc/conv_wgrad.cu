@@ -214,6 +214,7 @@ conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    pdl_trigger();
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_dy);
         prefetch_tmap(&tmap_x);
@@ -230,6 +231,7 @@ conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const 
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         if (elect_one()) {
@@ -384,8 +386,7 @@ int launch_wgrad_persistent_impl(const CUtensorMap &tdy, const CUtensorMap &tx, 
     const int m_tiles = (g.cout + kWgM - 1) / kWgM;
     const int num_items = g.n_tiles * m_tiles * g.r * g.s * g.splits;
     const int grid = std::min(num_items, sm_count());
-    kern<<<grid, kWgPersistThreads, smem, st>>>(tdy, tx, tdw, dw, g, m_tiles, num_items);
-    REGDA_LAUNCH_CHECK();
+    REGDA_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kWgPersistThreads), smem, st, tdy, tx, tdw, dw, g, m_tiles, num_items));
     return REGDA_OK;
 }
 

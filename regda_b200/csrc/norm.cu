@@ -74,6 +74,8 @@ __device__ __forceinline__ void block_channel_reduce(float (&a)[8], float (&b)[8
 __global__ void __launch_bounds__(kBnThreads)
 bn_stats_kernel(const __nv_bfloat16 *__restrict__ y, long long total, int c, long long span_per_block,
                 float *__restrict__ gsum, float *__restrict__ gsq) {
+    pdl_trigger();
+    pdl_wait();
     // blockIdx.y = statistics group (a contiguous range of `total` elements); group g accumulates into gsum + 2*c*g
     y += static_cast<long long>(blockIdx.y) * total;
     gsum += 2 * c * blockIdx.y;
@@ -111,6 +113,8 @@ bn_apply_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__rest
                 long long total, int c, const float *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta,
                 float inv_n, float unbias, float eps, float momentum, float *__restrict__ running_mean, float *__restrict__ running_var,
                 long long *__restrict__ num_batches) {
+    pdl_trigger();
+    pdl_wait();
     if (blockIdx.x == 0 && blockIdx.y == 0) {
         const int groups = gridDim.y;
         if (threadIdx.x == 0 && num_batches != nullptr) *num_batches += groups;
@@ -190,6 +194,8 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 *__restrict__ out, const __nv_bfloat16 *__restrict__ y,
                      long long total, int c, long long span_per_block, float *__restrict__ gdz, float *__restrict__ gdzy,
                      const float *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta, float inv_n, float eps) {
+    pdl_trigger();
+    pdl_wait();
     {
         const long long off = static_cast<long long>(blockIdx.y) * total;
         dout += off; y += off;
@@ -243,6 +249,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 
                     __nv_bfloat16 *__restrict__ dy, __nv_bfloat16 *__restrict__ dres, long long total, int c,
                     const float *__restrict__ stats, const float *__restrict__ red, const float *__restrict__ gamma, float inv_n, float eps,
                     float *__restrict__ dgamma, float *__restrict__ dbeta, const float *__restrict__ beta) {
+    pdl_trigger();
+    pdl_wait();
     if (blockIdx.x == 0 && blockIdx.y == 0 && (dgamma != nullptr || dbeta != nullptr)) {
         const int groups = gridDim.y;
         for (int ch = threadIdx.x; ch < c; ch += kBnThreads) {
@@ -355,8 +363,7 @@ extern "C" int regda_bn_forward_bf16(const void *y, const void *residual, void *
         if (!stats_zeroed) REGDA_CUDA_CHECK(cudaMemsetAsync(stats, 0, static_cast<size_t>(2 * c) * groups * sizeof(float), st));
         long long span = 0;
         const int rg = reduce_grid(total, groups, &span);
-        bn_stats_kernel<<<dim3(rg, groups), kBnThreads, 0, st>>>(yy, total, c, span, stats, stats + c);
-        REGDA_LAUNCH_CHECK();
+        REGDA_CUDA_CHECK(launch_pdl<2>(bn_stats_kernel, dim3(rg, groups), dim3(kBnThreads), 0, st, yy, total, c, span, stats, stats + c));
     }
     const float n = static_cast<float>(gpix);
     const float inv_n = 1.f / n, unbias = gpix > 1 ? n / (n - 1.f) : 1.f, e = static_cast<float>(eps), mom = static_cast<float>(momentum);
@@ -364,8 +371,8 @@ extern "C" int regda_bn_forward_bf16(const void *y, const void *residual, void *
     const dim3 ag(apply_grid(total, groups), groups);
     const __nv_bfloat16 *rr = static_cast<const __nv_bfloat16 *>(residual);
     __nv_bfloat16 *oo = static_cast<__nv_bfloat16 *>(out);
-#define REGDA_BN_APPLY(R, S) bn_apply_kernel<R, S><<<ag, kBnThreads, 0, st>>>(yy, rr, oo, total, c, stats, gamma, beta, inv_n, unbias, e, mom, \
-                                                                             running_mean, running_var, nbt)
+#define REGDA_BN_APPLY(R, S) REGDA_CUDA_CHECK(launch_pdl<2>(bn_apply_kernel<R, S>, ag, dim3(kBnThreads), 0, st, yy, rr, oo, total, c, stats, gamma, beta, inv_n, \
+                                                        unbias, e, mom, running_mean, running_var, nbt))
     if (relu) { if (rr) REGDA_BN_APPLY(true, true); else REGDA_BN_APPLY(true, false); }
     else { if (rr) REGDA_BN_APPLY(false, true); else REGDA_BN_APPLY(false, false); }
 #undef REGDA_BN_APPLY
@@ -391,14 +398,16 @@ extern "C" int regda_bn_backward_bf16(const void *dout, const void *out, const v
     const __nv_bfloat16 *oo = static_cast<const __nv_bfloat16 *>(out);
     const __nv_bfloat16 *yy = static_cast<const __nv_bfloat16 *>(y);
     const float inv_n = 1.f / static_cast<float>(gpix), e = static_cast<float>(eps);
-#define REGDA_BN_RED(R) bn_bwd_reduce_kernel<R><<<dim3(rg, groups), kBnThreads, 0, st>>>(dd, oo, yy, total, c, span, red, red + c, stats, gamma, beta, inv_n, e)
+#define REGDA_BN_RED(R) REGDA_CUDA_CHECK(launch_pdl<2>(bn_bwd_reduce_kernel<R>, dim3(rg, groups), dim3(kBnThreads), 0, st, dd, oo, yy, total, c, span, red, red + c, \
+                                                   stats, gamma, beta, inv_n, e))
     if (rmode == 0) REGDA_BN_RED(0); else if (rmode == 1) REGDA_BN_RED(1); else REGDA_BN_RED(2);
 #undef REGDA_BN_RED
     REGDA_LAUNCH_CHECK();
     const dim3 ag(apply_grid(total, groups), groups);
     __nv_bfloat16 *dyy = static_cast<__nv_bfloat16 *>(dy);
     __nv_bfloat16 *dr = static_cast<__nv_bfloat16 *>(dres);
-#define REGDA_BN_BWD(R, D) bn_bwd_apply_kernel<R, D><<<ag, kBnThreads, 0, st>>>(dd, oo, yy, dyy, dr, total, c, stats, red, gamma, inv_n, e, dgamma, dbeta, beta)
+#define REGDA_BN_BWD(R, D) REGDA_CUDA_CHECK(launch_pdl<2>(bn_bwd_apply_kernel<R, D>, ag, dim3(kBnThreads), 0, st, dd, oo, yy, dyy, dr, total, c, stats, red, gamma, \
+                                                      inv_n, e, dgamma, dbeta, beta))
     if (rmode == 2) REGDA_BN_BWD(2, false);
     else if (rmode == 1) { if (dr) REGDA_BN_BWD(1, true); else REGDA_BN_BWD(1, false); }
     else { if (dr) REGDA_BN_BWD(0, true); else REGDA_BN_BWD(0, false); }
