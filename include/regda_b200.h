@@ -193,6 +193,13 @@ int regda_conv_dgrad_bf16(const void *dy, const void *wgt, void *dx, int n, int 
                           int r, int s, int stride, int pad, int dil, const void *addend, void *stream);
 /* Weight gradient (stride 1 or 2), ACCUMULATED into dw fp32 [cout][r][s][cin] with global reductions:
  *   dy bf16 [n][oh][ow][cout], x bf16 [n][h][w][cin]. */
+/* Data gradient fused with the reductions of the BatchNorm(+ReLU) backward that consumes it (the BatchNorm whose OUTPUT is
+ * this convolution's input; regda/_resnets.py:92-112 chains conv -> bn -> relu -> conv): dx receives
+ * dz = (dgrad + addend) * [bn output > 0] (mask bits written by regda_bn_forward_bf16), red float32 [groups][2][cin]
+ * ACCUMULATES sum(dz), sum(dz * bn_y).  Follow with regda_bn_backward_bf16(..., dz_ready = 1). */
+int regda_conv_dgrad_bnred_bf16(const void *dy, const void *wgt, void *dx, int n, int h, int w, int cin, int cout,
+                                int r, int s, int stride, int pad, int dil, const void *addend, const void *bn_y,
+                                const void *relu_mask, float *red, int groups, void *stream);
 int regda_conv_wgrad_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil);
 int regda_conv_wgrad_bf16(const void *dy, const void *x, float *dw, int n, int h, int w, int cin, int cout,
                           int r, int s, int stride, int pad, int dil, void *stream);
@@ -216,13 +223,16 @@ int regda_bn_supported(int64_t npix, int c);
 int regda_bn_forward_bf16(const void *y, const void *residual, void *out, int64_t npix, int c, int groups,
                           const float *gamma, const float *beta, float *running_mean, float *running_var,
                           int64_t *num_batches_tracked, double eps, double momentum, int relu,
-                          float *stats, int have_stats, int stats_zeroed, void *stream);
+                          float *stats, int have_stats, int stats_zeroed, void *relu_mask, void *stream);
 /* red float32 [groups][2][c]: scratch for the two backward reductions (zeroed here unless red_zeroed != 0). */
-/* ReLU mask: from `out` (out > 0) when it is given; with relu != 0, out == NULL and dres == NULL (no residual) the mask is
+/* relu_mask (forward, may be NULL; needs relu != 0): uint8 [npix*c/8], bit e%8 of byte e/8 = [out element e > 0], for
+ * regda_conv_dgrad_bnred_bf16.  dz_ready != 0 (backward): dout is already dz and red already holds the two sums (both made
+ * by regda_conv_dgrad_bnred_bf16): only the apply pass runs, out / dres are not used (the residual gradient IS dout).
+ * ReLU mask: from `out` (out > 0) when it is given; with relu != 0, out == NULL and dres == NULL (no residual) the mask is
  * recomputed from y, gamma, beta and stats exactly as the forward computed the output, so `out` is not read at all. */
 int regda_bn_backward_bf16(const void *dout, const void *out, const void *y, void *dy, void *dres, int64_t npix, int c,
                            int groups, const float *gamma, const float *beta, const float *stats, double eps, float *dgamma,
-                           float *dbeta, int relu, float *red, int red_zeroed, void *stream);
+                           float *dbeta, int relu, float *red, int red_zeroed, int dz_ready, void *stream);
 
 /* MaxPool2d(3, stride 2, padding 1) over channels-last bf16 (regda/_resnets.py:153): x [n][h][w][c] -> y [n][oh][ow][c],
  * oh = (h-1)/2+1; argmax_u8 (may be NULL for inference) [n][oh][ow][c] receives the position 0..8 of the first maximum

@@ -195,15 +195,16 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 // of layer3 (K = 256 .. 2304, 4-36 k-blocks per tile) are bound by.  BLOCK_N = 256 halves the L2->SM bytes per
 // flop of the 128 x 128 tile.
 // ---------------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool YBUF = false>
 struct PersistSmem {
     static constexpr int kABytes = kBlockM * kBlockK * 2;
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kEpiWarps = BLOCK_N >= 128 ? 8 : 4; // TMA-store epilogue: warps that drain the accumulator
     static constexpr int kStoreOffset = STAGES * kStageBytes; // 4 KB per epilogue warp: one 32-row x 64-channel bf16 box
-    static constexpr int kBarOffset = kStoreOffset + 8 * 4096;
-    static constexpr int kNumBars = 2 * STAGES + 4;          // full, empty, tmem_full[2], tmem_empty[2]
+    static constexpr int kYOffset = kStoreOffset + 8 * 4096;  // BNRED: 4 KB per epilogue warp for the BatchNorm input box
+    static constexpr int kBarOffset = kYOffset + (YBUF ? 8 * 4096 : 0);
+    static constexpr int kNumBars = 2 * STAGES + 4 + 8;      // full, empty, tmem_full[2], tmem_empty[2], ybar[8]
     static constexpr int kTotal = kBarOffset + kNumBars * 8 + 8;
 };
 
@@ -216,20 +217,29 @@ struct PersistSmem {
 // TMA store (full 128-byte lines; the box is clipped at the image border) instead of 16-byte-per-lane scattered stores
 // (32 distinct lines per store instruction); the BatchNorm statistics are then column sums read back from the staged
 // tile (32 conflict-free LDS per lane for 2 channels) instead of a 31-shuffle warp transpose per quantity.
-template <int BLOCK_N, int STAGES, bool B_MN, bool STATS, bool TMA_EPI>
+//
+// BNRED (data-gradient launches whose output is the gradient of a BatchNorm+ReLU output): the epilogue also performs the
+// first half of that BatchNorm's backward.  It masks the gradient with the ReLU bit mask the forward wrote (the stored
+// tensor is dz = dout * [out > 0], which is also the residual branch's gradient), TMA-loads the matching box of the
+// BatchNorm INPUT y, and accumulates sum(dz) and sum(dz * y) per channel and statistics group into `stats` -- the two
+// reductions of bn_bwd_reduce_kernel, which then does not run at all (norm.cu, regda_bn_backward_bf16 dz_ready = 1).
+template <int BLOCK_N, int STAGES, bool B_MN, bool STATS, bool TMA_EPI, bool BNRED>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                       const __grid_constant__ CUtensorMap tmap_y,
+                       const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_bn,
                        __nv_bfloat16 *__restrict__ y, const ConvGeom g, const int n_tiles_n, const int num_tiles,
-                       float *__restrict__ stats, const int imgs_per_group, const __nv_bfloat16 *__restrict__ addend) {
-    using L = PersistSmem<BLOCK_N, STAGES>;
+                       float *__restrict__ stats, const int imgs_per_group, const __nv_bfloat16 *__restrict__ addend,
+                       const unsigned char *__restrict__ relu_mask) {
+    static_assert(!BNRED || (TMA_EPI && !STATS), "BNRED rides on the TMA-store epilogue and shares the statistics registers");
+    using L = PersistSmem<BLOCK_N, STAGES, BNRED>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::kBarOffset);
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *tfull_bar = empty_bar + STAGES;                // [2] accumulator ready for the epilogue
     uint64_t *tempty_bar = tfull_bar + 2;                    // [2] accumulator drained (4 epilogue warps arrive)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+    uint64_t *ybar = tempty_bar + 2;                         // [8] BNRED: per-epilogue-warp "BatchNorm input box landed"
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ybar + 8);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -240,10 +250,12 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         prefetch_tmap(&tmap_x);
         prefetch_tmap(&tmap_w);
         if (TMA_EPI) prefetch_tmap(&tmap_y);
+        if (BNRED) prefetch_tmap(&tmap_bn);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, TMA_EPI ? L::kEpiWarps : 8); }
+        for (int i = 0; i < 8; ++i) mbar_init(ybar + i, 1);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -331,6 +343,9 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             const uint32_t stage_s = smem_u32(smem + L::kStoreOffset + wq * 4096);
             const uint32_t my_row_s = stage_s + static_cast<uint32_t>(lane) * 128u;
             const uint32_t sw = static_cast<uint32_t>(lane & 7);
+            uint8_t *ybuf = smem + L::kYOffset + wq * 4096;          // BNRED only
+            const uint32_t ybuf_s = smem_u32(ybuf);
+            uint32_t yphase = 0;
             // BatchNorm statistics stay in registers across the tiles of this CTA for as long as (channel block, statistics
             // group) does not change -- with a tile stride of gridDim.x that is most of the walk -- and are flushed with
             // one coalesced fp32 reduction per 32 channels; per-tile atomics on the same few hundred addresses from every
@@ -369,7 +384,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                 const int img = m_blk / g.tiles_h;
                 const int oh = th * g.bh + ph, ow = tw * g.bw + pw;
                 const bool valid = oh < g.oh && ow < g.ow;
-                if (STATS) {
+                if (STATS || BNRED) {
                     const int key = (n_blk << 16) | (img / imgs_per_group);
                     if (key != stat_key) {
                         if (stat_key >= 0) flush_stats(stat_key);
@@ -383,6 +398,18 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                 if (has_add) {
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) cur[q4] = __ldg(ap + q4);
+                }
+                uint32_t mbits[kCols / 32];                  // BNRED: ReLU mask of this lane's pixel, one bit per channel
+                if (BNRED) {
+                    // the BatchNorm input box of the first 64-channel chunk (the buffer is free: the previous tile's column
+                    // sums ended with __syncwarp) and the mask words do not depend on the accumulator: request them first
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(ybar + wq, 4096);
+                        tma_load_4d(ybuf, &tmap_bn, ybar + wq, n_blk * BLOCK_N + col_lo, tw * g.bw + bpw0, th * g.bh + bph0, img);
+                    }
+                    const uint32_t *mp = reinterpret_cast<const uint32_t *>(relu_mask + ((pix_off + col_lo) >> 3));
+#pragma unroll
+                    for (int i = 0; i < kCols / 32; ++i) mbits[i] = valid ? __ldg(mp + i) : 0u;
                 }
                 mbar_wait(tfull_bar + acc, acc_phase);
                 tc_fence_after_sync();
@@ -419,11 +446,21 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                             }
                         }
                         uint32_t pkd[16];
+                        if (BNRED) {
+                            const uint32_t mb = mbits[(c64 + hseg * 32) / 32];       // 0 for rows outside the image
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            // rows outside the image are stored as zeros (the TMA store clips them; the statistics must not see them)
-                            __nv_bfloat162 b = __floats2bfloat162_rn(valid ? __uint_as_float(v[j]) : 0.f, valid ? __uint_as_float(v[j + 1]) : 0.f);
-                            pkd[j >> 1] = *reinterpret_cast<uint32_t *>(&b);
+                            for (int j = 0; j < 32; j += 2) {
+                                __nv_bfloat162 b = __floats2bfloat162_rn(((mb >> j) & 1u) ? __uint_as_float(v[j]) : 0.f,
+                                                                         ((mb >> (j + 1)) & 1u) ? __uint_as_float(v[j + 1]) : 0.f);
+                                pkd[j >> 1] = *reinterpret_cast<uint32_t *>(&b);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                // rows outside the image are stored as zeros (the TMA store clips them; the statistics must not see them)
+                                __nv_bfloat162 b = __floats2bfloat162_rn(valid ? __uint_as_float(v[j]) : 0.f, valid ? __uint_as_float(v[j + 1]) : 0.f);
+                                pkd[j >> 1] = *reinterpret_cast<uint32_t *>(&b);
+                            }
                         }
                         if (hseg == 0) {
                             // the previous TMA store of this warp must have finished reading the staging buffer
@@ -456,10 +493,32 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                         }
                         sacc[c64 / 64][0] += s0; sacc[c64 / 64][1] += s1; sacc[c64 / 64][2] += q0; sacc[c64 / 64][3] += q1;
                     }
+                    if (BNRED) {
+                        // sum(dz) and sum(dz * y) over the warp's 32 rows for channels 2L, 2L+1: dz from the staged tile, y from
+                        // the TMA-loaded BatchNorm input box (same swizzled layout)
+                        mbar_wait(ybar + wq, yphase);
+                        yphase ^= 1;
+                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                        const uint32_t lchunk = static_cast<uint32_t>(lane >> 2), lword = static_cast<uint32_t>(lane & 3) << 2;
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) {
+                            const uint32_t off = static_cast<uint32_t>(r) * 128u + ((lchunk ^ static_cast<uint32_t>(r & 7)) << 4) + lword;
+                            const uint32_t dv = ld_shared_u32(stage_s + off), yv = ld_shared_u32(ybuf_s + off);
+                            const float d0 = __uint_as_float(dv << 16), d1 = __uint_as_float(dv & 0xffff0000u);
+                            s0 += d0; s1 += d1;
+                            q0 = fmaf(d0, __uint_as_float(yv << 16), q0); q1 = fmaf(d1, __uint_as_float(yv & 0xffff0000u), q1);
+                        }
+                        sacc[c64 / 64][0] += s0; sacc[c64 / 64][1] += s1; sacc[c64 / 64][2] += q0; sacc[c64 / 64][3] += q1;
+                        __syncwarp();                                  // every lane is done with ybuf
+                        if (c64 + 64 < kCols && lane == 0) {
+                            mbar_arrive_expect_tx(ybar + wq, 4096);
+                            tma_load_4d(ybuf, &tmap_bn, ybar + wq, n_blk * BLOCK_N + col_lo + c64 + 64, tw * g.bw + bpw0, th * g.bh + bph0, img);
+                        }
+                    }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (STATS && stat_key >= 0) flush_stats(stat_key);
+            if ((STATS || BNRED) && stat_key >= 0) flush_stats(stat_key);
             if (lane == 0) bulk_wait_read0();          // shared memory must outlive the last TMA store's reads
         }
     } else {
@@ -608,24 +667,31 @@ bool use_tma_epilogue() {
     return !(e && strcmp(e, "direct") == 0);
 }
 
-template <int BLOCK_N, int STAGES, bool B_MN, bool STATS, bool TMA_EPI>
+struct BnRed {                       // BNRED launch: the BatchNorm whose output gradient this data-gradient launch produces
+    const void *bn_y = nullptr;      // its input y, bf16 [n][h][w][c] (same shape as the gradient)
+    const unsigned char *mask = nullptr;   // its ReLU mask, one bit per element
+};
+
+template <int BLOCK_N, int STAGES, bool B_MN, bool STATS, bool TMA_EPI, bool BNRED = false>
 int launch_persistent_impl(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bfloat16 *y, const ConvGeom &g, cudaStream_t st,
-                           float *stats, int imgs_per_group, const __nv_bfloat16 *addend) {
-    using L = PersistSmem<BLOCK_N, STAGES>;
-    auto kern = conv_persistent_kernel<BLOCK_N, STAGES, B_MN, STATS, TMA_EPI>;
+                           float *stats, int imgs_per_group, const __nv_bfloat16 *addend, const BnRed &br = BnRed()) {
+    using L = PersistSmem<BLOCK_N, STAGES, BNRED>;
+    auto kern = conv_persistent_kernel<BLOCK_N, STAGES, B_MN, STATS, TMA_EPI, BNRED>;
     const int smem = L::kTotal + 1024;
     static_assert(L::kTotal + 1024 <= 232448, "persistent conv kernel: shared memory over the 227 KB limit");
     REGDA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int n_tiles_n = g.cout / BLOCK_N;
     const int num_tiles = n_tiles_n * g.n * g.tiles_h * g.tiles_w;
     const int grid = std::min(num_tiles, sm_count());
-    CUtensorMap ty = tx;          // unused by the direct epilogue
+    CUtensorMap ty = tx, tbn = tx;          // unused by the direct epilogue / without BNRED
     if (TMA_EPI) {
         // output map [n][oh][ow][cout]; box = one epilogue warp's 32 pixels x 64 channels
         const int sbw = std::min(g.bw, 32), sbh = 32 / sbw;
         if (!encode_nhwc(&ty, y, g.n, g.oh, g.ow, g.cout, sbw, sbh, 1)) return REGDA_ERR_CUDA;
+        if (BNRED && !encode_nhwc(&tbn, br.bn_y, g.n, g.oh, g.ow, g.cout, sbw, sbh, 1)) return REGDA_ERR_CUDA;
     }
-    REGDA_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kPersistThreads), smem, st, tx, tw, ty, y, g, n_tiles_n, num_tiles, stats, imgs_per_group, addend));
+    REGDA_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kPersistThreads), smem, st, tx, tw, ty, tbn, y, g, n_tiles_n, num_tiles, stats,
+                                imgs_per_group, addend, br.mask));
     return REGDA_OK;
 }
 
@@ -648,6 +714,24 @@ bool use_persistent() {
         v = (e && strcmp(e, "classic") == 0) ? 0 : 1;
     }
     return v == 1;
+}
+
+// data gradient + the reductions of the BatchNorm backward that consumes it (BNRED); `red` [groups][2][g.cout]
+int launch_dgrad_bnred(const void *act, const void *wgt, __nv_bfloat16 *out, const ConvGeom &g, int taps, cudaStream_t st,
+                       float *red, int imgs_per_group, const __nv_bfloat16 *addend, const BnRed &br) {
+    CUtensorMap tx, tw;
+    int rc = make_tmap_x(&tx, act, g);
+    if (rc) return rc;
+    const long long m_tiles = static_cast<long long>(g.n) * g.tiles_h * g.tiles_w;
+    int block_n = 64;
+    if (g.cout % 256 == 0 && m_tiles * (g.cout / 256) >= sm_count() / 2) block_n = 256;
+    else if (g.cout % 128 == 0) block_n = 128;
+    rc = make_tmap_w_mn(&tw, wgt, g.cin, taps, g.cout);
+    if (rc) return rc;
+    // one pipeline stage fewer than the plain kernel at 256 / 128: the 32 KB of BatchNorm-input boxes take their place
+    if (block_n == 256) return launch_persistent_impl<256, 3, true, false, true, true>(tx, tw, out, g, st, red, imgs_per_group, addend, br);
+    if (block_n == 128) return launch_persistent_impl<128, 5, true, false, true, true>(tx, tw, out, g, st, red, imgs_per_group, addend, br);
+    return launch_persistent_impl<64, 6, true, false, true, true>(tx, tw, out, g, st, red, imgs_per_group, addend, br);
 }
 
 template <bool B_MN>
@@ -767,4 +851,33 @@ extern "C" int regda_conv_dgrad_bf16(const void *dy, const void *wgt, void *dx, 
     if (addend != nullptr && (reinterpret_cast<uintptr_t>(addend) & 15)) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad: addend must be 16-byte aligned");
     return launch_conv<true>(dy, wgt, static_cast<__nv_bfloat16 *>(dx), g, r * s, static_cast<cudaStream_t>(stream), nullptr, 1,
                              static_cast<const __nv_bfloat16 *>(addend));
+}
+
+// Data gradient fused with the first half of the backward of the BatchNorm(+ReLU) whose OUTPUT is this convolution's input:
+// dx receives dz = (dgrad + addend) masked by relu_mask (bit e of the mask = [BatchNorm output element e > 0], written by
+// regda_bn_forward_bf16), and red float32 [groups][2][cin] ACCUMULATES sum(dz) and sum(dz * bn_y) per statistics group and
+// channel (bn_y = that BatchNorm's input, bf16 [n][h][w][cin]).  regda_bn_backward_bf16(..., dz_ready = 1) then only applies.
+extern "C" int regda_conv_dgrad_bnred_bf16(const void *dy, const void *wgt, void *dx, int n, int h, int w, int cin, int cout,
+                                           int r, int s, int stride, int pad, int dil, const void *addend, const void *bn_y,
+                                           const void *relu_mask, float *red, int groups, void *stream) {
+    if (!regda_conv_dgrad_supported(n, h, w, cin, cout, r, s, stride, pad, dil))
+        return fail(REGDA_ERR_UNSUPPORTED, "conv_dgrad_bnred: shape not covered by the tcgen05 kernel");
+    if (!dy || !wgt || !dx || !bn_y || !relu_mask || !red) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_bnred: null pointer");
+    if (groups < 1 || n % groups != 0) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_bnred: groups must divide the batch");
+    if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(wgt) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(bn_y) |
+         reinterpret_cast<uintptr_t>(relu_mask)) & 15)
+        return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_bnred: tensors must be 16-byte aligned");
+    if (addend != nullptr && (reinterpret_cast<uintptr_t>(addend) & 15)) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_bnred: addend must be 16-byte aligned");
+    if (!use_persistent() || !use_tma_epilogue()) return fail(REGDA_ERR_UNSUPPORTED, "conv_dgrad_bnred: needs the persistent TMA-store kernel");
+    const int oh = h + 2 * pad - dil * (r - 1), ow = w + 2 * pad - dil * (s - 1);
+    ConvGeom g;
+    geom_init(g, n, oh, ow, cout, cin, r, s, 1, dil * (r - 1) - pad, dil);
+    g.flip = 1;
+    if (g.oh != h || g.ow != w) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_bnred: inconsistent geometry");
+    ensure_context(dy);
+    BnRed br;
+    br.bn_y = bn_y;
+    br.mask = static_cast<const unsigned char *>(relu_mask);
+    return launch_dgrad_bnred(dy, wgt, static_cast<__nv_bfloat16 *>(dx), g, r * s, static_cast<cudaStream_t>(stream), red, n / groups,
+                              static_cast<const __nv_bfloat16 *>(addend), br);
 }

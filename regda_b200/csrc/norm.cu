@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_apply_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__restrict__ res, __nv_bfloat16 *__restrict__ out,
                 long long total, int c, const float *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta,
                 float inv_n, float unbias, float eps, float momentum, float *__restrict__ running_mean, float *__restrict__ running_var,
-                long long *__restrict__ num_batches) {
+                long long *__restrict__ num_batches, unsigned char *__restrict__ relu_mask) {
     pdl_trigger();
     pdl_wait();
     if (blockIdx.x == 0 && blockIdx.y == 0) {
@@ -136,6 +136,7 @@ bn_apply_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__rest
         const long long off = static_cast<long long>(blockIdx.y) * total;
         y += off; out += off;
         if (RES) res += off;
+        if (RELU && relu_mask != nullptr) relu_mask += off >> 3;
         stats += 2 * c * blockIdx.y;
     }
     const long long stride = static_cast<long long>(gridDim.x) * kBnSpan;
@@ -176,6 +177,13 @@ bn_apply_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__rest
                 for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
             }
             if (RELU) {
+                if (relu_mask != nullptr) {
+                    // one bit per element: [output > 0], consumed by the data-gradient epilogue that forms this layer's dz
+                    unsigned bits = 0u;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) bits |= (f[i] > 0.f ? 1u : 0u) << i;
+                    relu_mask[(h ? e2 : e) >> 3] = static_cast<unsigned char>(bits);
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
             }
@@ -351,7 +359,7 @@ extern "C" int regda_bn_supported(int64_t npix, int c) { return bn_shape_ok(npix
 extern "C" int regda_bn_forward_bf16(const void *y, const void *residual, void *out, int64_t npix, int c, int groups,
                                      const float *gamma, const float *beta, float *running_mean, float *running_var,
                                      int64_t *num_batches_tracked, double eps, double momentum, int relu,
-                                     float *stats, int have_stats, int stats_zeroed, void *stream) {
+                                     float *stats, int have_stats, int stats_zeroed, void *relu_mask, void *stream) {
     if (!bn_shape_ok(npix, c)) return fail(REGDA_ERR_UNSUPPORTED, "bn_forward: channels must divide 2048 and be a multiple of 8");
     if (groups < 1 || npix % groups != 0) return fail(REGDA_ERR_INVALID_ARG, "bn_forward: groups must divide the pixel count");
     if (!y || !out || !stats) return fail(REGDA_ERR_INVALID_ARG, "bn_forward: null pointer");
@@ -372,7 +380,7 @@ extern "C" int regda_bn_forward_bf16(const void *y, const void *residual, void *
     const __nv_bfloat16 *rr = static_cast<const __nv_bfloat16 *>(residual);
     __nv_bfloat16 *oo = static_cast<__nv_bfloat16 *>(out);
 #define REGDA_BN_APPLY(R, S) REGDA_CUDA_CHECK(launch_pdl<2>(bn_apply_kernel<R, S>, ag, dim3(kBnThreads), 0, st, yy, rr, oo, total, c, stats, gamma, beta, inv_n, \
-                                                        unbias, e, mom, running_mean, running_var, nbt))
+                                                        unbias, e, mom, running_mean, running_var, nbt, static_cast<unsigned char *>(relu_mask)))
     if (relu) { if (rr) REGDA_BN_APPLY(true, true); else REGDA_BN_APPLY(true, false); }
     else { if (rr) REGDA_BN_APPLY(false, true); else REGDA_BN_APPLY(false, false); }
 #undef REGDA_BN_APPLY
@@ -382,12 +390,14 @@ extern "C" int regda_bn_forward_bf16(const void *y, const void *residual, void *
 
 extern "C" int regda_bn_backward_bf16(const void *dout, const void *out, const void *y, void *dy, void *dres, int64_t npix, int c,
                                       int groups, const float *gamma, const float *beta, const float *stats, double eps, float *dgamma,
-                                      float *dbeta, int relu, float *red, int red_zeroed, void *stream) {
+                                      float *dbeta, int relu, float *red, int red_zeroed, int dz_ready, void *stream) {
     if (!bn_shape_ok(npix, c)) return fail(REGDA_ERR_UNSUPPORTED, "bn_backward: channels must divide 2048 and be a multiple of 8");
     if (groups < 1 || npix % groups != 0) return fail(REGDA_ERR_INVALID_ARG, "bn_backward: groups must divide the pixel count");
     if (!dout || !y || !dy || !stats || !red) return fail(REGDA_ERR_INVALID_ARG, "bn_backward: null pointer");
     if (relu && !out && dres) return fail(REGDA_ERR_INVALID_ARG, "bn_backward: a residual layer needs the saved output for its ReLU mask");
-    const int rmode = !relu ? 0 : (out ? 1 : 2);      // 2: mask recomputed from y (no residual)
+    // dz_ready: dout is already the masked dz and red already holds sum(dz), sum(dz*y) (regda_conv_dgrad_bnred_bf16)
+    const int rmode = (dz_ready || !relu) ? 0 : (out ? 1 : 2);      // 2: mask recomputed from y (no residual)
+    if (dz_ready) { dres = nullptr; red_zeroed = 1; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long gpix = npix / groups;
     const long long total = gpix * c;
@@ -400,7 +410,8 @@ extern "C" int regda_bn_backward_bf16(const void *dout, const void *out, const v
     const float inv_n = 1.f / static_cast<float>(gpix), e = static_cast<float>(eps);
 #define REGDA_BN_RED(R) REGDA_CUDA_CHECK(launch_pdl<2>(bn_bwd_reduce_kernel<R>, dim3(rg, groups), dim3(kBnThreads), 0, st, dd, oo, yy, total, c, span, red, red + c, \
                                                    stats, gamma, beta, inv_n, e))
-    if (rmode == 0) REGDA_BN_RED(0); else if (rmode == 1) REGDA_BN_RED(1); else REGDA_BN_RED(2);
+    if (dz_ready) { /* reductions done by the producer of dout */ }
+    else if (rmode == 0) REGDA_BN_RED(0); else if (rmode == 1) REGDA_BN_RED(1); else REGDA_BN_RED(2);
 #undef REGDA_BN_RED
     REGDA_LAUNCH_CHECK();
     const dim3 ag(apply_grid(total, groups), groups);

@@ -110,12 +110,18 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         if (FUSED and self.training and x.is_cuda and x.dtype == torch.bfloat16) or _GROUPS > 1:
+            # fnorm.arm(t, k): t (a BatchNorm+ReLU output) has exactly k consumers, all of them the Conv2d calls below, so
+            # their data-gradient epilogues may carry the first half of that BatchNorm's backward (ops/norm.py BnHandle)
             if self.downsample is None:
+                fnorm.arm(x, 1)
                 out, identity = _conv_bn(self.conv1, self.bn1, x, relu=True, tap=True)
             else:
+                fnorm.arm(x, 2)
                 out = _conv_bn(self.conv1, self.bn1, x, relu=True)
                 identity = _conv_bn(self.downsample[0], self.downsample[1], x)
+            fnorm.arm(out, 1)
             out = _conv_bn(self.conv2, self.bn2, out, relu=True)
+            fnorm.arm(out, 1)
             return _conv_bn(self.conv3, self.bn3, out, residual=identity, relu=True)
         y = self.conv1(x)
         out = F.relu(self.bn1(y), inplace=True)

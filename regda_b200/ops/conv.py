@@ -39,7 +39,7 @@ class _ConvFn(torch.autograd.Function):
     The weight gradient is ACCUMULATED into weight.grad by the wgrad kernel (no autograd add)."""
 
     @staticmethod
-    def forward(ctx, x, weight, stride, padding, dilation, stats_groups=None, tap=False):
+    def forward(ctx, x, weight, stride, padding, dilation, stats_groups=None, tap=False, bn_handle=None):
         """returns y [, bn_stats] [, x_tap].  x_tap (tap=True) is x itself handed back as a second consumer handle: a
         residual branch that reads the same x goes through it, so this node's backward receives that branch's gradient and
         the dgrad kernel adds it in its epilogue (dx = dgrad(dy) + d_tap) instead of autograd launching an add."""
@@ -49,6 +49,15 @@ class _ConvFn(torch.autograd.Function):
         ctx.weight = weight
         ctx.geom = (stride, padding, dilation)
         ctx.has_stats, ctx.tap = stats_groups is not None, tap
+        # x is the output of a BatchNorm+ReLU whose backward reductions this node's dgrad epilogue can do (ops/norm.py BnHandle)
+        ctx.bn_handle = None
+        if bn_handle is not None and bn_handle.expected > 0:
+            if (ENGINE != "tcgen05-fwd" and FUSE_BN_STATS and os.environ.get("REGDA_CONV_EPILOGUE", "") != "direct"
+                    and tc.supports_dgrad(x.shape, weight.shape, stride, padding, dilation, x.dtype)):
+                bn_handle.seen += 1
+                ctx.bn_handle = bn_handle
+            else:
+                bn_handle.broken = True
         ctx.set_materialize_grads(False)        # no zero-filled gradient tensors for the statistics / unused tap outputs
         stats["tcgen05_fprop"] += 1
         outs = []
@@ -70,16 +79,27 @@ class _ConvFn(torch.autograd.Function):
         stride, padding, dilation = ctx.geom
         g_tap = rest[-1] if ctx.tap else None
         if gy is None:                           # only the tap branch carried a gradient
-            return g_tap, None, None, None, None, None, None
+            assert ctx.bn_handle is None or not ctx.bn_handle.fused, "fused BatchNorm backward needs this node's gradient"
+            return g_tap, None, None, None, None, None, None, None
         gy = gy.contiguous(memory_format=torch.channels_last)
         gx = gw = None
         if ctx.needs_input_grad[0]:
             if ENGINE != "tcgen05-fwd" and tc.supports_dgrad(x.shape, weight.shape, stride, padding, dilation, x.dtype):
                 stats["tcgen05_dgrad"] += 1
                 fuse = g_tap is not None and g_tap.dtype == torch.bfloat16 and FUSE_BN_STATS
-                gx = tc.dgrad(gy, w16, x.shape, stride, padding, dilation, addend=g_tap if fuse else None)
-                if g_tap is not None and not fuse:
-                    gx = gx + g_tap
+                hd = ctx.bn_handle
+                if hd is not None and hd.fused:
+                    assert g_tap is None or fuse
+                    if hd.red is None:
+                        hd.red, zeroed = capi_zero_take((hd.groups, 2, x.shape[1]), x.device)
+                        if not zeroed:
+                            hd.red.zero_()
+                    gx = tc.dgrad_bnred(gy, w16, x.shape, stride, padding, dilation, g_tap, hd.y, hd.mask, hd.red, hd.groups)
+                    hd.done += 1
+                else:
+                    gx = tc.dgrad(gy, w16, x.shape, stride, padding, dilation, addend=g_tap if fuse else None)
+                    if g_tap is not None and not fuse:
+                        gx = gx + g_tap
             else:
                 stats["cudnn"] += 1
                 gx = torch.ops.aten.convolution_backward(gy, x, w16, None, [stride] * 2, [padding] * 2,
@@ -96,7 +116,12 @@ class _ConvFn(torch.autograd.Function):
                 stats["cudnn"] += 1
                 gw = torch.ops.aten.convolution_backward(gy, x, w16, None, [stride] * 2, [padding] * 2,
                                                          [dilation] * 2, False, [0, 0], 1, [False, True, False])[1].float()
-        return gx, gw, None, None, None, None, None
+        return gx, gw, None, None, None, None, None, None
+
+
+def capi_zero_take(shape, device):
+    from .. import capi
+    return capi.zero_pool.take(shape, device)
 
 
 class Conv2d(nn.Module):
@@ -123,7 +148,10 @@ class Conv2d(nn.Module):
         residual branch should read x through (see _ConvFn.forward)."""
         if (ENGINE != "cudnn" and self.bias is None and x.is_cuda and x.dtype == torch.bfloat16 and FUSE_BN_STATS
                 and _tc().supports_fprop(x.shape, self.weight.shape, self.stride, self.padding, self.dilation, x.dtype)):
-            return _ConvFn.apply(x, self.weight, self.stride, self.padding, self.dilation, groups, tap)
+            return _ConvFn.apply(x, self.weight, self.stride, self.padding, self.dilation, groups, tap, getattr(x, "_bn_handle", None))
+        hd = getattr(x, "_bn_handle", None)
+        if hd is not None:
+            hd.broken = True
         return (self.forward(x), None, x) if tap else (self.forward(x), None)
 
     def forward(self, x):
@@ -132,6 +160,9 @@ class Conv2d(nn.Module):
             use_tc = _tc().supports_fprop(x.shape, self.weight.shape, self.stride, self.padding, self.dilation, x.dtype)
             if ENGINE == "tcgen05" and not use_tc and os.environ.get("REGDA_CONV_STRICT"):
                 raise RuntimeError(f"no tcgen05 kernel for conv {tuple(x.shape)} x {tuple(self.weight.shape)}")
+        hd = getattr(x, "_bn_handle", None)
+        if hd is not None:
+            hd.broken = True                     # plain forward: this consumer does not take part in the fused BatchNorm backward
         if use_tc:
             y = _ConvFn.apply(x, self.weight, self.stride, self.padding, self.dilation)
             if self.bias is not None:

@@ -16,6 +16,8 @@ running statistics are updated once per group, in order, exactly like two consec
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .. import capi
@@ -38,9 +40,34 @@ def _grad_buffer(p):
     return p.grad
 
 
+FUSE_BN_BWD = os.environ.get("REGDA_FUSE_BN_BWD", "1") != "0"
+
+
+class BnHandle:
+    """Rides on the OUTPUT of a BatchNorm+ReLU node so that the convolution(s) consuming it can do the first half of
+    this BatchNorm's backward in their data-gradient epilogue (regda_conv_dgrad_bnred_bf16): mask the gradient with
+    `mask`, accumulate sum(dz), sum(dz*y) into `red`.  The model arms a handle (`arm(out, k)`) where it knows that the
+    output has exactly k consumers and all of them are Conv2d calls; a consumer that cannot fuse sets `broken`."""
+    __slots__ = ("y", "mask", "groups", "red", "expected", "seen", "done", "broken")
+
+    def __init__(self):
+        self.y = self.mask = self.red = None
+        self.groups, self.expected, self.seen, self.done, self.broken = 1, 0, 0, 0, False
+
+    @property
+    def fused(self):
+        return self.expected > 0 and not self.broken
+
+
+def arm(t, consumers):
+    h = getattr(t, "_bn_handle", None)
+    if h is not None:
+        h.expected = consumers
+
+
 class _BnActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y, residual, gamma, beta, bn, relu, groups, ready_stats):
+    def forward(ctx, y, residual, gamma, beta, bn, relu, groups, ready_stats, handle=None):
         y = _cl(y)
         n, c, h, w = y.shape
         npix = n * h * w
@@ -53,10 +80,15 @@ class _BnActFn(torch.autograd.Function):
         else:
             stats, zeroed = capi.zero_pool.take((groups, 2, c), y.device)
             have = 0
+        mask = None
+        if handle is not None and relu:
+            mask = torch.empty(npix * c // 8, dtype=torch.uint8, device=y.device)
+            handle.y, handle.mask, handle.groups = y, mask, groups
+        ctx.handle = handle if mask is not None else None
         capi.call("regda_bn_forward_bf16", capi.ptr_any(y), capi.ptr_any(res) if res is not None else None, capi.ptr_any(out), npix, c,
                   groups, capi.ptr(gamma), capi.ptr(beta), capi.ptr(bn.running_mean), capi.ptr(bn.running_var),
                   capi.ptr(bn.num_batches_tracked), float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1), int(relu),
-                  capi.ptr_any(stats), have, int(zeroed), capi.stream())
+                  capi.ptr_any(stats), have, int(zeroed), capi.ptr(mask) if mask is not None else None, capi.stream())
         # the backward recomputes the ReLU mask of a residual-free layer from y (bit-identical to this forward), so the
         # output is only kept where a residual entered it
         ctx.save_for_backward(y, out if (relu and residual is not None) else None, stats)
@@ -69,22 +101,38 @@ class _BnActFn(torch.autograd.Function):
         n, c, h, w = y.shape
         dout = _cl(dout)
         dy = torch.empty_like(y)
-        dres = torch.empty_like(y) if (ctx.has_res and ctx.needs_input_grad[1]) else None
         gamma, beta = ctx.gamma, ctx.beta
         dgamma = _grad_buffer(gamma) if gamma.requires_grad else None
         dbeta = _grad_buffer(beta) if beta.requires_grad else None
+        hd = ctx.handle
+        if hd is not None and hd.fused:
+            # every consumer was a convolution whose data-gradient epilogue masked its share of dout and accumulated the
+            # two reductions: dout IS dz (and the residual branch's gradient), only the apply pass is left
+            assert hd.seen == hd.expected == hd.done and hd.red is not None, "BatchNorm handle: consumer bookkeeping mismatch"
+            capi.call("regda_bn_backward_bf16", capi.ptr_any(dout), None, capi.ptr_any(y), capi.ptr_any(dy), None, n * h * w, c,
+                      ctx.groups, capi.ptr(gamma), capi.ptr(beta), capi.ptr_any(stats), ctx.eps,
+                      capi.ptr(dgamma) if dgamma is not None else None, capi.ptr(dbeta) if dbeta is not None else None,
+                      int(ctx.relu), capi.ptr_any(hd.red), 1, 1, capi.stream())
+            hd.red, hd.done = None, 0          # (a second backward over a retained graph starts clean)
+            return dy, (dout if (ctx.has_res and ctx.needs_input_grad[1]) else None), None, None, None, None, None, None, None
+        assert hd is None or hd.done == 0, "BatchNorm handle: a consumer fused although the handle is broken"
+        dres = torch.empty_like(y) if (ctx.has_res and ctx.needs_input_grad[1]) else None
         red, zeroed = capi.zero_pool.take((ctx.groups, 2, c), y.device)
         capi.call("regda_bn_backward_bf16", capi.ptr_any(dout), capi.ptr_any(out) if out is not None else None, capi.ptr_any(y),
                   capi.ptr_any(dy), capi.ptr_any(dres) if dres is not None else None, n * h * w, c, ctx.groups, capi.ptr(gamma),
                   capi.ptr(beta), capi.ptr_any(stats), ctx.eps, capi.ptr(dgamma) if dgamma is not None else None,
-                  capi.ptr(dbeta) if dbeta is not None else None, int(ctx.relu), capi.ptr_any(red), int(zeroed), capi.stream())
+                  capi.ptr(dbeta) if dbeta is not None else None, int(ctx.relu), capi.ptr_any(red), int(zeroed), 0, capi.stream())
         # gamma / beta gradients were accumulated in place: nothing flows back through autograd for them
-        return dy, dres, None, None, None, None, None, None
+        return dy, dres, None, None, None, None, None, None, None
 
 
 def bn_act(y, bn, residual=None, relu=True, groups=1, stats=None):
     """stats: the [groups][2][c] sums produced by the convolution's epilogue (ops/tc.py fprop(..., stats_groups)), if any"""
-    return _BnActFn.apply(y, residual, bn.weight, bn.bias, bn, relu, groups, stats)
+    handle = BnHandle() if (relu and FUSE_BN_BWD and torch.is_grad_enabled() and y.requires_grad) else None
+    out = _BnActFn.apply(y, residual, bn.weight, bn.bias, bn, relu, groups, stats, handle)
+    if handle is not None:
+        out._bn_handle = handle
+    return out
 
 
 def bn_eager(x, bn, groups=1):
@@ -135,7 +183,7 @@ class _InstanceNormFn(torch.autograd.Function):
         out = torch.empty_like(x)
         stats, zeroed = capi.zero_pool.take((n, 2, c), x.device)
         capi.call("regda_bn_forward_bf16", capi.ptr_any(x), None, capi.ptr_any(out), n * h * w, c, n, None, None, None, None, None,
-                  float(eps), 0.0, 0, capi.ptr_any(stats), 0, int(zeroed), capi.stream())
+                  float(eps), 0.0, 0, capi.ptr_any(stats), 0, int(zeroed), None, capi.stream())
         ctx.save_for_backward(x, stats)
         ctx.eps = float(eps)
         return out
@@ -148,7 +196,7 @@ class _InstanceNormFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         red, zeroed = capi.zero_pool.take((n, 2, c), x.device)
         capi.call("regda_bn_backward_bf16", capi.ptr_any(dout), None, capi.ptr_any(x), capi.ptr_any(dx), None, n * h * w, c, n, None,
-                  None, capi.ptr_any(stats), ctx.eps, None, None, 0, capi.ptr_any(red), int(zeroed), capi.stream())
+                  None, capi.ptr_any(stats), ctx.eps, None, None, 0, capi.ptr_any(red), int(zeroed), 0, capi.stream())
         return dx, None
 
 

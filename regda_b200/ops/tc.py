@@ -99,6 +99,23 @@ def dgrad(gy, w16, xshape, stride, padding, dilation, addend=None):
     return gx
 
 
+def dgrad_bnred(gy, w16, xshape, stride, padding, dilation, addend, bn_y, relu_mask, red, groups):
+    """dz = (dgrad(gy) + addend) * relu_mask, red[groups][2][cin] += (sum dz, sum dz * bn_y): the data gradient fused with the
+    reductions of the BatchNorm(+ReLU) backward whose output is this convolution's input (regda_conv_dgrad_bnred_bf16)."""
+    n, cin, h, w = xshape
+    cout, _, r, s = w16.shape
+    gx = torch.empty((n, cin, h, w), dtype=torch.bfloat16, device=gy.device, memory_format=torch.channels_last)
+    gy, w16, bn_y = _nhwc(gy), _nhwc(w16), _nhwc(bn_y)
+    assert tuple(bn_y.shape) == tuple(xshape) and bn_y.dtype == torch.bfloat16 and red.shape == (groups, 2, cin)
+    if addend is not None:
+        assert tuple(addend.shape) == tuple(xshape) and addend.dtype == torch.bfloat16
+        addend = _nhwc(addend)
+    capi.call("regda_conv_dgrad_bnred_bf16", capi.ptr_any(gy), capi.ptr_any(w16), capi.ptr_any(gx), n, h, w, cin, cout, r, s,
+              stride, padding, dilation, capi.ptr_any(addend) if addend is not None else None, capi.ptr_any(bn_y),
+              capi.ptr_any(relu_mask), capi.ptr_any(red), groups, capi.stream())
+    return gx
+
+
 def wgrad_accumulate(gy, x, gw, stride, padding, dilation):
     """gw (float32 [O,I,kh,kw], channels-last memory) += dW(gy, x)"""
     n, cin, h, w = x.shape

@@ -188,3 +188,35 @@ def test_fused_bn_statistics_and_both_epilogues(shape, epilogue, monkeypatch):
     cnt = (n // groups) * y.shape[2] * y.shape[3]
     assert torch.allclose(st[:, 0], want_sum, rtol=1e-4, atol=1e-4 * cnt ** 0.5 * float(yf.abs().max()))
     assert torch.allclose(st[:, 1], want_sq, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("with_addend", [False, True])
+@pytest.mark.parametrize("shape", [SHAPES[1], SHAPES[2], SHAPES[4], SHAPES[5], SHAPES[8], SHAPES[11], (4, 1024, 32, 32, 256, 1, 0, 1)], ids=str)
+def test_dgrad_bnred_matches_masked_dgrad_and_reductions(shape, with_addend):
+    """regda_conv_dgrad_bnred_bf16: dz == bf16((dgrad + addend) * mask) bit for bit against the plain dgrad kernel's unrounded
+    sum (checked at bf16 resolution), and red == (sum dz, sum dz * bn_y) per statistics group and channel in float32."""
+    from regda_b200.ops import tc
+    n, cin, h, w, cout, k, pad, dil = shape
+    g = torch.Generator(device="cuda").manual_seed(11)
+    cl = torch.channels_last
+    wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5).bfloat16().contiguous(memory_format=cl)
+    oh, ow = tc.out_hw(h, w, k, k, 1, pad, dil)
+    gy = torch.randn(n, cout, oh, ow, device="cuda", generator=g).bfloat16().contiguous(memory_format=cl)
+    bn_y = torch.randn(n, cin, h, w, device="cuda", generator=g).bfloat16().contiguous(memory_format=cl)
+    keep = torch.rand(n, cin, h, w, device="cuda", generator=g) > 0.4
+    add = torch.randn(n, cin, h, w, device="cuda", generator=g).bfloat16().contiguous(memory_format=cl) if with_addend else None
+    # mask bytes: NHWC element e -> bit e % 8 of byte e / 8
+    bits = keep.permute(0, 2, 3, 1).reshape(-1, 8).to(torch.uint8)
+    mask = (bits << torch.arange(8, device="cuda", dtype=torch.uint8)).sum(dim=1).to(torch.uint8).contiguous()
+    groups = 2 if n % 2 == 0 else 1
+    red = torch.zeros(groups, 2, cin, device="cuda")
+    dz = tc.dgrad_bnred(gy, wt, (n, cin, h, w), 1, pad, dil, add, bn_y, mask, red, groups)
+    plain = tc.dgrad(gy, wt, (n, cin, h, w), 1, pad, dil, addend=add)        # same kernel family, unmasked
+    want = torch.where(keep, plain, torch.zeros_like(plain))
+    assert torch.equal(dz, want)
+    dzf = dz.float().reshape(groups, n // groups, cin, -1)
+    yf = bn_y.float().reshape(groups, n // groups, cin, -1)
+    s1, s2 = dzf.sum(dim=(1, 3)), (dzf * yf).sum(dim=(1, 3))
+    tol = 1e-4 * float(dzf.abs().max()) * (dzf.shape[1] * dzf.shape[3]) ** 0.5 * 4
+    assert torch.allclose(red[:, 0], s1, rtol=1e-4, atol=tol), float((red[:, 0] - s1).abs().max())
+    assert torch.allclose(red[:, 1], s2, rtol=1e-4, atol=4 * tol), float((red[:, 1] - s2).abs().max())

@@ -309,3 +309,68 @@ def test_instance_norm_matches_torch(shape):
     y.backward(gy)
     yr.backward(gy.float())
     _close(x.grad, xr.grad, 1.5e-2)
+
+
+@pytest.mark.parametrize("case", ["plain", "downsample_s1", "downsample_s2"])
+def test_bn_backward_fused_into_dgrad_epilogue_matches_standalone_reduce(case):
+    """Three bottleneck blocks, bf16, ONE forward and two backward passes over the retained graph: first with the BatchNorm
+    backward reductions done in the consumer convolutions' data-gradient epilogue (regda_conv_dgrad_bnred_bf16: masked dz +
+    sum dz, sum dz*y), then with every handle broken, i.e. the standalone reduce + apply kernels.  Same activations, same ReLU
+    masks; what differs is summation order and where the masked gradient is rounded to bf16, hence 1e-2 of the gradient
+    scale and 5e-3 of its mean (one bf16 ulp is 3.9e-3; measured 2.8e-3 after nine layers).  (Two separate forwards are NOT comparable at this tolerance: the statistics are fp32 atomics
+    and nine bf16 layers amplify their last bit.)  The exact op-level check is
+    tests/test_conv_gpu.py::test_dgrad_bnred_matches_masked_dgrad_and_reductions."""
+    from regda_b200.models import Encoder as E
+    from regda_b200.ops import norm as fnorm
+
+    handles = []
+    orig_init = fnorm.BnHandle.__init__
+
+    def tracking_init(self):
+        orig_init(self)
+        handles.append(self)
+
+    torch.manual_seed(7)
+    if case == "plain":
+        blocks = [E.Bottleneck(256, 64), E.Bottleneck(256, 64), E.Bottleneck(256, 64)]
+    elif case == "downsample_s1":
+        blocks = [E.Bottleneck(256, 64), E.Bottleneck(256, 128, 1, 2, downsample=True), E.Bottleneck(512, 128, 1, 2)]
+    else:
+        blocks = [E.Bottleneck(256, 64), E.Bottleneck(256, 128, 2, 1, downsample=True), E.Bottleneck(512, 128)]
+    net = torch.nn.Sequential(*blocks).cuda().train().to(memory_format=torch.channels_last)
+    x = torch.randn(4, 256, 24, 40, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    old = fnorm.FUSE_BN_BWD
+    fnorm.FUSE_BN_BWD = True
+    fnorm.BnHandle.__init__ = tracking_init
+    E._GROUPS = 2
+    try:
+        out = net(x)
+    finally:
+        E._GROUPS = 1
+        fnorm.BnHandle.__init__ = orig_init
+        fnorm.FUSE_BN_BWD = old
+    n_fused = sum(1 for h in handles if h.fused)
+    # every BatchNorm+ReLU output inside the stack is consumed by convolutions only; the stride-2 downsample conv of case 3
+    # has no tcgen05 data gradient, which breaks the handle of the block input it reads
+    assert n_fused == {"plain": 8, "downsample_s1": 8, "downsample_s2": 6}[case], (n_fused, len(handles))
+    g = torch.randn(out.shape, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+
+    def backward():
+        x.grad = None
+        for p in net.parameters():
+            p.grad = None
+        out.backward(g, retain_graph=True)
+        return x.grad.float().clone(), {n: p.grad.float().clone() for n, p in net.named_parameters()}
+
+    gx1, g1 = backward()
+    for h in handles:
+        h.broken = True
+    gx0, g0 = backward()
+
+    def close(a, b, name):
+        scale = float(b.abs().max()) + 1e-12
+        assert float((a - b).abs().max()) <= 1e-2 * scale, (name, float((a - b).abs().max()), scale)
+        assert float((a - b).abs().mean()) <= 5e-3 * (float(b.abs().mean()) + 1e-12), name
+    close(gx1, gx0, "dx")
+    for n in g0:
+        close(g1[n], g0[n], n)
