@@ -234,6 +234,11 @@ int regda_bn_backward_bf16(const void *dout, const void *out, const void *y, voi
                            int groups, const float *gamma, const float *beta, const float *stats, double eps, float *dgamma,
                            float *dbeta, int relu, float *red, int red_zeroed, int dz_ready, void *stream);
 
+/* Patch matrix of the stem convolution (regda/_resnets.py:150: Conv2d(3, 64, 7, stride 2, padding 3)): x bf16 [n][h][w][3]
+ * -> a bf16 [n][oh][ow][192], k = (r*7 + s)*3 + c for the 147 taps, zeros above; the stem then runs on the tcgen05 kernels
+ * as a 1x1 convolution over 192 channels (forward + weight gradient). */
+int regda_stem_im2col_bf16(const void *x, void *a, int n, int h, int w, void *stream);
+
 /* MaxPool2d(3, stride 2, padding 1) over channels-last bf16 (regda/_resnets.py:153): x [n][h][w][c] -> y [n][oh][ow][c],
  * oh = (h-1)/2+1; argmax_u8 (may be NULL for inference) [n][oh][ow][c] receives the position 0..8 of the first maximum
  * inside each window, which is all the backward needs. */

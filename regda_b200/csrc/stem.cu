@@ -1,0 +1,85 @@
+// Stem convolution support (regda/_resnets.py:150-153: Conv2d(3, 64, 7, stride 2, padding 3)).
+//
+// Three input channels cannot feed the implicit-GEMM kernel directly (its K-blocks are 64 channels of one filter tap), so
+// the stem is lowered to a GEMM explicitly: this kernel writes the patch matrix A [n*oh*ow][192] (k = (r*7 + s)*3 + c for
+// the 147 real taps, zero up to 192 = 3 K-blocks) and the tcgen05 kernels then run it as a 1x1 convolution with 192 input
+// channels -- forward (with the fused BatchNorm statistics) and weight gradient; the image needs no data gradient.
+// HBM-bound: 384 B written per output pixel; the 3-channel image is read through L1/L2 (each element is used ~12 times).
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace regda {
+namespace {
+
+constexpr int kStemK = 192, kStemTaps = 147;
+
+constexpr int kStemSeg = 64;                       // output pixels per block
+constexpr int kStemRow = (2 * kStemSeg + 5) * 3 + 1; // staged input elements per filter row: 133 pixels x 3 channels (+1 pad)
+
+// One block = 64 consecutive output pixels of one output row: the 7 input rows x 133 input pixels they read are staged in
+// shared memory with coalesced loads (zero outside the image), then every thread emits 16-byte chunks of the patch matrix
+// (fully coalesced 384-byte rows); tap k of pixel p reads staged element tab[k] + 6*p.
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restrict__ a, int n, int h, int w, int oh, int ow, int segs) {
+    __shared__ unsigned short sin[7 * kStemRow];
+    __shared__ unsigned short tab[kStemK];
+    int b = blockIdx.x;
+    const int seg = b % segs; b /= segs;
+    const int oy = b % oh;
+    const int img = b / oh;
+    const int ox0 = seg * kStemSeg;
+    const int ix_start = 2 * ox0 - 3;
+    const unsigned short *xi = reinterpret_cast<const unsigned short *>(x) + static_cast<long long>(img) * h * w * 3;
+    for (int k = threadIdx.x; k < kStemK; k += 256) {
+        const int r = k / 21, jj = k - r * 21;
+        tab[k] = static_cast<unsigned short>(k < kStemTaps ? r * kStemRow + jj : 7 * kStemRow - 1);   // padding taps read a zeroed slot
+    }
+    for (int e = threadIdx.x; e < 7 * kStemRow; e += 256) {
+        const int r = e / kStemRow, c = e - r * kStemRow;
+        const int iy = 2 * oy - 3 + r;
+        const int px = c / 3;
+        const int ix = ix_start + px;
+        unsigned short v = 0;
+        if (c < kStemRow - 1 && iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(xi + (static_cast<long long>(iy) * w + ix_start) * 3 + c);
+        sin[e] = v;
+    }
+    __syncthreads();
+    const int npx = min(kStemSeg, ow - ox0);
+    __nv_bfloat16 *arow = a + ((static_cast<long long>(img) * oh + oy) * ow + ox0) * kStemK;
+    for (int q = threadIdx.x; q < npx * (kStemK / 8); q += 256) {
+        const int p = q / (kStemK / 8), c = q - p * (kStemK / 8);
+        const int base = 6 * p;
+        unsigned short v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int t = tab[c * 8 + j];
+            v[j] = sin[t + (t == 7 * kStemRow - 1 ? 0 : base)];
+        }
+        uint4 o;
+        o.x = v[0] | (static_cast<unsigned>(v[1]) << 16); o.y = v[2] | (static_cast<unsigned>(v[3]) << 16);
+        o.z = v[4] | (static_cast<unsigned>(v[5]) << 16); o.w = v[6] | (static_cast<unsigned>(v[7]) << 16);
+        *reinterpret_cast<uint4 *>(arow + static_cast<long long>(q) * 8) = o;
+    }
+}
+
+}  // namespace
+}  // namespace regda
+
+using namespace regda;
+
+// x bf16 [n][h][w][3] (channels-last image), a bf16 [n][oh][ow][192] with oh = (h-1)/2+1, ow = (w-1)/2+1
+extern "C" int regda_stem_im2col_bf16(const void *x, void *a, int n, int h, int w, void *stream) {
+    if (!x || !a || n < 1 || h < 1 || w < 1) return fail(REGDA_ERR_INVALID_ARG, "stem_im2col: bad arguments");
+    if (reinterpret_cast<uintptr_t>(a) & 15) return fail(REGDA_ERR_INVALID_ARG, "stem_im2col: output must be 16-byte aligned");
+    const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
+    const int segs = (ow + kStemSeg - 1) / kStemSeg;
+    const long long blocks = static_cast<long long>(n) * oh * segs;
+    if (blocks > 0x7fffffffll) return fail(REGDA_ERR_UNSUPPORTED, "stem_im2col: too many output rows for one launch");
+    stem_im2col_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16 *>(x), static_cast<__nv_bfloat16 *>(a), n, h, w, oh, ow, segs);
+    REGDA_LAUNCH_CHECK();
+    return REGDA_OK;
+}

@@ -23,6 +23,7 @@ import os
 from ..ops.conv import Conv2d
 from ..ops import norm as fnorm
 from ..ops import ppm as fppm
+from ..ops import stem as fstem
 
 FUSED = os.environ.get("REGDA_FUSED", "1") != "0"     # hand-written BN / PPM kernels for bf16 training forward+backward
 
@@ -152,8 +153,13 @@ class ResNet(nn.Module):
             setattr(self, f"layer{li}", nn.Sequential(*blocks))
 
     def forward(self, x):
-        x = self.conv1(x)
-        x = _bn(x, self.bn1, relu=True)
+        if FUSED and self.training and fstem.supported(self.conv1, x) and fnorm.supported(x.new_empty((1, 64, 1, 1)), self.bn1):
+            # the 3-channel stem as an explicit patch matrix + 1x1 tcgen05 convolution, statistics from its epilogue
+            y, st = fstem.stem_conv(x, self.conv1.weight, _GROUPS)
+            x = fnorm.bn_act(y, self.bn1, relu=True, groups=_GROUPS, stats=st)
+        else:
+            x = self.conv1(x)
+            x = _bn(x, self.bn1, relu=True)
         x = fnorm.max_pool3s2(x) if FUSED else F.max_pool2d(x, 3, 2, 1)
         return self.layer4(self.layer3(self.layer2(self.layer1(x))))
 

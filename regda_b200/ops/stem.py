@@ -1,0 +1,64 @@
+"""Stem convolution Conv2d(3, 64, 7, stride 2, padding 3) (regda/_resnets.py:150) on the tcgen05 kernels.
+
+Three input channels cannot form the 64-channel K-blocks of the implicit-GEMM kernel, so the stem is lowered explicitly:
+`regda_stem_im2col_bf16` writes the patch matrix [n, oh, ow, 192] (147 taps + zero padding) and the forward / weight-gradient
+kernels run it as a 1x1 convolution over 192 channels, with the BatchNorm statistics from the forward epilogue like every
+other convolution of the network.  The image needs no data gradient.  (Replaces the library call this layer used to be.)
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import capi
+from . import tc
+
+K_PAD = 192
+
+
+def supported(conv, x) -> bool:
+    return (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] == 3 and conv.in_channels == 3
+            and conv.out_channels % 64 == 0 and conv.kernel_size == 7 and conv.stride == 2 and conv.padding == 3 and conv.dilation == 1
+            and conv.bias is None and not x.requires_grad)
+
+
+class _StemConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, groups):
+        n, _, h, w = x.shape
+        cout = weight.shape[0]
+        oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        x = x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
+        a = torch.empty((n, K_PAD, oh, ow), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+        capi.call("regda_stem_im2col_bf16", capi.ptr_any(x), capi.ptr_any(a), n, h, w, capi.stream())
+        w16 = tc.weight_shadow(weight)                       # bf16 [64,3,7,7] channels-last = OHWI rows of 147
+        wp = torch.zeros((cout, K_PAD, 1, 1), dtype=torch.bfloat16, device=x.device).contiguous(memory_format=torch.channels_last)
+        wp.view(cout, K_PAD)[:, :147] = w16.permute(0, 2, 3, 1).reshape(cout, 147)
+        y, stats = tc.fprop(a, wp, 1, 0, 1, groups)
+        ctx.save_for_backward(a)
+        ctx.weight = weight
+        ctx.mark_non_differentiable(stats)
+        ctx.set_materialize_grads(False)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, gy, _gstats=None):
+        if gy is None:
+            return None, None, None
+        a, = ctx.saved_tensors
+        weight = ctx.weight
+        cout = weight.shape[0]
+        gy = gy.contiguous(memory_format=torch.channels_last)
+        gw = torch.zeros((cout, K_PAD, 1, 1), dtype=torch.float32, device=gy.device).contiguous(memory_format=torch.channels_last)
+        tc.wgrad_accumulate(gy, a, gw, 1, 0, 1)
+        if weight.grad is None:
+            weight.grad = torch.zeros_like(weight)
+        # weight.grad is OHWI memory: rows of 147 = (r, s, c), the patch matrix's k order
+        gview = weight.grad.permute(0, 2, 3, 1).reshape(cout, 147)
+        assert gview.data_ptr() == weight.grad.data_ptr(), "stem weight gradient must live in channels-last (OHWI) memory"
+        gview.add_(gw.view(cout, K_PAD)[:, :147])
+        return None, None, None
+
+
+def stem_conv(x, weight, groups):
+    """(y, bn_stats): y = conv7x7/2(x, weight) bf16 channels-last, bn_stats float32 [groups][2][cout]"""
+    return _StemConvFn.apply(x, weight, groups)

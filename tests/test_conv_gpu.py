@@ -220,3 +220,29 @@ def test_dgrad_bnred_matches_masked_dgrad_and_reductions(shape, with_addend):
     tol = 1e-4 * float(dzf.abs().max()) * (dzf.shape[1] * dzf.shape[3]) ** 0.5 * 4
     assert torch.allclose(red[:, 0], s1, rtol=1e-4, atol=tol), float((red[:, 0] - s1).abs().max())
     assert torch.allclose(red[:, 1], s2, rtol=1e-4, atol=4 * tol), float((red[:, 1] - s2).abs().max())
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64), (4, 96, 160), (2, 37, 53)], ids=str)
+def test_stem_conv_patch_matrix_path_matches_float32_reference(shape):
+    """Conv2d(3, 64, 7, stride 2, padding 3) through regda_stem_im2col_bf16 + the 1x1 tcgen05 kernels: output, fused BatchNorm
+    statistics and weight gradient against a float32 convolution of the same bf16 operands."""
+    from regda_b200.ops import stem
+    from regda_b200.ops.conv import Conv2d
+    n, h, w = shape
+    torch.manual_seed(3)
+    conv = Conv2d(3, 64, 7, stride=2, padding=3, bias=False).cuda()
+    x = torch.randn(n, 3, h, w, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    assert stem.supported(conv, x)
+    groups = 2 if n % 2 == 0 else 1
+    y, st = stem.stem_conv(x, conv.weight, groups)
+    wr = conv.weight.detach().bfloat16().float().requires_grad_(True)
+    ref = F.conv2d(x.float(), wr, None, 2, 3, 1)
+    assert y.shape == ref.shape
+    assert float((y.float() - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
+    yf = y.float().reshape(groups, n // groups, 64, -1)
+    assert torch.allclose(st[:, 0], yf.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[:, 1], (yf * yf).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+    gy = torch.randn(ref.shape, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    y.backward(gy)
+    ref.backward(gy.float())
+    assert float((conv.weight.grad - wr.grad).abs().max()) <= 5e-3 * float(wr.grad.abs().max())
