@@ -234,6 +234,16 @@ int regda_bn_backward_bf16(const void *dout, const void *out, const void *y, voi
                            int groups, const float *gamma, const float *beta, const float *stats, double eps, float *dgamma,
                            float *dbeta, int relu, float *red, int red_zeroed, int dz_ready, void *stream);
 
+/* Eval-mode BatchNorm2d (+ residual + ReLU) over channels-last bf16 with the running statistics (regda/_resnets.py:92-112 under
+ * model.eval(): the offline teacher pass pseudo_generation.py:96-141 and evaluate() eval.py:14-56). */
+int regda_bn_inference_bf16(const void *y, const void *residual, void *out, int64_t npix, int c, const float *gamma,
+                            const float *beta, const float *running_mean, const float *running_var, double eps, int relu,
+                            void *stream);
+/* Eval tail of Deeplabv2.forward (regda/models/Encoder.py:152-155): out[b][c][H][W] = mean over the heads of
+ * softmax_c(bilinear_align_corners(x_head [b][c][h][w])), float32; x2 may be NULL (one head). */
+int regda_upsample_softmax_mean(const float *x1, const float *x2, float *out, int b, int c, int h, int w, int H, int W,
+                                void *stream);
+
 /* Patch matrix of the stem convolution (regda/_resnets.py:150: Conv2d(3, 64, 7, stride 2, padding 3)): x bf16 [n][h][w][3]
  * -> a bf16 [n][oh][ow][192], k = (r*7 + s)*3 + c for the 147 taps, zeros above; the stem then runs on the tcgen05 kernels
  * as a 1x1 convolution over 192 channels (forward + weight gradient). */

@@ -95,6 +95,65 @@ def _scatter(src, index, dim=-1, out=None, dim_size=None, reduce="sum"):
     return torch.zeros(shape, dtype=src.dtype, device=src.device).scatter_add_(dim, index, src)
 
 
+# ttach==0.0.3 (requirement.txt:165) is absent from this image.  Restatement of the three classes regda/utils/tools.py:132-152
+# uses, from the package's published source (ttach/base.py Compose / Transformer, ttach/transforms.py HorizontalFlip / Rotate90,
+# ttach/functional.py hflip = x.flip(3), rot90 = torch.rot90(x, k, (2, 3))): Compose iterates itertools.product of the
+# transforms' parameter lists in order; a view augments by applying the transforms in order and de-augments a mask by applying
+# the inverses in REVERSE order.  PARITY NOTE: this stub is a restatement, not the package -- the teacher-pass goldens are
+# pinned to it.
+class _TtaHorizontalFlip:
+    params = [False, True]
+
+    def aug(self, x, p):
+        return x.flip(3) if p else x
+
+    deaug = aug
+
+
+class _TtaRotate90:
+    def __init__(self, angles):
+        self.params = list(angles) if 0 in angles else [0] + list(angles)
+
+    def aug(self, x, angle):
+        import torch
+        k = angle // 90 if angle >= 0 else (angle + 360) // 90
+        return torch.rot90(x, k, (2, 3))
+
+    def deaug(self, x, angle):
+        return self.aug(x, -angle)
+
+
+class _TtaView:
+    def __init__(self, transforms, params):
+        self.transforms, self.params = transforms, params
+
+    def augment_image(self, x):
+        for t, p in zip(self.transforms, self.params):
+            x = t.aug(x, p)
+        return x
+
+    def deaugment_mask(self, x):
+        for t, p in zip(self.transforms[::-1], self.params[::-1]):
+            x = t.deaug(x, p)
+        return x
+
+
+class _TtaCompose:
+    def __init__(self, transforms):
+        self.transforms = list(transforms)
+
+    def __iter__(self):
+        import itertools
+        for params in itertools.product(*[t.params for t in self.transforms]):
+            yield _TtaView(self.transforms, params)
+
+    def __len__(self):
+        n = 1
+        for t in self.transforms:
+            n *= len(t.params)
+        return n
+
+
 def _mod(name, **attrs):
     m = types.ModuleType(name)
     m.__dict__.update(attrs)
@@ -119,7 +178,7 @@ def install_stubs():
     except Exception:
         mp = _mod("matplotlib")
         mp.pyplot = _mod("matplotlib.pyplot")
-    _mod("ttach")
+    _mod("ttach", Compose=_TtaCompose, HorizontalFlip=_TtaHorizontalFlip, Rotate90=_TtaRotate90)
     _mod("prettytable", PrettyTable=object)
 
     import logging

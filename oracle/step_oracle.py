@@ -348,3 +348,44 @@ def inner_step(state, images_s, label_s, images_t, soft_t, regs_t, *, class_num=
     state.opt.step()                                                                # :241
     return dict(loss=float(loss), loss_source=float(loss_s), loss_target=float(loss_t), grad_norm=float(gnorm),
                 hard=hard, soft=soft)
+
+
+# ---- offline teacher pass ---------------------------------------------------------------------------
+# Test infrastructure like the rest of this file.  Restates regda/utils/tools.py:52-57 (pad_image), :61-97 (pre_slide) and
+# :132-152 (tta_predict, through ttach==0.0.3's Compose([HorizontalFlip(), Rotate90([0, 90, 180, 270])])); pinned by
+# tests/golden/teacher_pass.npz, which the reference's own functions produced (tests/golden/make_golden.py teacher_pass).
+def tta_predict(model, img):
+    """mean over the 8 views (flip in {no, yes}) x (k quarter turns, k = 0..3): view = rot90^k(flip(img)); the prediction is
+    brought back by rot90^-k then flip.  One model call per view, as the reference does."""
+    outs = []
+    for flip in (False, True):
+        for k in range(4):
+            v = img.flip(3) if flip else img
+            v = torch.rot90(v, k, (2, 3))
+            o = torch.rot90(model(v), -k, (2, 3))
+            outs.append(o.flip(3) if flip else o)
+    return torch.cat(outs, 0).mean(dim=0, keepdim=True)
+
+
+def window_origins(size, tile):
+    """origins of the 50 %-overlap windows along one axis: 0, tile/2, ... with the last one shifted back inside"""
+    stride = math.ceil(tile * 0.5)
+    n = int(math.ceil((size - tile) / stride) + 1)          # tools.py:66-67 (1 when the image is smaller than the tile)
+    return [max(min(i * stride + tile, size) - tile, 0) for i in range(n)]
+
+
+def pre_slide(model, image, num_classes, tile=(512, 512), tta=False):
+    b, _, H, W = image.shape
+    prob = torch.zeros(b, num_classes, H, W)
+    cnt = torch.zeros(b, 1, H, W)
+    for y1 in window_origins(H, tile[0]):
+        for x1 in window_origins(W, tile[1]):
+            y2, x2 = min(y1 + tile[0], H), min(x1 + tile[1], W)
+            win = image[:, :, y1:y2, x1:x2]
+            # pad_image: F.pad(img, (0, 0, rows_missing, cols_missing)) = height padded by rows_missing on TOP and cols_missing
+            # at the bottom, width untouched (the reference's argument order, tools.py:56)
+            win_p = F.pad(win, (0, 0, tile[0] - win.shape[2], tile[1] - win.shape[3]))
+            out = tta_predict(model, win_p) if tta else model(win_p)
+            prob[:, :, y1:y2, x1:x2] += out[:, :, :win.shape[2], :win.shape[3]]
+            cnt[:, :, y1:y2, x1:x2] += 1
+    return prob / cnt

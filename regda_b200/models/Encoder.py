@@ -42,10 +42,22 @@ def _fused(x, bn):
 _GROUPS = 1
 
 
+def _inference(x):
+    """eval-mode, no-grad, bf16 on the GPU: the hand-written inference kernels apply (offline teacher pass / evaluate())"""
+    return FUSED and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.bfloat16
+
+
 def _conv_bn(conv, bn, x, residual=None, relu=False, tap=False):
     """relu?(bn(conv(x)) + residual); on the hand-written path the BatchNorm statistics come out of the convolution
     kernel's epilogue, so BatchNorm makes one pass (apply) instead of two over the activation.  tap=True returns
     (out, x_tap): x_tap is x for a residual branch, routed so that its gradient is added inside the dgrad kernel."""
+    if not bn.training and _inference(x):
+        y = conv(x)
+        if fnorm.inference_supported(y, bn):
+            out = fnorm.bn_inference(y, bn, residual, relu)
+        else:
+            out = _bn(y, bn, residual, relu)
+        return (out, x) if tap else out
     if FUSED and bn.training and x.is_cuda and x.dtype == torch.bfloat16:
         res = conv.forward_with_bn_stats(x, _GROUPS, tap)
         y, st = res[0], res[1]
@@ -62,6 +74,8 @@ def _bn(x, bn, residual=None, relu=False):
     """relu?(bn(x) + residual) through the fused kernels when they apply, else through torch; honours _GROUPS"""
     if _fused(x, bn):
         return fnorm.bn_act(x, bn, residual=residual, relu=relu, groups=_GROUPS)
+    if FUSED and fnorm.inference_supported(x, bn):
+        return fnorm.bn_inference(x, bn, residual, relu)
     out = fnorm.bn_eager(x, bn, _GROUPS)
     if residual is not None:
         out = out + residual
@@ -110,7 +124,7 @@ class Bottleneck(nn.Module):
             self.downsample = nn.Sequential(Conv2d(inplanes, planes * 4, 1, stride=stride, bias=False), nn.BatchNorm2d(planes * 4))
 
     def forward(self, x):
-        if (FUSED and self.training and x.is_cuda and x.dtype == torch.bfloat16) or _GROUPS > 1:
+        if (FUSED and self.training and x.is_cuda and x.dtype == torch.bfloat16) or _GROUPS > 1 or (not self.training and _inference(x)):
             # fnorm.arm(t, k): t (a BatchNorm+ReLU output) has exactly k consumers, all of them the Conv2d calls below, so
             # their data-gradient epilogues may carry the first half of that BatchNorm's backward (ops/norm.py BnHandle)
             if self.downsample is None:
@@ -157,6 +171,9 @@ class ResNet(nn.Module):
             # the 3-channel stem as an explicit patch matrix + 1x1 tcgen05 convolution, statistics from its epilogue
             y, st = fstem.stem_conv(x, self.conv1.weight, _GROUPS)
             x = fnorm.bn_act(y, self.bn1, relu=True, groups=_GROUPS, stats=st)
+        elif not self.training and _inference(x) and fstem.supported(self.conv1, x):
+            y, _ = fstem.stem_conv(x, self.conv1.weight, None)
+            x = _bn(y, self.bn1, relu=True)
         else:
             x = self.conv1(x)
             x = _bn(x, self.bn1, relu=True)
@@ -198,7 +215,8 @@ class PPMBilinear(nn.Module):
             nn.Dropout2d(dropout), Conv2d(512, num_classes, 1, bias=True))
 
     def fused_ok(self, conv_out):
-        return (FUSED and self.training and conv_out.is_cuda and conv_out.dtype == torch.bfloat16 and len(self.pool_scales) <= 4
+        return (FUSED and (self.training or not torch.is_grad_enabled()) and conv_out.is_cuda and conv_out.dtype == torch.bfloat16
+                and len(self.pool_scales) <= 4
                 and conv_out.shape[1] % 8 == 0 and self.ppm[0][1].out_channels % 8 == 0)
 
     def forward(self, conv_out, pooled=None):
@@ -266,7 +284,7 @@ class Deeplabv2(nn.Module):
     def forward(self, x):
         xin = x.to(self.compute_dtype).contiguous(memory_format=torch.channels_last)
         feat = self.encoder(xin)
-        if self._cfg.is_ins_norm and FUSED and self.training and fnorm.instance_norm_supported(feat):
+        if self._cfg.is_ins_norm and FUSED and (self.training or not torch.is_grad_enabled()) and fnorm.instance_norm_supported(feat):
             # hand-written path: per-image statistics groups of the BatchNorm kernels, bf16 in / bf16 out; the Aligner's
             # float32 feature view is one conversion of the result
             fin = fnorm.instance_norm(feat, self.instance_norm.eps)
@@ -286,6 +304,8 @@ class Deeplabv2(nn.Module):
             x2 = self.layer6(fin).float()
         if self.training:
             return x1, x2, feat
+        if FUSED and x1.is_cuda and not torch.is_grad_enabled() and x1.shape[1] <= 16:
+            return fppm.upsample_softmax_mean(x1, x2, x.shape[-2:])       # one pass, no [b,c,H,W] intermediates
         x1 = F.interpolate(x1, x.shape[-2:], mode="bilinear", align_corners=True)
         x2 = F.interpolate(x2, x.shape[-2:], mode="bilinear", align_corners=True)
         return (x1.softmax(dim=1) + x2.softmax(dim=1)) / 2

@@ -135,6 +135,27 @@ def bn_act(y, bn, residual=None, relu=True, groups=1, stats=None):
     return out
 
 
+def inference_supported(y, bn) -> bool:
+    """eval-mode fast path: running statistics, no autograd"""
+    if bn.training or torch.is_grad_enabled() or not (y.is_cuda and y.dtype == torch.bfloat16 and y.dim() == 4):
+        return False
+    if not (bn.affine and bn.track_running_stats) or bn.running_mean is None:
+        return False
+    return bool(capi.lib().regda_bn_supported(y.shape[0] * y.shape[2] * y.shape[3], y.shape[1]))
+
+
+def bn_inference(y, bn, residual=None, relu=True):
+    """relu?(bn(y) + residual) with the running statistics (model.eval(): the offline teacher pass and evaluate())"""
+    y = _cl(y)
+    n, c, h, w = y.shape
+    res = _cl(residual) if residual is not None else None
+    out = torch.empty_like(y)
+    capi.call("regda_bn_inference_bf16", capi.ptr_any(y), capi.ptr_any(res) if res is not None else None, capi.ptr_any(out), n * h * w, c,
+              capi.ptr(bn.weight), capi.ptr(bn.bias), capi.ptr(bn.running_mean), capi.ptr(bn.running_var), float(bn.eps), int(relu),
+              capi.stream())
+    return out
+
+
 def bn_eager(x, bn, groups=1):
     """nn.BatchNorm2d with the same statistics-group semantics, through torch (tiny maps, float32 parity mode)."""
     if groups == 1 or not bn.training:

@@ -78,3 +78,15 @@ def pool(feat, scales=(1, 2, 3, 6)):
 
 def upsample_concat(feat, branches, scales=(1, 2, 3, 6)):
     return _UpcatFn.apply(feat, tuple(scales), *branches)
+
+
+def upsample_softmax_mean(x1, x2, size):
+    """Eval tail of Deeplabv2.forward (regda/models/Encoder.py:152-155): mean over the heads of softmax(bilinear_align_corners(x))"""
+    x1 = x1.float().contiguous()
+    x2 = x2.float().contiguous() if x2 is not None else None
+    b, c, h, w = x1.shape
+    H, W = int(size[0]), int(size[1])
+    out = torch.empty((b, c, H, W), dtype=torch.float32, device=x1.device)
+    capi.call("regda_upsample_softmax_mean", capi.ptr(x1), capi.ptr(x2) if x2 is not None else None, capi.ptr(out), b, c, h, w, H, W,
+              capi.stream())
+    return out

@@ -33,6 +33,8 @@ class _StemConvFn(torch.autograd.Function):
         w16 = tc.weight_shadow(weight)                       # bf16 [64,3,7,7] channels-last = OHWI rows of 147
         wp = torch.zeros((cout, K_PAD, 1, 1), dtype=torch.bfloat16, device=x.device).contiguous(memory_format=torch.channels_last)
         wp.view(cout, K_PAD)[:, :147] = w16.permute(0, 2, 3, 1).reshape(cout, 147)
+        if groups is None:                                   # inference: no BatchNorm statistics wanted
+            return tc.fprop(a, wp, 1, 0, 1), None
         y, stats = tc.fprop(a, wp, 1, 0, 1, groups)
         ctx.save_for_backward(a)
         ctx.weight = weight

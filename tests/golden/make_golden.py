@@ -276,14 +276,42 @@ def model_and_step(ns):
     np.savez_compressed(os.path.join(HERE, "step_resnet50.npz"), **d)
 
 
+def teacher_pass(ns):
+    """Offline teacher pass: the reference's own pre_slide / tta_predict (regda/utils/tools.py:61-152)
+    around its eval-mode Deeplabv2, with the ttach restatement of oracle/ref_loader.py.  Tiles of 64 so the CPU run is quick:
+    a 96x112 image (2 x 3 windows, the last column shifted back inside) and a 48x64 image (smaller than the tile: the
+    reference's pad_image pads the TOP of the height, tools.py:56)."""
+    from regda.utils.tools import pre_slide, tta_predict
+    g = torch.Generator().manual_seed(SEED + 11)
+    C = 6
+    m = ref_loader.build_reference_model(ns, "resnet50", C)
+    m.load_state_dict(so.seeded_state_dict(m, SEED))
+    m.eval()
+    d = {}
+    with torch.no_grad():
+        x = torch.randn(1, 3, 96, 112, generator=g).clamp(max=1.0)
+        d["image"] = x.numpy()
+        d["tile_tta"] = tta_predict(m, x[:, :, :64, :64]).numpy()
+        d["slide_tta"] = pre_slide(m, x, num_classes=C, tile_size=(64, 64), tta=True).numpy()
+        d["slide_plain"] = pre_slide(m, x, num_classes=C, tile_size=(64, 64), tta=False).numpy()
+        xs = torch.randn(1, 3, 48, 64, generator=g).clamp(max=1.0)
+        d["image_small"] = xs.numpy()
+        d["slide_small_tta"] = pre_slide(m, xs, num_classes=C, tile_size=(64, 64), tta=True).numpy()
+    np.savez_compressed(os.path.join(HERE, "teacher_pass.npz"), **d)
+
+
 if __name__ == "__main__":
     assert ref_loader.reference_available(), "run this where /root/reference is mounted"
     torch.set_num_threads(os.cpu_count() or 1)
     ns = ref_loader.load()
+    if "--only-teacher" in sys.argv:
+        teacher_pass(ns)
+        sys.exit(0)
     lrh_cases(ns)
     select_and_downscale(ns)
     aligner_and_loss(ns)
     model_and_step(ns)
+    teacher_pass(ns)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

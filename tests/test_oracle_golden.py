@@ -137,3 +137,36 @@ def test_lrh_torch_port_bit_exact(case):
     out = so.lrh_torch(torch.from_numpy(case["labels"]), torch.from_numpy(case["regions"]),
                        int(case["class_num"]), int(case["ignore"]), float(case["percent"]))
     assert np.array_equal(out.numpy(), case["out"])
+
+
+def _teacher_model():
+    m = so.DeeplabOracle("resnet50", 6, dropout=0.0)
+    m.load_state_dict(so.seeded_state_dict(m, 2333))
+    return m.eval()
+
+
+def test_teacher_pass_oracle_matches_reference_fixture():
+    """offline teacher pass: the oracle's pre_slide / tta_predict against what the reference's own
+    functions produced (tests/golden/teacher_pass.npz)"""
+    z = load_golden("teacher_pass.npz")
+    m = _teacher_model()
+    x, xs = torch.from_numpy(z["image"]), torch.from_numpy(z["image_small"])
+    with torch.no_grad():
+        torch.testing.assert_close(so.tta_predict(m, x[:, :, :64, :64]), torch.from_numpy(z["tile_tta"]), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(so.pre_slide(m, x, 6, (64, 64), tta=False), torch.from_numpy(z["slide_plain"]), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(so.pre_slide(m, x, 6, (64, 64), tta=True), torch.from_numpy(z["slide_tta"]), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(so.pre_slide(m, xs, 6, (64, 64), tta=True), torch.from_numpy(z["slide_small_tta"]), rtol=1e-4, atol=1e-5)
+
+
+def test_teacher_pass_host_logic_matches_reference_fixture():
+    """the product's host-side pre_slide / tta_predict (device-agnostic window arithmetic, TTA view order, the stacked-views
+    batch, the pad quirk) around the oracle model on the CPU"""
+    from regda_b200.utils.tools import pre_slide, tta_predict
+    z = load_golden("teacher_pass.npz")
+    m = _teacher_model()
+    x, xs = torch.from_numpy(z["image"]), torch.from_numpy(z["image_small"])
+    with torch.no_grad():
+        torch.testing.assert_close(tta_predict(m, x[:, :, :64, :64]), torch.from_numpy(z["tile_tta"]), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(pre_slide(m, x, num_classes=6, tile_size=(64, 64), tta=True), torch.from_numpy(z["slide_tta"]), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(pre_slide(m, x, num_classes=6, tile_size=(64, 64), tta=False), torch.from_numpy(z["slide_plain"]), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(pre_slide(m, xs, num_classes=6, tile_size=(64, 64), tta=True), torch.from_numpy(z["slide_small_tta"]), rtol=1e-4, atol=1e-5)
