@@ -71,9 +71,14 @@ def test_trainer_and_prototype_tools_end_to_end(tmp_path):
     assert proto.shape == (6, 2048) and torch.isfinite(proto).all()
     for graph in ("0", "1"):
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "train_ssl_reg.py"), "--config-path", "st.regda.tiny", "--ckpt-proto",
-                            str(tmp_path / "proto.pth"), "--sam-refine", "--percent", "0.5", "--cuda-graph", graph],
+                            str(tmp_path / "proto.pth"), "--sam-refine", "--percent", "0.5", "--cuda-graph", graph] +
+                           (["--gene-every", "2"] if graph == "0" else []),
                            capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
         assert r.returncode == 0, r.stderr[-2000:]
         assert "iter=1, total=" in r.stdout and "images/s" in r.stdout, r.stdout[-1000:]
+        if graph == "0":                       # the GENE_EVERY teacher pass ran and its .pt soft labels are in the reference's format
+            assert "soft pseudo labels" in r.stdout, r.stdout[-1000:]
+            soft = torch.load("/tmp/regda_tiny/pseudo_label/synthetic_r0_0000.tif.pt")
+            assert soft.dtype == torch.float32 and soft.dim() == 3 and soft.shape[0] == 6
     sd = torch.load("/tmp/regda_tiny/Potsdam_curr.pth")
     assert "encoder.resnet.conv1.weight" in sd and "layer6.conv_last.4.bias" in sd

@@ -28,6 +28,7 @@ import torch.distributed as dist  # noqa: E402
 from regda_b200 import parallel, synth  # noqa: E402
 from regda_b200.gast.alignment import Aligner  # noqa: E402
 from regda_b200.gast.balance import ClassBalance, CrossEntropy  # noqa: E402
+from regda_b200.gast.pseudo_generation import gener_target_pseudo  # noqa: E402
 from regda_b200.models.Encoder import Deeplabv2  # noqa: E402
 from regda_b200.trainer import GraphedStep, SelfTrainingStep  # noqa: E402
 from regda_b200.utils.local_region_homog import Homogenizer  # noqa: E402
@@ -56,6 +57,9 @@ def parse():
     p.add_argument('--data', type=str, default='synthetic', choices=['synthetic', 'reference'])
     p.add_argument('--steps', type=int, default=0, help='override STAGE3_STEPS (0 = config)')
     p.add_argument('--cuda-graph', type=str2bool, default=1, help='replay the whole step as one CUDA graph')
+    p.add_argument('--gene-every', type=int, default=0, help='regenerate the soft pseudo labels with the current model every N '
+                   'iterations (the reference\'s GENE_EVERY block, tools/train_ssl_reg.py:180-194); synthetic data: over this rank\'s target tiles, '
+                   'written to SNAPSHOT_DIR/pseudo_label/*.pt and read back')
     p.add_argument('--region-bound', type=int, default=0, help='upper bound of region ids + 1 (0 = measured from the data once)')
     return p.parse_args()
 
@@ -132,10 +136,28 @@ def main():
     class _Opt:                                                 # adjust_learning_rate's optimizer surface (tools.py:199-207)
         param_groups = [dict(lr=0.0)]
 
+    def regenerate_pseudo_labels():
+        """:180-194 -- offline teacher pass with the current weights (8-view TTA, sliding windows), soft labels through the
+        reference's on-disk format (<pseudo_label>/<fname>.pt, float32 [C,H,W]) and back into the target batch"""
+        path = osp.join(cfg.SNAPSHOT_DIR, 'pseudo_label')
+        xs, ls, xt, _, regs = loader.t[:5]
+        names = [f'synthetic_r{rank}_{i:04d}.tif' for i in range(xt.shape[0])]
+        hw = tuple(xt.shape[-2:])
+        tile = (min(512, hw[0]), min(512, hw[1]))
+        gener_target_pseudo(cfg, model, [(xt[i:i + 1].float(), {'fname': [n]}) for i, n in enumerate(names)], path, size=hw,
+                            save_prob=True, slide=True, ignore_label=ignore_label, num_classes=class_num, tile_size=tile)
+        model.train()
+        soft = torch.stack([torch.load(osp.join(path, n + '.pt')) for n in names]).to(dev)
+        loader.t = (xs, ls, xt, soft, regs) + tuple(loader.t[5:])
+        log(f'###### generated {len(names)} soft pseudo labels in {path} ######')
+
     t0 = time.time()
     os.makedirs(cfg.SNAPSHOT_DIR, exist_ok=True)
     batch = first
     for i_iter in range(stop_steps):
+        if args.gene_every > 0 and args.data == 'synthetic' and i_iter % args.gene_every == 0:
+            regenerate_pseudo_labels()
+            batch = next_batch()
         lr = adjust_learning_rate(_Opt, i_iter, cfg)            # :178
         out = runner(*batch, lr=lr) if runner is not None else step(*batch, lr)
         if i_iter == 0 or (i_iter + 1) % 50 == 0:               # :246-251 (the only host sync: reading the loss to log it)
