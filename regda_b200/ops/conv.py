@@ -22,6 +22,46 @@ ENGINE = os.environ.get("REGDA_CONV", "auto")
 FUSE_BN_STATS = os.environ.get("REGDA_FUSE_BN_STATS", "1") != "0" and os.environ.get("REGDA_CONV_KERNEL", "") != "classic"
 stats = {"tcgen05_fprop": 0, "tcgen05_dgrad": 0, "tcgen05_wgrad": 0, "cudnn": 0}
 
+# Weight gradients are off the backward pass's critical path (only the optimiser reads them), so they are launched on a side
+# stream: the data-gradient chain continues on the main stream and the two kernel families fill each other's launch gaps and
+# tails.  The side stream forks from the main stream when dY exists (event) and is joined once, after loss.backward()
+# (join_wgrad_stream, called by the trainer); inside a CUDA-graph capture this becomes a parallel branch of the graph.
+WGRAD_STREAM = os.environ.get("REGDA_WGRAD_STREAM", "1") != "0"
+_side_streams = {}
+_side_used = set()
+_side_active = False          # only inside `with wgrad_side_stream():` -- a caller that does not join must not get async gradients
+
+
+def _wgrad_stream(device):
+    key = torch.device(device).index or 0
+    st = _side_streams.get(key)
+    if st is None:
+        st = _side_streams[key] = torch.cuda.Stream(device=device)
+    return key, st
+
+
+class wgrad_side_stream:
+    """`with wgrad_side_stream(): loss.backward()` -- weight-gradient kernels of the enclosed backward pass go to the side
+    stream; leaving the block makes the current stream wait for them."""
+
+    def __enter__(self):
+        global _side_active
+        _side_active = WGRAD_STREAM
+        return self
+
+    def __exit__(self, *exc):
+        global _side_active
+        _side_active = False
+        join_wgrad_stream()
+        return False
+
+
+def join_wgrad_stream():
+    """main stream waits for every weight-gradient kernel launched on the side stream since the last join"""
+    for key in list(_side_used):
+        torch.cuda.current_stream(key).wait_stream(_side_streams[key])
+    _side_used.clear()
+
 
 def set_engine(name: str):
     global ENGINE
@@ -111,7 +151,16 @@ class _ConvFn(torch.autograd.Function):
                 stats["tcgen05_wgrad"] += 1
                 if weight.grad is None:
                     weight.grad = torch.zeros_like(weight)
-                tc.wgrad_accumulate(gy, x, weight.grad, stride, padding, dilation)
+                if _side_active:
+                    key, side = _wgrad_stream(gy.device)
+                    side.wait_stream(torch.cuda.current_stream())           # dY (and the zeroed gradient arena) are ready
+                    with torch.cuda.stream(side):
+                        tc.wgrad_accumulate(gy, x, weight.grad, stride, padding, dilation)
+                    gy.record_stream(side)                                  # the allocator must not recycle dY / x under the kernel
+                    x.record_stream(side)
+                    _side_used.add(key)
+                else:
+                    tc.wgrad_accumulate(gy, x, weight.grad, stride, padding, dilation)
             else:
                 stats["cudnn"] += 1
                 gw = torch.ops.aten.convolution_backward(gy, x, w16, None, [stride] * 2, [padding] * 2,

@@ -21,6 +21,7 @@ import torch
 import torch.distributed as dist
 
 from . import capi, parallel
+from .ops import conv as conv_ops
 from .gast.balance import CrossEntropy
 from .utils.tools import loss_calc
 
@@ -151,7 +152,8 @@ class SelfTrainingStep:
         loss_source = loss_calc([pred_s1, pred_s2], label_s, loss_fn=self.loss_fn_s, multi=True)   # :228
         loss_target = loss_calc([pred_t1, pred_t2], hard, loss_fn=self.loss_fn_t, multi=True)      # :233
         loss = loss_source + loss_target
-        loss.backward()                                                            # :238
+        with conv_ops.wgrad_side_stream():                                         # weight gradients run on a side stream, joined here
+            loss.backward()                                                        # :238
         if self.world_size > 1:
             parallel.allreduce_sum_(self.arena.grad)                               # mean over ranks via grad_scale
         self.arena.clip_and_sgd(self.max_norm, self.momentum, self.weight_decay, 1.0 / self.world_size)   # :239-241
