@@ -63,8 +63,11 @@ def top_kernel_roofline(pk, reps=10):
     flop = 2.0 * n * hw * hw * cout * cin * 9
     ach = flop / (ms * 1e-3) / 1e12
     return {"bound": "tensor", "achieved": round(ach, 1), "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_burst"], 4),
-            "traffic": None, "peak_source": pk["source"] + " (burst: kernel timed alone)",
-            "kernel": "conv_fprop_kernel<128,3,false> on the PPM fuse conv (3x3, 4096->512, 16x32x32 px: M=16384 N=512 K=36864)",
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from profiles/ncu_conv_head_fprop_stats_round1b.txt
+            "traffic": 229619456, "traffic_note": "ncu --set full, one launch: 214.0 MB read + 15.7 MB written (operands 151 MB + output 16.8 MB algorithmic)",
+            "peak_source": pk["source"] + " (burst: kernel timed alone)",
+            "kernel": "conv_persistent_kernel<256,4> (tcgen05 128x256 tiles, TMA-store epilogue) on the PPM fuse conv (3x3, 4096->512, 16x32x32 px: M=16384 N=512 K=36864)",
+            "ncu_tensor_pipe_active_pct": 90.4,
             "algorithmic_flop_per_launch": flop, "us_per_launch": round(ms * 1e3, 1)}
 
 
