@@ -234,6 +234,20 @@ int regda_bn_backward_bf16(const void *dout, const void *out, const void *y, voi
                            int groups, const float *gamma, const float *beta, const float *stats, double eps, float *dgamma,
                            float *dbeta, int relu, float *red, int red_zeroed, int dz_ready, void *stream);
 
+/* PrototypeContrastiveLoss (regda/loss.py:18-47; the alignment loss of the stage-2 step, tools/train_align_reg.py:186-189):
+ * loss = mean over rows with label != ignore_label of CE(normalize(feat_row) . normalize(proto_c) / temperature, label).
+ * feat float32 [n][k] (k % 4 == 0), label int64 [n], proto float32 [c][k] (c <= 8); stats float32 [2] receives (loss, valid
+ * rows).  backward: dfeat float32 [n][k] = upstream[0] * dloss/dfeat (upstream = device scalar or NULL for 1), zeros for
+ * ignored rows; pass the forward call's workspace and stats.  A label outside [0, c) that is not ignore_label sets
+ * REGDA_FLAG_LABEL_RANGE (nn.CrossEntropyLoss raises there). */
+size_t regda_pcl_workspace_bytes(int64_t n);
+int regda_pcl_forward(const float *feat, const int64_t *label, const float *proto, float *stats, int64_t n, int k, int c,
+                      int64_t ignore_label, double temperature, int32_t *flags, void *workspace, size_t workspace_bytes,
+                      void *stream);
+int regda_pcl_backward(const float *feat, const int64_t *label, const float *proto, const float *stats, const float *upstream,
+                       float *dfeat, int64_t n, int k, int c, int64_t ignore_label, double temperature, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
 /* Eval-mode BatchNorm2d (+ residual + ReLU) over channels-last bf16 with the running statistics (regda/_resnets.py:92-112 under
  * model.eval(): the offline teacher pass pseudo_generation.py:96-141 and evaluate() eval.py:14-56). */
 int regda_bn_inference_bf16(const void *y, const void *residual, void *out, int64_t npix, int c, const float *gamma,

@@ -389,3 +389,50 @@ def pre_slide(model, image, num_classes, tile=(512, 512), tta=False):
             prob[:, :, y1:y2, x1:x2] += out[:, :, :win.shape[2], :win.shape[3]]
             cnt[:, :, y1:y2, x1:x2] += 1
     return prob / cnt
+
+
+# --------------------------------------------------------------------------------------
+# stage-2 step, tools/train_align_reg.py:144-196 with regda/loss.py:18-47
+# --------------------------------------------------------------------------------------
+def pcl_loss(prototypes, feat, labels, temperature=8.0, ignore_label=-1):
+    """PrototypeContrastiveLoss.forward (regda/loss.py:24-47): cross entropy of the cosine similarities (divided by the
+    temperature) between every non-ignored feature row and the class prototypes, mean over those rows."""
+    k = feat.shape[1]
+    rows = feat.permute(0, 2, 3, 1).reshape(-1, k) if feat.dim() == 4 else feat
+    lab = labels.reshape(-1)
+    keep = lab != ignore_label
+    rows, lab = rows[keep], lab[keep]
+    rows = rows / rows.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    pr = prototypes / prototypes.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    return F.cross_entropy(rows @ pr.t() / temperature, lab)
+
+
+def align_step(state, images_s, label_s, images_t, regs_t, *, class_num=6, ignore_label=-1, percent=0.5, cutoff_top=0.8,
+               cutoff_low=0.6, temp=2.0, decay=0.996, lr=None, max_norm=32.0, sam_refine=True, pcl_temp=8.0):
+    m = state.model
+    m.train()
+    if lr is not None:
+        state.opt.param_groups[0]["lr"] = lr
+    ps1, ps2, feat_s = m(images_s)                                                  # :155
+    state.prototypes, label_s_down = update_prototype(state.prototypes, feat_s.detach(), label_s, class_num, ignore_label, decay)  # :158
+    state.prototypes = state.prototypes.detach()
+    pt1, pt2, feat_t = m(images_t)                                                  # :163
+    size = images_t.shape[-2:]
+    x1 = F.interpolate(pt1, size, mode="bilinear", align_corners=True)
+    x2 = F.interpolate(pt2, size, mode="bilinear", align_corners=True)
+    soft_t = ((x1.softmax(dim=1) + x2.softmax(dim=1)) * 0.5).detach()               # :165-167
+    soft = label_refine(feat_t, [pt1, pt2], soft_t, state.prototypes, temp)         # :168
+    hard = pseudo_select(soft, cutoff_top, cutoff_low, ignore_label)                # :170
+    if sam_refine:
+        hard = lrh(hard, regs_t.squeeze(1), class_num, ignore_label, percent)       # :176-178
+    label_t = downscale_label(hard, 16, class_num, ignore_label)                    # :182
+    loss_seg = ce_loss_multi([ps1, ps2], label_s, ignore_label)                     # :186
+    loss_align = (pcl_loss(state.prototypes, feat_s, label_s_down, pcl_temp, ignore_label) +
+                  pcl_loss(state.prototypes, feat_t, label_t, pcl_temp, ignore_label)) * 0.5   # :188-189
+    loss = loss_seg + loss_align
+    state.opt.zero_grad()
+    loss.backward()                                                                 # :193
+    gnorm = torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=max_norm, norm_type=2)
+    state.opt.step()
+    return dict(loss=float(loss), loss_seg=float(loss_seg), loss_align=float(loss_align), grad_norm=float(gnorm), hard=hard,
+                label_t=label_t)

@@ -168,6 +168,58 @@ class SelfTrainingStep:
         raise NotImplementedError("use GraphedStep for CUDA-graph replay")
 
 
+class AlignStep(SelfTrainingStep):
+    """Stage-2 step (tools/train_align_reg.py:144-196): the same paired forward, prototype EMA, label
+    refinement, selection and LRH as stage 3, but the target soft labels come from the model's own predictions of this step
+    (:165-167), there is no target segmentation loss, and both domains' features are pulled towards the prototypes by the
+    prototype-contrastive loss (:186-189).  `_step_impl(images_s, label_s, images_t, regs_t)` returns
+    (loss, loss_seg, loss_align, hard) -- the slots GraphedStep reports as loss / loss_source / loss_target / hard.
+    CORAL (`--align-domain`, default off in the reference) is not part of it."""
+
+    def __init__(self, *args, pcl_temp=8.0, **kwargs):
+        super().__init__(*args, **kwargs)
+        from .loss import PrototypeContrastiveLoss
+        self.loss_fn_pcl = PrototypeContrastiveLoss(temperature=pcl_temp, ignore_label=self.ignore_label)
+
+    def _step_impl(self, images_s, label_s, images_t, regs_t):
+        from .ops import ppm as fppm
+        m = self.model
+        self.arena.zero_grad()
+        capi.zero_pool.reset(self.arena.param.device)
+        if self.pair_forward and images_s.shape == images_t.shape:
+            (pred_s1, pred_s2, feat_s), (pred_t1, pred_t2, feat_t) = m.forward_pair(images_s, images_t)   # :155, :163
+        else:
+            pred_s1, pred_s2, feat_s = m(images_s)
+            pred_t1, pred_t2, feat_t = m(images_t)
+        with torch.no_grad():
+            label_s_down = self.aligner.update_prototype(feat_s, label_s, reduce_fn=self._reduce_proto)   # :158 (before the refinement)
+            soft_t = fppm.upsample_softmax_mean(pred_t1.detach(), pred_t2.detach(), images_t.shape[-2:])   # :165-167
+            if self.refine_label:
+                hard = self.aligner.refine_select(feat_t, [pred_t1, pred_t2], soft_t, self.refine_temp, self.cutoff_top, self.cutoff_low)  # :168-171
+            else:
+                from .gast.pseudo_generation import pseudo_selection
+                hard = pseudo_selection(soft_t, self.cutoff_top, self.cutoff_low, 'tensor', self.ignore_label, check=False)
+            if self.sam_refine:
+                hard = self.homogenizer(hard, regs_t.squeeze(1))                   # :176-178
+            label_t = self.aligner.downscale_gt(hard)                              # :182
+        loss_seg = loss_calc([pred_s1, pred_s2], label_s, loss_fn=self.loss_fn_s, multi=True)          # :186
+        loss_align = (self.loss_fn_pcl(self.aligner.prototypes, feat_s, label_s_down) +
+                      self.loss_fn_pcl(self.aligner.prototypes, feat_t, label_t)) * 0.5                # :188-189
+        loss = loss_seg + loss_align
+        with conv_ops.wgrad_side_stream():
+            loss.backward()                                                        # :193
+        if self.world_size > 1:
+            parallel.allreduce_sum_(self.arena.grad)
+        self.arena.clip_and_sgd(self.max_norm, self.momentum, self.weight_decay, 1.0 / self.world_size)   # :194-196
+        capi.zero_pool.disarm()
+        return loss.detach(), loss_seg.detach(), loss_align.detach(), hard
+
+    def __call__(self, images_s, label_s, images_t, regs_t, lr):
+        self.arena.set_lr(lr)
+        loss, lseg, lal, hard = self._step_impl(images_s, label_s, images_t, regs_t)
+        return dict(loss=loss, loss_seg=lseg, loss_align=lal, hard=hard, grad_norm=self.arena.grad_norm())
+
+
 class GraphedStep:
     """Captures SelfTrainingStep into a CUDA graph (fixed shapes).  The learning rate lives in a
     device scalar, so the schedule is followed without re-capture."""

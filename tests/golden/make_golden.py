@@ -300,6 +300,72 @@ def teacher_pass(ns):
     np.savez_compressed(os.path.join(HERE, "teacher_pass.npz"), **d)
 
 
+def align_step(ns):
+    """Stage-2 step through the reference's own objects, tools/train_align_reg.py:144-196 (default flags:
+    refine-label on, align-domain off, pcl-temp 8), ResNet-50, 2 + 2 tiles of 64x64, two iterations; plus
+    PrototypeContrastiveLoss alone with its gradient."""
+    import torch.nn.functional as tnf
+    from regda.loss import PrototypeContrastiveLoss
+    g = torch.Generator().manual_seed(SEED + 21)
+    C, hw = 6, 64
+    d = {}
+    # the loss alone
+    pcl = PrototypeContrastiveLoss(temperature=8.0, ignore_label=-1)
+    proto = torch.randn(C, 256, generator=g).abs()
+    feat = torch.randn(2, 256, 5, 7, generator=g).requires_grad_(True)
+    lab = torch.randint(-1, C, (2, 1, 5, 7), generator=g)
+    loss = pcl(proto, feat, lab)
+    (loss * 0.5).backward()
+    d.update(pcl_proto=proto.numpy(), pcl_feat=feat.detach().numpy(), pcl_label=lab.numpy(), pcl_loss=loss.detach().numpy(),
+             pcl_dfeat_half=feat.grad.numpy())
+    # the step
+    m = ref_loader.build_reference_model(ns, "resnet50", C)
+    m.load_state_dict(so.seeded_state_dict(m, SEED))
+    _no_dropout(m)
+    m.train()
+    al = ns.Aligner(ns.logger, 2048, C, -1, 0.996)
+    proto = torch.randn(C, 2048, generator=g).abs()
+    al.prototypes = proto.clone()
+    hom = ns.Homogenizer(percent=0.5, class_num=C, ignore_label=-1)
+    ce = ns.CrossEntropy(ignore_label=-1, class_balancer=None)
+    opt = torch.optim.SGD(m.parameters(), lr=1e-2, momentum=0.9, weight_decay=5e-4)
+    xs = torch.randn(2, 3, hw, hw, generator=g).clamp(max=1.0)
+    xt = torch.randn(2, 3, hw, hw, generator=g).clamp(max=1.0)
+    ls = torch.randint(-1, C, (2, hw, hw), generator=g)
+    ls[:, :32, :32] = 2
+    ls[:, 32:, 16:48] = 4
+    regs = blocky_regions(g, 2, hw, hw, 9, 20).unsqueeze(1)
+    d.update(xs=xs.numpy(), xt=xt.numpy(), ls=ls.numpy(), regs=regs.numpy(), proto=proto.numpy())
+    losses = []
+    for it in range(2):
+        ps1, ps2, fs = m(xs)
+        label_s_down = al.update_prototype(fs, ls)
+        pt1, pt2, ft = m(xt)
+        x1 = tnf.interpolate(pt1, xt.shape[-2:], mode='bilinear', align_corners=True)
+        x2 = tnf.interpolate(pt2, xt.shape[-2:], mode='bilinear', align_corners=True)
+        soft = ((x1.softmax(dim=1) + x2.softmax(dim=1)) * 0.5).detach()
+        soft = al.label_refine(None, ft, [pt1, pt2], soft, refine=True, mode="all", temp=2.0)
+        hard = ns.pseudo_selection(soft, cutoff_top=0.8, cutoff_low=0.6, return_type="tensor", ignore_label=-1)
+        hard = hom(hard, regs.squeeze(1))
+        label_t = al.downscale_gt(hard)
+        l_seg = ns.loss_calc([ps1, ps2], ls, loss_fn=ce, multi=True)
+        l_al = (pcl(al.prototypes, fs, label_s_down) + pcl(al.prototypes, ft, label_t)) * 0.5
+        loss = l_seg + l_al
+        opt.zero_grad()
+        loss.backward()
+        gn = torch.nn.utils.clip_grad_norm_(filter(lambda p: p.requires_grad, m.parameters()), max_norm=32, norm_type=2)
+        opt.step()
+        losses.append([float(loss), float(l_seg), float(l_al), float(gn)])
+        if it == 0:
+            d["hard_0"] = hard.numpy()
+            d["label_t_0"] = label_t.numpy()
+            d["label_s_down_0"] = label_s_down.numpy()
+    d["losses"] = np.array(losses, dtype=np.float64)
+    d["proto_after"] = al.prototypes.numpy()
+    d["conv1_after"] = m.encoder.resnet.conv1.weight.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "align_step_resnet50.npz"), **d)
+
+
 if __name__ == "__main__":
     assert ref_loader.reference_available(), "run this where /root/reference is mounted"
     torch.set_num_threads(os.cpu_count() or 1)
@@ -307,11 +373,15 @@ if __name__ == "__main__":
     if "--only-teacher" in sys.argv:
         teacher_pass(ns)
         sys.exit(0)
+    if "--only-align" in sys.argv:
+        align_step(ns)
+        sys.exit(0)
     lrh_cases(ns)
     select_and_downscale(ns)
     aligner_and_loss(ns)
     model_and_step(ns)
     teacher_pass(ns)
+    align_step(ns)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

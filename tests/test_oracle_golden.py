@@ -170,3 +170,30 @@ def test_teacher_pass_host_logic_matches_reference_fixture():
         torch.testing.assert_close(pre_slide(m, x, num_classes=6, tile_size=(64, 64), tta=True), torch.from_numpy(z["slide_tta"]), rtol=1e-4, atol=1e-5)
         torch.testing.assert_close(pre_slide(m, x, num_classes=6, tile_size=(64, 64), tta=False), torch.from_numpy(z["slide_plain"]), rtol=1e-4, atol=1e-5)
         torch.testing.assert_close(pre_slide(m, xs, num_classes=6, tile_size=(64, 64), tta=True), torch.from_numpy(z["slide_small_tta"]), rtol=1e-4, atol=1e-5)
+
+
+def test_pcl_oracle_matches_reference_fixture():
+    z = load_golden("align_step_resnet50.npz")
+    feat = torch.from_numpy(z["pcl_feat"]).requires_grad_(True)
+    loss = so.pcl_loss(torch.from_numpy(z["pcl_proto"]), feat, torch.from_numpy(z["pcl_label"]), 8.0, -1)
+    (loss * 0.5).backward()
+    assert abs(float(loss) - float(z["pcl_loss"])) <= 1e-6 * abs(float(z["pcl_loss"]))
+    torch.testing.assert_close(feat.grad, torch.from_numpy(z["pcl_dfeat_half"]), rtol=1e-5, atol=1e-8)
+
+
+def test_align_step_oracle_matches_reference_fixture():
+    """stage-2 step: the oracle's restatement of tools/train_align_reg.py:144-196 against two iterations
+    of the reference's own objects"""
+    z = load_golden("align_step_resnet50.npz")
+    m = so.DeeplabOracle("resnet50", 6, dropout=0.0)
+    m.load_state_dict(so.seeded_state_dict(m, 2333))
+    st = so.StepState(m, torch.from_numpy(z["proto"]).clone())
+    t = lambda k: torch.from_numpy(z[k])  # noqa: E731
+    for it in range(2):
+        r = so.align_step(st, t("xs"), t("ls"), t("xt"), t("regs"))
+        np.testing.assert_allclose([r["loss"], r["loss_seg"], r["loss_align"], r["grad_norm"]], z["losses"][it], rtol=2e-4)
+        if it == 0:
+            assert (r["hard"].numpy() != z["hard_0"]).mean() < 1e-3   # fp-threshold flips only
+            assert (r["label_t"].numpy() != z["label_t_0"]).mean() < 1e-2
+    torch.testing.assert_close(st.prototypes, t("proto_after"), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(m.encoder.resnet.conv1.weight.detach(), t("conv1_after"), rtol=1e-3, atol=1e-5)

@@ -82,3 +82,12 @@ def test_trainer_and_prototype_tools_end_to_end(tmp_path):
             assert soft.dtype == torch.float32 and soft.dim() == 3 and soft.shape[0] == 6
     sd = torch.load("/tmp/regda_tiny/Potsdam_curr.pth")
     assert "encoder.resnet.conv1.weight" in sd and "layer6.conv_last.4.bias" in sd
+
+
+def test_stage2_align_tool_end_to_end():
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    for graph in ("0", "1"):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "train_align_reg.py"), "--config-path", "st.regda.tiny", "--steps", "4",
+                            "--sam-refine", "--percent", "0.5", "--cuda-graph", graph], capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert "iter=1, total=" in r.stdout and "loss_align=" in r.stdout and "images/s" in r.stdout, r.stdout[-1000:]
