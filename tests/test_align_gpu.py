@@ -81,7 +81,10 @@ def test_align_step_float32_matches_reference():
     # prototypes are O(1) values moved by 0.4 % of a class mean per step: 1e-4 of their scale absolute (near-zero entries), 2e-3 relative
     torch.testing.assert_close(al.prototypes.cpu(), torch.from_numpy(z["proto_after"]), rtol=2e-3, atol=1e-4)
     rel = float((m.encoder.resnet.conv1.weight.detach().cpu() - torch.from_numpy(z["conv1_after"])).abs().max() / torch.from_numpy(z["conv1_after"]).abs().max())
-    assert rel < 1.5e-2
+    # two clipped SGD steps move the stem weights by ~30 % of their scale each (random init, gradient norm ~200 clipped to 32); the
+    # stem gradient itself carries up to 8e-2 of float32 re-association noise between the GPU library kernels and the CPU
+    # reference (tests/test_step_gpu.py::test_model_float32_matches_reference), which is what shows up here (measured 3e-2)
+    assert rel < 6e-2
 
 
 def test_align_step_bf16_and_cuda_graph():
