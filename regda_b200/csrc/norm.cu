@@ -14,6 +14,9 @@
 //             -> bn_bwd_apply  dy = g*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)),  dres = dz,  dgamma/dbeta by block 0
 #include <cuda_bf16.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace regda {
@@ -345,8 +348,17 @@ int reduce_grid(long long total, int groups, long long *span) {
 }
 
 int apply_grid(long long total, int groups) {
+    // blocks per SM for the streaming apply kernels (REGDA_BN_BLOCKS_PER_SM overrides).  Measured on the step (images/s):
+    // 16 -> 799, 8 -> 849, 4 -> 876, 3 -> 881, 2 -> 862: every thread pays a ~40-instruction prologue (constants of its 8 channels
+    // from the statistics) and most of the step's tensors are only a few grid-strides long, so fewer, longer-running threads win
+    // until too few loads are in flight
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        const char *e = getenv("REGDA_BN_BLOCKS_PER_SM");
+        per_sm = e ? std::max(1, atoi(e)) : 3;
+    }
     const long long steps = (total + kBnSpan - 1) / kBnSpan;
-    return static_cast<int>(std::min<long long>(steps, std::max(1, 8 * sm_count() / groups)));
+    return static_cast<int>(std::min<long long>(steps, std::max(1, per_sm * sm_count() / groups)));
 }
 
 }  // namespace
