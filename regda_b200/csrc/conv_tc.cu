@@ -716,6 +716,16 @@ bool use_persistent() {
     return v == 1;
 }
 
+// 256-wide tiles are taken when they give at least this many tiles (REGDA_CONV_MIN_TILES_256 overrides; default: half the SMs)
+int min_tiles_256() {
+    static int v = 0;
+    if (v == 0) {
+        const char *e = getenv("REGDA_CONV_MIN_TILES_256");
+        v = e ? std::max(1, atoi(e)) : sm_count() / 2;
+    }
+    return v;
+}
+
 // data gradient + the reductions of the BatchNorm backward that consumes it (BNRED); `red` [groups][2][g.cout]
 int launch_dgrad_bnred(const void *act, const void *wgt, __nv_bfloat16 *out, const ConvGeom &g, int taps, cudaStream_t st,
                        float *red, int imgs_per_group, const __nv_bfloat16 *addend, const BnRed &br) {
@@ -724,7 +734,7 @@ int launch_dgrad_bnred(const void *act, const void *wgt, __nv_bfloat16 *out, con
     if (rc) return rc;
     const long long m_tiles = static_cast<long long>(g.n) * g.tiles_h * g.tiles_w;
     int block_n = 64;
-    if (g.cout % 256 == 0 && m_tiles * (g.cout / 256) >= sm_count() / 2) block_n = 256;
+    if (g.cout % 256 == 0 && m_tiles * (g.cout / 256) >= min_tiles_256()) block_n = 256;
     else if (g.cout % 128 == 0) block_n = 128;
     rc = make_tmap_w_mn(&tw, wgt, g.cin, taps, g.cout);
     if (rc) return rc;
@@ -743,7 +753,7 @@ int launch_conv(const void *act, const void *wgt, __nv_bfloat16 *out, const Conv
     if (rc) return rc;
     const long long m_tiles = static_cast<long long>(g.n) * g.tiles_h * g.tiles_w;
     int block_n = 64;
-    if (g.cout % 256 == 0 && use_persistent() && m_tiles * (g.cout / 256) >= sm_count() / 2) block_n = 256;
+    if (g.cout % 256 == 0 && use_persistent() && m_tiles * (g.cout / 256) >= min_tiles_256()) block_n = 256;
     else if (g.cout % 128 == 0) block_n = 128;
     rc = B_MN ? make_tmap_w_mn(&tw, wgt, g.cin, taps, g.cout) : make_tmap_w(&tw, wgt, g.cout, taps * g.cin, block_n);
     if (rc) return rc;

@@ -110,7 +110,7 @@ __device__ __forceinline__ void bn_moments(const float *__restrict__ st, int c, 
 // producing convolution's epilogue or from bn_stats_kernel); every thread derives the constants of its 8 channels itself
 // (no separate "finalize" launch), and block (0,0) updates the running statistics once per group, in group order
 // (= the reference's sequence of forward calls: source batch, then target batch).
-template <bool RELU, bool RES>
+template <bool RELU, bool RES, int U>
 __global__ void __launch_bounds__(kBnThreads)
 bn_apply_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__restrict__ res, __nv_bfloat16 *__restrict__ out,
                 long long total, int c, const float *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta,
@@ -155,24 +155,28 @@ bn_apply_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__rest
         sc[i] = g * rstd;
         sh[i] = fmaf(-mean, sc[i], b);
     }
-    // two grid-stride positions per iteration, all loads issued first: ~100 KB of reads in flight per SM
-    for (; e < total; e += 2 * stride) {
-        const long long e2 = e + stride;
-        const bool two = e2 < total;
-        bf16x8 y0 = ld8_stream(y + e), y1 = y0, r0 = y0, r1 = y0;
-        if (two) y1 = ld8_stream(y + e2);
-        if (RES) {
-            r0 = ld8_stream(res + e);
-            if (two) r1 = ld8_stream(res + e2);
+    // U grid-stride positions per iteration, all loads issued first (bytes in flight per SM = blocks x 256 threads x U x 16-32 B)
+    for (; e < total; e += U * stride) {
+        bf16x8 yv[U], rv[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long pos = e + u * stride;
+            ok[u] = pos < total;
+            if (ok[u]) {
+                yv[u] = ld8_stream(y + pos);
+                if (RES) rv[u] = ld8_stream(res + pos);
+            }
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (h == 1 && !two) break;
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) break;
+            const long long pos = e + u * stride;
             float f[8];
-            unpack(h ? y1 : y0, f);
+            unpack(yv[u], f);
             if (RES) {
                 float r[8];
-                unpack(h ? r1 : r0, r);
+                unpack(rv[u], r);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sh[i]) + r[i];
             } else {
@@ -185,12 +189,12 @@ bn_apply_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__rest
                     unsigned bits = 0u;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) bits |= (f[i] > 0.f ? 1u : 0u) << i;
-                    relu_mask[(h ? e2 : e) >> 3] = static_cast<unsigned char>(bits);
+                    relu_mask[pos >> 3] = static_cast<unsigned char>(bits);
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
             }
-            st8(out + (h ? e2 : e), pack(f));
+            st8(out + pos, pack(f));
         }
     }
 }
@@ -254,7 +258,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16
 
 // dy = a * (dz - k1 - (y - mean) * k2) with a = gamma*rstd, k1 = mean(dz), k2 = mean(dz*xhat)*rstd, all derived per thread from
 // red [groups][2][c] (sum dz, sum dz*y) and the forward stats; dres = dz.  Block (0,0) accumulates dgamma / dbeta over the groups.
-template <int RELU, bool DRES>
+template <int RELU, bool DRES, int U>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 *__restrict__ out, const __nv_bfloat16 *__restrict__ y,
                     __nv_bfloat16 *__restrict__ dy, __nv_bfloat16 *__restrict__ dres, long long total, int c,
@@ -300,25 +304,29 @@ bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 
         k2[i] = sdzx * inv_n * rstd;
         sh[i] = RELU == 2 ? fmaf(-mu[i], a[i], beta ? beta[ch + i] : 0.f) : 0.f;     // forward shift (a = forward scale)
     }
-    for (; e < total; e += 2 * stride) {
-        const long long e2 = e + stride;
-        const bool two = e2 < total;
-        bf16x8 d0 = ld8_stream(dout + e), v0 = ld8_stream(y + e), o0 = d0, d1 = d0, v1 = v0, o1 = d0;
-        if (RELU == 1) o0 = ld8_stream(out + e);
-        if (two) {
-            d1 = ld8_stream(dout + e2);
-            v1 = ld8_stream(y + e2);
-            if (RELU == 1) o1 = ld8_stream(out + e2);
+    for (; e < total; e += U * stride) {
+        bf16x8 dv[U], vv[U], ov[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long pos = e + u * stride;
+            ok[u] = pos < total;
+            if (ok[u]) {
+                dv[u] = ld8_stream(dout + pos);
+                vv[u] = ld8_stream(y + pos);
+                if (RELU == 1) ov[u] = ld8_stream(out + pos);
+            }
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (h == 1 && !two) break;
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) break;
+            const long long pos = e + u * stride;
             float d[8], v[8];
-            unpack(h ? d1 : d0, d);
-            unpack(h ? v1 : v0, v);
+            unpack(dv[u], d);
+            unpack(vv[u], v);
             if (RELU == 1) {
                 float o[8];
-                unpack(h ? o1 : o0, o);
+                unpack(ov[u], o);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
             }
@@ -326,7 +334,6 @@ bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) d[i] = fmaf(v[i], a[i], sh[i]) > 0.f ? d[i] : 0.f;
             }
-            const long long pos = h ? e2 : e;
             if (DRES) st8(dres + pos, pack(d));
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = a[i] * (d[i] - k1[i] - (v[i] - mu[i]) * k2[i]);
@@ -340,22 +347,38 @@ bool bn_shape_ok(long long npix, int c) { return npix > 0 && c >= 8 && c % 8 == 
 int reduce_grid(long long total, int groups, long long *span) {
     // whole steps of kBnSpan elements per block, about 4 blocks per SM over all groups
     const long long steps = (total + kBnSpan - 1) / kBnSpan;
-    long long blocks = std::min<long long>(steps, std::max(1, 4 * sm_count() / groups));
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        const char *e = getenv("REGDA_BN_REDUCE_BLOCKS_PER_SM");
+        per_sm = e ? std::max(1, atoi(e)) : 4;
+    }
+    long long blocks = std::min<long long>(steps, std::max(1, per_sm * sm_count() / groups));
     const long long steps_per_block = (steps + blocks - 1) / blocks;
     blocks = (steps + steps_per_block - 1) / steps_per_block;
     *span = steps_per_block * kBnSpan;
     return static_cast<int>(blocks);
 }
 
+// grid-stride positions each thread of the apply kernels keeps in flight (REGDA_BN_UNROLL = 2 | 4, default 4)
+int apply_unroll() {
+    static int u = 0;
+    if (u == 0) {
+        const char *e = getenv("REGDA_BN_UNROLL");
+        u = (e && atoi(e) == 2) ? 2 : 4;
+    }
+    return u;
+}
+
 int apply_grid(long long total, int groups) {
     // blocks per SM for the streaming apply kernels (REGDA_BN_BLOCKS_PER_SM overrides).  Measured on the step (images/s):
-    // 16 -> 799, 8 -> 849, 4 -> 876, 3 -> 881, 2 -> 862: every thread pays a ~40-instruction prologue (constants of its 8 channels
+    // 16 -> 799, 8 -> 849, 4 -> 876, 3 -> 881, 2 -> 862 with 2 positions in flight per thread; 2 blocks x 4 positions -> 904
+    // (3 x 4 -> 887): every thread pays a ~40-instruction prologue (constants of its 8 channels
     // from the statistics) and most of the step's tensors are only a few grid-strides long, so fewer, longer-running threads win
     // until too few loads are in flight
     static int per_sm = 0;
     if (per_sm == 0) {
         const char *e = getenv("REGDA_BN_BLOCKS_PER_SM");
-        per_sm = e ? std::max(1, atoi(e)) : 3;
+        per_sm = e ? std::max(1, atoi(e)) : 2;
     }
     const long long steps = (total + kBnSpan - 1) / kBnSpan;
     return static_cast<int>(std::min<long long>(steps, std::max(1, per_sm * sm_count() / groups)));
@@ -391,11 +414,13 @@ extern "C" int regda_bn_forward_bf16(const void *y, const void *residual, void *
     const dim3 ag(apply_grid(total, groups), groups);
     const __nv_bfloat16 *rr = static_cast<const __nv_bfloat16 *>(residual);
     __nv_bfloat16 *oo = static_cast<__nv_bfloat16 *>(out);
-#define REGDA_BN_APPLY(R, S) REGDA_CUDA_CHECK(launch_pdl<2>(bn_apply_kernel<R, S>, ag, dim3(kBnThreads), 0, st, yy, rr, oo, total, c, stats, gamma, beta, inv_n, \
+#define REGDA_BN_APPLY(R, S) do { if (apply_unroll() == 4) REGDA_BN_APPLY_U(R, S, 4); else REGDA_BN_APPLY_U(R, S, 2); } while (0)
+#define REGDA_BN_APPLY_U(R, S, UU) REGDA_CUDA_CHECK(launch_pdl<2>(bn_apply_kernel<R, S, UU>, ag, dim3(kBnThreads), 0, st, yy, rr, oo, total, c, stats, gamma, beta, inv_n, \
                                                         unbias, e, mom, running_mean, running_var, nbt, static_cast<unsigned char *>(relu_mask)))
     if (relu) { if (rr) REGDA_BN_APPLY(true, true); else REGDA_BN_APPLY(true, false); }
     else { if (rr) REGDA_BN_APPLY(false, true); else REGDA_BN_APPLY(false, false); }
 #undef REGDA_BN_APPLY
+#undef REGDA_BN_APPLY_U
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
 }
@@ -429,12 +454,14 @@ extern "C" int regda_bn_backward_bf16(const void *dout, const void *out, const v
     const dim3 ag(apply_grid(total, groups), groups);
     __nv_bfloat16 *dyy = static_cast<__nv_bfloat16 *>(dy);
     __nv_bfloat16 *dr = static_cast<__nv_bfloat16 *>(dres);
-#define REGDA_BN_BWD(R, D) REGDA_CUDA_CHECK(launch_pdl<2>(bn_bwd_apply_kernel<R, D>, ag, dim3(kBnThreads), 0, st, dd, oo, yy, dyy, dr, total, c, stats, red, gamma, \
+#define REGDA_BN_BWD(R, D) do { if (apply_unroll() == 4) REGDA_BN_BWD_U(R, D, 4); else REGDA_BN_BWD_U(R, D, 2); } while (0)
+#define REGDA_BN_BWD_U(R, D, UU) REGDA_CUDA_CHECK(launch_pdl<2>(bn_bwd_apply_kernel<R, D, UU>, ag, dim3(kBnThreads), 0, st, dd, oo, yy, dyy, dr, total, c, stats, red, gamma, \
                                                       inv_n, e, dgamma, dbeta, beta))
     if (rmode == 2) REGDA_BN_BWD(2, false);
     else if (rmode == 1) { if (dr) REGDA_BN_BWD(1, true); else REGDA_BN_BWD(1, false); }
     else { if (dr) REGDA_BN_BWD(0, true); else REGDA_BN_BWD(0, false); }
 #undef REGDA_BN_BWD
+#undef REGDA_BN_BWD_U
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
 }
