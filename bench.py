@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- the measurement contract of this repo (see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload step|lrh] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload step|lrh|align] [--impl ours|reference]
 
 One JSON line on stdout (rank 0).  Under torchrun (N>1) every rank processes its own shard of
 images (the path partitions by image, no data-path collective for LRH; gradient all-reduce for
@@ -264,7 +264,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=None, choices=["step", "lrh"])
+    ap.add_argument("--workload", default=None, choices=["step", "lrh", "align"])
     ap.add_argument("--regions", type=int, default=500, help="LRH microbench: regions per tile (50..5000)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

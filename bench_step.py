@@ -18,10 +18,12 @@ MODEL_CFG = dict(backbone=dict(resnet_type="resnet101", output_stride=16, pretra
                  num_classes=CLASS_NUM, is_ins_norm=True)
 
 
-def build(device, world, resnet="resnet101", use_graph=True, n_regions=200, seed=2333, batch=B, hw=(H, W)):
+def build(device, world, resnet="resnet101", use_graph=True, n_regions=200, seed=2333, batch=B, hw=(H, W), stage=3):
+    """stage 3: the self-training step (tools/train_ssl_reg.py, the headline workload); stage 2: the alignment step
+    (tools/train_align_reg.py) -- same model and shapes, inputs without the offline soft labels"""
     from regda_b200.gast.alignment import Aligner
     from regda_b200.models.Encoder import Deeplabv2
-    from regda_b200.trainer import GraphedStep, SelfTrainingStep
+    from regda_b200.trainer import AlignStep, GraphedStep, SelfTrainingStep
     from regda_b200.utils.local_region_homog import Homogenizer
     torch.manual_seed(seed)
     cfg = dict(MODEL_CFG)
@@ -33,8 +35,12 @@ def build(device, world, resnet="resnet101", use_graph=True, n_regions=200, seed
     aligner.prototypes = proto.clone()
     bound = int(regs_t.max()) + 1
     hom = Homogenizer(percent=0.5, class_num=CLASS_NUM, ignore_label=-1, region_bound=bound, strict=False)
-    step = SelfTrainingStep(model, aligner, hom, class_num=CLASS_NUM, ignore_label=-1, world_size=world)
-    tensors = [images_s, label_s, images_t, soft_t, regs_t]
+    if stage == 2:
+        step = AlignStep(model, aligner, hom, class_num=CLASS_NUM, ignore_label=-1, world_size=world)
+        tensors = [images_s, label_s, images_t, regs_t]
+    else:
+        step = SelfTrainingStep(model, aligner, hom, class_num=CLASS_NUM, ignore_label=-1, world_size=world)
+        tensors = [images_s, label_s, images_t, soft_t, regs_t]
     runner = None
     if use_graph:
         runner = GraphedStep(step, tensors, lr=1e-2)
@@ -75,7 +81,8 @@ def run(args, rank, world, local, pk, ClockSampler, barrier, max_over_ranks):
     dev = torch.device("cuda", local)
     use_graph = os.environ.get("REGDA_GRAPH", "1") != "0"
     calls0 = capi.launch_count
-    model, step, runner, tensors = build(dev, world, use_graph=use_graph, seed=2333 + rank)
+    stage = 2 if getattr(args, "workload", None) == "align" else 3
+    model, step, runner, tensors = build(dev, world, use_graph=use_graph, seed=2333 + rank, stage=stage)
     lr = 1e-2
 
     def one_step(inp):
@@ -163,8 +170,11 @@ def run(args, rank, world, local, pk, ClockSampler, barrier, max_over_ranks):
         "metric": "train images/sec (512x512, 6-class)", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "st.regda.2potsdam self-training step: ResNet-101 DeepLab (2 PPM heads), 8 source + 8 target 512x512 "
-                               "tiles per GPU, refine+select+LRH+prototype EMA+4 CE+backward+clip+SGD", "global_batch": imgs,
+        "config": {"workload": ("st.regda.2potsdam self-training step: ResNet-101 DeepLab (2 PPM heads), 8 source + 8 target 512x512 "
+                                "tiles per GPU, refine+select+LRH+prototype EMA+4 CE+backward+clip+SGD") if stage == 3 else
+                               ("st.regda.2potsdam stage-2 alignment step (tools/train_align_reg.py): ResNet-101 DeepLab, 8 source + 8 target "
+                                "512x512 tiles per GPU, prototype EMA+own-prediction soft labels+refine+select+LRH+2 CE+2 prototype-contrastive "
+                                "losses+backward+clip+SGD"), "global_batch": imgs,
                    "parallelism": f"dp{world}", "cuda_graph": use_graph, "conv_engine": convmod.ENGINE,
                    "l2": "per-step working set (activations ~6 GB) far larger than L2"},
         "e2e": {"value": round(imgs / (e2e_ms * 1e-3), 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},

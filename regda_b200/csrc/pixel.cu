@@ -229,24 +229,31 @@ __device__ __forceinline__ void block_class_max(float (&v)[CMAX], int c, unsigne
     }
 }
 
+// Grid-stride over the pixels of one image (blockIdx.y): a thread keeps the running per-class maximum of the pixels it visits, so
+// the block-wide reduction and the c atomicMax per block happen once per block, not once per 256 pixels (8192 blocks x 6
+// same-address atomics per image serialise in L2).
 template <int CMAX, bool WRITE>
 __global__ void __launch_bounds__(kPxThreads)
 refine_max_kernel(const RefineArgs a, float *__restrict__ soft_out, unsigned *__restrict__ gmax) {
     const int img = blockIdx.y;
     const int HW = a.H * a.W;
-    const int pos = blockIdx.x * kPxThreads + threadIdx.x;
-    float r[CMAX];
+    float m[CMAX];
 #pragma unroll
-    for (int j = 0; j < CMAX; ++j) r[j] = 0.f;
-    if (pos < HW) {
+    for (int j = 0; j < CMAX; ++j) m[j] = 0.f;
+    for (int pos = blockIdx.x * kPxThreads + threadIdx.x; pos < HW; pos += gridDim.x * kPxThreads) {
+        float r[CMAX];
+#pragma unroll
+        for (int j = 0; j < CMAX; ++j) r[j] = 0.f;
         refine_pixel<CMAX>(a, img, pos, r);
         if (WRITE) {
             float *o = soft_out + static_cast<size_t>(img) * a.c * HW + pos;
 #pragma unroll
             for (int j = 0; j < CMAX; ++j) if (j < a.c) o[static_cast<size_t>(j) * HW] = r[j];
         }
+#pragma unroll
+        for (int j = 0; j < CMAX; ++j) m[j] = fmaxf(m[j], r[j]);
     }
-    if (gmax != nullptr) block_class_max<CMAX>(r, a.c, gmax + img * a.c);
+    if (gmax != nullptr) block_class_max<CMAX>(m, a.c, gmax + img * a.c);
 }
 
 // pseudo_generation.py:76-88 for one pixel whose c probabilities are in v[]
@@ -424,12 +431,14 @@ extern "C" int regda_refine_select(const float *feat_nhwc, const float *prototyp
     const RefineArgs a = make_refine_args(ws.simi, pred1, pred2, soft_in, c, h, w, H, W, temp);
     const dim3 grid((H * W + kPxThreads - 1) / kPxThreads, b);
     const float top = static_cast<float>(cutoff_top), low = static_cast<float>(cutoff_low);
+    // max pass: ~8 blocks per SM over all images, each block walks its image with a grid stride
+    const dim3 mgrid(std::min<int>(grid.x, std::max(1, 8 * sm_count() / b)), b);
     if (c <= 8) {
-        refine_max_kernel<8, false><<<grid, kPxThreads, 0, st>>>(a, nullptr, ws.gmax);
+        refine_max_kernel<8, false><<<mgrid, kPxThreads, 0, st>>>(a, nullptr, ws.gmax);
         REGDA_LAUNCH_CHECK();
         refine_select_kernel<8><<<grid, kPxThreads, 0, st>>>(a, ws.gmax, reinterpret_cast<long long *>(hard_out), top, low, ignore_label);
     } else {
-        refine_max_kernel<16, false><<<grid, kPxThreads, 0, st>>>(a, nullptr, ws.gmax);
+        refine_max_kernel<16, false><<<mgrid, kPxThreads, 0, st>>>(a, nullptr, ws.gmax);
         REGDA_LAUNCH_CHECK();
         refine_select_kernel<16><<<grid, kPxThreads, 0, st>>>(a, ws.gmax, reinterpret_cast<long long *>(hard_out), top, low, ignore_label);
     }
