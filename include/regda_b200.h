@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define REGDA_ABI_VERSION 1
+#define REGDA_ABI_VERSION 2   /* 2: bn_forward relu_mask, bn_backward beta + dz_ready; new entry points (dgrad_bnred, stem, inference, pcl) */
 
 #define REGDA_OK 0
 #define REGDA_ERR_INVALID_ARG 1
