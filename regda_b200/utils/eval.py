@@ -47,14 +47,18 @@ def miou_from_confusion(cm, skip_class0=False):
 
 
 @torch.no_grad()
-def evaluate(model, loader, num_classes, ignore_label=-1, skip_class0=False, tile=512, logger=None):
+def evaluate(model, loader, num_classes, ignore_label=-1, skip_class0=False, tile=512, logger=None, tta=False):
     was_training = model.training
     model.eval()
     dev = next(model.parameters()).device
     cm = torch.zeros((num_classes, num_classes), dtype=torch.int64, device=dev)
     for image, label in loader:
         image, label = image.to(dev), label.to(dev)
-        pred = slide_predict(model, image, num_classes, tile).argmax(dim=1)
+        if tta:                                       # eval.py:41 with tta=True: 8-view TTA inside every sliding window
+            from .tools import pre_slide
+            pred = pre_slide(model, image, num_classes=num_classes, tile_size=(tile, tile), tta=True).argmax(dim=1)
+        else:
+            pred = slide_predict(model, image, num_classes, tile).argmax(dim=1)
         cm += confusion_matrix(pred, label, num_classes, ignore_label)
     iou, miou = miou_from_confusion(cm, skip_class0)
     if logger is not None:

@@ -39,3 +39,17 @@ def test_rejects_bad_maps(tmp_path):
     Image.fromarray(np.zeros((4, 4, 3), dtype=np.uint8)).save(tmp_path / "rgb.tif")
     with pytest.raises(ValueError):
         regions.load_region_map(str(tmp_path / "rgb.tif"))
+
+
+def test_eval_tool_cli_surface():
+    """tools/eval.py keeps the reference's flags (tools/eval.py:17-25) and refuses to run without a GPU"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("regda_tools_eval", os.path.join(os.path.dirname(__file__), "..", "tools", "eval.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    a = mod.parse(["--config-path", "st.regda.tiny", "--ckpt-path", "x.pth", "--tta", "1", "--test", "0"])
+    assert a.tta is True and a.test is False and a.ckpt_path == "x.pth" and a.ins_norm is True
+    if not torch.cuda.is_available():
+        with pytest.raises(SystemExit):
+            mod.main(["--config-path", "st.regda.tiny"])
