@@ -60,6 +60,7 @@ def main(argv=None):
     else:
         print('WARNING: no --ckpt-path: evaluating random weights')
     model = model.cuda()
+    tile = 512
     if args.data == 'reference':
         from regda.datasets.daLoader import DALoader                 # the reference's own loaders (not part of this repo)
         rcfg = __import__('configs.' + args.config_path, fromlist=['x'])
@@ -69,7 +70,10 @@ def main(argv=None):
         h, w = cfg.SYNTHETIC["size"]
         xs, ls, *_ = synth.step_inputs(args.tiles, h, w, class_num, cfg.SYNTHETIC["regions_per_tile"], device="cuda", seed=2333)
         loader = [(xs[i:i + 1], ls[i:i + 1]) for i in range(args.tiles)]
-    iou, miou = evaluate(model, loader, class_num, ignore_label=cfg.IGNORE_LABEL, skip_class0=True, tile=512, tta=args.tta)
+        # tiles smaller than the reference's 512 window would hit its pad_image quirk (tools.py:56 pads the TOP of the height and
+        # pre_slide then crops the padding, see regda_b200/utils/tools.py): evaluate synthetic tiles with a window of their own size
+        tile = min(tile, h, w)
+    iou, miou = evaluate(model, loader, class_num, ignore_label=cfg.IGNORE_LABEL, skip_class0=True, tile=tile, tta=args.tta)
     print("IoU per class: " + ", ".join(f"{v:.4f}" for v in iou.tolist()) + f"; mIoU = {miou:.4f}")
     return miou
 
