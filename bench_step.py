@@ -126,7 +126,7 @@ def run(args, rank, world, local, pk, ClockSampler, barrier, max_over_ranks):
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
-    def stage(slot):
+    def stage_inputs(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])
             for d, h in zip(bufs[slot], host):
@@ -140,11 +140,11 @@ def run(args, rank, world, local, pk, ClockSampler, barrier, max_over_ranks):
     n_e2e = max(3, min(args.steps, 10))
 
     def e2e_loop(n):
-        stage(0)
+        stage_inputs(0)
         for i in range(n):
             slot = i & 1
             if i + 1 < n:
-                stage(slot ^ 1)
+                stage_inputs(slot ^ 1)
             torch.cuda.current_stream().wait_event(ready[slot])
             o = one_step(bufs[slot])
             consumed[slot].record()

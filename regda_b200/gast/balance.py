@@ -58,7 +58,8 @@ class ClassBalance(nn.Module):
         return counts[:-1].float() / (counts[-1].float() + self.eps)
 
     def ema_update(self, label):
-        self.freq = (1.0 - self.decay) * self._local_freq(label) + self.decay * self.freq
+        # in place: the tensor's address is what a captured CUDA graph replays against
+        self.freq.copy_((1.0 - self.decay) * self._local_freq(label) + self.decay * self.freq)
 
     def _get_class_wight(self):
         _prob = torch.softmax((1.0 - self.freq) / self.temperature, dim=0)

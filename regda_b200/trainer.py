@@ -63,7 +63,11 @@ class ParamArena:
             p.data = v
             p.grad = view(self.grad)
             p._bf16 = view(self.param_bf16)            # what the tcgen05 convolutions read (ops/tc.py weight_shadow)
+            p._arena = self                            # writers of p.data outside the SGD kernel call p._arena.sync_shadow()
         self.param_bf16.copy_(self.param)
+        # load_state_dict() (resume, reload-best, evaluate(ckpt)) writes the fp32 arena behind the SGD kernel's back:
+        # refresh the bf16 shadow the convolutions read
+        module.register_load_state_dict_post_hook(lambda _m, _incompatible: self.sync_shadow())
         self.first_step = True
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.lr_device = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -124,7 +128,18 @@ class SelfTrainingStep:
         self._static = None
         self._lr = torch.zeros((), dtype=torch.float64)
 
-    # ---- the step proper (no host sync inside) ------------------------------------------------
+    # ---- state that a step advances (besides the weights): what a CUDA-graph warm-up must not leave changed ----
+    def persistent_state(self):
+        """every tensor one step mutates in place and the next step reads: parameters (+ bf16 shadow), momentum, the
+        aligner's prototypes, the BatchNorm running statistics / counters, ClassBalance frequencies"""
+        ts = [self.arena.param, self.arena.param_bf16, self.arena.momentum, self.aligner.prototypes]
+        ts += [b for b in self.model.buffers()]
+        for fn in (self.loss_fn_s, self.loss_fn_t):
+            cb = getattr(fn, "class_balancer", None)
+            if cb is not None and isinstance(getattr(cb, "freq", None), torch.Tensor):
+                ts.append(cb.freq)
+        return ts
+
     def _reduce_proto(self, sums, counts):
         if self.world_size > 1:
             parallel.allreduce_sum_(sums, counts)
@@ -228,6 +243,13 @@ class GraphedStep:
         self.step = step
         self.static_in = [t.clone() for t in example_inputs]
         step.arena.set_lr(lr)
+        # The warm-up runs real steps (allocator / autotune warm-up before capture).  Training must start from the state
+        # it was given -- the reference's loop has no warm-up -- so everything a step advances is snapshotted here and
+        # put back after the capture: weights, momentum, prototypes, BatchNorm running statistics, ClassBalance state.
+        state = step.persistent_state()
+        assert all(t.data_ptr() != 0 for t in state)
+        saved = [t.clone() for t in state]
+        first_step = step.arena.first_step
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -238,6 +260,14 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = step._step_impl(*self.static_in)
+        with torch.no_grad():
+            for t, v in zip(step.persistent_state(), saved):
+                t.copy_(v)
+        if first_step:
+            # the captured SGD launch has first_step = 0 baked in (momentum * buf + g); with a zero buffer that IS the
+            # first-step rule buf = g, so a fresh run replays correctly from the very first step
+            step.arena.momentum.zero_()
+        torch.cuda.synchronize()
 
     def __call__(self, *inputs, lr=None):
         if lr is not None:

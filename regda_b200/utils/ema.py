@@ -45,14 +45,28 @@ class ExponentialMovingAverage:
             sh = self.shadow[n]
             capi.call("regda_ema_update", capi.ptr_any(sh), capi.ptr_any(p.data), p.numel(), float(self.decay), capi.stream())
 
+    def _written(self, params):
+        """the fp32 parameters were rewritten outside the SGD kernel: refresh the bf16 copies the tcgen05 convolutions read
+        (a trainer.ParamArena keeps one shadow for all of them; a free-standing parameter's cached copy is keyed on
+        `_version`, which the no_grad `p.copy_()` below bumps)"""
+        arenas = {id(a): a for a in (getattr(p, "_arena", None) for _, p in params) if a is not None}
+        for a in arenas.values():
+            a.sync_shadow()
+
+    @torch.no_grad()
     def apply_shadow(self):                                            # ema.py:53-58
-        for n, p in self._params():
+        ps = self._params()
+        for n, p in ps:
             assert n in self.shadow
             self.backup[n] = p.data.clone()
-            p.data.copy_(self.shadow[n])
+            p.copy_(self.shadow[n])
+        self._written(ps)
 
+    @torch.no_grad()
     def restore(self):                                                 # ema.py:60-65
-        for n, p in self._params():
+        ps = self._params()
+        for n, p in ps:
             assert n in self.backup
-            p.data.copy_(self.backup[n])
+            p.copy_(self.backup[n])
         self.backup = {}
+        self._written(ps)
