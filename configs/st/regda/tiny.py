@@ -8,6 +8,7 @@ CLASS_NUM = 6                # len(IsprsDA.LABEL_MAP)
 MOMENTUM = 0.9
 SNAPSHOT_DIR = '/tmp/regda_tiny'
 TARGET_SET = 'Potsdam'
+DATASETS = 'IsprsDA'        # class 0 is dropped from the mIoU (regda/utils/eval.py:16-17)
 WEIGHT_DECAY = 0.0005
 LEARNING_RATE = 1e-2
 STAGE1_STEPS = 4000

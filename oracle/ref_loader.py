@@ -154,6 +154,79 @@ class _TtaCompose:
         return n
 
 
+# ever-beta==0.2.3 (requirement.txt:33) is absent from this image.  Restatement of ever/api/metric/pixel.py PixelMetric from the
+# package's published source -- the base class of the reference's own PixelMetricIgnore (regda/gast/metrics.py:19), which is
+# imported UNMODIFIED on top of it: a float32 scipy-sparse [C,C] confusion matrix (rows = y_true, columns = y_pred) accumulated
+# by forward(); static per-class IoU / F / precision / recall on the dense matrix.  PARITY NOTE: a restatement, not the
+# package -- tests/golden/miou.npz is pinned to it (like the ttach stub above).
+class _PixelMetric:
+    def __init__(self, num_classes, logdir=None, logger=None, class_names=None):
+        import numpy as np
+        from scipy import sparse
+        self.num_classes = num_classes
+        self._total = sparse.coo_matrix((num_classes, num_classes), dtype=np.float32)
+        self._logger = logger
+        self._class_names = class_names
+        self.logdir = logdir
+
+    def reset(self):
+        import numpy as np
+        from scipy import sparse
+        self._total = sparse.coo_matrix((self.num_classes, self.num_classes), dtype=np.float32)
+
+    def forward(self, y_true, y_pred):
+        import numpy as np
+        from scipy import sparse
+        if isinstance(y_pred, torch.Tensor):
+            y_pred = y_pred.cpu().numpy()
+        if isinstance(y_true, torch.Tensor):
+            y_true = y_true.cpu().numpy()
+        y_pred = y_pred.reshape((-1,))
+        y_true = y_true.reshape((-1,))
+        v = np.ones_like(y_pred)
+        cm = sparse.coo_matrix((v, (y_true, y_pred)), shape=(self.num_classes, self.num_classes), dtype=np.float32)
+        self._total += cm
+        return cm
+
+    def _log_summary(self, table, dense_cm):
+        pass
+
+    @staticmethod
+    def compute_iou_per_class(confusion_matrix):
+        import numpy as np
+        sum_over_row = np.sum(confusion_matrix, axis=0)
+        sum_over_col = np.sum(confusion_matrix, axis=1)
+        diag = np.diag(confusion_matrix)
+        return diag / (sum_over_row + sum_over_col - diag)
+
+    @staticmethod
+    def compute_recall_per_class(confusion_matrix):
+        import numpy as np
+        return np.diag(confusion_matrix) / np.sum(confusion_matrix, axis=1)
+
+    @staticmethod
+    def compute_precision_per_class(confusion_matrix):
+        import numpy as np
+        return np.diag(confusion_matrix) / np.sum(confusion_matrix, axis=0)
+
+    @staticmethod
+    def compute_F_measure_per_class(confusion_matrix, beta=1.0):
+        p = _PixelMetric.compute_precision_per_class(confusion_matrix)
+        r = _PixelMetric.compute_recall_per_class(confusion_matrix)
+        return (1 + beta ** 2) * p * r / ((beta ** 2) * p + r)
+
+
+class _PrettyTable:
+    """prettytable.PrettyTable surface used by regda/gast/metrics.py:47-61 (field_names, add_row)"""
+
+    def __init__(self):
+        self.field_names = []
+        self.rows = []
+
+    def add_row(self, row):
+        self.rows.append(list(row))
+
+
 def _mod(name, **attrs):
     m = types.ModuleType(name)
     m.__dict__.update(attrs)
@@ -179,7 +252,7 @@ def install_stubs():
         mp = _mod("matplotlib")
         mp.pyplot = _mod("matplotlib.pyplot")
     _mod("ttach", Compose=_TtaCompose, HorizontalFlip=_TtaHorizontalFlip, Rotate90=_TtaRotate90)
-    _mod("prettytable", PrettyTable=object)
+    _mod("prettytable", PrettyTable=_PrettyTable)
 
     import logging
 
@@ -200,7 +273,10 @@ def install_stubs():
 
     param_util = _mod("ever.util.param_util", freeze_params=freeze_params, freeze_modules=freeze_modules)
     util = _mod("ever.util", param_util=param_util)
-    ever.core, ever.interface, ever.util, ever.registry = core, interface, util, registry
+    pixel = _mod("ever.api.metric.pixel", PixelMetric=_PixelMetric)
+    metric = _mod("ever.api.metric", pixel=pixel)
+    api = _mod("ever.api", metric=metric)
+    ever.core, ever.interface, ever.util, ever.registry, ever.api = core, interface, util, registry, api
 
     if not torch.cuda.is_available():
         # Aligner.__init__ calls .cuda() (alignment.py:48,56,60,76-77)

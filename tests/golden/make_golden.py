@@ -366,6 +366,36 @@ def align_step(ns):
     np.savez_compressed(os.path.join(HERE, "align_step_resnet50.npz"), **d)
 
 
+def miou_metric(ns):
+    """mIoU through the reference's own PixelMetricIgnore.summary_all (regda/gast/metrics.py:19-65: 5-decimal rounding of the
+    per-class figures, class-0 pop for IsprsDA, rounded means) fed as regda/utils/eval.py:43-49 feeds it, on top of the
+    restated ever PixelMetric of oracle/ref_loader.py."""
+    from regda.gast.metrics import PixelMetricIgnore
+    g = torch.Generator().manual_seed(SEED + 31)
+    d = {}
+    for k, (C, ignore, absent) in enumerate([(6, [0], None), (7, [], None), (6, [0], 4)]):
+        gt = torch.randint(-1, C, (3, 40, 56), generator=g)
+        # a prediction that agrees with the label on ~70 % of the pixels
+        pred = torch.where(torch.rand(gt.shape, generator=g) < 0.7, gt.clamp(min=0), torch.randint(0, C, gt.shape, generator=g))
+        if absent is not None:      # a class that never occurs in label or prediction: 0/0 = nan in the reference
+            gt = torch.where(gt == absent, torch.zeros_like(gt), gt)
+            pred = torch.where(pred == absent, torch.zeros_like(pred), pred)
+        op = PixelMetricIgnore(C, class_names=[f"c{i}" for i in range(C)], logdir=None, logger=None, ignore_labels=list(ignore))
+        for i in range(gt.shape[0]):                       # one forward per image, as the eval loop does
+            cls_gt = gt[i].numpy().astype(np.int32)
+            mask = cls_gt >= 0
+            op.forward(cls_gt[mask].ravel(), pred[i].numpy()[mask].ravel())
+        tb, miou = op.summary_all()
+        d[f"{k}/gt"] = gt.numpy()
+        d[f"{k}/pred"] = pred.numpy()
+        d[f"{k}/num_classes"] = np.array(C)
+        d[f"{k}/ignore"] = np.array(ignore, dtype=np.int64)
+        d[f"{k}/miou"] = np.array(miou, dtype=np.float64)
+        d[f"{k}/rows"] = np.array([[float(v) for v in r[2:]] for r in tb.rows[:-1]], dtype=np.float64)     # iou, f1, precision, recall
+        d[f"{k}/means"] = np.array([float(v) for v in tb.rows[-1][2:]], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "miou.npz"), **d)
+
+
 if __name__ == "__main__":
     assert ref_loader.reference_available(), "run this where /root/reference is mounted"
     torch.set_num_threads(os.cpu_count() or 1)
@@ -376,12 +406,16 @@ if __name__ == "__main__":
     if "--only-align" in sys.argv:
         align_step(ns)
         sys.exit(0)
+    if "--only-miou" in sys.argv:
+        miou_metric(ns)
+        sys.exit(0)
     lrh_cases(ns)
     select_and_downscale(ns)
     aligner_and_loss(ns)
     model_and_step(ns)
     teacher_pass(ns)
     align_step(ns)
+    miou_metric(ns)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

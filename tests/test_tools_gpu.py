@@ -50,16 +50,85 @@ def test_miou_matches_reference_formula():
     assert abs(miou - float(iou.mean())) < 1e-12
 
 
-def test_evaluate_runs_sliding_window():
+def test_evaluate_matches_reference_metric_on_reference_predictions():
+    """evaluate() end to end against the reference: the image and the reference model's sliding-window probabilities come from
+    tests/golden/teacher_pass.npz (the reference's own pre_slide on its own Deeplabv2); the expected table is the reference
+    metric's arithmetic (tests/test_metrics.py pins the mirror to it) over the arg-max of those probabilities."""
+    from conftest import load_golden
+    from oracle import step_oracle as so
+    from regda_b200.gast.metrics import PixelMetricIgnore
     from regda_b200.models.Encoder import Deeplabv2
     from regda_b200.utils.eval import evaluate
+    z = load_golden("teacher_pass.npz")
+    cfg = dict(backbone=dict(resnet_type="resnet50", output_stride=16, pretrained=False), multi_layer=True, cascade=False, use_ppm=True,
+               ppm=dict(num_classes=6, use_aux=False, fc_dim=2048), inchannels=2048, num_classes=6, is_ins_norm=True)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = Deeplabv2(cfg, compute_dtype=torch.float32)
+    m.load_state_dict(so.seeded_state_dict(m, 2333), strict=True)
+    m = m.cuda().train()                           # evaluate() must switch to eval mode and restore train mode
+    image = torch.from_numpy(z["image"])
+    g = torch.Generator().manual_seed(5)
+    ref_pred = torch.from_numpy(z["slide_plain"]).argmax(dim=1)
+    label = torch.where(torch.rand(ref_pred.shape, generator=g) < 0.6, ref_pred, torch.randint(-1, 6, ref_pred.shape, generator=g))
+    want = PixelMetricIgnore(6, ignore_labels=[0])
+    want.forward(label[label >= 0], ref_pred[label >= 0])
+    _, want_miou = want.summary_all()
+    tb, miou = evaluate(m, [(image, label)], 6, ignore_label=-1, skip_class0=True, tile=64)
+    assert m.training
+    assert len(tb.iou_per_class) == 5
+    # float32 compute: at most a handful of arg-max ties may resolve differently
+    assert abs(miou - float(want_miou)) <= 2e-3, (miou, want_miou)
+    np_rows = [r[2:] for r in tb.rows[:-1]]
+    assert all(0.0 <= float(v) <= 1.0 for r in np_rows for v in r)
+
+
+def test_evaluate_sliding_window_geometry():
+    """one axis shorter than the tile, the other longer (negative window origin): every pixel is predicted
+    exactly as the windows cover it, no duplicated window"""
+    from regda_b200.utils.eval import _origins, slide_predict
+    assert _origins(192, 512, 256) == [0] and _origins(600, 512, 256) == [0, 88] and _origins(1024, 512, 256) == [0, 256, 512]
+    calls = []
+
+    def fake_model(x):
+        calls.append(tuple(x.shape[-2:]))
+        return torch.ones((x.shape[0], 2) + tuple(x.shape[-2:]), device=x.device)
+
+    out = slide_predict(fake_model, torch.zeros(1, 3, 192, 600, device="cuda"), 2, tile=512)
+    assert calls == [(192, 512), (192, 512)]
+    assert torch.equal(out, torch.ones_like(out))
+
+
+def test_weight_shadow_follows_parameter_writes():
+    """the bf16 copy the tcgen05 convolutions read must follow load_state_dict() and EMA apply_shadow()/restore()"""
+    from regda_b200.models.Encoder import Deeplabv2
+    from regda_b200.trainer import ParamArena
+    from regda_b200.utils.ema import ExponentialMovingAverage
     cfg = dict(backbone=dict(resnet_type="resnet50", output_stride=16, pretrained=False), multi_layer=True, cascade=False, use_ppm=True,
                ppm=dict(num_classes=6, use_aux=False, fc_dim=2048), inchannels=2048, num_classes=6, is_ins_norm=True)
     torch.manual_seed(0)
-    m = Deeplabv2(cfg).cuda()
-    data = [(torch.randn(1, 3, 192, 160), torch.randint(-1, 6, (1, 192, 160)))]
-    iou, miou = evaluate(m, data, 6, ignore_label=-1, skip_class0=True, tile=128)
-    assert iou.shape == (5,) and 0.0 <= miou <= 1.0 and not m.training is None
+    m = Deeplabv2(cfg).cuda().eval()
+    arena = ParamArena(m)
+    x = torch.randn(2, 3, 256, 256, device="cuda")
+    with torch.no_grad():
+        p0 = m(x).clone()
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        sd2 = {k: (v * 1.5 if k.endswith("conv3.weight") or k.endswith("conv_last.0.weight") else v) for k, v in sd.items()}
+        m.load_state_dict(sd2)
+        p1 = m(x).clone()
+        assert float((p1 - p0).abs().max()) > 1e-4, "forward ignored load_state_dict (stale bf16 weights)"
+        m.load_state_dict(sd)
+        assert torch.equal(m(x), p0)
+        ema = ExponentialMovingAverage(m, 0.5)
+        ema.register()
+        for p in m.parameters():
+            p.mul_(1.5)
+        arena.sync_shadow()
+        p2 = m(x).clone()
+        ema.apply_shadow()                      # back to the registered (original) weights
+        assert torch.equal(m(x), p0)
+        ema.restore()
+        assert torch.equal(m(x), p2)
 
 
 def test_trainer_and_prototype_tools_end_to_end(tmp_path):

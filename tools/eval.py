@@ -73,8 +73,9 @@ def main(argv=None):
         # tiles smaller than the reference's 512 window would hit its pad_image quirk (tools.py:56 pads the TOP of the height and
         # pre_slide then crops the padding, see regda_b200/utils/tools.py): evaluate synthetic tiles with a window of their own size
         tile = min(tile, h, w)
-    iou, miou = evaluate(model, loader, class_num, ignore_label=cfg.IGNORE_LABEL, skip_class0=True, tile=tile, tta=args.tta)
-    print("IoU per class: " + ", ".join(f"{v:.4f}" for v in iou.tolist()) + f"; mIoU = {miou:.4f}")
+    tb, miou = evaluate(model, loader, class_num, ignore_label=cfg.IGNORE_LABEL, skip_class0=True, tile=tile, tta=args.tta)
+    print(tb)
+    print("IoU per class: " + ", ".join(f"{v:.5f}" for v in tb.iou_per_class) + f"; mIoU = {miou:.5f}")
     return miou
 
 

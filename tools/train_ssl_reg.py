@@ -151,6 +151,41 @@ def main():
         loader.t = (xs, ls, xt, soft, regs) + tuple(loader.t[5:])
         log(f'###### generated {len(names)} soft pseudo labels in {path} ######')
 
+    best = dict(miou=-1.0)
+
+    def checkpoint_and_evaluate(i_iter):
+        """:253-265 -- <TARGET_SET>_curr.pth every EVAL_EVERY iterations (and at iteration 0 / the end), evaluate(), and
+        <TARGET_SET>_best.pth + prototypes_best.pth (what the downstream stages and tools/eval.py load) when the mIoU improves.
+        Data parallel: BatchNorm running statistics are per rank (each rank normalises its own images, like the reference's
+        single process); the checkpoint carries their mean over the ranks."""
+        import shutil
+        from regda_b200.utils.eval import evaluate
+        if world > 1:
+            for buf in model.buffers():
+                if buf.dtype.is_floating_point:
+                    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+                    buf.div_(world)
+        if rank != 0:
+            return
+        ckpt = osp.join(cfg.SNAPSHOT_DIR, cfg.TARGET_SET + '_curr.pth')
+        torch.save({k: v.detach().cpu() for k, v in model.state_dict().items()}, ckpt)
+        torch.save(aligner.prototypes.cpu(), osp.join(cfg.SNAPSHOT_DIR, 'prototypes_curr.pth'))
+        if args.data == 'reference':
+            from regda.datasets.daLoader import DALoader
+            eval_loader = ((ret, ret_gt['cls']) for ret, ret_gt in DALoader(rcfg.EVAL_DATA_CONFIG, rcfg.DATASETS))
+            tile = 512
+        else:       # synthetic: the labelled source-like tiles stand in for the evaluation split
+            xs, ls = loader.t[0], loader.t[1]
+            eval_loader = [(xs[i:i + 1], ls[i:i + 1]) for i in range(xs.shape[0])]
+            tile = min(512, xs.shape[-2], xs.shape[-1])
+        _, miou = evaluate(model, eval_loader, class_num, ignore_label=ignore_label, skip_class0=(cfg.DATASETS == 'IsprsDA'), tile=tile)
+        model.train()
+        log(f'iter={i_iter + 1}, mIoU = {miou:.5f} (best so far {max(best["miou"], -1.0):.5f})')
+        if miou == miou and miou > best['miou']:
+            best['miou'] = miou
+            shutil.copyfile(ckpt, osp.join(cfg.SNAPSHOT_DIR, cfg.TARGET_SET + '_best.pth'))
+            shutil.copyfile(osp.join(cfg.SNAPSHOT_DIR, 'prototypes_curr.pth'), osp.join(cfg.SNAPSHOT_DIR, 'prototypes_best.pth'))
+
     t0 = time.time()
     os.makedirs(cfg.SNAPSHOT_DIR, exist_ok=True)
     batch = first
@@ -164,10 +199,8 @@ def main():
             log(f"iter={i_iter + 1}, total={float(out['loss']):.3f}, loss_source={float(out['loss_source']):.3f}, "
                 f"loss_target={float(out['loss_target']):.3f},, lr = {lr:.3e}")
             hom.check()
-        if (i_iter + 1) % cfg.EVAL_EVERY == 0 or (i_iter + 1) >= stop_steps:        # :253-256
-            if rank == 0:
-                torch.save({k: v.detach().cpu() for k, v in model.state_dict().items()}, osp.join(cfg.SNAPSHOT_DIR, cfg.TARGET_SET + '_curr.pth'))
-                torch.save(aligner.prototypes.cpu(), osp.join(cfg.SNAPSHOT_DIR, 'prototypes_curr.pth'))
+        if i_iter == 0 or (i_iter + 1) % cfg.EVAL_EVERY == 0 or (i_iter + 1) >= stop_steps:        # :253-265
+            checkpoint_and_evaluate(i_iter)
         batch = next_batch()
     torch.cuda.synchronize()
     dt = time.time() - t0
