@@ -166,43 +166,68 @@ int regda_ema_update(float *shadow, const float *param, int64_t n, double decay,
 
 /* ---- convolution on the tcgen05 tensor cores -------------------------------------------
  * Replaces the cuDNN convolutions behind nn.Conv2d in regda/_resnets.py:92-112 (Bottleneck) and
- * regda/models/Encoder.py:33-40 (PPM fuse conv).  Stride-1 implicit GEMM, any dilation / padding:
+ * regda/models/Encoder.py:17-23,33-40 (PPM branch convs, fuse conv).  Implicit GEMM, any dilation / padding:
  *   x   bf16 [n][h][w][cin]        (channels-last)
  *   wgt bf16 [cout][r][s][cin]     (OHWI = the channels-last memory of the reference's weight)
- *   y   bf16 [n][oh][ow][cout],  oh = h + 2*pad - dil*(r-1)
- * Also computes the data gradient of a stride-1 convolution when given dY, the flipped /
- * transposed weights [cin][r][s][cout] and pad' = dil*(r-1) - pad.
- * Stride 2 is handled through TMA element strides (every other input pixel is fetched).
- * regda_conv_fprop_supported returns 1 when the shape is covered (cin, cout multiples of 64,
- * stride 1 or 2, at least 128 output pixels per image). */
+ *   y   bf16 [n][oh][ow][cout],  oh = (h + 2*pad - dil*(r-1) - 1)/stride + 1
+ * Stride 2 is handled through TMA element strides (every other input pixel is fetched).  Feature maps smaller than
+ * 128 pixels (pyramid-pooling branches: 1x1 .. 6x6) put several images into one 128-row M tile.
+ * regda_conv_fprop_supported returns 1 when the shape is covered: cin, cout multiples of 64, stride 1 or 2. */
 int regda_conv_fprop_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil);
 int regda_conv_fprop_bf16(const void *x, const void *wgt, void *y, int n, int h, int w, int cin, int cout,
                           int r, int s, int stride, int pad, int dil, void *stream);
+/* same convolution, raw float32 accumulators out: y float32 [n][oh][ow][cout].  With the operands of a float32 convolution
+ * split into bf16 (hi, hi, lo) x (hi, lo, hi) channel triples this is the float32 PARITY path (error ~2^-17 per product). */
+int regda_conv_fprop_bf16_f32out(const void *x, const void *wgt, float *y, int n, int h, int w, int cin, int cout,
+                                 int r, int s, int stride, int pad, int dil, void *stream);
 /* same, and the epilogue also accumulates the train-mode BatchNorm statistics of y: bn_stats float32
  * [groups][2][cout] (per-group per-channel sum and sum of squares of the bf16 outputs; zeroed inside unless
- * stats_zeroed != 0, i.e. the caller hands out slices of a pool it zeroes once per step). */
+ * stats_zeroed != 0, i.e. the caller hands out slices of a pool it zeroes once per step).  Needs every M tile inside one
+ * statistics group (regda_conv_fprop_stats_supported; always true for maps of >= 128 pixels). */
+int regda_conv_fprop_stats_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil, int groups);
 int regda_conv_fprop_stats_bf16(const void *x, const void *wgt, void *y, int n, int h, int w, int cin, int cout,
                                 int r, int s, int stride, int pad, int dil, float *bn_stats, int groups, int stats_zeroed, void *stream);
 
 /* Data gradient of a stride-1 convolution, reading the forward OHWI weights in place (MN-major B operand):
  *   dy bf16 [n][oh][ow][cout], wgt bf16 [cout][r][s][cin] -> dx bf16 [n][h][w][cin]   (h, w, cin, cout, ... are the
  *   FORWARD convolution's geometry).  addend (may be NULL): bf16 [n][h][w][cin] added in the epilogue, dx = dgrad + addend --
- *   the gradient of a residual branch that also reads x (`out += identity`, regda/_resnets.py:108) joins here. */
+ *   the gradient of a residual branch that also reads x (`out += identity`, regda/_resnets.py:108) joins here.
+ * The data gradient of a stride-2 convolution is this call on regda_zero_insert2_bf16(dy) with stride = 1. */
 int regda_conv_dgrad_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil);
 int regda_conv_dgrad_bf16(const void *dy, const void *wgt, void *dx, int n, int h, int w, int cin, int cout,
                           int r, int s, int stride, int pad, int dil, const void *addend, void *stream);
-/* Weight gradient (stride 1 or 2), ACCUMULATED into dw fp32 [cout][r][s][cin] with global reductions:
- *   dy bf16 [n][oh][ow][cout], x bf16 [n][h][w][cin]. */
+/* float32 accumulators out (dx float32 [n][h][w][cin]; addend float32 or NULL): data gradient of the float32 parity path */
+int regda_conv_dgrad_bf16_f32out(const void *dy, const void *wgt, float *dx, int n, int h, int w, int cin, int cout,
+                                 int r, int s, int stride, int pad, int dil, const float *addend, void *stream);
 /* Data gradient fused with the reductions of the BatchNorm(+ReLU) backward that consumes it (the BatchNorm whose OUTPUT is
  * this convolution's input; regda/_resnets.py:92-112 chains conv -> bn -> relu -> conv): dx receives
  * dz = (dgrad + addend) * [bn output > 0] (mask bits written by regda_bn_forward_bf16), red float32 [groups][2][cin]
  * ACCUMULATES sum(dz), sum(dz * bn_y).  Follow with regda_bn_backward_bf16(..., dz_ready = 1). */
+int regda_conv_dgrad_bnred_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil, int groups);
 int regda_conv_dgrad_bnred_bf16(const void *dy, const void *wgt, void *dx, int n, int h, int w, int cin, int cout,
                                 int r, int s, int stride, int pad, int dil, const void *addend, const void *bn_y,
                                 const void *relu_mask, float *red, int groups, void *stream);
+/* Weight gradient (stride 1 or 2), ACCUMULATED into dw fp32 [cout][r][s][cin] with TMA reduce-stores:
+ *   dy bf16 [n][oh][ow][cout], x bf16 [n][h][w][cin]. */
 int regda_conv_wgrad_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil);
 int regda_conv_wgrad_bf16(const void *dy, const void *x, float *dw, int n, int h, int w, int cin, int cout,
                           int r, int s, int stride, int pad, int dil, void *stream);
+/* dst bf16 [n][OH][OW][c] = zero-inserted src bf16 [n][oh][ow][c]: dst[n][2i][2j] = src[n][i][j], zero elsewhere
+ * (the dY operand of a stride-2 convolution's data gradient: regda/_resnets.py:92-112, layer2.0 / layer3.0). */
+int regda_zero_insert2_bf16(const void *src, void *dst, int n, int oh, int ow, int OH, int OW, int c, void *stream);
+
+/* ---- PPM head tail: Dropout2d + classifier (regda/models/Encoder.py:39-40) ----------------------------
+ * regda_dropout2d_mask: keep_scale float32 [n] = 0 with probability p, else 1/(1-p), n = images * channels; the generator
+ *   state (uint64 {seed, draw counter}) lives in DEVICE memory and is advanced by the kernel, so a replayed CUDA graph
+ *   draws a fresh mask every step (torch's Dropout2d stream is not reproduced: parity tests run with p = 0).
+ * regda_classifier_fwd: out float32 [b][ncls][hw] = bias + W (keep * y); y [b][hw][cin] bf16 (or float32 if y_is_f32),
+ *   w float32 [ncls][cin], bias [ncls] or NULL, keep float32 [b][cin] or NULL.
+ * regda_classifier_bwd: dout float32 [b][ncls][hw] -> dy (written, same type as y), dw / dbias (ACCUMULATED). */
+int regda_dropout2d_mask(void *state_u64x2, double p, float *keep_scale, int n, void *stream);
+int regda_classifier_fwd(const void *y, int y_is_f32, const float *w, const float *bias, const float *keep, float *out, int b,
+                         int hw, int cin, int ncls, void *stream);
+int regda_classifier_bwd(const void *y, int y_is_f32, const float *w, const float *keep, const float *dout, void *dy, float *dw,
+                         float *dbias, int b, int hw, int cin, int ncls, void *stream);
 
 /* ---- train-mode BatchNorm2d (+ residual add + ReLU) over channels-last bf16 -------------------
  * Replaces nn.BatchNorm2d / F.relu / `out += identity` in regda/_resnets.py:92-112 and

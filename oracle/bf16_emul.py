@@ -1,0 +1,96 @@
+"""TEST INFRASTRUCTURE ONLY -- bf16-emulating forward of the Deeplabv2 oracle (oracle/step_oracle.py DeeplabOracle).
+
+The benchmarked configuration of regda_b200 computes in bf16: every activation tensor the kernels WRITE is rounded to bf16,
+every convolution reads bf16 weights, and everything in between (tensor-memory accumulation, BatchNorm statistics and
+normalisation constants, pooling sums, bilinear interpolation, the classifier) is fp32.  This module restates the reference's
+forward (regda/models/Encoder.py:8-65,129-155, regda/resnet.py:140-166, regda/_resnets.py:92-112) with EXACT arithmetic
+(float64) between those rounding points and a round-to-nearest-even bf16 cast AT each of them, i.e. the function the bf16
+kernels compute up to fp32 accumulation order.  Comparing the CUDA bf16 path with it on the reference-generated golden inputs
+(tests/test_bf16_parity_gpu.py) ties the tcgen05 network to the reference's architecture and weights at 1e-3-class tolerance --
+a bound that the float32 golden comparison cannot give for bf16 arithmetic.
+
+Rounding points (regda_b200 file that rounds):
+  image -> bf16 (models/Encoder.py Deeplabv2.forward); conv weights -> bf16 (ops/tc.py weight_shadow / optim.cu shadow);
+  conv output -> bf16 (csrc/conv_tc.cu epilogue); BatchNorm statistics from the ROUNDED conv output (same epilogue);
+  BatchNorm(+residual)(+ReLU) output -> bf16 (csrc/norm.cu bn_apply_kernel); InstanceNorm output -> bf16 (same kernel);
+  pooled pyramid maps -> bf16 (models/Encoder.py PPMBilinear.forward); upsampled branch maps -> bf16 (csrc/ppm.cu upcat);
+  the classifier reads the fp32 master weights and writes fp32 logits (csrc/misc.cu) -- no rounding.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+ROUND = True      # False: no rounding at all -- the restatement must then reproduce the reference's float32 goldens (the pin
+                  # of this file: tests/test_oracle_golden.py::test_bf16_emulation_without_rounding_is_the_reference)
+
+
+def r16(t):
+    """round to nearest-even bf16, keep carrying float64"""
+    return t.float().bfloat16().double() if ROUND else t.double()
+
+
+def _conv(x, conv):
+    w = r16(conv.weight.detach())
+    return r16(F.conv2d(x, w, None, conv.stride, conv.padding, conv.dilation))
+
+
+def _bn_train(y, bn, relu, residual=None, groups=1):
+    """train-mode BatchNorm on the bf16 tensor y with `groups` statistics groups over equal batch parts, fp32-style constants"""
+    outs = []
+    for part, res in zip(y.chunk(groups, 0), (residual.chunk(groups, 0) if residual is not None else [None] * groups)):
+        mean = part.mean(dim=(0, 2, 3), keepdim=True)
+        var = (part * part).mean(dim=(0, 2, 3), keepdim=True) - mean * mean
+        rstd = 1.0 / torch.sqrt(var.clamp_min(0.0) + bn.eps)
+        g = bn.weight.detach().double().view(1, -1, 1, 1) if bn.weight is not None else 1.0
+        b = bn.bias.detach().double().view(1, -1, 1, 1) if bn.bias is not None else 0.0
+        o = (part - mean) * rstd * g + b
+        if res is not None:
+            o = o + res
+        if relu:
+            o = o.clamp_min(0.0)
+        outs.append(r16(o))
+    return torch.cat(outs, 0)
+
+
+def _bottleneck(blk, x, groups):
+    o = _bn_train(_conv(x, blk.conv1), blk.bn1, True, groups=groups)
+    o = _bn_train(_conv(o, blk.conv2), blk.bn2, True, groups=groups)
+    identity = x if blk.downsample is None else _bn_train(_conv(x, blk.downsample[0]), blk.downsample[1], False, groups=groups)
+    return _bn_train(_conv(o, blk.conv3), blk.bn3, True, residual=identity, groups=groups)
+
+
+def _instance_norm(x, eps):
+    mean = x.mean(dim=(2, 3), keepdim=True)
+    var = (x * x).mean(dim=(2, 3), keepdim=True) - mean * mean
+    return r16((x - mean) / torch.sqrt(var.clamp_min(0.0) + eps))
+
+
+def _head(head, fin, groups):
+    size = fin.shape[-2:]
+    cat = [fin]
+    for br in head.ppm:
+        pooled = r16(br[0](fin))                                   # AdaptiveAvgPool2d in exact arithmetic, then the bf16 cast
+        t = _bn_train(_conv(pooled, br[1]), br[2], True, groups=groups)
+        cat.append(r16(F.interpolate(t, size, mode="bilinear", align_corners=False)))
+    y = _bn_train(_conv(torch.cat(cat, 1), head.conv_last[0]), head.conv_last[1], True, groups=groups)
+    cls = head.conv_last[4]                                        # Dropout2d is the identity in the parity runs (p = 0)
+    return F.conv2d(y, cls.weight.detach().double(), cls.bias.detach().double())
+
+
+@torch.no_grad()
+def forward_train(model, x, groups=1):
+    """train-mode forward of step_oracle.DeeplabOracle as the bf16 kernels compute it: returns (x1, x2, feat) float32.
+    groups = 2 restates Deeplabv2.forward_pair (source and target batch in one tensor, BatchNorm statistics per domain)."""
+    rn = model.encoder.resnet
+    t = r16(x.double())
+    t = _bn_train(_conv(t, rn.conv1), rn.bn1, True, groups=groups)
+    t = F.max_pool2d(t, 3, 2, 1)
+    for layer in (rn.layer1, rn.layer2, rn.layer3, rn.layer4):
+        for blk in layer:
+            t = _bottleneck(blk, t, groups)
+    fin = _instance_norm(t, model.instance_norm.eps)
+    x1 = _head(model.layer5, fin, groups)
+    x2 = _head(model.layer6, fin, groups)
+    return x1.float(), x2.float(), fin.float()

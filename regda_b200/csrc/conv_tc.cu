@@ -14,10 +14,14 @@
 //   * the B operand is a 2-D box {64 k, BLOCK_N} of the OHWI weight matrix [Cout][R*S*Cin];
 //   * both land in 128B-swizzled K-major shared-memory tiles consumed directly by tcgen05.mma
 //     (UMMA 128 x BLOCK_N x 16), accumulating in TMEM;
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2-5 = epilogue
-//     (tcgen05.ld -> bf16 -> global), STAGES-deep mbarrier ring between producer and MMA.
-// The same kernel computes the data gradient of a stride-1 convolution when it is given dY and
-// the flipped / transposed weights (host side prepares them).
+//   * feature maps smaller than 128 pixels (the 1x1 .. 6x6 pyramid-pooling branches, the deep layers of small
+//     tiles) put SEVERAL images into one M tile: the box becomes {64 ch, BW, BH, BN} with BN*BH*BW = 128 -- still
+//     one TMA instruction, every image's halo still zero-filled;
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2-9 = epilogue
+//     (tcgen05.ld -> bf16 -> swizzled smem -> TMA store), STAGES-deep mbarrier ring between producer and MMA.
+// The same kernel computes the data gradient of a stride-1 convolution when it is given dY and reads the forward
+// weights MN-major in place (tap order flipped).  A stride-2 data gradient is the stride-1 one on the zero-inserted dY
+// (regda_zero_insert2_bf16).
 #include <cstdlib>
 #include <cstring>
 
@@ -32,158 +36,29 @@ using namespace tc;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;          // bf16: 128 bytes = one swizzle span
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 192;        // classic kernel: warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
-constexpr int kPersistThreads = 320; // persistent kernel: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane
-                                     // quadrant, each draining half of the accumulator's columns)
+constexpr int kPersistThreads = 320; // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quadrant, each
+                                     // draining half of the accumulator's columns)
 
 struct ConvGeom {
     int n, h, w, cin, cout;          // input image, reduction channels, output channels
     int oh, ow;                      // output image
     int r, s, pad, dil, stride;
     int flip;                        // dgrad: weight tap = taps-1-tap
-    int bh, bw;                      // spatial patch of one M tile (bh*bw == 128)
-    int tiles_h, tiles_w;            // patches per image
+    int bh, bw, bn;                  // M tile = bn images x (bh x bw) output pixels, bn*bh*bw == 128
+    int tiles_h, tiles_w, tiles_img; // patches per image, image blocks (ceil(n / bn))
     int kc;                          // cin / 64
 };
 
-template <int BLOCK_N, int STAGES>
-struct SmemLayout {
-    static constexpr int kABytes = kBlockM * kBlockK * 2;
-    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarOffset = STAGES * kStageBytes;
-    static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 8;
-};
+struct TileCoord { int n_blk, tw, th, img0; };
 
-// B_MN = false: weights [cout][taps*cin] (K-major B tile, one 2-D box).  B_MN = true (dgrad): weights
-// [cin][taps][cout] read in place as an MN-major B tile: BLOCK_N/64 boxes of {64 cout, 1 tap, 64 cin}, i.e. 64
-// K-rows of 128 bytes each; descriptor LBO = 8 KB between the 64-wide N blocks, SBO = 1 KB between 8-row K groups.
-template <int BLOCK_N, int STAGES, bool B_MN>
-__global__ void __launch_bounds__(kThreads, 2)
-conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                  __nv_bfloat16 *__restrict__ y, const ConvGeom g) {
-    using L = SmemLayout<BLOCK_N, STAGES>;
-    extern __shared__ uint8_t smem_raw[];
-    // 128B-swizzled tiles must start on a 1024-byte boundary of the shared window
-    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::kBarOffset);
-    uint64_t *empty_bar = full_bar + STAGES;
-    uint64_t *accum_bar = empty_bar + STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-
-    // tile coordinates: blockIdx.x = N tile (fastest, so CTAs sharing an A tile run together), blockIdx.y = M tile
-    const int n_blk = blockIdx.x;
-    int m_blk = blockIdx.y;
-    const int tw = m_blk % g.tiles_w; m_blk /= g.tiles_w;
-    const int th = m_blk % g.tiles_h;
-    const int img = m_blk / g.tiles_h;
-    const int oh0 = th * g.bh, ow0 = tw * g.bw;
-    const int num_k = g.r * g.s * g.kc;
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tmap_x);
-        prefetch_tmap(&tmap_w);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-        mbar_init(accum_bar, 1);
-        fence_barrier_init();
-        fence_proxy_async();
-    }
-    if (warp == 2) tmem_alloc(tmem_slot, BLOCK_N);          // power of two >= 32 columns
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===== TMA producer =====
-        if (elect_one()) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int kb = 0; kb < num_k; ++kb) {
-                const int tap = kb / g.kc, c0 = (kb - tap * g.kc) * kBlockK;
-                const int fr = tap / g.s, fs = tap - fr * g.s;
-                mbar_wait(empty_bar + stage, phase ^ 1);
-                uint8_t *sa = smem + stage * L::kStageBytes;
-                uint8_t *sb = sa + L::kABytes;
-                mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes);
-                tma_load_4d(sa, &tmap_x, full_bar + stage, c0, ow0 * g.stride + fs * g.dil - g.pad, oh0 * g.stride + fr * g.dil - g.pad, img);
-                if (B_MN) {
-                    const int wtap = g.flip ? g.r * g.s - 1 - tap : tap;
-#pragma unroll
-                    for (int i = 0; i < BLOCK_N / 64; ++i)
-                        tma_load_3d(sb + i * 8192, &tmap_w, full_bar + stage, n_blk * BLOCK_N + i * 64, wtap, c0);
-                } else {
-                    tma_load_2d(sb, &tmap_w, full_bar + stage, tap * g.cin + c0, n_blk * BLOCK_N);
-                }
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, B_MN ? 1 : 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int kb = 0; kb < num_k; ++kb) {
-                mbar_wait(full_bar + stage, phase);
-                tc_fence_after_sync();
-                const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-                const uint32_t sb = sa + L::kABytes;
-                const uint64_t adesc = make_smem_desc(sa, 0, 1024);
-                const uint64_t bdesc = B_MN ? make_smem_desc(sb, 8192, 1024) : make_smem_desc(sb, 0, 1024);
-#pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                    // K-major: advance the start address by 16 elements * 2 B = 32 B (>> 4 = 2) inside the swizzle span;
-                    // MN-major: by 16 K-rows * 128 B = 2048 B (>> 4 = 128)
-                    umma_bf16(tmem_base, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>((B_MN ? 128 : 2) * k), idesc,
-                              (kb | k) != 0 ? 1u : 0u);
-                }
-                umma_commit(empty_bar + stage);          // frees the smem stage when these MMAs retire
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
-            umma_commit(accum_bar);                       // accumulator complete
-        }
-    } else {
-        // ===== epilogue: TMEM -> registers -> bf16 -> global (NHWC) =====
-        const int q = warp & 3;                           // TMEM lane quadrant this warp may access
-        const int row = q * 32 + lane;                    // pixel index inside the patch
-        const int ph = row / g.bw, pw = row - ph * g.bw;
-        const int oh = oh0 + ph, ow = ow0 + pw;
-        const bool valid = oh < g.oh && ow < g.ow;
-        __nv_bfloat16 *dst = y + ((static_cast<size_t>(img) * g.oh + oh) * g.ow + ow) * g.cout + static_cast<size_t>(n_blk) * BLOCK_N;
-        mbar_wait(accum_bar, 0);
-        tc_fence_after_sync();
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
-            tmem_ld_wait();
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    uint4 pk;
-                    __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
-                    __nv_bfloat162 b1 = __floats2bfloat162_rn(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                    __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-                    __nv_bfloat162 b3 = __floats2bfloat162_rn(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-                    pk.x = *reinterpret_cast<uint32_t *>(&b0); pk.y = *reinterpret_cast<uint32_t *>(&b1);
-                    pk.z = *reinterpret_cast<uint32_t *>(&b2); pk.w = *reinterpret_cast<uint32_t *>(&b3);
-                    *reinterpret_cast<uint4 *>(dst + c + j) = pk;
-                }
-            }
-        }
-        tc_fence_before_sync();
-    }
-    __syncthreads();
-    if (warp == 2) {
-        tc_fence_after_sync();
-        tmem_dealloc(tmem_base, BLOCK_N);
-    }
+__device__ __forceinline__ TileCoord decode_tile(int t, int n_tiles_n, const ConvGeom &g) {
+    TileCoord c;
+    c.n_blk = t % n_tiles_n;
+    int m = t / n_tiles_n;
+    c.tw = m % g.tiles_w; m /= g.tiles_w;
+    c.th = m % g.tiles_h;
+    c.img0 = (m / g.tiles_h) * g.bn;
+    return c;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -213,24 +88,30 @@ struct PersistSmem {
 // atomic per channel per warp per tile (warp-transposing butterfly: 31 shuffles per quantity per 32 channels),
 // which removes BatchNorm's own pass over the activation.  group = image / imgs_per_group.
 //
-// TMA_EPI: the epilogue stages each warp's 32 pixels x 64 channels in 128B-swizzled shared memory and writes it with ONE
-// TMA store (full 128-byte lines; the box is clipped at the image border) instead of 16-byte-per-lane scattered stores
-// (32 distinct lines per store instruction); the BatchNorm statistics are then column sums read back from the staged
-// tile (32 conflict-free LDS per lane for 2 channels) instead of a 31-shuffle warp transpose per quantity.
+// Epilogue (bf16 output): each warp stages its 32 pixels x 64 channels in 128B-swizzled shared memory and writes them with
+// ONE TMA store (full 128-byte lines; the box is clipped at the image border) instead of 16-byte-per-lane scattered stores
+// (32 distinct lines per store instruction); the BatchNorm statistics are column sums read back from the staged tile
+// (32 conflict-free LDS per lane for 2 channels).
+//
+// OUT_F32: the accumulator is written as float32 (each lane stores whole 128-byte lines of its pixel row; an optional
+// float32 addend is added first).  This is the epilogue of the float32 PARITY mode (ops/tc.py: every float32 operand is
+// split into bf16 hi + lo parts and the product hi*hi + hi*lo + lo*hi is accumulated in one pass over a 3x longer K) and of
+// any caller that wants the raw fp32 accumulators.
 //
 // BNRED (data-gradient launches whose output is the gradient of a BatchNorm+ReLU output): the epilogue also performs the
 // first half of that BatchNorm's backward.  It masks the gradient with the ReLU bit mask the forward wrote (the stored
 // tensor is dz = dout * [out > 0], which is also the residual branch's gradient), TMA-loads the matching box of the
 // BatchNorm INPUT y, and accumulates sum(dz) and sum(dz * y) per channel and statistics group into `stats` -- the two
 // reductions of bn_bwd_reduce_kernel, which then does not run at all (norm.cu, regda_bn_backward_bf16 dz_ready = 1).
-template <int BLOCK_N, int STAGES, bool B_MN, bool STATS, bool TMA_EPI, bool BNRED>
+template <int BLOCK_N, int STAGES, bool B_MN, bool STATS, bool OUT_F32, bool BNRED>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                        const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_bn,
                        __nv_bfloat16 *__restrict__ y, const ConvGeom g, const int n_tiles_n, const int num_tiles,
                        float *__restrict__ stats, const int imgs_per_group, const __nv_bfloat16 *__restrict__ addend,
                        const unsigned char *__restrict__ relu_mask) {
-    static_assert(!BNRED || (TMA_EPI && !STATS), "BNRED rides on the TMA-store epilogue and shares the statistics registers");
+    static_assert(!BNRED || (!OUT_F32 && !STATS), "BNRED rides on the TMA-store epilogue and shares the statistics registers");
+    static_assert(!OUT_F32 || !STATS, "the float32-output epilogue carries no BatchNorm statistics");
     using L = PersistSmem<BLOCK_N, STAGES, BNRED>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -249,12 +130,12 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_x);
         prefetch_tmap(&tmap_w);
-        if (TMA_EPI) prefetch_tmap(&tmap_y);
+        if (!OUT_F32) prefetch_tmap(&tmap_y);
         if (BNRED) prefetch_tmap(&tmap_bn);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, TMA_EPI ? L::kEpiWarps : 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, OUT_F32 ? 8 : L::kEpiWarps); }
         for (int i = 0; i < 8; ++i) mbar_init(ybar + i, 1);
         fence_barrier_init();
         fence_proxy_async();
@@ -272,12 +153,9 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int n_blk = t % n_tiles_n;
-                int m_blk = t / n_tiles_n;
-                const int tw = m_blk % g.tiles_w; m_blk /= g.tiles_w;
-                const int th = m_blk % g.tiles_h;
-                const int img = m_blk / g.tiles_h;
-                const int ix0 = tw * g.bw * g.stride - g.pad, iy0 = th * g.bh * g.stride - g.pad;
+                const TileCoord tc_ = decode_tile(t, n_tiles_n, g);
+                const int n_blk = tc_.n_blk, img = tc_.img0;
+                const int ix0 = tc_.tw * g.bw * g.stride - g.pad, iy0 = tc_.th * g.bh * g.stride - g.pad;
                 int tap = 0, fr = 0, fs = 0, c0 = 0;
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(empty_bar + stage, phase ^ 1);
@@ -329,7 +207,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (TMA_EPI) {
+    } else if (!OUT_F32) {
         // ===== epilogue: TMEM -> registers -> bf16 -> swizzled shared memory -> TMA store (NHWC) =====
         constexpr int kCols = BLOCK_N >= 128 ? BLOCK_N / 2 : BLOCK_N;   // columns per warp: 128 / 64 / 64
         const int wq = warp - 2;
@@ -337,9 +215,10 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         if (wq < L::kEpiWarps) {
             const int col_lo = (BLOCK_N >= 128 ? (wq >> 2) : 0) * kCols;
             const int row = q * 32 + lane;
-            const int ph = row / g.bw, pw = row - ph * g.bw;
-            // the warp's 32 rows are one box {64 ch, min(bw,32) px, 32/min(bw,32) rows}: its origin inside the patch
-            const int bph0 = (q * 32) / g.bw, bpw0 = (q * 32) - bph0 * g.bw;
+            // row -> (image, y, x) inside the tile: x fastest, then y, then the image of a multi-image tile
+            const int pw = row % g.bw, ph = (row / g.bw) % g.bh, pn = row / (g.bw * g.bh);
+            // the warp's 32 rows are one box {64 ch, sbw px, sbh rows, sbn images} (launch_persistent_impl): its origin in the tile
+            const int bpw0 = (q * 32) % g.bw, bph0 = ((q * 32) / g.bw) % g.bh, bpn0 = (q * 32) / (g.bw * g.bh);
             const uint32_t stage_s = smem_u32(smem + L::kStoreOffset + wq * 4096);
             const uint32_t my_row_s = stage_s + static_cast<uint32_t>(lane) * 128u;
             const uint32_t sw = static_cast<uint32_t>(lane & 7);
@@ -377,15 +256,14 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int n_blk = t % n_tiles_n;
-                int m_blk = t / n_tiles_n;
-                const int tw = m_blk % g.tiles_w; m_blk /= g.tiles_w;
-                const int th = m_blk % g.tiles_h;
-                const int img = m_blk / g.tiles_h;
+                const TileCoord tc_ = decode_tile(t, n_tiles_n, g);
+                const int n_blk = tc_.n_blk, tw = tc_.tw, th = tc_.th;
+                const int img = tc_.img0 + pn, bimg = tc_.img0 + bpn0;
                 const int oh = th * g.bh + ph, ow = tw * g.bw + pw;
-                const bool valid = oh < g.oh && ow < g.ow;
+                const bool valid = oh < g.oh && ow < g.ow && img < g.n;
                 if (STATS || BNRED) {
-                    const int key = (n_blk << 16) | (img / imgs_per_group);
+                    // (the host only selects STATS / BNRED when all images of a tile belong to one statistics group)
+                    const int key = (n_blk << 16) | (tc_.img0 / imgs_per_group);
                     if (key != stat_key) {
                         if (stat_key >= 0) flush_stats(stat_key);
                         stat_key = key;
@@ -405,7 +283,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                     // sums ended with __syncwarp) and the mask words do not depend on the accumulator: request them first
                     if (lane == 0) {
                         mbar_arrive_expect_tx(ybar + wq, 4096);
-                        tma_load_4d(ybuf, &tmap_bn, ybar + wq, n_blk * BLOCK_N + col_lo, tw * g.bw + bpw0, th * g.bh + bph0, img);
+                        tma_load_4d(ybuf, &tmap_bn, ybar + wq, n_blk * BLOCK_N + col_lo, tw * g.bw + bpw0, th * g.bh + bph0, bimg);
                     }
                     const uint32_t *mp = reinterpret_cast<const uint32_t *>(relu_mask + ((pix_off + col_lo) >> 3));
 #pragma unroll
@@ -476,7 +354,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_4d(&tmap_y, smem + L::kStoreOffset + wq * 4096, n_blk * BLOCK_N + col_lo + c64, tw * g.bw + bpw0, th * g.bh + bph0, img);
+                        tma_store_4d(&tmap_y, smem + L::kStoreOffset + wq * 4096, n_blk * BLOCK_N + col_lo + c64, tw * g.bw + bpw0, th * g.bh + bph0, bimg);
                         bulk_commit();
                     }
                     if (STATS) {
@@ -512,7 +390,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                         __syncwarp();                                  // every lane is done with ybuf
                         if (c64 + 64 < kCols && lane == 0) {
                             mbar_arrive_expect_tx(ybar + wq, 4096);
-                            tma_load_4d(ybuf, &tmap_bn, ybar + wq, n_blk * BLOCK_N + col_lo + c64 + 64, tw * g.bw + bpw0, th * g.bh + bph0, img);
+                            tma_load_4d(ybuf, &tmap_bn, ybar + wq, n_blk * BLOCK_N + col_lo + c64 + 64, tw * g.bw + bpw0, th * g.bh + bph0, bimg);
                         }
                     }
                 }
@@ -522,31 +400,22 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             if (lane == 0) bulk_wait_read0();          // shared memory must outlive the last TMA store's reads
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> bf16 -> global (NHWC) =====
+        // ===== epilogue (OUT_F32): TMEM -> registers (+ float32 addend) -> float32 global (NHWC) =====
+        float *yf = reinterpret_cast<float *>(y);
+        const float *addf = reinterpret_cast<const float *>(addend);
         const int q = warp & 3;                                        // TMEM lane quadrant of this warp
         const int col_lo = ((warp - 2) >> 2) * (BLOCK_N / 2), col_hi = col_lo + BLOCK_N / 2;    // this warp's half of the columns
         const int row = q * 32 + lane;
-        const int ph = row / g.bw, pw = row - ph * g.bw;
+        const int pw = row % g.bw, ph = (row / g.bw) % g.bh, pn = row / (g.bw * g.bh);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const int n_blk = t % n_tiles_n;
-            int m_blk = t / n_tiles_n;
-            const int tw = m_blk % g.tiles_w; m_blk /= g.tiles_w;
-            const int th = m_blk % g.tiles_h;
-            const int img = m_blk / g.tiles_h;
-            const int oh = th * g.bh + ph, ow = tw * g.bw + pw;
-            const bool valid = oh < g.oh && ow < g.ow;
-            __nv_bfloat16 *dst = y + ((static_cast<size_t>(img) * g.oh + oh) * g.ow + ow) * g.cout + static_cast<size_t>(n_blk) * BLOCK_N;
-            // the addend (if any) does not depend on the accumulator: its first chunk is requested before waiting for the
-            // MMAs, and chunk c+1 while chunk c is converted and stored, so its latency stays off the epilogue's critical path
-            const bool has_add = addend != nullptr && valid;
-            const uint4 *ap = reinterpret_cast<const uint4 *>(addend + (dst - y) + col_lo);
-            uint4 cur[4], nxt[4];
-            if (has_add) {
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) cur[q4] = __ldg(ap + q4);
-            }
+            const TileCoord tc_ = decode_tile(t, n_tiles_n, g);
+            const int img = tc_.img0 + pn;
+            const int oh = tc_.th * g.bh + ph, ow = tc_.tw * g.bw + pw;
+            const bool valid = oh < g.oh && ow < g.ow && img < g.n;
+            const size_t pix_off = ((static_cast<size_t>(img) * g.oh + oh) * g.ow + ow) * g.cout + static_cast<size_t>(tc_.n_blk) * BLOCK_N;
+            const bool has_add = addf != nullptr && valid;
             mbar_wait(tfull_bar + acc, acc_phase);
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
@@ -554,64 +423,26 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             for (int c = col_lo; c < col_hi; c += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
-                if (has_add && c + 32 < col_hi) {
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) nxt[q4] = __ldg(ap + (c + 32 - col_lo) / 8 + q4);
-                }
-                tmem_ld_wait();
+                float4 ad[8];
                 if (has_add) {
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const uint32_t w4[4] = {cur[q4].x, cur[q4].y, cur[q4].z, cur[q4].w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w4[e]));
-                            v[q4 * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[q4 * 8 + 2 * e]) + f.x);
-                            v[q4 * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(v[q4 * 8 + 2 * e + 1]) + f.y);
-                        }
-                        cur[q4] = nxt[q4];
-                    }
+                    for (int j = 0; j < 8; ++j) ad[j] = __ldg(reinterpret_cast<const float4 *>(addf + pix_off + c) + j);
                 }
-                uint32_t pkd[16];
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-                    pkd[j >> 1] = *reinterpret_cast<uint32_t *>(&b);
-                }
+                tmem_ld_wait();
                 if (valid) {
+                    float4 *dst = reinterpret_cast<float4 *>(yf + pix_off + c);        // one whole 128-byte line per lane
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<uint4 *>(dst + c + 2 * j) = make_uint4(pkd[j], pkd[j + 1], pkd[j + 2], pkd[j + 3]);
-                }
-                if (STATS) {
-                    // statistics of what BatchNorm will read back: the bf16-rounded values; rows outside the image count 0
-                    float a[32], b2[32];
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&pkd[j >> 1]));
-                        a[j] = valid ? f.x : 0.f; a[j + 1] = valid ? f.y : 0.f;
-                        b2[j] = a[j] * a[j]; b2[j + 1] = a[j + 1] * a[j + 1];
+                    for (int j = 0; j < 8; ++j) {
+                        float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                               __uint_as_float(v[4 * j + 3]));
+                        if (has_add) { o.x += ad[j].x; o.y += ad[j].y; o.z += ad[j].z; o.w += ad[j].w; }
+                        dst[j] = o;
                     }
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-                        const bool up = (lane & off) != 0;
-#pragma unroll
-                        for (int j = 0; j < off; ++j) {
-                            const float sa_ = up ? a[j] : a[j + off], ka = up ? a[j + off] : a[j];
-                            const float sb_ = up ? b2[j] : b2[j + off], kb_ = up ? b2[j + off] : b2[j];
-                            a[j] = ka + __shfl_xor_sync(0xffffffffu, sa_, off);
-                            b2[j] = kb_ + __shfl_xor_sync(0xffffffffu, sb_, off);
-                        }
-                    }
-                    // lane L now holds the warp totals of channel c + L
-                    float *sp = stats + static_cast<size_t>(img / imgs_per_group) * 2 * g.cout + static_cast<size_t>(n_blk) * BLOCK_N + c + lane;
-                    atomicAdd(sp, a[0]);
-                    atomicAdd(sp + g.cout, b2[0]);
                 }
             }
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar + acc);            // this warp's quadrant of the accumulator is free
+            if (lane == 0) mbar_arrive(tempty_bar + acc);            // this warp's part of the accumulator is free
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -624,7 +455,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 }
 
 int make_tmap_x(CUtensorMap *m, const void *x, const ConvGeom &g) {
-    if (!encode_nhwc(m, x, g.n, g.h, g.w, g.cin, g.bw, g.bh, g.stride))
+    if (!encode_nhwc(m, x, g.n, g.h, g.w, g.cin, g.bw, g.bh, g.stride, g.bn))
         return REGDA_ERR_CUDA;   /* text set by encode_bf16_sw128 (activations) */
     return REGDA_OK;
 }
@@ -649,81 +480,43 @@ int make_tmap_w_mn(CUtensorMap *m, const void *w, int red, int taps, int out) {
     return REGDA_OK;
 }
 
-template <int BLOCK_N, int STAGES, bool B_MN>
-int launch_fprop(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bfloat16 *y, const ConvGeom &g, cudaStream_t st) {
-    using L = SmemLayout<BLOCK_N, STAGES>;
-    auto kern = conv_fprop_kernel<BLOCK_N, STAGES, B_MN>;
-    const int smem = L::kTotal + 1024;     // slack for the 1024-byte alignment of the dynamic segment
-    REGDA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const dim3 grid(g.cout / BLOCK_N, g.n * g.tiles_h * g.tiles_w);
-    kern<<<grid, kThreads, smem, st>>>(tx, tw, y, g);
-    REGDA_LAUNCH_CHECK();
-    return REGDA_OK;
-}
-
-// REGDA_CONV_EPILOGUE=direct selects the per-lane global-store epilogue (A/B comparisons); default: TMA store
-bool use_tma_epilogue() {
-    const char *e = getenv("REGDA_CONV_EPILOGUE");
-    return !(e && strcmp(e, "direct") == 0);
-}
-
 struct BnRed {                       // BNRED launch: the BatchNorm whose output gradient this data-gradient launch produces
     const void *bn_y = nullptr;      // its input y, bf16 [n][h][w][c] (same shape as the gradient)
     const unsigned char *mask = nullptr;   // its ReLU mask, one bit per element
 };
 
-template <int BLOCK_N, int STAGES, bool B_MN, bool STATS, bool TMA_EPI, bool BNRED = false>
-int launch_persistent_impl(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bfloat16 *y, const ConvGeom &g, cudaStream_t st,
-                           float *stats, int imgs_per_group, const __nv_bfloat16 *addend, const BnRed &br = BnRed()) {
+// `y` / `addend` are bf16, or float32 when OUT_F32
+template <int BLOCK_N, int STAGES, bool B_MN, bool STATS, bool OUT_F32, bool BNRED = false>
+int launch_persistent_impl(const CUtensorMap &tx, const CUtensorMap &tw, void *y, const ConvGeom &g, cudaStream_t st,
+                           float *stats, int imgs_per_group, const void *addend, const BnRed &br = BnRed()) {
     using L = PersistSmem<BLOCK_N, STAGES, BNRED>;
-    auto kern = conv_persistent_kernel<BLOCK_N, STAGES, B_MN, STATS, TMA_EPI, BNRED>;
+    auto kern = conv_persistent_kernel<BLOCK_N, STAGES, B_MN, STATS, OUT_F32, BNRED>;
     const int smem = L::kTotal + 1024;
     static_assert(L::kTotal + 1024 <= 232448, "persistent conv kernel: shared memory over the 227 KB limit");
     REGDA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int n_tiles_n = g.cout / BLOCK_N;
-    const int num_tiles = n_tiles_n * g.n * g.tiles_h * g.tiles_w;
+    const int num_tiles = n_tiles_n * g.tiles_img * g.tiles_h * g.tiles_w;
     const int grid = std::min(num_tiles, sm_count());
-    CUtensorMap ty = tx, tbn = tx;          // unused by the direct epilogue / without BNRED
-    if (TMA_EPI) {
-        // output map [n][oh][ow][cout]; box = one epilogue warp's 32 pixels x 64 channels
-        const int sbw = std::min(g.bw, 32), sbh = 32 / sbw;
-        if (!encode_nhwc(&ty, y, g.n, g.oh, g.ow, g.cout, sbw, sbh, 1)) return REGDA_ERR_CUDA;
-        if (BNRED && !encode_nhwc(&tbn, br.bn_y, g.n, g.oh, g.ow, g.cout, sbw, sbh, 1)) return REGDA_ERR_CUDA;
+    CUtensorMap ty = tx, tbn = tx;          // unused by the float32 epilogue / without BNRED
+    if (!OUT_F32) {
+        // output map [n][oh][ow][cout]; box = one epilogue warp's 32 tile rows x 64 channels: {sbw px, sbh rows, sbn images}
+        const int sbw = std::min(g.bw, 32), sbh = std::min(g.bh, 32 / sbw), sbn = 32 / (sbw * sbh);
+        if (!encode_nhwc(&ty, y, g.n, g.oh, g.ow, g.cout, sbw, sbh, 1, sbn)) return REGDA_ERR_CUDA;
+        if (BNRED && !encode_nhwc(&tbn, br.bn_y, g.n, g.oh, g.ow, g.cout, sbw, sbh, 1, sbn)) return REGDA_ERR_CUDA;
     }
-    REGDA_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kPersistThreads), smem, st, tx, tw, ty, tbn, y, g, n_tiles_n, num_tiles, stats,
-                                imgs_per_group, addend, br.mask));
+    REGDA_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kPersistThreads), smem, st, tx, tw, ty, tbn, static_cast<__nv_bfloat16 *>(y), g, n_tiles_n,
+                                num_tiles, stats, imgs_per_group, static_cast<const __nv_bfloat16 *>(addend), br.mask));
     return REGDA_OK;
 }
 
-template <int BLOCK_N, int STAGES, bool B_MN>
-int launch_persistent(const CUtensorMap &tx, const CUtensorMap &tw, __nv_bfloat16 *y, const ConvGeom &g, cudaStream_t st,
-                      float *stats, int imgs_per_group, const __nv_bfloat16 *addend) {
-    if (use_tma_epilogue()) {
-        if (!B_MN && stats != nullptr) return launch_persistent_impl<BLOCK_N, STAGES, false, true, true>(tx, tw, y, g, st, stats, imgs_per_group, addend);
-        return launch_persistent_impl<BLOCK_N, STAGES, B_MN, false, true>(tx, tw, y, g, st, nullptr, 1, addend);
-    }
-    if (!B_MN && stats != nullptr) return launch_persistent_impl<BLOCK_N, STAGES, false, true, false>(tx, tw, y, g, st, stats, imgs_per_group, addend);
-    return launch_persistent_impl<BLOCK_N, STAGES, B_MN, false, false>(tx, tw, y, g, st, nullptr, 1, addend);
-}
+// 256-wide tiles are taken when they give at least half an SM-count of tiles (otherwise 128-wide tiles fill the machine better)
+int min_tiles_256() { return sm_count() / 2; }
 
-// Tile shape policy.  REGDA_CONV_KERNEL=classic selects the one-tile-per-CTA kernel (A/B comparisons).
-bool use_persistent() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("REGDA_CONV_KERNEL");
-        v = (e && strcmp(e, "classic") == 0) ? 0 : 1;
-    }
-    return v == 1;
-}
-
-// 256-wide tiles are taken when they give at least this many tiles (REGDA_CONV_MIN_TILES_256 overrides; default: half the SMs)
-int min_tiles_256() {
-    static int v = 0;
-    if (v == 0) {
-        const char *e = getenv("REGDA_CONV_MIN_TILES_256");
-        v = e ? std::max(1, atoi(e)) : sm_count() / 2;
-    }
-    return v;
+int pick_block_n(const ConvGeom &g) {
+    const long long m_tiles = static_cast<long long>(g.tiles_img) * g.tiles_h * g.tiles_w;
+    if (g.cout % 256 == 0 && m_tiles * (g.cout / 256) >= min_tiles_256()) return 256;
+    if (g.cout % 128 == 0) return 128;
+    return 64;
 }
 
 // data gradient + the reductions of the BatchNorm backward that consumes it (BNRED); `red` [groups][2][g.cout]
@@ -732,40 +525,82 @@ int launch_dgrad_bnred(const void *act, const void *wgt, __nv_bfloat16 *out, con
     CUtensorMap tx, tw;
     int rc = make_tmap_x(&tx, act, g);
     if (rc) return rc;
-    const long long m_tiles = static_cast<long long>(g.n) * g.tiles_h * g.tiles_w;
-    int block_n = 64;
-    if (g.cout % 256 == 0 && m_tiles * (g.cout / 256) >= min_tiles_256()) block_n = 256;
-    else if (g.cout % 128 == 0) block_n = 128;
+    const int block_n = pick_block_n(g);
     rc = make_tmap_w_mn(&tw, wgt, g.cin, taps, g.cout);
     if (rc) return rc;
     // one pipeline stage fewer than the plain kernel at 256 / 128: the 32 KB of BatchNorm-input boxes take their place
-    if (block_n == 256) return launch_persistent_impl<256, 3, true, false, true, true>(tx, tw, out, g, st, red, imgs_per_group, addend, br);
-    if (block_n == 128) return launch_persistent_impl<128, 5, true, false, true, true>(tx, tw, out, g, st, red, imgs_per_group, addend, br);
-    return launch_persistent_impl<64, 6, true, false, true, true>(tx, tw, out, g, st, red, imgs_per_group, addend, br);
+    if (block_n == 256) return launch_persistent_impl<256, 3, true, false, false, true>(tx, tw, out, g, st, red, imgs_per_group, addend, br);
+    if (block_n == 128) return launch_persistent_impl<128, 5, true, false, false, true>(tx, tw, out, g, st, red, imgs_per_group, addend, br);
+    return launch_persistent_impl<64, 6, true, false, false, true>(tx, tw, out, g, st, red, imgs_per_group, addend, br);
+}
+
+template <int BLOCK_N, int STAGES, bool B_MN>
+int launch_persistent(const CUtensorMap &tx, const CUtensorMap &tw, void *y, const ConvGeom &g, cudaStream_t st, float *stats,
+                      int imgs_per_group, const void *addend, bool out_f32) {
+    if (out_f32) return launch_persistent_impl<BLOCK_N, STAGES, B_MN, false, true>(tx, tw, y, g, st, nullptr, 1, addend);
+    if (!B_MN && stats != nullptr) return launch_persistent_impl<BLOCK_N, STAGES, false, true, false>(tx, tw, y, g, st, stats, imgs_per_group, addend);
+    return launch_persistent_impl<BLOCK_N, STAGES, B_MN, false, false>(tx, tw, y, g, st, nullptr, 1, addend);
 }
 
 template <bool B_MN>
-int launch_conv(const void *act, const void *wgt, __nv_bfloat16 *out, const ConvGeom &g, int taps, cudaStream_t st,
-                float *stats = nullptr, int imgs_per_group = 1, const __nv_bfloat16 *addend = nullptr) {
+int launch_conv(const void *act, const void *wgt, void *out, const ConvGeom &g, int taps, cudaStream_t st, float *stats = nullptr,
+                int imgs_per_group = 1, const void *addend = nullptr, bool out_f32 = false) {
     // g.cin = reduction channels, g.cout = output channels of THIS GEMM (already swapped for dgrad)
     CUtensorMap tx, tw;
     int rc = make_tmap_x(&tx, act, g);
     if (rc) return rc;
-    const long long m_tiles = static_cast<long long>(g.n) * g.tiles_h * g.tiles_w;
-    int block_n = 64;
-    if (g.cout % 256 == 0 && use_persistent() && m_tiles * (g.cout / 256) >= min_tiles_256()) block_n = 256;
-    else if (g.cout % 128 == 0) block_n = 128;
+    const int block_n = pick_block_n(g);
     rc = B_MN ? make_tmap_w_mn(&tw, wgt, g.cin, taps, g.cout) : make_tmap_w(&tw, wgt, g.cout, taps * g.cin, block_n);
     if (rc) return rc;
-    if (use_persistent()) {
-        if (block_n == 256) return launch_persistent<256, 4, B_MN>(tx, tw, out, g, st, stats, imgs_per_group, addend);
-        if (block_n == 128) return launch_persistent<128, 6, B_MN>(tx, tw, out, g, st, stats, imgs_per_group, addend);
-        return launch_persistent<64, 8, B_MN>(tx, tw, out, g, st, stats, imgs_per_group, addend);
+    if (block_n == 256) return launch_persistent<256, 4, B_MN>(tx, tw, out, g, st, stats, imgs_per_group, addend, out_f32);
+    if (block_n == 128) return launch_persistent<128, 6, B_MN>(tx, tw, out, g, st, stats, imgs_per_group, addend, out_f32);
+    return launch_persistent<64, 8, B_MN>(tx, tw, out, g, st, stats, imgs_per_group, addend, out_f32);
+}
+
+int geom_init(ConvGeom &g, int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil) {
+    g.n = n; g.h = h; g.w = w; g.cin = cin; g.cout = cout; g.r = r; g.s = s; g.pad = pad; g.dil = dil; g.stride = stride; g.flip = 0;
+    g.oh = (h + 2 * pad - dil * (r - 1) - 1) / stride + 1;
+    g.ow = (w + 2 * pad - dil * (s - 1) - 1) / stride + 1;
+    int bw = 1;
+    while (bw * 2 <= g.ow && bw * 2 <= kBlockM) bw *= 2;         // largest power of two <= min(ow, 128)
+    int bh = kBlockM / bw, bn = 1;
+    if (static_cast<long long>(g.oh) * g.ow < kBlockM) {
+        // small map: the patch does not reach 128 pixels inside one image -- fill the M tile with several images
+        bh = 1;
+        while (bh * 2 <= g.oh && bw * bh * 2 <= kBlockM) bh *= 2;
+        bn = kBlockM / (bw * bh);
     }
-    if (stats != nullptr || addend != nullptr)
-        return fail(REGDA_ERR_UNSUPPORTED, "conv: fused BatchNorm statistics / addend need the persistent kernel");
-    if (block_n == 128) return launch_fprop<128, 3, B_MN>(tx, tw, out, g, st);
-    return launch_fprop<64, 4, B_MN>(tx, tw, out, g, st);
+    g.bw = bw; g.bh = bh; g.bn = bn;
+    g.tiles_w = (g.ow + g.bw - 1) / g.bw;
+    g.tiles_h = (g.oh + g.bh - 1) / g.bh;
+    g.tiles_img = (n + bn - 1) / bn;
+    g.kc = cin / kBlockK;
+    return REGDA_OK;
+}
+
+bool shape_ok(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil) {
+    if (n < 1 || h < 1 || w < 1 || stride < 1 || stride > 2 || r < 1 || s < 1 || r * s > 49 || dil < 1 || pad < 0) return false;
+    if (cin % 64 != 0 || cout % 64 != 0 || cin < 64 || cout < 64) return false;
+    if (h + 2 * pad < dil * (r - 1) + 1 || w + 2 * pad < dil * (s - 1) + 1) return false;
+    return true;
+}
+
+// all images of one M tile must fall into one BatchNorm statistics group (fused statistics / fused backward reductions)
+bool groups_ok(const ConvGeom &g, int groups) {
+    if (groups < 1 || g.n % groups != 0) return false;
+    return g.bn == 1 || groups == 1 || (g.n / groups) % g.bn == 0;
+}
+
+bool aligned16(const void *a, const void *b, const void *c) {
+    return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
+}
+
+// geometry of the data gradient as a stride-1 convolution over dy [n][oh][ow][cout] producing [n][h][w][cin]
+bool dgrad_geom(ConvGeom &g, int n, int h, int w, int cin, int cout, int r, int s, int pad, int dil) {
+    const int oh = h + 2 * pad - dil * (r - 1), ow = w + 2 * pad - dil * (s - 1);
+    geom_init(g, n, oh, ow, cout, cin, r, s, 1, dil * (r - 1) - pad, dil);
+    g.flip = 1;
+    return g.oh == h && g.ow == w;
 }
 
 }  // namespace
@@ -773,29 +608,17 @@ int launch_conv(const void *act, const void *wgt, __nv_bfloat16 *out, const Conv
 
 using namespace regda;
 
-namespace {
-int geom_init(ConvGeom &g, int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil) {
-    g.n = n; g.h = h; g.w = w; g.cin = cin; g.cout = cout; g.r = r; g.s = s; g.pad = pad; g.dil = dil; g.stride = stride; g.flip = 0;
-    g.oh = (h + 2 * pad - dil * (r - 1) - 1) / stride + 1;
-    g.ow = (w + 2 * pad - dil * (s - 1) - 1) / stride + 1;
-    int bw = 1;
-    while (bw * 2 <= g.ow && bw * 2 <= 128) bw *= 2;             // largest power of two <= min(ow, 128)
-    g.bw = bw; g.bh = kBlockM / bw;
-    g.tiles_w = (g.ow + g.bw - 1) / g.bw;
-    g.tiles_h = (g.oh + g.bh - 1) / g.bh;
-    g.kc = cin / kBlockK;
-    return REGDA_OK;
-}
-}  // namespace
-
-// 1 if (shape, alignment) is covered by the tcgen05 kernel
+// 1 if (shape, alignment) is covered by the tcgen05 kernel: channel counts multiples of 64, stride 1 or 2, any map size
 extern "C" int regda_conv_fprop_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil) {
-    if (n < 1 || h < 1 || w < 1 || stride < 1 || stride > 2 || r < 1 || s < 1 || r * s > 49 || dil < 1 || pad < 0) return 0;
-    if (cin % 64 != 0 || cout % 64 != 0) return 0;
-    if (h + 2 * pad < dil * (r - 1) + 1 || w + 2 * pad < dil * (s - 1) + 1) return 0;
-    const int oh = (h + 2 * pad - dil * (r - 1) - 1) / stride + 1, ow = (w + 2 * pad - dil * (s - 1) - 1) / stride + 1;
-    if (static_cast<long long>(oh) * ow < 128) return 0;          // tiny maps (PPM branches) stay on the library path
-    return 1;
+    return shape_ok(n, h, w, cin, cout, r, s, stride, pad, dil) ? 1 : 0;
+}
+
+// 1 if the forward kernel can also produce the BatchNorm statistics of its output for `groups` statistics groups
+extern "C" int regda_conv_fprop_stats_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil, int groups) {
+    if (!shape_ok(n, h, w, cin, cout, r, s, stride, pad, dil)) return 0;
+    ConvGeom g;
+    geom_init(g, n, h, w, cin, cout, r, s, stride, pad, dil);
+    return groups_ok(g, groups) ? 1 : 0;
 }
 
 extern "C" int regda_conv_fprop_bf16(const void *x, const void *wgt, void *y, int n, int h, int w, int cin, int cout,
@@ -803,12 +626,24 @@ extern "C" int regda_conv_fprop_bf16(const void *x, const void *wgt, void *y, in
     if (!regda_conv_fprop_supported(n, h, w, cin, cout, r, s, stride, pad, dil))
         return fail(REGDA_ERR_UNSUPPORTED, "conv_fprop: shape not covered by the tcgen05 kernel");
     if (!x || !wgt || !y) return fail(REGDA_ERR_INVALID_ARG, "conv_fprop: null pointer");
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wgt) | reinterpret_cast<uintptr_t>(y)) & 15)
-        return fail(REGDA_ERR_INVALID_ARG, "conv_fprop: tensors must be 16-byte aligned");
+    if (!aligned16(x, wgt, y)) return fail(REGDA_ERR_INVALID_ARG, "conv_fprop: tensors must be 16-byte aligned");
     ConvGeom g;
     geom_init(g, n, h, w, cin, cout, r, s, stride, pad, dil);
     ensure_context(x);
-    return launch_conv<false>(x, wgt, static_cast<__nv_bfloat16 *>(y), g, r * s, static_cast<cudaStream_t>(stream));
+    return launch_conv<false>(x, wgt, y, g, r * s, static_cast<cudaStream_t>(stream));
+}
+
+// Same convolution with the raw float32 accumulators as output: y float32 [n][oh][ow][cout].
+extern "C" int regda_conv_fprop_bf16_f32out(const void *x, const void *wgt, float *y, int n, int h, int w, int cin, int cout,
+                                            int r, int s, int stride, int pad, int dil, void *stream) {
+    if (!regda_conv_fprop_supported(n, h, w, cin, cout, r, s, stride, pad, dil))
+        return fail(REGDA_ERR_UNSUPPORTED, "conv_fprop_f32out: shape not covered by the tcgen05 kernel");
+    if (!x || !wgt || !y) return fail(REGDA_ERR_INVALID_ARG, "conv_fprop_f32out: null pointer");
+    if (!aligned16(x, wgt, y)) return fail(REGDA_ERR_INVALID_ARG, "conv_fprop_f32out: tensors must be 16-byte aligned");
+    ConvGeom g;
+    geom_init(g, n, h, w, cin, cout, r, s, stride, pad, dil);
+    ensure_context(x);
+    return launch_conv<false>(x, wgt, y, g, r * s, static_cast<cudaStream_t>(stream), nullptr, 1, nullptr, true);
 }
 
 // Forward convolution that also produces the train-mode BatchNorm statistics of its output:
@@ -817,24 +652,22 @@ extern "C" int regda_conv_fprop_bf16(const void *x, const void *wgt, void *y, in
 extern "C" int regda_conv_fprop_stats_bf16(const void *x, const void *wgt, void *y, int n, int h, int w, int cin, int cout,
                                            int r, int s, int stride, int pad, int dil, float *bn_stats, int groups, int stats_zeroed,
                                            void *stream) {
-    if (!regda_conv_fprop_supported(n, h, w, cin, cout, r, s, stride, pad, dil))
-        return fail(REGDA_ERR_UNSUPPORTED, "conv_fprop: shape not covered by the tcgen05 kernel");
+    if (!regda_conv_fprop_stats_supported(n, h, w, cin, cout, r, s, stride, pad, dil, groups))
+        return fail(REGDA_ERR_UNSUPPORTED, "conv_fprop_stats: shape / statistics groups not covered by the tcgen05 kernel");
     if (!x || !wgt || !y || !bn_stats) return fail(REGDA_ERR_INVALID_ARG, "conv_fprop_stats: null pointer");
-    if (groups < 1 || n % groups != 0) return fail(REGDA_ERR_INVALID_ARG, "conv_fprop_stats: groups must divide the batch");
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wgt) | reinterpret_cast<uintptr_t>(y)) & 15)
-        return fail(REGDA_ERR_INVALID_ARG, "conv_fprop: tensors must be 16-byte aligned");
-    if (!use_persistent()) return fail(REGDA_ERR_UNSUPPORTED, "conv_fprop_stats: needs the persistent kernel");
+    if (!aligned16(x, wgt, y)) return fail(REGDA_ERR_INVALID_ARG, "conv_fprop: tensors must be 16-byte aligned");
     ConvGeom g;
     geom_init(g, n, h, w, cin, cout, r, s, stride, pad, dil);
     ensure_context(x);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!stats_zeroed) REGDA_CUDA_CHECK(cudaMemsetAsync(bn_stats, 0, static_cast<size_t>(groups) * 2 * cout * sizeof(float), st));
-    return launch_conv<false>(x, wgt, static_cast<__nv_bfloat16 *>(y), g, r * s, st, bn_stats, n / groups);
+    return launch_conv<false>(x, wgt, y, g, r * s, st, bn_stats, n / groups);
 }
 
-// Data gradient of a stride-1 convolution, reading the forward weights IN PLACE:
+// Data gradient of a STRIDE-1 convolution, reading the forward weights IN PLACE:
 //   dx[n][h][w][cin] = sum_{r,s,co} dy[n][y + pad - r*dil][x + pad - s*dil][co] * wgt[co][r][s][cin]
 // dy bf16 [n][oh][ow][cout], wgt bf16 [cout][r][s][cin] (OHWI), dx bf16 [n][h][w][cin].
+// (A stride-2 convolution's data gradient is this call on the zero-inserted dy: regda_zero_insert2_bf16.)
 extern "C" int regda_conv_dgrad_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil) {
     if (stride != 1 || r != s) return 0;
     const int pad2 = dil * (r - 1) - pad;
@@ -844,23 +677,38 @@ extern "C" int regda_conv_dgrad_supported(int n, int h, int w, int cin, int cout
     return regda_conv_fprop_supported(n, oh, ow, cout, cin, r, s, 1, pad2, dil);
 }
 
+extern "C" int regda_conv_dgrad_bnred_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil, int groups) {
+    if (!regda_conv_dgrad_supported(n, h, w, cin, cout, r, s, stride, pad, dil)) return 0;
+    ConvGeom g;
+    if (!dgrad_geom(g, n, h, w, cin, cout, r, s, pad, dil)) return 0;
+    return groups_ok(g, groups) ? 1 : 0;
+}
+
 extern "C" int regda_conv_dgrad_bf16(const void *dy, const void *wgt, void *dx, int n, int h, int w, int cin, int cout,
                                      int r, int s, int stride, int pad, int dil, const void *addend, void *stream) {
     if (!regda_conv_dgrad_supported(n, h, w, cin, cout, r, s, stride, pad, dil))
         return fail(REGDA_ERR_UNSUPPORTED, "conv_dgrad: shape not covered by the tcgen05 kernel");
     if (!dy || !wgt || !dx) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad: null pointer");
-    if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(wgt) | reinterpret_cast<uintptr_t>(dx)) & 15)
-        return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad: tensors must be 16-byte aligned");
-    const int oh = h + 2 * pad - dil * (r - 1), ow = w + 2 * pad - dil * (s - 1);
+    if (!aligned16(dy, wgt, dx)) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad: tensors must be 16-byte aligned");
     ConvGeom g;
-    // a stride-1 convolution of dy [n][oh][ow][cout] with reduction over cout, producing [n][h][w][cin]
-    geom_init(g, n, oh, ow, cout, cin, r, s, 1, dil * (r - 1) - pad, dil);
-    g.flip = 1;
-    if (g.oh != h || g.ow != w) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad: inconsistent geometry");
+    if (!dgrad_geom(g, n, h, w, cin, cout, r, s, pad, dil)) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad: inconsistent geometry");
     ensure_context(dy);
     if (addend != nullptr && (reinterpret_cast<uintptr_t>(addend) & 15)) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad: addend must be 16-byte aligned");
-    return launch_conv<true>(dy, wgt, static_cast<__nv_bfloat16 *>(dx), g, r * s, static_cast<cudaStream_t>(stream), nullptr, 1,
-                             static_cast<const __nv_bfloat16 *>(addend));
+    return launch_conv<true>(dy, wgt, dx, g, r * s, static_cast<cudaStream_t>(stream), nullptr, 1, addend);
+}
+
+// float32 output (and float32 addend): the raw accumulators of the same data gradient
+extern "C" int regda_conv_dgrad_bf16_f32out(const void *dy, const void *wgt, float *dx, int n, int h, int w, int cin, int cout,
+                                            int r, int s, int stride, int pad, int dil, const float *addend, void *stream) {
+    if (!regda_conv_dgrad_supported(n, h, w, cin, cout, r, s, stride, pad, dil))
+        return fail(REGDA_ERR_UNSUPPORTED, "conv_dgrad_f32out: shape not covered by the tcgen05 kernel");
+    if (!dy || !wgt || !dx) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_f32out: null pointer");
+    if (!aligned16(dy, wgt, dx)) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_f32out: tensors must be 16-byte aligned");
+    ConvGeom g;
+    if (!dgrad_geom(g, n, h, w, cin, cout, r, s, pad, dil)) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_f32out: inconsistent geometry");
+    ensure_context(dy);
+    if (addend != nullptr && (reinterpret_cast<uintptr_t>(addend) & 15)) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_f32out: addend must be 16-byte aligned");
+    return launch_conv<true>(dy, wgt, dx, g, r * s, static_cast<cudaStream_t>(stream), nullptr, 1, addend, true);
 }
 
 // Data gradient fused with the first half of the backward of the BatchNorm(+ReLU) whose OUTPUT is this convolution's input:
@@ -870,20 +718,14 @@ extern "C" int regda_conv_dgrad_bf16(const void *dy, const void *wgt, void *dx, 
 extern "C" int regda_conv_dgrad_bnred_bf16(const void *dy, const void *wgt, void *dx, int n, int h, int w, int cin, int cout,
                                            int r, int s, int stride, int pad, int dil, const void *addend, const void *bn_y,
                                            const void *relu_mask, float *red, int groups, void *stream) {
-    if (!regda_conv_dgrad_supported(n, h, w, cin, cout, r, s, stride, pad, dil))
-        return fail(REGDA_ERR_UNSUPPORTED, "conv_dgrad_bnred: shape not covered by the tcgen05 kernel");
+    if (!regda_conv_dgrad_bnred_supported(n, h, w, cin, cout, r, s, stride, pad, dil, groups))
+        return fail(REGDA_ERR_UNSUPPORTED, "conv_dgrad_bnred: shape / statistics groups not covered by the tcgen05 kernel");
     if (!dy || !wgt || !dx || !bn_y || !relu_mask || !red) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_bnred: null pointer");
-    if (groups < 1 || n % groups != 0) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_bnred: groups must divide the batch");
-    if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(wgt) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(bn_y) |
-         reinterpret_cast<uintptr_t>(relu_mask)) & 15)
+    if (!aligned16(dy, wgt, dx) || !aligned16(bn_y, relu_mask, nullptr))
         return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_bnred: tensors must be 16-byte aligned");
     if (addend != nullptr && (reinterpret_cast<uintptr_t>(addend) & 15)) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_bnred: addend must be 16-byte aligned");
-    if (!use_persistent() || !use_tma_epilogue()) return fail(REGDA_ERR_UNSUPPORTED, "conv_dgrad_bnred: needs the persistent TMA-store kernel");
-    const int oh = h + 2 * pad - dil * (r - 1), ow = w + 2 * pad - dil * (s - 1);
     ConvGeom g;
-    geom_init(g, n, oh, ow, cout, cin, r, s, 1, dil * (r - 1) - pad, dil);
-    g.flip = 1;
-    if (g.oh != h || g.ow != w) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_bnred: inconsistent geometry");
+    if (!dgrad_geom(g, n, h, w, cin, cout, r, s, pad, dil)) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_bnred: inconsistent geometry");
     ensure_context(dy);
     BnRed br;
     br.bn_y = bn_y;

@@ -13,9 +13,10 @@
 // lands as 64 K-rows of 128 swizzled bytes; UMMA descriptors: LBO = 8 KB between 64-wide M/N blocks, SBO = 1 KB
 // between 8-row K groups, +2 KB start address per K=16 step.
 //
-// CTA = (128-cout tile, BLOCK_N-cin tile, tap, K split); fp32 accumulators in TMEM; the epilogue adds the tile
-// into the fp32 OHWI gradient with 16-byte global reductions (split-K partials and the two forward passes of a
-// training step accumulate in place).  Warp 0 = TMA, warp 1 = MMA issuer, warps 2-5 = epilogue.
+// Work item = (128-cout tile, BLOCK_N-cin tile, tap, K split); fp32 accumulators in TMEM; the epilogue adds the tile
+// into the fp32 OHWI gradient with TMA reduce-stores (split-K partials and the two forward passes of a training step
+// accumulate in place).  Warp 0 = TMA, warp 1 = MMA issuer, warps 2-9 = epilogue.  Feature maps smaller than 64 pixels
+// (pyramid-pooling branches) put several images into one K-block: box {64 ch, BW, BH, BN}, BN*BH*BW = 64.
 #include <cstdlib>
 #include <cstring>
 
@@ -29,138 +30,15 @@ using namespace tc;
 
 constexpr int kWgM = 128;            // cout tile
 constexpr int kWgK = 64;             // pixels per stage
-constexpr int kWgThreads = 192;
 
 struct WgradGeom {
     int n, h, w, cin, cout, oh, ow;
     int r, s, pad, dil, stride;
-    int bh, bw, tiles_h, tiles_w;    // 64-pixel patches of the OUTPUT image
-    int ksteps;                      // n * tiles_h * tiles_w
+    int bh, bw, bn, tiles_h, tiles_w; // K-block = bn images x (bh x bw) OUTPUT pixels, bn*bh*bw == 64
+    int ksteps;                      // ceil(n / bn) * tiles_h * tiles_w
     int splits, steps_per_split;
     int n_tiles;                     // ceil(cin / BLOCK_N)
 };
-
-template <int BLOCK_N, int STAGES>
-struct WgSmem {
-    static constexpr int kABytes = kWgM * kWgK * 2;        // 16 KB: two 8 KB boxes
-    static constexpr int kBBytes = BLOCK_N * kWgK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarOffset = STAGES * kStageBytes;
-    static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 8;
-};
-
-template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(kWgThreads, 2)
-conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
-                  float *__restrict__ dw, const WgradGeom g) {
-    using L = WgSmem<BLOCK_N, STAGES>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::kBarOffset);
-    uint64_t *empty_bar = full_bar + STAGES;
-    uint64_t *accum_bar = empty_bar + STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-
-    const int n_blk = blockIdx.x % g.n_tiles;             // cin tile
-    const int m_blk = blockIdx.x / g.n_tiles;             // cout tile
-    const int tap = blockIdx.y;
-    const int fr = tap / g.s, fs = tap - fr * g.s;
-    const int k_lo = blockIdx.z * g.steps_per_split;
-    const int k_hi = min(g.ksteps, k_lo + g.steps_per_split);
-    const int num_k = k_hi - k_lo;                        // >= 1 by construction
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tmap_dy);
-        prefetch_tmap(&tmap_x);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-        mbar_init(accum_bar, 1);
-        fence_barrier_init();
-        fence_proxy_async();
-    }
-    if (warp == 2) tmem_alloc(tmem_slot, BLOCK_N);
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (elect_one()) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const int per_img = g.tiles_h * g.tiles_w;
-            for (int kb = k_lo; kb < k_hi; ++kb) {
-                const int img = kb / per_img;
-                const int t = kb - img * per_img;
-                const int th = t / g.tiles_w, tw = t - th * g.tiles_w;
-                const int oh0 = th * g.bh, ow0 = tw * g.bw;
-                mbar_wait(empty_bar + stage, phase ^ 1);
-                uint8_t *sa = smem + stage * L::kStageBytes;
-                uint8_t *sb = sa + L::kABytes;
-                mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes);
-#pragma unroll
-                for (int i = 0; i < kWgM / 64; ++i)
-                    tma_load_4d(sa + i * 8192, &tmap_dy, full_bar + stage, m_blk * kWgM + i * 64, ow0, oh0, img);
-                const int ix = ow0 * g.stride + fs * g.dil - g.pad, iy = oh0 * g.stride + fr * g.dil - g.pad;
-#pragma unroll
-                for (int i = 0; i < BLOCK_N / 64; ++i)
-                    tma_load_4d(sb + i * 8192, &tmap_x, full_bar + stage, n_blk * BLOCK_N + i * 64, ix, iy, img);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else if (warp == 1) {
-        if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(kWgM, BLOCK_N, 1, 1);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int kb = 0; kb < num_k; ++kb) {
-                mbar_wait(full_bar + stage, phase);
-                tc_fence_after_sync();
-                const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-                const uint32_t sb = sa + L::kABytes;
-                const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
-                const uint64_t bdesc = make_smem_desc(sb, 8192, 1024);
-#pragma unroll
-                for (int k = 0; k < kWgK / 16; ++k)
-                    umma_bf16(tmem_base, adesc + static_cast<uint64_t>(128 * k), bdesc + static_cast<uint64_t>(128 * k), idesc,
-                              (kb | k) != 0 ? 1u : 0u);
-                umma_commit(empty_bar + stage);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
-            umma_commit(accum_bar);
-        }
-    } else {
-        // ===== epilogue: TMEM lane = cout row, 32 consecutive cin columns per load =====
-        const int q = warp & 3;
-        const int co = m_blk * kWgM + q * 32 + lane;
-        const int ci0 = n_blk * BLOCK_N;
-        float *dst = dw + (static_cast<size_t>(co) * (g.r * g.s) + tap) * g.cin + ci0;
-        mbar_wait(accum_bar, 0);
-        tc_fence_after_sync();
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), v);
-            tmem_ld_wait();
-            if (co < g.cout && ci0 + c < g.cin) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    red_add_f32x4(dst + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                  __uint_as_float(v[j + 3]));
-            }
-        }
-        tc_fence_before_sync();
-    }
-    __syncthreads();
-    if (warp == 2) {
-        tc_fence_after_sync();
-        tmem_dealloc(tmem_base, BLOCK_N);
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // Persistent variant: one CTA per SM loops over the work items (cout tile, cin tile, tap, K split), ordered so that
@@ -194,10 +72,10 @@ __device__ __forceinline__ WgItem wg_decode(int item, const WgradGeom &g, int m_
 
 constexpr int kWgPersistThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant, half the columns each)
 
-// TMA_EPI: each epilogue warp stages 32 cout rows x 32 cin columns of fp32 in 128B-swizzled shared memory and adds the box
-// to the gradient with ONE TMA reduce-store (cp.reduce.async.bulk.tensor .add: whole 128-byte lines, reduced in L2)
-// instead of 16-byte-per-lane red.global instructions that touch 32 different lines each.
-template <int BLOCK_N, int STAGES, bool TMA_EPI>
+// Epilogue: each warp stages 32 cout rows x 32 cin columns of fp32 in 128B-swizzled shared memory and adds the box to the
+// gradient with ONE TMA reduce-store (cp.reduce.async.bulk.tensor .add: whole 128-byte lines, reduced in L2) instead of
+// 16-byte-per-lane red.global instructions that touch 32 different lines each.
+template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kWgPersistThreads, 1)
 conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                              const __grid_constant__ CUtensorMap tmap_dw,
@@ -218,7 +96,7 @@ conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_dy);
         prefetch_tmap(&tmap_x);
-        if (TMA_EPI) prefetch_tmap(&tmap_dw);
+        prefetch_tmap(&tmap_dw);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
@@ -242,8 +120,9 @@ conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const 
                 const WgItem it = wg_decode(item, g, m_tiles);
                 const int fr = it.tap / g.s, fs = it.tap - fr * g.s;
                 for (int kb = it.k_lo; kb < it.k_hi; ++kb) {
-                    const int img = kb / per_img;
-                    const int t = kb - img * per_img;
+                    const int iblk = kb / per_img;
+                    const int img = iblk * g.bn;                       // first image of the K-block (small maps: bn images per block)
+                    const int t = kb - iblk * per_img;
                     const int th = t / g.tiles_w, tw = t - th * g.tiles_w;
                     const int oh0 = th * g.bh, ow0 = tw * g.bw;
                     mbar_wait(empty_bar + stage, phase ^ 1);
@@ -292,7 +171,7 @@ conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const 
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (TMA_EPI) {
+    } else {
         const int q = warp & 3;
         const int col_lo = ((warp - 2) >> 2) * (BLOCK_N / 2), col_hi = col_lo + BLOCK_N / 2;
         uint8_t *stage_p = smem + L::kStoreOffset + (warp - 2) * 4096;
@@ -335,36 +214,6 @@ conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const 
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (lane == 0) bulk_wait_read0();
-    } else {
-        const int q = warp & 3;
-        const int col_lo = ((warp - 2) >> 2) * (BLOCK_N / 2), col_hi = col_lo + BLOCK_N / 2;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-            const WgItem it = wg_decode(item, g, m_tiles);
-            const int co = it.m_blk * kWgM + q * 32 + lane;
-            const int ci0 = it.n_blk * BLOCK_N;
-            float *dst = dw + (static_cast<size_t>(co) * (g.r * g.s) + it.tap) * g.cin + ci0;
-            mbar_wait(tfull_bar + acc, acc_phase);
-            tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
-#pragma unroll 1
-            for (int c = col_lo; c < col_hi; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
-                tmem_ld_wait();
-                if (co < g.cout && it.k_hi > it.k_lo) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        red_add_f32x4(dst + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                      __uint_as_float(v[j + 3]));
-                }
-            }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar + acc);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        }
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -374,38 +223,19 @@ conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const 
     }
 }
 
-template <int BLOCK_N, int STAGES, bool TMA_EPI>
-int launch_wgrad_persistent_impl(const CUtensorMap &tdy, const CUtensorMap &tx, float *dw, const WgradGeom &g, cudaStream_t st) {
+template <int BLOCK_N, int STAGES>
+int launch_wgrad_persistent(const CUtensorMap &tdy, const CUtensorMap &tx, float *dw, const WgradGeom &g, cudaStream_t st) {
     using L = WgPersistSmem<BLOCK_N, STAGES>;
-    auto kern = conv_wgrad_persistent_kernel<BLOCK_N, STAGES, TMA_EPI>;
+    auto kern = conv_wgrad_persistent_kernel<BLOCK_N, STAGES>;
     const int smem = L::kTotal + 1024;
     static_assert(L::kTotal + 1024 <= 232448, "persistent wgrad kernel: shared memory over the 227 KB limit");
-    CUtensorMap tdw = tdy;        // unused by the direct epilogue
-    if (TMA_EPI && !encode_f32_2d_sw128(&tdw, dw, g.cout, static_cast<long long>(g.r) * g.s * g.cin, 32)) return REGDA_ERR_CUDA;
+    CUtensorMap tdw;
+    if (!encode_f32_2d_sw128(&tdw, dw, g.cout, static_cast<long long>(g.r) * g.s * g.cin, 32)) return REGDA_ERR_CUDA;
     REGDA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int m_tiles = (g.cout + kWgM - 1) / kWgM;
     const int num_items = g.n_tiles * m_tiles * g.r * g.s * g.splits;
     const int grid = std::min(num_items, sm_count());
     REGDA_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kWgPersistThreads), smem, st, tdy, tx, tdw, dw, g, m_tiles, num_items));
-    return REGDA_OK;
-}
-
-template <int BLOCK_N, int STAGES>
-int launch_wgrad_persistent(const CUtensorMap &tdy, const CUtensorMap &tx, float *dw, const WgradGeom &g, cudaStream_t st) {
-    const char *e = getenv("REGDA_CONV_EPILOGUE");          // "direct": per-lane red.global epilogue (A/B comparisons)
-    if (e && strcmp(e, "direct") == 0) return launch_wgrad_persistent_impl<BLOCK_N, STAGES, false>(tdy, tx, dw, g, st);
-    return launch_wgrad_persistent_impl<BLOCK_N, STAGES, true>(tdy, tx, dw, g, st);
-}
-
-template <int BLOCK_N, int STAGES>
-int launch_wgrad(const CUtensorMap &tdy, const CUtensorMap &tx, float *dw, const WgradGeom &g, cudaStream_t st) {
-    using L = WgSmem<BLOCK_N, STAGES>;
-    auto kern = conv_wgrad_kernel<BLOCK_N, STAGES>;
-    const int smem = L::kTotal + 1024;
-    REGDA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const dim3 grid(g.n_tiles * ((g.cout + kWgM - 1) / kWgM), g.r * g.s, g.splits);
-    kern<<<grid, kWgThreads, smem, st>>>(tdy, tx, dw, g);
-    REGDA_LAUNCH_CHECK();
     return REGDA_OK;
 }
 
@@ -418,8 +248,6 @@ extern "C" int regda_conv_wgrad_supported(int n, int h, int w, int cin, int cout
     if (n < 1 || h < 1 || w < 1 || stride < 1 || stride > 2 || r < 1 || s < 1 || r * s > 49 || dil < 1 || pad < 0) return 0;
     if (cin % 64 != 0 || cout % 64 != 0) return 0;
     if (h + 2 * pad < dil * (r - 1) + 1 || w + 2 * pad < dil * (s - 1) + 1) return 0;
-    const int oh = (h + 2 * pad - dil * (r - 1) - 1) / stride + 1, ow = (w + 2 * pad - dil * (s - 1) - 1) / stride + 1;
-    if (static_cast<long long>(oh) * ow < 64) return 0;
     return 1;
 }
 
@@ -437,30 +265,31 @@ extern "C" int regda_conv_wgrad_bf16(const void *dy, const void *x, float *dw, i
     g.ow = (w + 2 * pad - dil * (s - 1) - 1) / stride + 1;
     int bw = 1;
     while (bw * 2 <= g.ow && bw * 2 <= kWgK) bw *= 2;
-    g.bw = bw; g.bh = kWgK / bw;
+    int bh = kWgK / bw, bn = 1;
+    if (static_cast<long long>(g.oh) * g.ow < kWgK) {
+        // small map (pyramid-pooling branches): a K-block of 64 pixels spans several images
+        bh = 1;
+        while (bh * 2 <= g.oh && bw * bh * 2 <= kWgK) bh *= 2;
+        bn = kWgK / (bw * bh);
+    }
+    g.bw = bw; g.bh = bh; g.bn = bn;
     g.tiles_w = (g.ow + g.bw - 1) / g.bw;
     g.tiles_h = (g.oh + g.bh - 1) / g.bh;
-    g.ksteps = n * g.tiles_h * g.tiles_w;
-    const char *kenv = getenv("REGDA_CONV_KERNEL");
-    const bool persistent = !(kenv && strcmp(kenv, "classic") == 0);
-    const int block_n = (persistent && cin % 256 == 0) ? 256 : (cin % 128 == 0 ? 128 : 64);
+    g.ksteps = ((n + bn - 1) / bn) * g.tiles_h * g.tiles_w;
+    const int block_n = cin % 256 == 0 ? 256 : (cin % 128 == 0 ? 128 : 64);
     g.n_tiles = cin / block_n;
     const int tiles = g.n_tiles * ((cout + kWgM - 1) / kWgM) * r * s;
-    // split K so that every SM gets work (persistent: ~2 items per SM; classic: ~4 CTAs per SM), >= 8 K-steps per item
-    int splits = ((persistent ? 2 : 4) * sm_count() + tiles - 1) / tiles;
+    // split K so that every SM gets work (~2 items per SM), >= 8 K-steps per item
+    int splits = (2 * sm_count() + tiles - 1) / tiles;
     splits = std::max(1, std::min(splits, g.ksteps / 8));
     g.steps_per_split = (g.ksteps + splits - 1) / splits;
     g.splits = (g.ksteps + g.steps_per_split - 1) / g.steps_per_split;
     ensure_context(dy);
     CUtensorMap tdy, tx;
-    if (!encode_nhwc(&tdy, dy, n, g.oh, g.ow, cout, g.bw, g.bh, 1)) return REGDA_ERR_CUDA;   /* text set by encode_bf16_sw128 (dy) */
-    if (!encode_nhwc(&tx, x, n, h, w, cin, g.bw, g.bh, stride)) return REGDA_ERR_CUDA;   /* text set by encode_bf16_sw128 (x) */
+    if (!encode_nhwc(&tdy, dy, n, g.oh, g.ow, cout, g.bw, g.bh, 1, g.bn)) return REGDA_ERR_CUDA;   /* text set by encode_bf16_sw128 (dy) */
+    if (!encode_nhwc(&tx, x, n, h, w, cin, g.bw, g.bh, stride, g.bn)) return REGDA_ERR_CUDA;   /* text set by encode_bf16_sw128 (x) */
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (persistent) {
-        if (block_n == 256) return launch_wgrad_persistent<256, 4>(tdy, tx, dw, g, st);
-        if (block_n == 128) return launch_wgrad_persistent<128, 6>(tdy, tx, dw, g, st);
-        return launch_wgrad_persistent<64, 8>(tdy, tx, dw, g, st);
-    }
-    if (block_n == 128) return launch_wgrad<128, 3>(tdy, tx, dw, g, st);
-    return launch_wgrad<64, 4>(tdy, tx, dw, g, st);
+    if (block_n == 256) return launch_wgrad_persistent<256, 4>(tdy, tx, dw, g, st);
+    if (block_n == 128) return launch_wgrad_persistent<128, 6>(tdy, tx, dw, g, st);
+    return launch_wgrad_persistent<64, 8>(tdy, tx, dw, g, st);
 }

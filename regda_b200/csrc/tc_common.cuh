@@ -242,11 +242,11 @@ inline bool encode_f32_2d_sw128(CUtensorMap *m, const void *base, long long rows
     return true;
 }
 
-// NHWC activation map [n][h][w][c] with a {64 ch, bw, bh, 1}-pixel box sampled every `stride` pixels
-inline bool encode_nhwc(CUtensorMap *m, const void *base, int n, int h, int w, int c, int bw, int bh, int stride) {
+// NHWC activation map [n][h][w][c] with a {64 ch, bw, bh, bn}-pixel box (bn images) sampled every `stride` pixels
+inline bool encode_nhwc(CUtensorMap *m, const void *base, int n, int h, int w, int c, int bw, int bh, int stride, int bn = 1) {
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w) * c * 2, static_cast<cuuint64_t>(h) * w * c * 2};
-    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw * stride), static_cast<cuuint32_t>(bh * stride), 1};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw * stride), static_cast<cuuint32_t>(bh * stride), static_cast<cuuint32_t>(bn)};
     const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
     return encode_bf16_sw128(m, base, 4, dims, strides, box, estr);
 }

@@ -21,6 +21,8 @@ import torch.nn.functional as F
 import os
 
 from ..ops.conv import Conv2d
+from ..ops import conv as conv_ops
+from ..ops import head as fhead
 from ..ops import norm as fnorm
 from ..ops import ppm as fppm
 from ..ops import stem as fstem
@@ -167,15 +169,14 @@ class ResNet(nn.Module):
             setattr(self, f"layer{li}", nn.Sequential(*blocks))
 
     def forward(self, x):
-        if FUSED and self.training and fstem.supported(self.conv1, x) and fnorm.supported(x.new_empty((1, 64, 1, 1)), self.bn1):
-            # the 3-channel stem as an explicit patch matrix + 1x1 tcgen05 convolution, statistics from its epilogue
-            y, st = fstem.stem_conv(x, self.conv1.weight, _GROUPS)
-            x = fnorm.bn_act(y, self.bn1, relu=True, groups=_GROUPS, stats=st)
-        elif not self.training and _inference(x) and fstem.supported(self.conv1, x):
-            y, _ = fstem.stem_conv(x, self.conv1.weight, None)
-            x = _bn(y, self.bn1, relu=True)
+        if conv_ops.ENGINE != "cudnn" and fstem.supported(self.conv1, x):
+            # the 3-channel stem as an explicit patch matrix + 1x1 tcgen05 convolution (float32 parity mode: hi/lo-split patch
+            # matrices on the same kernels); in bf16 training the BatchNorm statistics come from its epilogue
+            stats = FUSED and self.training and x.dtype == torch.bfloat16 and fnorm.supported(x.new_empty((1, 64, 1, 1)), self.bn1)
+            y, st = fstem.stem_conv(x, self.conv1.weight, _GROUPS if stats else None)
+            x = fnorm.bn_act(y, self.bn1, relu=True, groups=_GROUPS, stats=st) if stats else _bn(y, self.bn1, relu=True)
         else:
-            x = self.conv1(x)
+            x = self.conv1(x)             # the library baseline (conv_ops.ENGINE == "cudnn"); anything else raises in Conv2d
             x = _bn(x, self.bn1, relu=True)
         x = fnorm.max_pool3s2(x) if FUSED else F.max_pool2d(x, 3, 2, 1)
         return self.layer4(self.layer3(self.layer2(self.layer1(x))))
@@ -230,10 +231,11 @@ class PPMBilinear(nn.Module):
             for s, branch in zip(self.pool_scales, self.ppm):
                 p = pooled[:, off:off + s * s, :].reshape(b, s, s, c).permute(0, 3, 1, 2).to(conv_out.dtype)
                 off += s * s
-                branches.append(branch[3](fnorm.bn_eager(branch[1](p), branch[2], _GROUPS)))
+                # 1x1 conv on the s x s map (several images per tcgen05 M tile) + BatchNorm + ReLU, all hand-written kernels
+                branches.append(_conv_bn(branch[1], branch[2], p, relu=True))
             cat = fppm.upsample_concat(conv_out, branches, self.pool_scales)
             y = _conv_bn(self.conv_last[0], self.conv_last[1], cat, relu=True)
-            return self.conv_last[4](self.conv_last[3](y))
+            return self._classify(y)
         size = conv_out.shape[-2:]
         outs = [conv_out]
         for branch in self.ppm:
@@ -241,7 +243,14 @@ class PPMBilinear(nn.Module):
             outs.append(F.interpolate(t, size, mode="bilinear", align_corners=False))
         y = self.conv_last[0](torch.cat(outs, 1))
         y = self.conv_last[2](fnorm.bn_eager(y, self.conv_last[1], _GROUPS))
-        return self.conv_last[4](self.conv_last[3](y))
+        return self._classify(y)
+
+    def _classify(self, y):
+        """Dropout2d -> 1x1 conv + bias (Encoder.py:39-40): one streaming kernel (ops/head.py), float32 logits out"""
+        drop, cls = self.conv_last[3], self.conv_last[4]
+        if conv_ops.ENGINE != "cudnn" and fhead.supported(y, cls.weight):
+            return fhead.dropout_classifier(y, cls.weight, cls.bias, drop.p, self.training)
+        return cls(drop(y))
 
 
 class Deeplabv2(nn.Module):

@@ -3,11 +3,13 @@
 
 Engines
   tcgen05 : the hand-written sm_100a implicit-GEMM kernels (regda_b200/csrc/conv_tc.cu fprop / dgrad,
-            conv_wgrad.cu) -- bf16 operands, fp32 accumulation in tensor memory, TMA-fed.  Used for
-            every shape `tc.supports_*` accepts ("tcgen05-fwd": forward only, library backward).
-  cudnn   : torch.nn.functional.conv2d (library call).  Baseline and float32 parity runs; also
-            the shapes the tcgen05 kernels do not cover yet (listed in DESIGN.md).
-Select with REGDA_CONV=auto|tcgen05|cudnn (auto: tcgen05 where supported).
+            conv_wgrad.cu) -- bf16 operands, fp32 accumulation in tensor memory, TMA-fed.  bf16 activations run
+            directly; float32 activations (the parity mode) run on the SAME kernels with every operand split into
+            bf16 hi + lo parts (ops/tc.py fprop_f32).  A shape the kernels do not cover RAISES: there is no
+            library fallback on the product path.
+  cudnn   : torch.nn.functional.conv2d (library call) -- only as the measured baseline
+            (bench.py `gpu_library_baseline`, scripts/bench_conv.py) and for A/B tests; never chosen implicitly.
+Select with set_engine("tcgen05" | "cudnn") (REGDA_CONV presets it; "auto" is an alias of "tcgen05").
 """
 from __future__ import annotations
 
@@ -18,8 +20,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-ENGINE = os.environ.get("REGDA_CONV", "auto")
-FUSE_BN_STATS = os.environ.get("REGDA_FUSE_BN_STATS", "1") != "0" and os.environ.get("REGDA_CONV_KERNEL", "") != "classic"
+ENGINE = {"auto": "tcgen05"}.get(os.environ.get("REGDA_CONV", "tcgen05"), os.environ.get("REGDA_CONV", "tcgen05"))
+FUSE_BN_STATS = True          # BatchNorm statistics / backward reductions in the convolution epilogues
 stats = {"tcgen05_fprop": 0, "tcgen05_dgrad": 0, "tcgen05_wgrad": 0, "cudnn": 0}
 
 # Weight gradients are off the backward pass's critical path (only the optimiser reads them), so they are launched on a side
@@ -65,8 +67,8 @@ def join_wgrad_stream():
 
 def set_engine(name: str):
     global ENGINE
-    assert name in ("auto", "tcgen05", "tcgen05-fwd", "cudnn")
-    ENGINE = name
+    assert name in ("auto", "tcgen05", "cudnn")
+    ENGINE = "tcgen05" if name == "auto" else name
 
 
 def _tc():
@@ -92,8 +94,7 @@ class _ConvFn(torch.autograd.Function):
         # x is the output of a BatchNorm+ReLU whose backward reductions this node's dgrad epilogue can do (ops/norm.py BnHandle)
         ctx.bn_handle = None
         if bn_handle is not None and bn_handle.expected > 0:
-            if (ENGINE != "tcgen05-fwd" and FUSE_BN_STATS and os.environ.get("REGDA_CONV_EPILOGUE", "") != "direct"
-                    and tc.supports_dgrad(x.shape, weight.shape, stride, padding, dilation, x.dtype)):
+            if FUSE_BN_STATS and tc.supports_dgrad_bnred(x.shape, weight.shape, stride, padding, dilation, x.dtype, bn_handle.groups):
                 bn_handle.seen += 1
                 ctx.bn_handle = bn_handle
             else:
@@ -124,48 +125,74 @@ class _ConvFn(torch.autograd.Function):
         gy = gy.contiguous(memory_format=torch.channels_last)
         gx = gw = None
         if ctx.needs_input_grad[0]:
-            if ENGINE != "tcgen05-fwd" and tc.supports_dgrad(x.shape, weight.shape, stride, padding, dilation, x.dtype):
-                stats["tcgen05_dgrad"] += 1
-                fuse = g_tap is not None and g_tap.dtype == torch.bfloat16 and FUSE_BN_STATS
-                hd = ctx.bn_handle
-                if hd is not None and hd.fused:
-                    assert g_tap is None or fuse
-                    if hd.red is None:
-                        hd.red, zeroed = capi_zero_take((hd.groups, 2, x.shape[1]), x.device)
-                        if not zeroed:
-                            hd.red.zero_()
-                    gx = tc.dgrad_bnred(gy, w16, x.shape, stride, padding, dilation, g_tap, hd.y, hd.mask, hd.red, hd.groups)
-                    hd.done += 1
-                else:
-                    gx = tc.dgrad(gy, w16, x.shape, stride, padding, dilation, addend=g_tap if fuse else None)
-                    if g_tap is not None and not fuse:
-                        gx = gx + g_tap
+            if not tc.supports_dgrad(x.shape, weight.shape, stride, padding, dilation, x.dtype):
+                raise RuntimeError(f"no tcgen05 data-gradient kernel for conv {tuple(x.shape)} x {tuple(weight.shape)} stride {stride}")
+            stats["tcgen05_dgrad"] += 1
+            fuse = g_tap is not None and g_tap.dtype == torch.bfloat16 and FUSE_BN_STATS
+            hd = ctx.bn_handle
+            if hd is not None and hd.fused:
+                assert g_tap is None or fuse
+                if hd.red is None:
+                    hd.red, zeroed = capi_zero_take((hd.groups, 2, x.shape[1]), x.device)
+                    if not zeroed:
+                        hd.red.zero_()
+                gx = tc.dgrad_bnred(gy, w16, x.shape, stride, padding, dilation, g_tap, hd.y, hd.mask, hd.red, hd.groups)
+                hd.done += 1
             else:
-                stats["cudnn"] += 1
-                gx = torch.ops.aten.convolution_backward(gy, x, w16, None, [stride] * 2, [padding] * 2,
-                                                         [dilation] * 2, False, [0, 0], 1, [True, False, False])[0]
-                if g_tap is not None:
+                gx = tc.dgrad(gy, w16, x.shape, stride, padding, dilation, addend=g_tap if fuse else None)
+                if g_tap is not None and not fuse:
                     gx = gx + g_tap
         if ctx.needs_input_grad[1]:
-            if ENGINE != "tcgen05-fwd" and tc.supports_wgrad(x.shape, weight.shape, stride, padding, dilation, x.dtype):
-                stats["tcgen05_wgrad"] += 1
-                if weight.grad is None:
-                    weight.grad = torch.zeros_like(weight)
-                if _side_active:
-                    key, side = _wgrad_stream(gy.device)
-                    side.wait_stream(torch.cuda.current_stream())           # dY (and the zeroed gradient arena) are ready
-                    with torch.cuda.stream(side):
-                        tc.wgrad_accumulate(gy, x, weight.grad, stride, padding, dilation)
-                    gy.record_stream(side)                                  # the allocator must not recycle dY / x under the kernel
-                    x.record_stream(side)
-                    _side_used.add(key)
-                else:
+            if not tc.supports_wgrad(x.shape, weight.shape, stride, padding, dilation, x.dtype):
+                raise RuntimeError(f"no tcgen05 weight-gradient kernel for conv {tuple(x.shape)} x {tuple(weight.shape)}")
+            stats["tcgen05_wgrad"] += 1
+            if weight.grad is None:
+                weight.grad = torch.zeros_like(weight)
+            if _side_active:
+                key, side = _wgrad_stream(gy.device)
+                side.wait_stream(torch.cuda.current_stream())           # dY (and the zeroed gradient arena) are ready
+                with torch.cuda.stream(side):
                     tc.wgrad_accumulate(gy, x, weight.grad, stride, padding, dilation)
+                gy.record_stream(side)                                  # the allocator must not recycle dY / x under the kernel
+                x.record_stream(side)
+                _side_used.add(key)
             else:
-                stats["cudnn"] += 1
-                gw = torch.ops.aten.convolution_backward(gy, x, w16, None, [stride] * 2, [padding] * 2,
-                                                         [dilation] * 2, False, [0, 0], 1, [False, True, False])[1].float()
+                tc.wgrad_accumulate(gy, x, weight.grad, stride, padding, dilation)
         return gx, gw, None, None, None, None, None, None
+
+
+class _ConvF32Fn(torch.autograd.Function):
+    """float32 parity mode: x float32 channels-last, weight float32 master; every contraction runs on the tcgen05 kernels
+    through the bf16 hi/lo split of ops/tc.py (fprop_f32 / dgrad_f32 / wgrad_accumulate_f32).  The weight gradient is
+    accumulated into weight.grad like the bf16 path."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, padding, dilation):
+        tc = _tc()
+        x = x.contiguous(memory_format=torch.channels_last)
+        ctx.save_for_backward(x)
+        ctx.weight = weight
+        ctx.geom = (stride, padding, dilation)
+        stats["tcgen05_fprop"] += 1
+        return tc.fprop_f32(x, weight, stride, padding, dilation)
+
+    @staticmethod
+    def backward(ctx, gy):
+        tc = _tc()
+        (x,) = ctx.saved_tensors
+        weight = ctx.weight
+        stride, padding, dilation = ctx.geom
+        gy = gy.contiguous(memory_format=torch.channels_last)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            stats["tcgen05_dgrad"] += 1
+            gx = tc.dgrad_f32(gy, weight, x.shape, stride, padding, dilation)
+        if ctx.needs_input_grad[1]:
+            stats["tcgen05_wgrad"] += 1
+            if weight.grad is None:
+                weight.grad = torch.zeros_like(weight)
+            tc.wgrad_accumulate_f32(gy, x, weight.grad, stride, padding, dilation)
+        return gx, None, None, None, None
 
 
 def capi_zero_take(shape, device):
@@ -193,10 +220,10 @@ class Conv2d(nn.Module):
 
     def forward_with_bn_stats(self, x, groups, tap=False):
         """(y, stats[, x_tap]): the convolution plus the BatchNorm statistics of its output from the kernel's epilogue
-        (stats is None when this shape / engine does not run on the tcgen05 kernel); with tap=True also the handle a
-        residual branch should read x through (see _ConvFn.forward)."""
+        (stats is None when the statistics groups do not align with this shape's tiles -- tiny maps -- or on the library
+        engine); with tap=True also the handle a residual branch should read x through (see _ConvFn.forward)."""
         if (ENGINE != "cudnn" and self.bias is None and x.is_cuda and x.dtype == torch.bfloat16 and FUSE_BN_STATS
-                and _tc().supports_fprop(x.shape, self.weight.shape, self.stride, self.padding, self.dilation, x.dtype)):
+                and _tc().supports_fprop_stats(x.shape, self.weight.shape, self.stride, self.padding, self.dilation, x.dtype, groups)):
             return _ConvFn.apply(x, self.weight, self.stride, self.padding, self.dilation, groups, tap, getattr(x, "_bn_handle", None))
         hd = getattr(x, "_bn_handle", None)
         if hd is not None:
@@ -204,23 +231,26 @@ class Conv2d(nn.Module):
         return (self.forward(x), None, x) if tap else (self.forward(x), None)
 
     def forward(self, x):
-        use_tc = False
-        if ENGINE != "cudnn" and x.is_cuda and x.dtype == torch.bfloat16:
-            use_tc = _tc().supports_fprop(x.shape, self.weight.shape, self.stride, self.padding, self.dilation, x.dtype)
-            if ENGINE == "tcgen05" and not use_tc and os.environ.get("REGDA_CONV_STRICT"):
-                raise RuntimeError(f"no tcgen05 kernel for conv {tuple(x.shape)} x {tuple(self.weight.shape)}")
         hd = getattr(x, "_bn_handle", None)
         if hd is not None:
             hd.broken = True                     # plain forward: this consumer does not take part in the fused BatchNorm backward
-        if use_tc:
-            y = _ConvFn.apply(x, self.weight, self.stride, self.padding, self.dilation)
+        geom = (self.stride, self.padding, self.dilation)
+        if ENGINE != "cudnn":
+            # the product path: hand-written kernels or an error -- never a silent library / CPU fallback
+            if not x.is_cuda:
+                raise RuntimeError("regda_b200.Conv2d needs a CUDA tensor (no CPU fallback)")
+            tc = _tc()
+            if x.dtype == torch.bfloat16 and tc.supports_fprop(x.shape, self.weight.shape, *geom, x.dtype):
+                y = _ConvFn.apply(x, self.weight, *geom)
+            elif x.dtype == torch.float32 and tc.supports_f32(x.shape, self.weight.shape, *geom):
+                y = _ConvF32Fn.apply(x, self.weight, *geom)
+            else:
+                raise RuntimeError(f"no tcgen05 kernel for conv {tuple(x.shape)} ({x.dtype}) x {tuple(self.weight.shape)} "
+                                   f"stride {self.stride} (channel counts must be multiples of 64); set_engine('cudnn') is the "
+                                   "library baseline, not a fallback")
             if self.bias is not None:
                 y = y + self.bias.to(y.dtype).view(1, -1, 1, 1)
             return y
         stats["cudnn"] += 1
         b = self.bias.to(x.dtype) if self.bias is not None else None
-        w = self.weight if x.dtype == self.weight.dtype else (getattr(self.weight, "_bf16", None) if x.dtype == torch.bfloat16 and
-                                                             not torch.is_grad_enabled() else None)
-        if w is None:
-            w = self.weight.to(x.dtype)
-        return F.conv2d(x, w, b, self.stride, self.padding, self.dilation)
+        return F.conv2d(x, self.weight.to(x.dtype), b, self.stride, self.padding, self.dilation)

@@ -16,7 +16,7 @@ K_PAD = 192
 
 
 def supported(conv, x) -> bool:
-    return (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] == 3 and conv.in_channels == 3
+    return (x.is_cuda and x.dtype in (torch.bfloat16, torch.float32) and x.dim() == 4 and x.shape[1] == 3 and conv.in_channels == 3
             and conv.out_channels % 64 == 0 and conv.kernel_size == 7 and conv.stride == 2 and conv.padding == 3 and conv.dilation == 1
             and conv.bias is None and not x.requires_grad)
 
@@ -33,13 +33,13 @@ class _StemConvFn(torch.autograd.Function):
         w16 = tc.weight_shadow(weight)                       # bf16 [64,3,7,7] channels-last = OHWI rows of 147
         wp = torch.zeros((cout, K_PAD, 1, 1), dtype=torch.bfloat16, device=x.device).contiguous(memory_format=torch.channels_last)
         wp.view(cout, K_PAD)[:, :147] = w16.permute(0, 2, 3, 1).reshape(cout, 147)
-        if groups is None:                                   # inference: no BatchNorm statistics wanted
-            return tc.fprop(a, wp, 1, 0, 1), None
-        y, stats = tc.fprop(a, wp, 1, 0, 1, groups)
         ctx.save_for_backward(a)
         ctx.weight = weight
-        ctx.mark_non_differentiable(stats)
         ctx.set_materialize_grads(False)
+        if groups is None:                                   # no BatchNorm statistics wanted (inference, un-fused BatchNorm)
+            return tc.fprop(a, wp, 1, 0, 1), None
+        y, stats = tc.fprop(a, wp, 1, 0, 1, groups)
+        ctx.mark_non_differentiable(stats)
         return y, stats
 
     @staticmethod
@@ -61,6 +61,52 @@ class _StemConvFn(torch.autograd.Function):
         return None, None, None
 
 
+def _im2col(x16):
+    n, _, h, w = x16.shape
+    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    x16 = x16 if x16.is_contiguous(memory_format=torch.channels_last) else x16.contiguous(memory_format=torch.channels_last)
+    a = torch.empty((n, K_PAD, oh, ow), dtype=torch.bfloat16, device=x16.device, memory_format=torch.channels_last)
+    capi.call("regda_stem_im2col_bf16", capi.ptr_any(x16), capi.ptr_any(a), n, h, w, capi.stream())
+    return a
+
+
+class _StemConvF32Fn(torch.autograd.Function):
+    """float32 parity mode of the stem: the patch matrix is a pure gather, so im2col(x) = im2col(x_hi) + im2col(x_lo); the
+    1x1 convolution over the 192-wide patches then runs as the hi/lo-split product of ops/tc.py on the tcgen05 kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        cout = weight.shape[0]
+        xh, xl = tc.split_bf16(x)
+        ah, al = _im2col(xh), _im2col(xl)
+        wp = torch.zeros((cout, K_PAD), dtype=torch.float32, device=x.device)
+        wp[:, :147] = weight.detach().permute(0, 2, 3, 1).reshape(cout, 147)
+        wh, wl = tc.split_bf16(wp.view(cout, K_PAD, 1, 1))
+        y = tc.fprop(tc._cat_cl([ah, ah, al], 1), tc._cat_cl([wh, wl, wh], 1), 1, 0, 1, out_f32=True)
+        ctx.save_for_backward(ah, al)
+        ctx.weight = weight
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        ah, al = ctx.saved_tensors
+        weight = ctx.weight
+        cout = weight.shape[0]
+        gh, gl = tc.split_bf16(gy.contiguous(memory_format=torch.channels_last))
+        gw = torch.zeros((cout, K_PAD, 1, 1), dtype=torch.float32, device=gy.device).contiguous(memory_format=torch.channels_last)
+        for g_, a_ in ((gh, ah), (gh, al), (gl, ah)):
+            tc.wgrad_accumulate(tc._nhwc(g_), a_, gw, 1, 0, 1)
+        if weight.grad is None:
+            weight.grad = torch.zeros_like(weight)
+        gview = weight.grad.permute(0, 2, 3, 1).reshape(cout, 147)
+        assert gview.data_ptr() == weight.grad.data_ptr(), "stem weight gradient must live in channels-last (OHWI) memory"
+        gview.add_(gw.view(cout, K_PAD)[:, :147])
+        return None, None
+
+
 def stem_conv(x, weight, groups):
-    """(y, bn_stats): y = conv7x7/2(x, weight) bf16 channels-last, bn_stats float32 [groups][2][cout]"""
+    """(y, bn_stats): y = conv7x7/2(x, weight) channels-last, bn_stats float32 [groups][2][cout] (bf16 input), or
+    (y float32, None) for a float32 input (parity mode: statistics are taken by the BatchNorm that follows)"""
+    if x.dtype == torch.float32:
+        return _StemConvF32Fn.apply(x, weight), None
     return _StemConvFn.apply(x, weight, groups)

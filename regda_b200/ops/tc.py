@@ -28,10 +28,31 @@ def supports_fprop(xshape, wshape, stride, padding, dilation, dtype):
     return bool(capi.lib().regda_conv_fprop_supported(*_geom(xshape, wshape, stride, padding, dilation)))
 
 
-def supports_dgrad(xshape, wshape, stride, padding, dilation, dtype):
+def supports_fprop_stats(xshape, wshape, stride, padding, dilation, dtype, groups):
+    """forward kernel + the BatchNorm statistics of its output for `groups` statistics groups (every M tile in one group)"""
     if dtype != torch.bfloat16:
         return False
-    return bool(capi.lib().regda_conv_dgrad_supported(*_geom(xshape, wshape, stride, padding, dilation)))
+    return bool(capi.lib().regda_conv_fprop_stats_supported(*_geom(xshape, wshape, stride, padding, dilation), groups))
+
+
+def _up2_shape(xshape, wshape, padding, dilation):
+    """(oh1, ow1): the stride-1 output size of the convolution -- the size of the zero-inserted dY of its stride-2 form"""
+    n, cin, h, w = xshape
+    cout, _, r, s = wshape
+    return h + 2 * padding - dilation * (r - 1), w + 2 * padding - dilation * (s - 1)
+
+
+def supports_dgrad(xshape, wshape, stride, padding, dilation, dtype):
+    """stride 2 runs as the stride-1 data gradient of the zero-inserted dY (regda_zero_insert2_bf16)"""
+    if dtype != torch.bfloat16 or stride not in (1, 2):
+        return False
+    return bool(capi.lib().regda_conv_dgrad_supported(*_geom(xshape, wshape, 1, padding, dilation)))
+
+
+def supports_dgrad_bnred(xshape, wshape, stride, padding, dilation, dtype, groups):
+    if dtype != torch.bfloat16 or stride not in (1, 2):
+        return False
+    return bool(capi.lib().regda_conv_dgrad_bnred_supported(*_geom(xshape, wshape, 1, padding, dilation), groups))
 
 
 def supports_wgrad(xshape, wshape, stride, padding, dilation, dtype):
@@ -66,14 +87,20 @@ def out_hw(h, w, r, s, stride, padding, dilation):
     return (h + 2 * padding - dilation * (r - 1) - 1) // stride + 1, (w + 2 * padding - dilation * (s - 1) - 1) // stride + 1
 
 
-def fprop(x, w16, stride, padding, dilation, stats_groups=None):
+def fprop(x, w16, stride, padding, dilation, stats_groups=None, out_f32=False):
     """y = conv(x, w16).  With stats_groups = G the kernel's epilogue also accumulates the train-mode BatchNorm
-    statistics of y (float32 [G][2][cout]: per-group per-channel sum, sum of squares) and (y, stats) is returned."""
+    statistics of y (float32 [G][2][cout]: per-group per-channel sum, sum of squares) and (y, stats) is returned.
+    out_f32: y is the float32 accumulator (regda_conv_fprop_bf16_f32out)."""
     n, cin, h, w = x.shape
     cout, _, r, s = w16.shape
     oh, ow = out_hw(h, w, r, s, stride, padding, dilation)
-    y = torch.empty((n, cout, oh, ow), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    y = torch.empty((n, cout, oh, ow), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device, memory_format=torch.channels_last)
     x, w16 = _nhwc(x), _nhwc(w16)
+    if out_f32:
+        assert stats_groups is None
+        capi.call("regda_conv_fprop_bf16_f32out", capi.ptr_any(x), capi.ptr_any(w16), capi.ptr_any(y), n, h, w, cin, cout, r, s,
+                  stride, padding, dilation, capi.stream())
+        return y
     if stats_groups is None:
         capi.call("regda_conv_fprop_bf16", capi.ptr_any(x), capi.ptr_any(w16), capi.ptr_any(y), n, h, w, cin, cout, r, s,
                   stride, padding, dilation, capi.stream())
@@ -84,18 +111,35 @@ def fprop(x, w16, stride, padding, dilation, stats_groups=None):
     return y, stats
 
 
-def dgrad(gy, w16, xshape, stride, padding, dilation, addend=None):
+def zero_insert2(gy, oh1, ow1):
+    """dY [n,c,oh,ow] of a stride-2 convolution -> [n,c,oh1,ow1] with dY at the even positions and zeros elsewhere"""
+    n, c, oh, ow = gy.shape
+    gy = _nhwc(gy)
+    up = torch.empty((n, c, oh1, ow1), dtype=torch.bfloat16, device=gy.device, memory_format=torch.channels_last)
+    capi.call("regda_zero_insert2_bf16", capi.ptr_any(gy), capi.ptr_any(up), n, oh, ow, oh1, ow1, c, capi.stream())
+    return up
+
+
+def _dgrad_input(gy, xshape, wshape, stride, padding, dilation):
+    if stride == 1:
+        return _nhwc(gy)
+    assert stride == 2
+    return zero_insert2(gy, *_up2_shape(xshape, wshape, padding, dilation))
+
+
+def dgrad(gy, w16, xshape, stride, padding, dilation, addend=None, out_f32=False):
     """dX from dY and the forward weights [O,I,kh,kw] (bf16, channels-last); `addend` (same shape as x) is added in the
-    kernel's epilogue."""
+    kernel's epilogue.  out_f32: dX (and the addend) are float32."""
     n, cin, h, w = xshape
     cout, _, r, s = w16.shape
-    gx = torch.empty((n, cin, h, w), dtype=torch.bfloat16, device=gy.device, memory_format=torch.channels_last)
-    gy, w16 = _nhwc(gy), _nhwc(w16)
+    odt = torch.float32 if out_f32 else torch.bfloat16
+    gx = torch.empty((n, cin, h, w), dtype=odt, device=gy.device, memory_format=torch.channels_last)
+    gy, w16 = _dgrad_input(gy, xshape, w16.shape, stride, padding, dilation), _nhwc(w16)
     if addend is not None:
-        assert tuple(addend.shape) == tuple(xshape) and addend.dtype == torch.bfloat16
+        assert tuple(addend.shape) == tuple(xshape) and addend.dtype == odt
         addend = _nhwc(addend)
-    capi.call("regda_conv_dgrad_bf16", capi.ptr_any(gy), capi.ptr_any(w16), capi.ptr_any(gx), n, h, w, cin, cout, r, s,
-              stride, padding, dilation, capi.ptr_any(addend) if addend is not None else None, capi.stream())
+    capi.call("regda_conv_dgrad_bf16_f32out" if out_f32 else "regda_conv_dgrad_bf16", capi.ptr_any(gy), capi.ptr_any(w16), capi.ptr_any(gx),
+              n, h, w, cin, cout, r, s, 1, padding, dilation, capi.ptr_any(addend) if addend is not None else None, capi.stream())
     return gx
 
 
@@ -105,13 +149,13 @@ def dgrad_bnred(gy, w16, xshape, stride, padding, dilation, addend, bn_y, relu_m
     n, cin, h, w = xshape
     cout, _, r, s = w16.shape
     gx = torch.empty((n, cin, h, w), dtype=torch.bfloat16, device=gy.device, memory_format=torch.channels_last)
-    gy, w16, bn_y = _nhwc(gy), _nhwc(w16), _nhwc(bn_y)
+    gy, w16, bn_y = _dgrad_input(gy, xshape, w16.shape, stride, padding, dilation), _nhwc(w16), _nhwc(bn_y)
     assert tuple(bn_y.shape) == tuple(xshape) and bn_y.dtype == torch.bfloat16 and red.shape == (groups, 2, cin)
     if addend is not None:
         assert tuple(addend.shape) == tuple(xshape) and addend.dtype == torch.bfloat16
         addend = _nhwc(addend)
     capi.call("regda_conv_dgrad_bnred_bf16", capi.ptr_any(gy), capi.ptr_any(w16), capi.ptr_any(gx), n, h, w, cin, cout, r, s,
-              stride, padding, dilation, capi.ptr_any(addend) if addend is not None else None, capi.ptr_any(bn_y),
+              1, padding, dilation, capi.ptr_any(addend) if addend is not None else None, capi.ptr_any(bn_y),
               capi.ptr_any(relu_mask), capi.ptr_any(red), groups, capi.stream())
     return gx
 
@@ -124,3 +168,50 @@ def wgrad_accumulate(gy, x, gw, stride, padding, dilation):
     gy, x = _nhwc(gy), _nhwc(x)
     capi.call("regda_conv_wgrad_bf16", capi.ptr_any(gy), capi.ptr_any(x), capi.ptr_any(gw), n, h, w, cin, cout, r, s,
               stride, padding, dilation, capi.stream())
+
+
+# ---- float32 parity path: every float32 operand as bf16 hi + lo, product = hi*hi + hi*lo + lo*hi --------------------------------
+def split_bf16(t):
+    """float32 t -> (hi, lo) bf16 with t ~ hi + lo to 2^-17 relative"""
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def _cat_cl(parts, dim):
+    return torch.cat(parts, dim=dim).contiguous(memory_format=torch.channels_last)
+
+
+def supports_f32(xshape, wshape, stride, padding, dilation):
+    n, cin, h, w = xshape
+    cout = wshape[0]
+    if cin % 64 or cout % 64 or stride not in (1, 2):
+        return False
+    x3, w3 = (n, 3 * cin, h, w), (cout, 3 * cin, wshape[2], wshape[3])
+    wd = (3 * cout, cin, wshape[2], wshape[3])
+    return (supports_fprop(x3, w3, stride, padding, dilation, torch.bfloat16) and supports_dgrad(xshape, wd, stride, padding, dilation, torch.bfloat16)
+            and supports_wgrad(xshape, wshape, stride, padding, dilation, torch.bfloat16))
+
+
+def fprop_f32(x, weight, stride, padding, dilation):
+    """float32 convolution on the bf16 tensor-core kernel: K runs over the channel triples (x_hi, x_hi, x_lo) . (w_hi, w_lo, w_hi),
+    fp32 accumulation in tensor memory, float32 output.  Dropped term lo*lo ~ 2^-16 of a product: float32-class accuracy."""
+    xh, xl = split_bf16(x)
+    wh, wl = split_bf16(weight.detach())
+    return fprop(_cat_cl([xh, xh, xl], 1), _cat_cl([wh, wl, wh], 1), stride, padding, dilation, out_f32=True)
+
+
+def dgrad_f32(gy, weight, xshape, stride, padding, dilation, addend=None):
+    gh, gl = split_bf16(gy)
+    wh, wl = split_bf16(weight.detach())
+    # reduction over cout: dY triples (hi, hi, lo) against the weights stacked along O as (hi, lo, hi), read MN-major in place
+    return dgrad(_cat_cl([gh, gh, gl], 1), _cat_cl([wh, wl, wh], 0), xshape, stride, padding, dilation, addend=addend, out_f32=True)
+
+
+def wgrad_accumulate_f32(gy, x, gw, stride, padding, dilation):
+    gh, gl = split_bf16(gy)
+    xh, xl = split_bf16(x)
+    gh, gl, xh, xl = (_nhwc(t) for t in (gh, gl, xh, xl))
+    wgrad_accumulate(gh, xh, gw, stride, padding, dilation)
+    wgrad_accumulate(gh, xl, gw, stride, padding, dilation)
+    wgrad_accumulate(gl, xh, gw, stride, padding, dilation)

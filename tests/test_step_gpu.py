@@ -1,8 +1,10 @@
 """GPU: the model and the whole self-training step against golden vectors produced by the
 unmodified reference (tests/golden/model_*.npz, step_resnet50.npz).
 
-float32 compute (parity mode): logits / loss within 1e-3 relative (north_star tolerance);
-bf16 compute (benchmark mode): loss within 3e-2 relative, reported for information."""
+float32 compute (parity mode): logits / loss within 1e-3 relative (north_star tolerance) -- every convolution of this mode
+runs on the hand-written tcgen05 kernels (operands split into bf16 hi + lo parts, ops/tc.py), asserted through the dispatch
+counters: no library convolution takes part;
+bf16 compute (benchmark mode): checked against the bf16-emulating oracle in tests/test_bf16_parity_gpu.py."""
 import numpy as np
 import pytest
 import torch
@@ -38,9 +40,11 @@ def _rel(a, b):
 def test_model_float32_matches_reference(rt):
     from regda_b200.gast.balance import CrossEntropy
     from regda_b200.utils.tools import loss_calc
+    from regda_b200.ops import conv as C
     z = load_golden(f"model_{rt}.npz")
     m = _model(rt, torch.float32)
     x = torch.from_numpy(z["x"]).cuda()
+    before = dict(C.stats)
     m.eval()
     with torch.no_grad():
         p = m(x)
@@ -53,6 +57,12 @@ def test_model_float32_matches_reference(rt):
     assert _rel(feat.detach().cpu(), torch.from_numpy(z["feat"])) < 1e-3
     loss = loss_calc([x1, x2], torch.from_numpy(z["label"]).cuda(), CrossEntropy(-1), multi=True)
     loss.backward()
+    # the 1e-3 gate ran on the repo's own kernels: every convolution (stem, bottlenecks, PPM branches, fuse conv) forward,
+    # data gradient and weight gradient went through tcgen05, none through the library
+    n_convs = sum(1 for mod in m.modules() if isinstance(mod, C.Conv2d)) - 2          # the two classifiers are ops/head.py
+    assert C.stats["cudnn"] == before["cudnn"]
+    assert C.stats["tcgen05_fprop"] - before["tcgen05_fprop"] >= 2 * (n_convs - 1)    # eval + train forward (stem counted apart)
+    assert C.stats["tcgen05_wgrad"] - before["tcgen05_wgrad"] >= n_convs - 1
     assert abs(float(loss) - float(z["loss"])) < 1e-3 * abs(float(z["loss"]))
     names = [str(n) for n in z["grad_names"]]
     got = dict(m.named_parameters())
@@ -86,8 +96,11 @@ def _step_objects(dtype, sync_free=False):
 
 
 def test_full_step_float32_matches_reference():
+    from regda_b200.ops import conv as C
     z, m, al, step, t = _step_objects(torch.float32)
+    before = dict(C.stats)
     outs = [step(*t, 1e-2) for _ in range(2)]
+    assert C.stats["cudnn"] == before["cudnn"] and C.stats["tcgen05_fprop"] > before["tcgen05_fprop"] + 100
     want = z["losses"]
     for it in range(2):
         for k, name in enumerate(("loss", "loss_source", "loss_target", "grad_norm")):
@@ -114,18 +127,30 @@ def test_full_step_bf16_runs_and_stays_close():
 
 
 def test_cuda_graph_replay_matches_eager():
+    """the graph warm-up must leave no trace.  A GraphedStep built with a non-zero warm-up learning rate replays
+    N steps to the same losses, prototypes, BatchNorm running statistics / counters and momentum-driven weights as N eager
+    steps from the same start (bf16 kernels; float atomics in the statistics make the last bits run-dependent)."""
     from regda_b200.trainer import GraphedStep
-    z, m, al, step, t = _step_objects(torch.bfloat16)
+    z, m, al, step, t = _step_objects(torch.bfloat16, sync_free=True)
     z2, m2, al2, step2, t2 = _step_objects(torch.bfloat16, sync_free=True)
-    g = GraphedStep(step2, t2, lr=0.0, warmup=2)        # lr 0 during warm-up/capture: weights only move through replay
-    # graph warm-up ran 3 (2 + capture does not execute) zero-lr steps: BN running stats moved, weights did not
+    w0 = step2.arena.param.clone()
+    g = GraphedStep(step2, t2, lr=1e-2, warmup=3)        # real steps at lr 1e-2 during warm-up: everything must be put back
+    assert torch.equal(step2.arena.param, w0) and float(step2.arena.momentum.abs().max()) == 0.0
+    assert torch.equal(al2.prototypes, al.prototypes)
+    assert int(m2.encoder.resnet.bn1.num_batches_tracked) == 0
     losses_g = [float(g(*t2, lr=1e-2)["loss"]) for _ in range(3)]
     losses_e = [float(step(*t, 1e-2)["loss"]) for _ in range(3)]
-    assert all(np.isfinite(losses_g))
-    # same weights at the start, same data: first replayed loss equals the first eager loss up to
-    # momentum-buffer state of the zero-lr warm-up steps (which do not change parameters)
-    assert abs(losses_g[0] - losses_e[0]) <= 2e-2 * abs(losses_e[0])
-    assert losses_g[2] < losses_g[0] * 1.5
+    for a, b in zip(losses_g, losses_e):
+        assert abs(a - b) <= 3e-3 * abs(b), (losses_g, losses_e)
+    torch.testing.assert_close(al2.prototypes, al.prototypes, rtol=2e-3, atol=1e-5)
+    bn_g, bn_e = m2.encoder.resnet.layer3[0].bn2, m.encoder.resnet.layer3[0].bn2
+    assert int(bn_g.num_batches_tracked) == int(bn_e.num_batches_tracked) == 6        # 3 steps x 2 domain batches
+    torch.testing.assert_close(bn_g.running_mean, bn_e.running_mean, rtol=2e-2, atol=2e-3)
+    torch.testing.assert_close(bn_g.running_var, bn_e.running_var, rtol=2e-2, atol=2e-3)
+    # weights after 3 momentum steps: the first-step rule (buf = g) was reproduced by the replay
+    dw_g = (step2.arena.param - w0)
+    dw_e = (step.arena.param - w0)
+    assert float((dw_g - dw_e).norm()) <= 1e-1 * float(dw_e.norm())
 
 
 def test_state_dict_abi():
