@@ -267,6 +267,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=["step", "lrh", "align"])
     ap.add_argument("--regions", type=int, default=500, help="LRH microbench: regions per tile (50..5000)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="step workload: skip the lrh sub-record and the GPU library baseline")
     args = ap.parse_args()
     rank, world, local = dist_setup(args.gpus)
     import bench_step as step_bench

@@ -22,6 +22,8 @@ import torch
 import torch.nn.functional as F
 
 
+ACC32 = False     # True: convolutions accumulate in float32 (torch CPU order) instead of exactly -- a second, equally valid
+                  # evaluation of the same bf16 function, used to measure the arithmetic's own run-to-run noise floor
 ROUND = True      # False: no rounding at all -- the restatement must then reproduce the reference's float32 goldens (the pin
                   # of this file: tests/test_oracle_golden.py::test_bf16_emulation_without_rounding_is_the_reference)
 
@@ -33,6 +35,8 @@ def r16(t):
 
 def _conv(x, conv):
     w = r16(conv.weight.detach())
+    if ACC32:
+        return r16(F.conv2d(x.float(), w.float(), None, conv.stride, conv.padding, conv.dilation))
     return r16(F.conv2d(x, w, None, conv.stride, conv.padding, conv.dilation))
 
 
@@ -80,17 +84,23 @@ def _head(head, fin, groups):
 
 
 @torch.no_grad()
-def forward_train(model, x, groups=1):
+def forward_train(model, x, groups=1, taps=None):
     """train-mode forward of step_oracle.DeeplabOracle as the bf16 kernels compute it: returns (x1, x2, feat) float32.
     groups = 2 restates Deeplabv2.forward_pair (source and target batch in one tensor, BatchNorm statistics per domain)."""
     rn = model.encoder.resnet
     t = r16(x.double())
     t = _bn_train(_conv(t, rn.conv1), rn.bn1, True, groups=groups)
+    if taps is not None:
+        taps["stem"] = t.float()
     t = F.max_pool2d(t, 3, 2, 1)
-    for layer in (rn.layer1, rn.layer2, rn.layer3, rn.layer4):
-        for blk in layer:
+    for li, layer in enumerate((rn.layer1, rn.layer2, rn.layer3, rn.layer4), start=1):
+        for bi, blk in enumerate(layer):
             t = _bottleneck(blk, t, groups)
+            if taps is not None:
+                taps[f"layer{li}.{bi}"] = t.float()
     fin = _instance_norm(t, model.instance_norm.eps)
     x1 = _head(model.layer5, fin, groups)
     x2 = _head(model.layer6, fin, groups)
+    if taps is not None:
+        taps.update(fin=fin.float(), x1=x1.float(), x2=x2.float())
     return x1.float(), x2.float(), fin.float()

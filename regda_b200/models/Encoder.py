@@ -170,7 +170,7 @@ class ResNet(nn.Module):
 
     def forward(self, x):
         if conv_ops.ENGINE != "cudnn" and fstem.supported(self.conv1, x):
-            # the 3-channel stem as an explicit patch matrix + 1x1 tcgen05 convolution (float32 parity mode: hi/lo-split patch
+            # the 3-channel stem as an explicit patch matrix + 1x1 tcgen05 convolution (float32 parity mode: split-operand patch
             # matrices on the same kernels); in bf16 training the BatchNorm statistics come from its epilogue
             stats = FUSED and self.training and x.dtype == torch.bfloat16 and fnorm.supported(x.new_empty((1, 64, 1, 1)), self.bn1)
             y, st = fstem.stem_conv(x, self.conv1.weight, _GROUPS if stats else None)

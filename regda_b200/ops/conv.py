@@ -5,7 +5,7 @@ Engines
   tcgen05 : the hand-written sm_100a implicit-GEMM kernels (regda_b200/csrc/conv_tc.cu fprop / dgrad,
             conv_wgrad.cu) -- bf16 operands, fp32 accumulation in tensor memory, TMA-fed.  bf16 activations run
             directly; float32 activations (the parity mode) run on the SAME kernels with every operand split into
-            bf16 hi + lo parts (ops/tc.py fprop_f32).  A shape the kernels do not cover RAISES: there is no
+            three bf16 parts (ops/tc.py fprop_f32).  A shape the kernels do not cover RAISES: there is no
             library fallback on the product path.
   cudnn   : torch.nn.functional.conv2d (library call) -- only as the measured baseline
             (bench.py `gpu_library_baseline`, scripts/bench_conv.py) and for A/B tests; never chosen implicitly.
@@ -163,7 +163,7 @@ class _ConvFn(torch.autograd.Function):
 
 class _ConvF32Fn(torch.autograd.Function):
     """float32 parity mode: x float32 channels-last, weight float32 master; every contraction runs on the tcgen05 kernels
-    through the bf16 hi/lo split of ops/tc.py (fprop_f32 / dgrad_f32 / wgrad_accumulate_f32).  The weight gradient is
+    through the three-way bf16 operand split of ops/tc.py (fprop_f32 / dgrad_f32 / wgrad_accumulate_f32).  The weight gradient is
     accumulated into weight.grad like the bf16 path."""
 
     @staticmethod

@@ -72,30 +72,31 @@ def _im2col(x16):
 
 class _StemConvF32Fn(torch.autograd.Function):
     """float32 parity mode of the stem: the patch matrix is a pure gather, so im2col(x) = im2col(x_hi) + im2col(x_lo); the
-    1x1 convolution over the 192-wide patches then runs as the hi/lo-split product of ops/tc.py on the tcgen05 kernels."""
+    1x1 convolution over the 192-wide patches then runs as the split-operand product of ops/tc.py on the tcgen05 kernels."""
 
     @staticmethod
     def forward(ctx, x, weight):
         cout = weight.shape[0]
-        xh, xl = tc.split_bf16(x)
-        ah, al = _im2col(xh), _im2col(xl)
+        ap = [_im2col(t) for t in tc.split_bf16(x)]
         wp = torch.zeros((cout, K_PAD), dtype=torch.float32, device=x.device)
         wp[:, :147] = weight.detach().permute(0, 2, 3, 1).reshape(cout, 147)
-        wh, wl = tc.split_bf16(wp.view(cout, K_PAD, 1, 1))
-        y = tc.fprop(tc._cat_cl([ah, ah, al], 1), tc._cat_cl([wh, wl, wh], 1), 1, 0, 1, out_f32=True)
-        ctx.save_for_backward(ah, al)
+        wps = tc.split_bf16(wp.view(cout, K_PAD, 1, 1))
+        y = (tc.fprop(ap[0], tc._cat_cl([wps[0]], 1), 1, 0, 1, out_f32=True) +
+             tc.fprop(tc._cat_cl([ap[i] for i in tc._A_PARTS], 1), tc._cat_cl([wps[i] for i in tc._W_PARTS], 1), 1, 0, 1, out_f32=True))
+        ctx.save_for_backward(*ap)
         ctx.weight = weight
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        ah, al = ctx.saved_tensors
+        ap = ctx.saved_tensors
         weight = ctx.weight
         cout = weight.shape[0]
-        gh, gl = tc.split_bf16(gy.contiguous(memory_format=torch.channels_last))
+        gp = [tc._nhwc(t) for t in tc.split_bf16(gy.contiguous(memory_format=torch.channels_last))]
         gw = torch.zeros((cout, K_PAD, 1, 1), dtype=torch.float32, device=gy.device).contiguous(memory_format=torch.channels_last)
-        for g_, a_ in ((gh, ah), (gh, al), (gl, ah)):
-            tc.wgrad_accumulate(tc._nhwc(g_), a_, gw, 1, 0, 1)
+        tc.wgrad_accumulate(gp[0], ap[0], gw, 1, 0, 1)
+        for i, j in zip(tc._A_PARTS, tc._W_PARTS):
+            tc.wgrad_accumulate(gp[i], ap[j], gw, 1, 0, 1)
         if weight.grad is None:
             weight.grad = torch.zeros_like(weight)
         gview = weight.grad.permute(0, 2, 3, 1).reshape(cout, 147)

@@ -170,16 +170,35 @@ def wgrad_accumulate(gy, x, gw, stride, padding, dilation):
               stride, padding, dilation, capi.stream())
 
 
-# ---- float32 parity path: every float32 operand as bf16 hi + lo, product = hi*hi + hi*lo + lo*hi --------------------------------
+# ---- float32 parity path: every float32 operand as three bf16 parts, products of the parts accumulated in fp32 -----------------
 def split_bf16(t):
-    """float32 t -> (hi, lo) bf16 with t ~ hi + lo to 2^-17 relative"""
+    """float32 t -> (hi, mid, lo) bf16 with t = hi + mid + lo up to the last bit or two of the 24-bit mantissa"""
     hi = t.to(torch.bfloat16)
-    lo = (t - hi.float()).to(torch.bfloat16)
-    return hi, lo
+    r1 = t - hi.float()
+    mid = r1.to(torch.bfloat16)
+    lo = (r1 - mid.float()).to(torch.bfloat16)
+    return hi, mid, lo
 
 
 def _cat_cl(parts, dim):
     return torch.cat(parts, dim=dim).contiguous(memory_format=torch.channels_last)
+
+
+# Products kept: hi*hi (the main term) and the five cross terms down to 2^-16 of it (hi*mid, mid*hi, mid*mid, hi*lo, lo*hi); the
+# dropped ones are <= 2^-24.  The tensor cores accumulate K in steps of 16 and -- unlike an IEEE fp32 sum -- TRUNCATE when they
+# align an update with a large accumulator: ~2^-25 of the running sum per update, same sign (measured: 1.4e-4 of the output after
+# the 6912 updates of the PPM fuse convolution's K = 36864 x 3, tests/test_conv_gpu.py).  The float32 path therefore (a) keeps
+# the big hi*hi term and the 2^-8-times smaller cross terms in SEPARATE accumulators, and (b) cuts the reduction into chunks of
+# at most kF32MaxK products of the main term per accumulator, summed in IEEE float32 outside the kernel (<= 72 updates: ~2e-6).
+kF32MaxK = 1152
+_A_PARTS = (0, 1, 1, 0, 2)          # activation part of cross term j  (hi, mid, mid, hi, lo)
+_W_PARTS = (1, 0, 1, 2, 0)          # weight part of cross term j      (mid, hi, mid, lo, hi)
+
+
+def _chunks(channels, taps):
+    """channel ranges [lo, hi) (multiples of 64) with (hi - lo) * taps <= kF32MaxK (at least 64 channels)"""
+    step = max(64, (kF32MaxK // taps) // 64 * 64)
+    return [(lo, min(lo + step, channels)) for lo in range(0, channels, step)]
 
 
 def supports_f32(xshape, wshape, stride, padding, dilation):
@@ -187,31 +206,46 @@ def supports_f32(xshape, wshape, stride, padding, dilation):
     cout = wshape[0]
     if cin % 64 or cout % 64 or stride not in (1, 2):
         return False
-    x3, w3 = (n, 3 * cin, h, w), (cout, 3 * cin, wshape[2], wshape[3])
-    wd = (3 * cout, cin, wshape[2], wshape[3])
-    return (supports_fprop(x3, w3, stride, padding, dilation, torch.bfloat16) and supports_dgrad(xshape, wd, stride, padding, dilation, torch.bfloat16)
+    return (supports_fprop(xshape, wshape, stride, padding, dilation, torch.bfloat16) and supports_dgrad(xshape, wshape, stride, padding, dilation, torch.bfloat16)
             and supports_wgrad(xshape, wshape, stride, padding, dilation, torch.bfloat16))
 
 
 def fprop_f32(x, weight, stride, padding, dilation):
-    """float32 convolution on the bf16 tensor-core kernel: K runs over the channel triples (x_hi, x_hi, x_lo) . (w_hi, w_lo, w_hi),
-    fp32 accumulation in tensor memory, float32 output.  Dropped term lo*lo ~ 2^-16 of a product: float32-class accuracy."""
-    xh, xl = split_bf16(x)
-    wh, wl = split_bf16(weight.detach())
-    return fprop(_cat_cl([xh, xh, xl], 1), _cat_cl([wh, wl, wh], 1), stride, padding, dilation, out_f32=True)
+    """float32 convolution on the bf16 tensor-core kernels (see the note above): fp32 accumulation in tensor memory, float32
+    partial outputs added in float32 -- float32-class accuracy with no library convolution."""
+    xp = split_bf16(x)
+    wp = split_bf16(weight.detach())
+    r, s = weight.shape[2], weight.shape[3]
+    y = None
+    for lo, hi in _chunks(x.shape[1], r * s):
+        main = fprop(_cat_cl([xp[0][:, lo:hi]], 1), _cat_cl([wp[0][:, lo:hi]], 1), stride, padding, dilation, out_f32=True)
+        cross = fprop(_cat_cl([xp[i][:, lo:hi] for i in _A_PARTS], 1), _cat_cl([wp[i][:, lo:hi] for i in _W_PARTS], 1), stride, padding,
+                      dilation, out_f32=True)
+        part = main + cross
+        y = part if y is None else y + part
+    return y
 
 
 def dgrad_f32(gy, weight, xshape, stride, padding, dilation, addend=None):
-    gh, gl = split_bf16(gy)
-    wh, wl = split_bf16(weight.detach())
-    # reduction over cout: dY triples (hi, hi, lo) against the weights stacked along O as (hi, lo, hi), read MN-major in place
-    return dgrad(_cat_cl([gh, gh, gl], 1), _cat_cl([wh, wl, wh], 0), xshape, stride, padding, dilation, addend=addend, out_f32=True)
+    """reduction over cout: dY parts against the weight parts stacked along O, read MN-major in place; chunked over cout"""
+    gp = split_bf16(gy)
+    wp = split_bf16(weight.detach())
+    r, s = weight.shape[2], weight.shape[3]
+    gx = addend
+    for lo, hi in _chunks(gy.shape[1], r * s):
+        main = dgrad(_cat_cl([gp[0][:, lo:hi]], 1), _cat_cl([wp[0][lo:hi]], 0), xshape, stride, padding, dilation, out_f32=True)
+        cross = dgrad(_cat_cl([gp[i][:, lo:hi] for i in _A_PARTS], 1), _cat_cl([wp[i][lo:hi] for i in _W_PARTS], 0), xshape, stride, padding,
+                      dilation, out_f32=True)
+        part = main + cross
+        gx = part if gx is None else gx + part
+    return gx
 
 
 def wgrad_accumulate_f32(gy, x, gw, stride, padding, dilation):
-    gh, gl = split_bf16(gy)
-    xh, xl = split_bf16(x)
-    gh, gl, xh, xl = (_nhwc(t) for t in (gh, gl, xh, xl))
-    wgrad_accumulate(gh, xh, gw, stride, padding, dilation)
-    wgrad_accumulate(gh, xl, gw, stride, padding, dilation)
-    wgrad_accumulate(gl, xh, gw, stride, padding, dilation)
+    """pixels are the reduction: the six part products are separate launches that add into gw through the kernel's fp32
+    TMA reduce-stores (IEEE adds in L2); split-K keeps every accumulator short"""
+    gp = [_nhwc(t) for t in split_bf16(gy)]
+    xp = [_nhwc(t) for t in split_bf16(x)]
+    wgrad_accumulate(gp[0], xp[0], gw, stride, padding, dilation)
+    for i, j in zip(_A_PARTS, _W_PARTS):
+        wgrad_accumulate(gp[i], xp[j], gw, stride, padding, dilation)

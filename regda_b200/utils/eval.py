@@ -22,13 +22,15 @@ def _origins(size, tile, stride):
     return out
 
 
-def slide_predict(model, image, num_classes, tile=512, stride=256):
-    """averaged eval-mode probabilities over overlapping tile x tile windows (tools.py:61-97); one window if it fits.
+def slide_predict(model, image, num_classes, tile=512, stride=None):
+    """averaged eval-mode probabilities over 50 %-overlap tile x tile windows (tools.py:61-97: stride = ceil(tile / 2)); one
+    window if it fits.
     (An axis shorter than the tile is taken whole -- the reference pads such a window to the tile size, pad_image
     tools.py:52-57; use utils.tools.pre_slide for that exact behaviour.)"""
     b, _, H, W = image.shape
     if H <= tile and W <= tile:
         return model(image)
+    stride = stride or (tile + 1) // 2
     prob = torch.zeros((b, num_classes, H, W), device=image.device)
     cnt = torch.zeros((1, 1, H, W), device=image.device)
     for y in _origins(H, tile, stride):

@@ -316,9 +316,10 @@ F32 = [(2, 64, 16, 16, 64, 3, 1, 1, 1), (2, 256, 6, 6, 512, 1, 1, 0, 1), (2, 128
 
 @pytest.mark.parametrize("shape", F32, ids=str)
 def test_float32_parity_convolution_on_the_tcgen05_kernels(shape):
-    """compute_dtype=float32: Conv2d runs on the bf16 tensor-core kernels through the hi/lo operand split (hi*hi + hi*lo +
-    lo*hi, fp32 accumulation) -- float32-class accuracy (1e-4 of the output scale; a plain bf16 product is at 1e-2) for the
-    output, the input gradient and the weight gradient, with no library convolution."""
+    """compute_dtype=float32: Conv2d runs on the bf16 tensor-core kernels through the three-way operand split of ops/tc.py (hi*hi
+    in one accumulator, the five cross terms in another, K cut into short chunks because the tensor cores truncate when they
+    align an update with a long accumulation) -- float32-class accuracy (3e-5 of the output scale; a plain bf16 product is at
+    1e-2) for the output, the input gradient and the weight gradient, with no library convolution."""
     from regda_b200.ops import conv as C
     n, cin, h, w, cout, k, stride, pad, dil = shape
     torch.manual_seed(4)
@@ -337,7 +338,7 @@ def test_float32_parity_convolution_on_the_tcgen05_kernels(shape):
     yr.backward(gy.double())
     for name, got, want in (("y", y, yr), ("dx", x.grad, xr.grad), ("dw", m.weight.grad, wr.grad)):
         err = float((got.double() - want).abs().max()) / float(want.abs().max())
-        assert err <= 1e-4, (name, err)
+        assert err <= 3e-5, (name, err)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])

@@ -87,7 +87,9 @@ def test_teacher_pass_bf16_inference_kernels_match_reference_fixture():
     assert capi.launch_count - before > 100, "the eval forward did not run on the hand-written kernels"
     # yardstick: the same bf16 model through the library kernels (torch bf16 convolutions / batch norm), same inputs
     from regda_b200.models import Encoder as E
+    from regda_b200.ops import conv as C
     E.set_fused(False)
+    C.set_engine("cudnn")
     try:
         with torch.no_grad():
             lib = {"tile_tta": tta_predict(m, x[:, :, :64, :64]),
@@ -96,6 +98,7 @@ def test_teacher_pass_bf16_inference_kernels_match_reference_fixture():
                    "slide_small_tta": pre_slide(m, xs, num_classes=6, tile_size=(64, 64), tta=True)}
     finally:
         E.set_fused(True)
+        C.set_engine("tcgen05")
     for k, v in got.items():
         want = torch.from_numpy(z[k])
         err = (v.cpu() - want).abs()

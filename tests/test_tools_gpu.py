@@ -88,6 +88,7 @@ def test_evaluate_sliding_window_geometry():
     exactly as the windows cover it, no duplicated window"""
     from regda_b200.utils.eval import _origins, slide_predict
     assert _origins(192, 512, 256) == [0] and _origins(600, 512, 256) == [0, 88] and _origins(1024, 512, 256) == [0, 256, 512]
+    assert _origins(112, 64, 32) == [0, 32, 48] and _origins(96, 64, 32) == [0, 32]         # the reference's windows (tools.py:66-79)
     calls = []
 
     def fake_model(x):
@@ -100,7 +101,9 @@ def test_evaluate_sliding_window_geometry():
 
 
 def test_weight_shadow_follows_parameter_writes():
-    """the bf16 copy the tcgen05 convolutions read must follow load_state_dict() and EMA apply_shadow()/restore()"""
+    """the bf16 copy the tcgen05 convolutions read must follow load_state_dict() and EMA apply_shadow()/restore().
+    Observed at the output of layer1 in eval mode: convolutions + running-statistics BatchNorm only, so two forwards with the
+    same weights agree bit for bit (further down, InstanceNorm's fp32 atomics make repeated forwards differ in the last bits)."""
     from regda_b200.models.Encoder import Deeplabv2
     from regda_b200.trainer import ParamArena
     from regda_b200.utils.ema import ExponentialMovingAverage
@@ -110,25 +113,35 @@ def test_weight_shadow_follows_parameter_writes():
     m = Deeplabv2(cfg).cuda().eval()
     arena = ParamArena(m)
     x = torch.randn(2, 3, 256, 256, device="cuda")
+    seen = {}
+    m.encoder.resnet.layer1.register_forward_hook(lambda mod, i, o: seen.__setitem__("l1", o.detach().float().clone()))
+
+    def l1():
+        m(x)
+        return seen["l1"]
+
     with torch.no_grad():
-        p0 = m(x).clone()
+        p0 = l1()
+        assert torch.equal(l1(), p0)
         sd = {k: v.clone() for k, v in m.state_dict().items()}
-        sd2 = {k: (v * 1.5 if k.endswith("conv3.weight") or k.endswith("conv_last.0.weight") else v) for k, v in sd.items()}
+        sd2 = {k: (v * 1.5 if k.endswith("conv2.weight") else v) for k, v in sd.items()}
         m.load_state_dict(sd2)
-        p1 = m(x).clone()
-        assert float((p1 - p0).abs().max()) > 1e-4, "forward ignored load_state_dict (stale bf16 weights)"
+        p1 = l1()
+        assert float((p1 - p0).abs().max()) > 1e-2 * float(p0.abs().max()), "forward ignored load_state_dict (stale bf16 weights)"
         m.load_state_dict(sd)
-        assert torch.equal(m(x), p0)
+        assert torch.equal(l1(), p0)
         ema = ExponentialMovingAverage(m, 0.5)
         ema.register()
-        for p in m.parameters():
-            p.mul_(1.5)
+        for n, p in m.named_parameters():
+            if n.endswith("conv2.weight"):
+                p.mul_(1.5)
         arena.sync_shadow()
-        p2 = m(x).clone()
+        p2 = l1()
+        assert not torch.equal(p2, p0)
         ema.apply_shadow()                      # back to the registered (original) weights
-        assert torch.equal(m(x), p0)
+        assert torch.equal(l1(), p0)
         ema.restore()
-        assert torch.equal(m(x), p2)
+        assert torch.equal(l1(), p2)
 
 
 def test_trainer_and_prototype_tools_end_to_end(tmp_path):
