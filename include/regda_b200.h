@@ -91,6 +91,11 @@ int regda_label_refine(const float *feat_nhwc, const float *prototypes,
                        const float *soft_in, float *soft_out,
                        int b, int c, int k, int h, int w, int H, int W, double temp,
                        void *workspace, size_t workspace_bytes, void *stream);
+/* regda_refine_select with the feature rows in bf16 (the model's InstanceNorm kernel writes bf16; float32 arithmetic inside) */
+int regda_refine_select_bf16feat(const void *feat_nhwc_bf16, const float *prototypes, const float *pred1, const float *pred2,
+                                 const float *soft_in, int64_t *hard_out, int b, int c, int k, int h, int w, int H, int W,
+                                 double temp, double cutoff_top, double cutoff_low, int64_t ignore_label,
+                                 void *workspace, size_t workspace_bytes, void *stream);
 int regda_refine_select(const float *feat_nhwc, const float *prototypes,
                         const float *pred1, const float *pred2,
                         const float *soft_in, int64_t *hard_out,
@@ -116,6 +121,9 @@ int regda_downscale_label(const int64_t *label, int64_t *out, int b, int H, int 
                           int n_classes, int64_t ignore_label, double min_ratio,
                           int32_t *flags, void *stream);
 size_t regda_class_sums_workspace_bytes(int64_t n, int c, int k);
+int regda_class_sums_bf16feat(const void *feat_nhwc_bf16, const int64_t *label_ds, float *sums, float *counts,
+                              int64_t n, int c, int k, int64_t ignore_label, int accumulate,
+                              void *workspace, size_t workspace_bytes, void *stream);
 int regda_class_sums(const float *feat_nhwc, const int64_t *label_ds, float *sums, float *counts,
                      int64_t n, int c, int k, int64_t ignore_label, int accumulate,
                      void *workspace, size_t workspace_bytes, void *stream);

@@ -5,6 +5,8 @@
 //
 // Data layout: soft / pred / simi are [b][c][plane] float32 exactly as the reference's NCHW
 // tensors; the feature map is consumed as channels-last rows [b*h*w][k].
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace regda {
@@ -52,31 +54,39 @@ proto_stats_kernel(const float *__restrict__ proto, float *__restrict__ pc, floa
     }
 }
 
+// feature rows are float32 (the reference's feat) or bf16 (the layout the model's InstanceNorm kernel writes: the trainer
+// hands it over without the 200 MB float32 copy); elements 4i .. 4i+3 of a row:
+__device__ __forceinline__ float4 load_row4(const float *x, int i) { return reinterpret_cast<const float4 *>(x)[i]; }
+__device__ __forceinline__ float4 load_row4(const __nv_bfloat16 *x, int i) {
+    const uint2 u = reinterpret_cast<const uint2 *>(x)[i];
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+}
+__device__ __forceinline__ float load_row1(const float *x, int i) { return x[i]; }
+__device__ __forceinline__ float load_row1(const __nv_bfloat16 *x, int i) { return __bfloat162float(x[i]); }
+
 // one warp per feature row.  out_mode 0: dist[n][c];  1: 1/dist written as planes [b][c][hw]
-template <int CMAX>
+template <int CMAX, typename T>
 __global__ void __launch_bounds__(256)
-pearson_kernel(const float *__restrict__ rows, const float *__restrict__ pc, const float *__restrict__ pstd,
+pearson_kernel(const T *__restrict__ rows, const float *__restrict__ pc, const float *__restrict__ pstd,
                float *__restrict__ out, long long n, int c, int k, int hw, int out_mode, float kdiv) {
     const int lane = threadIdx.x & 31;
     const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n) return;
-    const float *x = rows + row * k;
+    const T *x = rows + row * k;
     const bool vec = (k % 4 == 0) && ((reinterpret_cast<uintptr_t>(rows) & 15) == 0);
     float s = 0.f;
     if (vec) {
-        const float4 *x4 = reinterpret_cast<const float4 *>(x);
-        for (int i = lane; i < k / 4; i += 32) { const float4 v = x4[i]; s += (v.x + v.y) + (v.z + v.w); }
+        for (int i = lane; i < k / 4; i += 32) { const float4 v = load_row4(x, i); s += (v.x + v.y) + (v.z + v.w); }
     } else {
-        for (int i = lane; i < k; i += 32) s += x[i];
+        for (int i = lane; i < k; i += 32) s += load_row1(x, i);
     }
     const float mean = warp_sum(s) / static_cast<float>(k);
     float q = 0.f, dot[CMAX];
 #pragma unroll
     for (int j = 0; j < CMAX; ++j) dot[j] = 0.f;
     if (vec) {
-        const float4 *x4 = reinterpret_cast<const float4 *>(x);
         for (int i = lane; i < k / 4; i += 32) {
-            float4 v = x4[i];
+            float4 v = load_row4(x, i);
             v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
             q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
 #pragma unroll
@@ -88,7 +98,7 @@ pearson_kernel(const float *__restrict__ rows, const float *__restrict__ pc, con
         }
     } else {
         for (int i = lane; i < k; i += 32) {
-            const float d = x[i] - mean;
+            const float d = load_row1(x, i) - mean;
             q += d * d;
 #pragma unroll
             for (int j = 0; j < CMAX; ++j)
@@ -338,14 +348,22 @@ RefineWs carve_refine_ws(void *ws, int b, int c, int k, int h, int w) {
     return r;
 }
 
-int launch_pearson(const float *rows, const float *protos, float *pc, float *pstd, float *out, long long n, int c, int k,
+// rows: float32, or bf16 when rows_bf16
+int launch_pearson(const void *rows, bool rows_bf16, const float *protos, float *pc, float *pstd, float *out, long long n, int c, int k,
                    int hw, int out_mode, cudaStream_t st) {
     proto_stats_kernel<<<c, 256, 0, st>>>(protos, pc, pstd, k);
     REGDA_LAUNCH_CHECK();
     const float kdiv = static_cast<float>(static_cast<double>(k - 1) + 1e-7);
     const unsigned blocks = static_cast<unsigned>((n + 7) / 8);
-    if (c <= 8) pearson_kernel<8><<<blocks, 256, 0, st>>>(rows, pc, pstd, out, n, c, k, hw, out_mode, kdiv);
-    else pearson_kernel<16><<<blocks, 256, 0, st>>>(rows, pc, pstd, out, n, c, k, hw, out_mode, kdiv);
+    const float *rf = static_cast<const float *>(rows);
+    const __nv_bfloat16 *rb = static_cast<const __nv_bfloat16 *>(rows);
+    if (rows_bf16) {
+        if (c <= 8) pearson_kernel<8><<<blocks, 256, 0, st>>>(rb, pc, pstd, out, n, c, k, hw, out_mode, kdiv);
+        else pearson_kernel<16><<<blocks, 256, 0, st>>>(rb, pc, pstd, out, n, c, k, hw, out_mode, kdiv);
+    } else {
+        if (c <= 8) pearson_kernel<8><<<blocks, 256, 0, st>>>(rf, pc, pstd, out, n, c, k, hw, out_mode, kdiv);
+        else pearson_kernel<16><<<blocks, 256, 0, st>>>(rf, pc, pstd, out, n, c, k, hw, out_mode, kdiv);
+    }
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
 }
@@ -391,7 +409,7 @@ extern "C" int regda_pearson_dist(const float *rows, const float *prototypes, fl
     if (!workspace || workspace_bytes < regda_pearson_workspace_bytes(c, k)) return fail(REGDA_ERR_WORKSPACE, "pearson_dist: workspace too small");
     float *pc = static_cast<float *>(workspace);
     float *pstd = reinterpret_cast<float *>(static_cast<char *>(workspace) + align_up(static_cast<size_t>(c) * k * 4, 256));
-    return launch_pearson(rows, prototypes, pc, pstd, dist, n, c, k, 1, 0, static_cast<cudaStream_t>(stream));
+    return launch_pearson(rows, false, prototypes, pc, pstd, dist, n, c, k, 1, 0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int regda_label_refine(const float *feat_nhwc, const float *prototypes, const float *pred1, const float *pred2,
@@ -404,7 +422,7 @@ extern "C" int regda_label_refine(const float *feat_nhwc, const float *prototype
     const RefineWs ws = carve_refine_ws(workspace, b, c, k, h, w);
     if (!workspace || workspace_bytes < ws.bytes) return fail(REGDA_ERR_WORKSPACE, "label_refine: workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    rc = launch_pearson(feat_nhwc, prototypes, ws.pc, ws.pstd, ws.simi, static_cast<long long>(b) * h * w, c, k, h * w, 1, st);
+    rc = launch_pearson(feat_nhwc, false, prototypes, ws.pc, ws.pstd, ws.simi, static_cast<long long>(b) * h * w, c, k, h * w, 1, st);
     if (rc) return rc;
     const RefineArgs a = make_refine_args(ws.simi, pred1, pred2, soft_in, c, h, w, H, W, temp);
     const dim3 grid((H * W + kPxThreads - 1) / kPxThreads, b);
@@ -414,10 +432,10 @@ extern "C" int regda_label_refine(const float *feat_nhwc, const float *prototype
     return REGDA_OK;
 }
 
-extern "C" int regda_refine_select(const float *feat_nhwc, const float *prototypes, const float *pred1, const float *pred2,
-                                   const float *soft_in, int64_t *hard_out, int b, int c, int k, int h, int w, int H, int W,
-                                   double temp, double cutoff_top, double cutoff_low, int64_t ignore_label,
-                                   void *workspace, size_t workspace_bytes, void *stream) {
+static int refine_select_impl(const void *feat_nhwc, bool feat_bf16, const float *prototypes, const float *pred1, const float *pred2,
+                              const float *soft_in, int64_t *hard_out, int b, int c, int k, int h, int w, int H, int W,
+                              double temp, double cutoff_top, double cutoff_low, int64_t ignore_label,
+                              void *workspace, size_t workspace_bytes, void *stream) {
     int rc = check_refine_args(b, c, k, h, w, H, W, temp);
     if (rc) return rc;
     if (b == 0) return REGDA_OK;
@@ -425,7 +443,7 @@ extern "C" int regda_refine_select(const float *feat_nhwc, const float *prototyp
     const RefineWs ws = carve_refine_ws(workspace, b, c, k, h, w);
     if (!workspace || workspace_bytes < ws.bytes) return fail(REGDA_ERR_WORKSPACE, "refine_select: workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    rc = launch_pearson(feat_nhwc, prototypes, ws.pc, ws.pstd, ws.simi, static_cast<long long>(b) * h * w, c, k, h * w, 1, st);
+    rc = launch_pearson(feat_nhwc, feat_bf16, prototypes, ws.pc, ws.pstd, ws.simi, static_cast<long long>(b) * h * w, c, k, h * w, 1, st);
     if (rc) return rc;
     REGDA_CUDA_CHECK(cudaMemsetAsync(ws.gmax, 0, static_cast<size_t>(b) * c * 4, st));
     const RefineArgs a = make_refine_args(ws.simi, pred1, pred2, soft_in, c, h, w, H, W, temp);
@@ -444,6 +462,23 @@ extern "C" int regda_refine_select(const float *feat_nhwc, const float *prototyp
     }
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
+}
+
+extern "C" int regda_refine_select(const float *feat_nhwc, const float *prototypes, const float *pred1, const float *pred2,
+                                   const float *soft_in, int64_t *hard_out, int b, int c, int k, int h, int w, int H, int W,
+                                   double temp, double cutoff_top, double cutoff_low, int64_t ignore_label,
+                                   void *workspace, size_t workspace_bytes, void *stream) {
+    return refine_select_impl(feat_nhwc, false, prototypes, pred1, pred2, soft_in, hard_out, b, c, k, h, w, H, W, temp, cutoff_top, cutoff_low,
+                              ignore_label, workspace, workspace_bytes, stream);
+}
+
+// same with the feature rows in bf16 (what the model's InstanceNorm kernel writes; float32 arithmetic inside as before)
+extern "C" int regda_refine_select_bf16feat(const void *feat_nhwc_bf16, const float *prototypes, const float *pred1, const float *pred2,
+                                            const float *soft_in, int64_t *hard_out, int b, int c, int k, int h, int w, int H, int W,
+                                            double temp, double cutoff_top, double cutoff_low, int64_t ignore_label,
+                                            void *workspace, size_t workspace_bytes, void *stream) {
+    return refine_select_impl(feat_nhwc_bf16, true, prototypes, pred1, pred2, soft_in, hard_out, b, c, k, h, w, H, W, temp, cutoff_top, cutoff_low,
+                              ignore_label, workspace, workspace_bytes, stream);
 }
 
 extern "C" size_t regda_select_workspace_bytes(int b, int c) {

@@ -2,6 +2,8 @@
 //   DownscaleLabel.forward            :466-481   (integer majority vote per scale x scale block)
 //   _compute_local_prototypes sums    :300-327   (6-row segmented sum instead of the [n,c,k] temp)
 //   _ema / init_avg                   :435-438, :121-122
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace regda {
@@ -52,9 +54,15 @@ downscale_kernel(const long long *__restrict__ label, long long *__restrict__ ou
 // Segmented sum: rows [n][k] float32 by label in [0,c) -> partial[chunk][c][k] (+ counts).
 // Block = (chunk of rows) x (slab of 4*blockDim columns); per-class float4 accumulators in
 // registers; label is uniform per row so the class test is warp-uniform.
-template <int CMAX>
+__device__ __forceinline__ float4 load_feat4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ float4 load_feat4(const __nv_bfloat16 *p) {
+    const uint2 u = *reinterpret_cast<const uint2 *>(p);
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+}
+
+template <int CMAX, typename T>
 __global__ void __launch_bounds__(256)
-class_sums_partial_kernel(const float *__restrict__ feat, const long long *__restrict__ lab, float *__restrict__ partial,
+class_sums_partial_kernel(const T *__restrict__ feat, const long long *__restrict__ lab, float *__restrict__ partial,
                           float *__restrict__ pcount, long long n, int c, int k, int rows_per_chunk, long long ignore_label) {
     const int chunk = blockIdx.y;
     const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -68,7 +76,7 @@ class_sums_partial_kernel(const float *__restrict__ feat, const long long *__res
         for (long long r = r0; r < r1; ++r) {
             const long long l = lab[r];
             if (l == ignore_label || l < 0 || l >= c) continue;             // (:442-452) ignored rows add nothing
-            const float4 v = *reinterpret_cast<const float4 *>(feat + r * k + col);
+            const float4 v = load_feat4(feat + r * k + col);
 #pragma unroll
             for (int j = 0; j < CMAX; ++j)
                 if (j == static_cast<int>(l)) { acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w; cnt[j] += 1.f; }
@@ -141,12 +149,12 @@ extern "C" size_t regda_class_sums_workspace_bytes(int64_t n, int c, int k) {
     return align_up(nchunks * c * k * 4, 256) + align_up(nchunks * c * 4, 256);
 }
 
-extern "C" int regda_class_sums(const float *feat_nhwc, const int64_t *label_ds, float *sums, float *counts,
-                                int64_t n, int c, int k, int64_t ignore_label, int accumulate,
-                                void *workspace, size_t workspace_bytes, void *stream) {
+static int class_sums_impl(const void *feat_nhwc, bool feat_bf16, const int64_t *label_ds, float *sums, float *counts,
+                           int64_t n, int c, int k, int64_t ignore_label, int accumulate,
+                           void *workspace, size_t workspace_bytes, void *stream) {
     if (n < 0 || c < 1 || k < 1) return fail(REGDA_ERR_INVALID_ARG, "class_sums: bad shape");
     if (c > 16) return fail(REGDA_ERR_UNSUPPORTED, "class_sums: at most 16 classes");
-    if (k % 4 != 0 || (reinterpret_cast<uintptr_t>(feat_nhwc) & 15)) return fail(REGDA_ERR_UNSUPPORTED, "class_sums: k must be a multiple of 4 and rows 16-byte aligned");
+    if (k % 4 != 0 || (reinterpret_cast<uintptr_t>(feat_nhwc) & 15) || (feat_bf16 && k % 8 != 0)) return fail(REGDA_ERR_UNSUPPORTED, "class_sums: k must be a multiple of 4 (bf16 rows: 8) and rows 16-byte aligned");
     if (!sums || !counts) return fail(REGDA_ERR_INVALID_ARG, "class_sums: null output");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n == 0) {
@@ -165,12 +173,32 @@ extern "C" int regda_class_sums(const float *feat_nhwc, const int64_t *label_ds,
     const int threads = 128;
     const dim3 grid((k / 4 + threads - 1) / threads, nchunks);
     const long long *lab = reinterpret_cast<const long long *>(label_ds);
-    if (c <= 8) class_sums_partial_kernel<8><<<grid, threads, 0, st>>>(feat_nhwc, lab, partial, pcount, n, c, k, kRowsPerChunk, ignore_label);
-    else class_sums_partial_kernel<16><<<grid, threads, 0, st>>>(feat_nhwc, lab, partial, pcount, n, c, k, kRowsPerChunk, ignore_label);
+    const float *ff = static_cast<const float *>(feat_nhwc);
+    const __nv_bfloat16 *fb = static_cast<const __nv_bfloat16 *>(feat_nhwc);
+    if (feat_bf16) {
+        if (c <= 8) class_sums_partial_kernel<8><<<grid, threads, 0, st>>>(fb, lab, partial, pcount, n, c, k, kRowsPerChunk, ignore_label);
+        else class_sums_partial_kernel<16><<<grid, threads, 0, st>>>(fb, lab, partial, pcount, n, c, k, kRowsPerChunk, ignore_label);
+    } else {
+        if (c <= 8) class_sums_partial_kernel<8><<<grid, threads, 0, st>>>(ff, lab, partial, pcount, n, c, k, kRowsPerChunk, ignore_label);
+        else class_sums_partial_kernel<16><<<grid, threads, 0, st>>>(ff, lab, partial, pcount, n, c, k, kRowsPerChunk, ignore_label);
+    }
     REGDA_LAUNCH_CHECK();
     class_sums_reduce_kernel<<<(c * k + 255) / 256, 256, 0, st>>>(partial, pcount, sums, counts, nchunks, c, k, accumulate);
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
+}
+
+extern "C" int regda_class_sums(const float *feat_nhwc, const int64_t *label_ds, float *sums, float *counts,
+                                int64_t n, int c, int k, int64_t ignore_label, int accumulate,
+                                void *workspace, size_t workspace_bytes, void *stream) {
+    return class_sums_impl(feat_nhwc, false, label_ds, sums, counts, n, c, k, ignore_label, accumulate, workspace, workspace_bytes, stream);
+}
+
+// same with bf16 feature rows (float32 sums as before)
+extern "C" int regda_class_sums_bf16feat(const void *feat_nhwc_bf16, const int64_t *label_ds, float *sums, float *counts,
+                                         int64_t n, int c, int k, int64_t ignore_label, int accumulate,
+                                         void *workspace, size_t workspace_bytes, void *stream) {
+    return class_sums_impl(feat_nhwc_bf16, true, label_ds, sums, counts, n, c, k, ignore_label, accumulate, workspace, workspace_bytes, stream);
 }
 
 extern "C" int regda_prototype_ema(float *prototypes, const float *sums, const float *counts, int c, int k, double decay, void *stream) {

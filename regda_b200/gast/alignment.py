@@ -16,10 +16,14 @@ import torch.nn as nn
 from .. import capi
 
 
-def _rows(feat):
-    """[b,k,h,w] -> contiguous channels-last rows [b*h*w, k] float32 (no copy for channels_last input)."""
+def _rows(feat, keep_bf16=False):
+    """[b,k,h,w] -> contiguous channels-last rows [b*h*w, k] (no copy for channels_last input): float32, or -- keep_bf16 -- the
+    bf16 rows as they are (the kernels that take them convert on load)"""
     b, k, h, w = feat.shape
-    return feat.detach().float().permute(0, 2, 3, 1).contiguous().view(b * h * w, k)
+    f = feat.detach()
+    if not (keep_bf16 and f.dtype == torch.bfloat16 and k % 8 == 0):
+        f = f.float()
+    return f.permute(0, 2, 3, 1).contiguous().view(b * h * w, k)
 
 
 class DownscaleLabel(nn.Module):
@@ -76,12 +80,12 @@ class Aligner:
 
     # ---- prototypes ----------------------------------------------------------------------
     def _class_sums(self, feat, label_ds, sums, counts, accumulate):
-        rows = _rows(feat)
+        rows = _rows(feat, keep_bf16=True)
         n, k = rows.shape
         lab = label_ds.reshape(-1).contiguous()
         assert lab.numel() == n, "label and feature map disagree"
         ws = capi.workspace.get(capi.lib().regda_class_sums_workspace_bytes(n, self.class_num, k), rows.device)
-        capi.call("regda_class_sums", capi.ptr(rows), capi.ptr(lab), capi.ptr(sums), capi.ptr(counts), n, self.class_num, k,
+        capi.call("regda_class_sums_bf16feat" if rows.dtype == torch.bfloat16 else "regda_class_sums", capi.ptr(rows), capi.ptr(lab), capi.ptr(sums), capi.ptr(counts), n, self.class_num, k,
                   int(self.ignore_label), int(accumulate), capi.ptr(ws), ws.numel(), capi.stream())
 
     def update_prototype(self, feat, label, reduce_fn=None):
@@ -132,7 +136,7 @@ class Aligner:
         capi.call("regda_pearson_dist", capi.ptr(rows), capi.ptr(protos), capi.ptr(out), n, m, k, capi.ptr(ws), ws.numel(), capi.stream())
         return out
 
-    def _refine_inputs(self, feat_t, preds_t, label_t_soft):
+    def _refine_inputs(self, feat_t, preds_t, label_t_soft, keep_bf16=False):
         b, k, h, w = feat_t.shape
         H, W = label_t_soft.shape[-2:]
         if isinstance(preds_t, (list, tuple)):
@@ -140,7 +144,7 @@ class Aligner:
             p1, p2 = preds_t[0].detach().float().contiguous(), preds_t[1].detach().float().contiguous()
         else:
             p1, p2 = preds_t.detach().float().contiguous(), None
-        rows = _rows(feat_t)
+        rows = _rows(feat_t, keep_bf16)
         soft = label_t_soft.detach().float().contiguous()
         c = soft.shape[1]
         assert c == self.class_num == p1.shape[1]
@@ -164,9 +168,9 @@ class Aligner:
     def refine_select(self, feat_t, preds_t, label_t_soft, temp=2.0, cutoff_top=0.8, cutoff_low=0.6):
         """Fused label_refine -> pseudo_selection (tools/train_ssl_reg.py:214-218): returns the hard
         pseudo label [b,H,W] int64 without materialising the refined probabilities."""
-        rows, p1, p2, soft, ws, (b, c, k, h, w, H, W) = self._refine_inputs(feat_t, preds_t, label_t_soft)
+        rows, p1, p2, soft, ws, (b, c, k, h, w, H, W) = self._refine_inputs(feat_t, preds_t, label_t_soft, keep_bf16=True)
         out = torch.empty((b, H, W), dtype=torch.int64, device=soft.device)
-        capi.call("regda_refine_select", capi.ptr(rows), capi.ptr(self.prototypes), capi.ptr(p1), capi.ptr(p2), capi.ptr(soft),
+        capi.call("regda_refine_select_bf16feat" if rows.dtype == torch.bfloat16 else "regda_refine_select", capi.ptr(rows), capi.ptr(self.prototypes), capi.ptr(p1), capi.ptr(p2), capi.ptr(soft),
                   capi.ptr(out), b, c, k, h, w, H, W, float(temp), float(cutoff_top), float(cutoff_low), int(self.ignore_label),
                   capi.ptr(ws), ws.numel(), capi.stream())
         return out

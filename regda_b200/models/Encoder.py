@@ -276,7 +276,7 @@ class Deeplabv2(nn.Module):
     def config(self):
         return self._cfg
 
-    def forward_pair(self, x_s, x_t):
+    def forward_pair(self, x_s, x_t, feat_dtype=None):
         """Train-mode forward of the source and the target batch as ONE tensor (tools/train_ssl_reg.py:210-212 makes two
         calls): every convolution sees twice the rows, BatchNorm keeps one statistics group per domain, so the results
         are those of two separate calls.  Returns ((x1_s, x2_s, feat_s), (x1_t, x2_t, feat_t))."""
@@ -285,19 +285,23 @@ class Deeplabv2(nn.Module):
         b = x_s.shape[0]
         _GROUPS = 2
         try:
-            x1, x2, feat = self.forward(torch.cat([x_s, x_t], 0))
+            x1, x2, feat = self.forward(torch.cat([x_s, x_t], 0), feat_dtype=feat_dtype)
         finally:
             _GROUPS = 1
         return (x1[:b], x2[:b], feat[:b]), (x1[b:], x2[b:], feat[b:])
 
-    def forward(self, x):
+    def forward(self, x, feat_dtype=None):
+        """feat_dtype: dtype of the returned feature map in train mode (default float32, as the reference returns it; the trainer
+        asks for the bf16 tensor the InstanceNorm kernel wrote -- its Aligner kernels read bf16 rows -- which saves a 200 MB
+        float32 copy per step)"""
         xin = x.to(self.compute_dtype).contiguous(memory_format=torch.channels_last)
         feat = self.encoder(xin)
         if self._cfg.is_ins_norm and FUSED and (self.training or not torch.is_grad_enabled()) and fnorm.instance_norm_supported(feat):
             # hand-written path: per-image statistics groups of the BatchNorm kernels, bf16 in / bf16 out; the Aligner's
             # float32 feature view is one conversion of the result
             fin = fnorm.instance_norm(feat, self.instance_norm.eps)
-            feat = fin.float()
+            # (the float32 copy is made on the dense NHWC view: a contiguous, vectorised cast instead of a strided one)
+            feat = fin if (feat_dtype == torch.bfloat16 and self.training) else fin.permute(0, 2, 3, 1).float().permute(0, 3, 1, 2)
         else:
             if self._cfg.is_ins_norm:
                 feat = self.instance_norm(feat.float())      # float32 statistics and output (feeds the Aligner)

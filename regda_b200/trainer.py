@@ -150,7 +150,8 @@ class SelfTrainingStep:
         capi.zero_pool.reset(self.arena.param.device)      # one memset for every small accumulator of the step
         if self.pair_forward and images_s.shape == images_t.shape:
             # both domain batches through the network as one tensor, BatchNorm statistics per domain (models/Encoder.py)
-            (pred_s1, pred_s2, feat_s), (pred_t1, pred_t2, feat_t) = m.forward_pair(images_s, images_t)   # :210-212
+            # (features stay bf16: the Aligner kernels of this step read bf16 rows and nothing differentiates through them)
+            (pred_s1, pred_s2, feat_s), (pred_t1, pred_t2, feat_t) = m.forward_pair(images_s, images_t, feat_dtype=torch.bfloat16)   # :210-212
         else:
             pred_s1, pred_s2, feat_s = m(images_s)                                 # :210
             pred_t1, pred_t2, feat_t = m(images_t)                                 # :212
