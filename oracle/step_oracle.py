@@ -407,8 +407,26 @@ def pcl_loss(prototypes, feat, labels, temperature=8.0, ignore_label=-1):
     return F.cross_entropy(rows @ pr.t() / temperature, lab)
 
 
+def coral_loss(source, target, is_sqrt=False):
+    """CoralLoss.forward (regda/gast/coral.py:26-47): squared Frobenius distance of the two feature covariances / (4 d^2)"""
+    d = source.shape[1]
+    ns, nt = source.shape[0], target.shape[0]
+    xm = torch.mean(source, 0, keepdim=True) - source
+    xc = xm.t() @ xm / (ns - 1)
+    xmt = torch.mean(target, 0, keepdim=True) - target
+    xct = xmt.t() @ xmt / (nt - 1)
+    loss = torch.sum((xc - xct) * (xc - xct))
+    return (loss.sqrt() if is_sqrt else loss) / (4 * d * d)
+
+
+def align_domain(feat_s, feat_t):
+    """Aligner.align_domain (regda/gast/alignment.py:79-84)"""
+    k = feat_s.shape[1]
+    return coral_loss(feat_s.permute(0, 2, 3, 1).reshape(-1, k), feat_t.permute(0, 2, 3, 1).reshape(-1, k))
+
+
 def align_step(state, images_s, label_s, images_t, regs_t, *, class_num=6, ignore_label=-1, percent=0.5, cutoff_top=0.8,
-               cutoff_low=0.6, temp=2.0, decay=0.996, lr=None, max_norm=32.0, sam_refine=True, pcl_temp=8.0):
+               cutoff_low=0.6, temp=2.0, decay=0.996, lr=None, max_norm=32.0, sam_refine=True, pcl_temp=8.0, use_coral=False):
     m = state.model
     m.train()
     if lr is not None:
@@ -429,10 +447,11 @@ def align_step(state, images_s, label_s, images_t, regs_t, *, class_num=6, ignor
     loss_seg = ce_loss_multi([ps1, ps2], label_s, ignore_label)                     # :186
     loss_align = (pcl_loss(state.prototypes, feat_s, label_s_down, pcl_temp, ignore_label) +
                   pcl_loss(state.prototypes, feat_t, label_t, pcl_temp, ignore_label)) * 0.5   # :188-189
-    loss = loss_seg + loss_align
+    loss_domain = align_domain(feat_s, feat_t) if use_coral else 0.0                # :187
+    loss = loss_seg + loss_domain + loss_align
     state.opt.zero_grad()
     loss.backward()                                                                 # :193
     gnorm = torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=max_norm, norm_type=2)
     state.opt.step()
-    return dict(loss=float(loss), loss_seg=float(loss_seg), loss_align=float(loss_align), grad_norm=float(gnorm), hard=hard,
-                label_t=label_t)
+    return dict(loss=float(loss), loss_seg=float(loss_seg), loss_align=float(loss_align), loss_domain=float(loss_domain),
+                grad_norm=float(gnorm), hard=hard, label_t=label_t)

@@ -2,8 +2,8 @@
 self-training path: prototypes state, update_prototype (:86-90), update_avg / init_avg
 (:107-126), label_refine with label_t_sup=None (:194-265), _pearson_dist (:396-423).
 
-The alignment *losses* of the reference (CORAL, whitening, class/instance alignment) belong to
-stages 1-2 and are out of scope; asking for them raises NotImplementedError.
+`align_domain` (CORAL, alignment.py:79-84; stage 2 with --align-domain 1) is gast/coral.py on the tcgen05 kernels; the
+class / instance alignment and whitening losses have no live call site and raise NotImplementedError.
 
 Feature maps are accepted as the reference passes them ([b,k,h,w]); a channels-last tensor
 (the layout the CUDA model produces) is consumed without a copy.
@@ -175,8 +175,20 @@ class Aligner:
                   capi.ptr(ws), ws.numel(), capi.stream())
         return out
 
-    # ---- stage-1/2 alignment losses: out of scope ------------------------------------------
-    def align_domain(self, *a, **k):
-        raise NotImplementedError("CORAL domain alignment belongs to stages 1-2 (out of scope of the stage-3 hot path)")
+    # ---- stage-1/2 alignment losses --------------------------------------------------------
+    def align_domain(self, feat_s, feat_t, precise=False):
+        """alignment.py:79-84: Deep CORAL between the source and the target feature rows (gast/coral.py; the covariance
+        contractions run on the tcgen05 kernels).  precise: float32-accuracy contractions (the float32 parity mode)."""
+        assert feat_s.shape == feat_t.shape, 'tensor "feat_s" has the same shape as tensor "feat_t"'
+        assert len(feat_s.shape) == 4, 'tensor "feat_s" and "feat_t" must have 4 dimensions'
+        from .coral import CoralLoss
+        k = self.feat_channels
+        rows_s = feat_s.permute(0, 2, 3, 1).reshape([-1, k])
+        rows_t = feat_t.permute(0, 2, 3, 1).reshape([-1, k])
+        return CoralLoss(precise=precise)(rows_s, rows_t)
 
-    align_class = align_instance = whiten_class_ware = align_domain
+    def _out_of_scope(self, *a, **k):
+        raise NotImplementedError("class / instance alignment and whitening losses have no call site on the stage-2/3 paths "
+                                  "(regda/gast/alignment.py:128-170 are only reached from dead code)")
+
+    align_class = align_instance = whiten_class_ware = _out_of_scope

@@ -190,12 +190,15 @@ class AlignStep(SelfTrainingStep):
     (:165-167), there is no target segmentation loss, and both domains' features are pulled towards the prototypes by the
     prototype-contrastive loss (:186-189).  `_step_impl(images_s, label_s, images_t, regs_t)` returns
     (loss, loss_seg, loss_align, hard) -- the slots GraphedStep reports as loss / loss_source / loss_target / hard.
-    CORAL (`--align-domain`, default off in the reference) is not part of it."""
+    align_domain=True adds the CORAL loss between the two domains' features (:187, --align-domain 1 as in the shipped
+    recipe runs/regda/run_2potsdam.sh:15); its value is kept in `self.loss_domain`."""
 
-    def __init__(self, *args, pcl_temp=8.0, **kwargs):
+    def __init__(self, *args, pcl_temp=8.0, align_domain=False, **kwargs):
         super().__init__(*args, **kwargs)
         from .loss import PrototypeContrastiveLoss
         self.loss_fn_pcl = PrototypeContrastiveLoss(temperature=pcl_temp, ignore_label=self.ignore_label)
+        self.align_domain = bool(align_domain)
+        self.loss_domain = None
 
     def _step_impl(self, images_s, label_s, images_t, regs_t):
         from .ops import ppm as fppm
@@ -222,6 +225,11 @@ class AlignStep(SelfTrainingStep):
         loss_align = (self.loss_fn_pcl(self.aligner.prototypes, feat_s, label_s_down) +
                       self.loss_fn_pcl(self.aligner.prototypes, feat_t, label_t)) * 0.5                # :188-189
         loss = loss_seg + loss_align
+        if self.align_domain:                                                      # :187
+            precise = getattr(m, "compute_dtype", None) == torch.float32
+            loss_domain = self.aligner.align_domain(feat_s, feat_t, precise=precise)
+            self.loss_domain = loss_domain.detach()
+            loss = loss + loss_domain
         with conv_ops.wgrad_side_stream():
             loss.backward()                                                        # :193
         if self.world_size > 1:
@@ -233,7 +241,7 @@ class AlignStep(SelfTrainingStep):
     def __call__(self, images_s, label_s, images_t, regs_t, lr):
         self.arena.set_lr(lr)
         loss, lseg, lal, hard = self._step_impl(images_s, label_s, images_t, regs_t)
-        return dict(loss=loss, loss_seg=lseg, loss_align=lal, hard=hard, grad_norm=self.arena.grad_norm())
+        return dict(loss=loss, loss_seg=lseg, loss_align=lal, loss_domain=self.loss_domain, hard=hard, grad_norm=self.arena.grad_norm())
 
 
 class GraphedStep:

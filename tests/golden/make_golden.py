@@ -366,6 +366,69 @@ def align_step(ns):
     np.savez_compressed(os.path.join(HERE, "align_step_resnet50.npz"), **d)
 
 
+def coral(ns):
+    """CORAL: the reference's CoralLoss alone with its gradients (regda/gast/coral.py:26-47), and two
+    iterations of the stage-2 step with --align-domain 1 (tools/train_align_reg.py:187; the shipped recipe
+    runs/regda/run_2potsdam.sh:15 turns it on), ResNet-50, 2 + 2 tiles of 64x64."""
+    import torch.nn.functional as tnf
+    from regda.gast.coral import CoralLoss
+    from regda.loss import PrototypeContrastiveLoss
+    g = torch.Generator().manual_seed(SEED + 41)
+    d = {}
+    for k, (nsrc, ntgt, dim, is_sqrt) in enumerate([(96, 96, 128, False), (200, 136, 64, False), (64, 64, 256, True)]):
+        mix = torch.randn(dim, dim, generator=g) / dim ** 0.5
+        src = (torch.randn(nsrc, dim, generator=g) @ mix + 0.3).requires_grad_(True)
+        tgt = (torch.randn(ntgt, dim, generator=g) * 1.3 - 0.2).requires_grad_(True)
+        loss = CoralLoss(is_sqrt=is_sqrt)(src, tgt)
+        loss.backward()
+        d.update({f"loss{k}/src": src.detach().numpy(), f"loss{k}/tgt": tgt.detach().numpy(), f"loss{k}/is_sqrt": np.array(is_sqrt),
+                  f"loss{k}/loss": loss.detach().numpy(), f"loss{k}/dsrc": src.grad.numpy(), f"loss{k}/dtgt": tgt.grad.numpy()})
+    C, hw = 6, 64
+    pcl = PrototypeContrastiveLoss(temperature=8.0, ignore_label=-1)
+    m = ref_loader.build_reference_model(ns, "resnet50", C)
+    m.load_state_dict(so.seeded_state_dict(m, SEED))
+    _no_dropout(m)
+    m.train()
+    al = ns.Aligner(ns.logger, 2048, C, -1, 0.996)
+    proto = torch.randn(C, 2048, generator=g).abs()
+    al.prototypes = proto.clone()
+    hom = ns.Homogenizer(percent=0.5, class_num=C, ignore_label=-1)
+    ce = ns.CrossEntropy(ignore_label=-1, class_balancer=None)
+    opt = torch.optim.SGD(m.parameters(), lr=1e-2, momentum=0.9, weight_decay=5e-4)
+    xs = torch.randn(2, 3, hw, hw, generator=g).clamp(max=1.0)
+    xt = (torch.randn(2, 3, hw, hw, generator=g) * 0.8 + 0.2).clamp(max=1.0)
+    ls = torch.randint(-1, C, (2, hw, hw), generator=g)
+    ls[:, :32, :32] = 2
+    ls[:, 32:, 16:48] = 4
+    regs = blocky_regions(g, 2, hw, hw, 9, 20).unsqueeze(1)
+    d.update(xs=xs.numpy(), xt=xt.numpy(), ls=ls.numpy(), regs=regs.numpy(), proto=proto.numpy())
+    losses = []
+    for it in range(2):
+        ps1, ps2, fs = m(xs)
+        label_s_down = al.update_prototype(fs, ls)
+        pt1, pt2, ft = m(xt)
+        x1 = tnf.interpolate(pt1, xt.shape[-2:], mode='bilinear', align_corners=True)
+        x2 = tnf.interpolate(pt2, xt.shape[-2:], mode='bilinear', align_corners=True)
+        soft = ((x1.softmax(dim=1) + x2.softmax(dim=1)) * 0.5).detach()
+        soft = al.label_refine(None, ft, [pt1, pt2], soft, refine=True, mode="all", temp=2.0)
+        hard = ns.pseudo_selection(soft, cutoff_top=0.8, cutoff_low=0.6, return_type="tensor", ignore_label=-1)
+        hard = hom(hard, regs.squeeze(1))
+        label_t = al.downscale_gt(hard)
+        l_seg = ns.loss_calc([ps1, ps2], ls, loss_fn=ce, multi=True)
+        l_dom = al.align_domain(fs, ft)
+        l_al = (pcl(al.prototypes, fs, label_s_down) + pcl(al.prototypes, ft, label_t)) * 0.5
+        loss = l_seg + l_dom + l_al
+        opt.zero_grad()
+        loss.backward()
+        gn = torch.nn.utils.clip_grad_norm_(filter(lambda p: p.requires_grad, m.parameters()), max_norm=32, norm_type=2)
+        opt.step()
+        losses.append([float(loss), float(l_seg), float(l_al), float(l_dom), float(gn)])
+    d["losses"] = np.array(losses, dtype=np.float64)
+    d["proto_after"] = al.prototypes.numpy()
+    d["conv1_after"] = m.encoder.resnet.conv1.weight.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "coral.npz"), **d)
+
+
 def miou_metric(ns):
     """mIoU through the reference's own PixelMetricIgnore.summary_all (regda/gast/metrics.py:19-65: 5-decimal rounding of the
     per-class figures, class-0 pop for IsprsDA, rounded means) fed as regda/utils/eval.py:43-49 feeds it, on top of the
@@ -406,6 +469,9 @@ if __name__ == "__main__":
     if "--only-align" in sys.argv:
         align_step(ns)
         sys.exit(0)
+    if "--only-coral" in sys.argv:
+        coral(ns)
+        sys.exit(0)
     if "--only-miou" in sys.argv:
         miou_metric(ns)
         sys.exit(0)
@@ -416,6 +482,7 @@ if __name__ == "__main__":
     teacher_pass(ns)
     align_step(ns)
     miou_metric(ns)
+    coral(ns)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -220,3 +220,16 @@ def test_bf16_emulation_without_rounding_is_the_reference():
     # and with rounding it is a different function (bf16 arithmetic drifts by percents on these random weights)
     y1, _, _ = be.forward_train(m, torch.from_numpy(z["x"]))
     assert float((y1 - torch.from_numpy(z["x1"])).abs().max()) > 1e-3 * float(np.abs(z["x1"]).max())
+
+
+def test_coral_oracle_matches_reference():
+    """so.coral_loss (restating regda/gast/coral.py:26-47) against the reference's own CoralLoss outputs and gradients"""
+    z = load_golden("coral.npz")
+    for k in range(3):
+        src = torch.from_numpy(z[f"loss{k}/src"]).requires_grad_(True)
+        tgt = torch.from_numpy(z[f"loss{k}/tgt"]).requires_grad_(True)
+        loss = so.coral_loss(src, tgt, bool(z[f"loss{k}/is_sqrt"]))
+        loss.backward()
+        assert abs(float(loss) - float(z[f"loss{k}/loss"])) <= 1e-6 * abs(float(z[f"loss{k}/loss"]))
+        np.testing.assert_allclose(src.grad.numpy(), z[f"loss{k}/dsrc"], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(tgt.grad.numpy(), z[f"loss{k}/dtgt"], rtol=1e-4, atol=1e-9)

@@ -7,8 +7,9 @@
 
 Per iteration (regda_b200/trainer.py AlignStep): paired source/target forward, prototype EMA from the source features, target
 soft labels from the model's own two heads, label refinement + selection + LRH, source segmentation loss and the
-prototype-contrastive loss on both domains, backward, clip, SGD.  Same flags and meaning as the reference; `--align-domain 1`
-(CORAL, off by default in the reference) and `--ls OhemCrossEntropy` belong to code that is out of scope and are refused.
+prototype-contrastive loss on both domains (+ the CORAL domain loss with `--align-domain 1`, as the shipped recipe
+runs/regda/run_2potsdam.sh:15 sets it), backward, clip, SGD.  Same flags and meaning as the reference; `--ls OhemCrossEntropy`
+belongs to code that is out of scope and is refused.
 Data: synthetic tensors of the reference's shapes (`--data synthetic`), as tools/train_ssl_reg.py."""
 from __future__ import annotations
 
@@ -44,7 +45,7 @@ def parse():
     p.add_argument('--ckpt-model', type=str, default='', help='model ckpt from stage 1 (reference state_dict keys)')
     p.add_argument('--ckpt-proto', type=str, default='', help='prototypes [C,2048] from tools/init_prototypes.py')
     p.add_argument('--gen', type=str2bool, default=1)
-    p.add_argument('--align-domain', type=str2bool, default=0, choices=[False], help='CORAL domain alignment: out of scope')
+    p.add_argument('--align-domain', type=str2bool, default=0, help='CORAL domain alignment (regda/gast/coral.py) between the source and target features')
     p.add_argument('--refine-label', type=str2bool, default=1)
     p.add_argument('--refine-mode', type=str, default='all', choices=['all'])
     p.add_argument('--refine-temp', type=float, default=2.0)
@@ -102,7 +103,7 @@ def main():
     step = AlignStep(model, aligner, hom, class_num=class_num, ignore_label=ignore_label, cutoff_top=cfg.CUTOFF_TOP,
                      cutoff_low=cfg.CUTOFF_LOW, refine_temp=args.refine_temp, sam_refine=args.sam_refine,
                      refine_label=bool(args.refine_label), momentum=cfg.MOMENTUM, weight_decay=cfg.WEIGHT_DECAY,
-                     loss_fn_s=loss_s, world_size=world, pcl_temp=args.pcl_temp)
+                     loss_fn_s=loss_s, world_size=world, pcl_temp=args.pcl_temp, align_domain=bool(args.align_domain))
     use_graph = bool(args.cuda_graph) and not args.bcs
     runner = GraphedStep(step, batch, lr=0.0) if use_graph else None
 
@@ -120,7 +121,8 @@ def main():
             out = step(*batch, lr)
         if i_iter == 0 or (i_iter + 1) % 50 == 0:               # :197-201
             log(f"iter={i_iter + 1}, total={float(out['loss']):.3f}, loss_seg={float(out['loss_seg']):.3f}, "
-                f"loss_align={float(out['loss_align']):.3e}, loss_domain={0.0:.3e} lr={lr:.3e}")
+                f"loss_align={float(out['loss_align']):.3e}, "
+                f"loss_domain={(float(step.loss_domain) if step.loss_domain is not None else 0.0):.3e} lr={lr:.3e}")
             hom.check()
             step.loss_fn_pcl.check()
         if (i_iter + 1) % cfg.EVAL_EVERY == 0 or (i_iter + 1) >= stop_steps:        # :203-211
