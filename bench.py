@@ -266,6 +266,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=["step", "lrh", "align"])
     ap.add_argument("--regions", type=int, default=500, help="LRH microbench: regions per tile (50..5000)")
+    ap.add_argument("--config", default="P", choices=["P", "L"], help="step workload: P = BASELINE.json configs[1] (the headline: ResNet-101, "
+                    "512x512), L = configs[3] (ResNet-50, 7 classes, 1024x1024 tiles, 8 + 8 per GPU; quoted at 2 GPUs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="step workload: skip the lrh sub-record and the GPU library baseline")
     args = ap.parse_args()

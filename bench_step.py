@@ -13,12 +13,26 @@ from regda_b200 import capi, synth
 
 CLASS_NUM, H, W, B = 6, 512, 512, 8
 FLOP_PER_IMG_FWD_BWD = 543.5e9       # 2 * 90.59 GMAC * 3 (R101, 512^2, C=6)
-MODEL_CFG = dict(backbone=dict(resnet_type="resnet101", output_stride=16, pretrained=False), multi_layer=True, cascade=False,
-                 use_ppm=True, ppm=dict(num_classes=CLASS_NUM, use_aux=False, fc_dim=2048), inchannels=2048,
-                 num_classes=CLASS_NUM, is_ins_norm=True)
+# BASELINE.json configs: P = configs[1] (the headline: st.regda.2potsdam, ResNet-101, 6 classes, 8 + 8 tiles of 512x512 per GPU);
+# L = configs[3] (ResNet-50, 7 classes, 1024x1024 tiles, global batch 16 over 2 GPUs = 8 + 8 tiles per GPU: the large-tile stress)
+CONFIGS = {
+    "P": dict(resnet="resnet101", classes=6, hw=(512, 512), batch=8, flop_per_img=543.5e9,
+              name="st.regda.2potsdam (ResNet-101 DeepLab, 6 classes, 512x512 tiles)"),
+    "L": dict(resnet="resnet50", classes=7, hw=(1024, 1024), batch=8, flop_per_img=1706.8e9,
+              name="large-tile stress (ResNet-50 DeepLab, 7 classes, 1024x1024 tiles; BASELINE.json configs[3])"),
+}
 
 
-def build(device, world, resnet="resnet101", use_graph=True, n_regions=200, seed=2333, batch=B, hw=(H, W), stage=3):
+def model_cfg(resnet, classes):
+    return dict(backbone=dict(resnet_type=resnet, output_stride=16, pretrained=False), multi_layer=True, cascade=False,
+                use_ppm=True, ppm=dict(num_classes=classes, use_aux=False, fc_dim=2048), inchannels=2048,
+                num_classes=classes, is_ins_norm=True)
+
+
+MODEL_CFG = model_cfg("resnet101", CLASS_NUM)
+
+
+def build(device, world, resnet="resnet101", use_graph=True, n_regions=200, seed=2333, batch=B, hw=(H, W), stage=3, classes=CLASS_NUM):
     """stage 3: the self-training step (tools/train_ssl_reg.py, the headline workload); stage 2: the alignment step
     (tools/train_align_reg.py) -- same model and shapes, inputs without the offline soft labels"""
     from regda_b200.gast.alignment import Aligner
@@ -26,20 +40,18 @@ def build(device, world, resnet="resnet101", use_graph=True, n_regions=200, seed
     from regda_b200.trainer import AlignStep, GraphedStep, SelfTrainingStep
     from regda_b200.utils.local_region_homog import Homogenizer
     torch.manual_seed(seed)
-    cfg = dict(MODEL_CFG)
-    cfg["backbone"] = dict(cfg["backbone"], resnet_type=resnet)
-    model = Deeplabv2(cfg, compute_dtype=torch.bfloat16).to(device).train()
-    inputs = synth.step_inputs(batch, hw[0], hw[1], CLASS_NUM, n_regions, device=device, seed=seed)
+    model = Deeplabv2(model_cfg(resnet, classes), compute_dtype=torch.bfloat16).to(device).train()
+    inputs = synth.step_inputs(batch, hw[0], hw[1], classes, n_regions, device=device, seed=seed)
     images_s, label_s, images_t, soft_t, regs_t, proto = inputs
-    aligner = Aligner(None, 2048, CLASS_NUM, -1, 0.996, device=device)
+    aligner = Aligner(None, 2048, classes, -1, 0.996, device=device)
     aligner.prototypes = proto.clone()
     bound = int(regs_t.max()) + 1
-    hom = Homogenizer(percent=0.5, class_num=CLASS_NUM, ignore_label=-1, region_bound=bound, strict=False)
+    hom = Homogenizer(percent=0.5, class_num=classes, ignore_label=-1, region_bound=bound, strict=False)
     if stage == 2:
-        step = AlignStep(model, aligner, hom, class_num=CLASS_NUM, ignore_label=-1, world_size=world)
+        step = AlignStep(model, aligner, hom, class_num=classes, ignore_label=-1, world_size=world)
         tensors = [images_s, label_s, images_t, regs_t]
     else:
-        step = SelfTrainingStep(model, aligner, hom, class_num=CLASS_NUM, ignore_label=-1, world_size=world)
+        step = SelfTrainingStep(model, aligner, hom, class_num=classes, ignore_label=-1, world_size=world)
         tensors = [images_s, label_s, images_t, soft_t, regs_t]
     runner = None
     if use_graph:
@@ -151,10 +163,13 @@ def library_baseline(device, steps=5):
         C.set_engine(old[1])
 
 
-def workload_config(stage, imgs, world, use_graph, engine):
+def workload_config(stage, imgs, world, use_graph, engine, config="P"):
     """the `config` object of the bench line; `stage` is the integer the run was BUILT with (3: the headline workload)"""
     assert stage in (2, 3)
-    if stage == 3:
+    if stage == 3 and config == "L":
+        what = ("self-training step (tools/train_ssl_reg.py:198-241) at BASELINE.json configs[3]: ResNet-50 DeepLab (2 PPM heads), 7 classes, "
+                "8 source + 8 target 1024x1024 tiles per GPU, refine+select+LRH+prototype EMA+4 CE+backward+clip+SGD")
+    elif stage == 3:
         what = ("st.regda.2potsdam self-training step (tools/train_ssl_reg.py:198-241): ResNet-101 DeepLab (2 PPM heads), 8 source + 8 target "
                 "512x512 tiles per GPU, refine+select+LRH+prototype EMA+4 CE+backward+clip+SGD")
     else:
@@ -170,7 +185,10 @@ def run(args, rank, world, local, pk, ClockSampler, barrier, max_over_ranks):
     use_graph = os.environ.get("REGDA_GRAPH", "1") != "0"
     calls0 = capi.launch_count
     stage = 2 if getattr(args, "workload", None) == "align" else 3
-    model, step, runner, tensors = build(dev, world, use_graph=use_graph, seed=2333 + rank, stage=stage)
+    cname = getattr(args, "config", "P") or "P"
+    conf = CONFIGS[cname]
+    model, step, runner, tensors = build(dev, world, resnet=conf["resnet"], use_graph=use_graph, seed=2333 + rank, stage=stage,
+                                         batch=conf["batch"], hw=conf["hw"], classes=conf["classes"])
     lr = 1e-2
 
     def one_step(inp):
@@ -204,7 +222,7 @@ def run(args, rank, world, local, pk, ClockSampler, barrier, max_over_ranks):
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
     clocks = sampler.stop() if rank == 0 else None
-    imgs = 2 * B * world
+    imgs = 2 * conf["batch"] * world
     value = imgs / (ms * 1e-3)
 
     # ---- e2e: pinned host inputs -> H2D every step (double-buffered on a copy stream) -> step -> loss D2H
@@ -252,13 +270,14 @@ def run(args, rank, world, local, pk, ClockSampler, barrier, max_over_ranks):
     if rank != 0:
         return
     from regda_b200.ops import conv as convmod
-    flops = FLOP_PER_IMG_FWD_BWD * 2 * B
+    flops = conf["flop_per_img"] * 2 * conf["batch"]
     ach = flops / (ms * 1e-3) / 1e12
     line = {
-        "metric": "train images/sec (512x512, 6-class)", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
+        "metric": "train images/sec (512x512, 6-class)" if cname == "P" else "train images/sec (1024x1024, 7-class)",
+        "value": round(value, 2), "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(stage, imgs, world, use_graph, convmod.ENGINE),
+        "config": workload_config(stage, imgs, world, use_graph, convmod.ENGINE, cname),
         "e2e": {"value": round(imgs / (e2e_ms * 1e-3), 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(calls_per_step) * args.steps,
         "roofline": top_kernel_roofline(pk),
@@ -268,14 +287,14 @@ def run(args, rank, world, local, pk, ClockSampler, barrier, max_over_ranks):
     }
     # the dominant kernel explains the ceiling; the whole step is what the metric is made of: both live in `roofline`
     line["roofline"]["whole_step"] = {"achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_sustained"], 4),
-                                      "note": "8.70 TFLOP algorithmic conv work (543.5 GFLOP/img fwd+bwd, SURVEY.md 8d) per 16-image step / step time, "
-                                              "sustained bf16 peak"}
-    if world == 1 and stage == 3 and not getattr(args, "no_extras", False):
+                                      "note": f"{flops / 1e12:.2f} TFLOP algorithmic conv work ({conf['flop_per_img'] / 1e9:.1f} GFLOP/img fwd+bwd, SURVEY.md 8d) "
+                                              "per 16-image step / step time, sustained bf16 peak"}
+    if world == 1 and stage == 3 and cname == "P" and not getattr(args, "no_extras", False):
         del model, step, runner, tensors, bufs, host
         torch.cuda.empty_cache()
         line["lrh"] = lrh_subrecords(pk, dev)
         line["gpu_library_baseline"] = library_baseline(dev)
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and cname == "P":
         line["cpu_baseline"] = cpu_step_baseline(reps=2)
     print(json.dumps(line), flush=True)
 

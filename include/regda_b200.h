@@ -295,6 +295,8 @@ int regda_upsample_softmax_mean(const float *x1, const float *x2, float *out, in
  * -> a bf16 [n][oh][ow][192], k = (r*7 + s)*3 + c for the 147 taps, zeros above; the stem then runs on the tcgen05 kernels
  * as a 1x1 convolution over 192 channels (forward + weight gradient). */
 int regda_stem_im2col_bf16(const void *x, void *a, int n, int h, int w, void *stream);
+/* same patch matrix straight from the loader's float32 [n][3][h][w] image (rounded to bf16 while staged) */
+int regda_stem_im2col_f32nchw(const float *x, void *a, int n, int h, int w, void *stream);
 
 /* MaxPool2d(3, stride 2, padding 1) over channels-last bf16 (regda/_resnets.py:153): x [n][h][w][c] -> y [n][oh][ow][c],
  * oh = (h-1)/2+1; argmax_u8 (may be NULL for inference) [n][oh][ow][c] receives the position 0..8 of the first maximum

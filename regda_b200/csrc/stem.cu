@@ -22,8 +22,11 @@ constexpr int kStemRow = (2 * kStemSeg + 5) * 3 + 1; // staged input elements pe
 // One block = 64 consecutive output pixels of one output row: the 7 input rows x 133 input pixels they read are staged in
 // shared memory with coalesced loads (zero outside the image), then every thread emits 16-byte chunks of the patch matrix
 // (fully coalesced 384-byte rows); tap k of pixel p reads staged element tab[k] + 6*p.
+// F32_NCHW: the image is the float32 [n][3][h][w] tensor the data loader delivers (regda/datasets: CHW float images); it is
+// rounded to bf16 while it is staged, so the separate NCHW float32 -> NHWC bf16 conversion pass over the batch disappears.
+template <bool F32_NCHW>
 __global__ void __launch_bounds__(256)
-stem_im2col_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restrict__ a, int n, int h, int w, int oh, int ow, int segs) {
+stem_im2col_kernel(const void *__restrict__ xv, __nv_bfloat16 *__restrict__ a, int n, int h, int w, int oh, int ow, int segs) {
     __shared__ unsigned short sin[7 * kStemRow];
     __shared__ unsigned short tab[kStemK];
     int b = blockIdx.x;
@@ -32,19 +35,34 @@ stem_im2col_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restric
     const int img = b / oh;
     const int ox0 = seg * kStemSeg;
     const int ix_start = 2 * ox0 - 3;
-    const unsigned short *xi = reinterpret_cast<const unsigned short *>(x) + static_cast<long long>(img) * h * w * 3;
     for (int k = threadIdx.x; k < kStemK; k += 256) {
         const int r = k / 21, jj = k - r * 21;
         tab[k] = static_cast<unsigned short>(k < kStemTaps ? r * kStemRow + jj : 7 * kStemRow - 1);   // padding taps read a zeroed slot
     }
-    for (int e = threadIdx.x; e < 7 * kStemRow; e += 256) {
-        const int r = e / kStemRow, c = e - r * kStemRow;
-        const int iy = 2 * oy - 3 + r;
-        const int px = c / 3;
-        const int ix = ix_start + px;
-        unsigned short v = 0;
-        if (c < kStemRow - 1 && iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(xi + (static_cast<long long>(iy) * w + ix_start) * 3 + c);
-        sin[e] = v;
+    if (F32_NCHW) {
+        // one plane row at a time (coalesced float loads): element (r, ch, px) -> staged slot r*kStemRow + px*3 + ch
+        const float *xi = static_cast<const float *>(xv) + static_cast<long long>(img) * 3 * h * w;
+        constexpr int kPx = (kStemRow - 1) / 3;
+        for (int e = threadIdx.x; e < 7 * 3 * kPx; e += 256) {
+            const int r = e / (3 * kPx), rem = e - r * (3 * kPx);
+            const int ch = rem / kPx, px = rem - ch * kPx;
+            const int iy = 2 * oy - 3 + r, ix = ix_start + px;
+            float v = 0.f;
+            if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(xi + (static_cast<long long>(ch) * h + iy) * w + ix);
+            sin[r * kStemRow + px * 3 + ch] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+        }
+        if (threadIdx.x < 7) sin[threadIdx.x * kStemRow + kStemRow - 1] = 0;
+    } else {
+        const unsigned short *xi = static_cast<const unsigned short *>(xv) + static_cast<long long>(img) * h * w * 3;
+        for (int e = threadIdx.x; e < 7 * kStemRow; e += 256) {
+            const int r = e / kStemRow, c = e - r * kStemRow;
+            const int iy = 2 * oy - 3 + r;
+            const int px = c / 3;
+            const int ix = ix_start + px;
+            unsigned short v = 0;
+            if (c < kStemRow - 1 && iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(xi + (static_cast<long long>(iy) * w + ix_start) * 3 + c);
+            sin[e] = v;
+        }
     }
     __syncthreads();
     const int npx = min(kStemSeg, ow - ox0);
@@ -70,16 +88,27 @@ stem_im2col_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restric
 
 using namespace regda;
 
-// x bf16 [n][h][w][3] (channels-last image), a bf16 [n][oh][ow][192] with oh = (h-1)/2+1, ow = (w-1)/2+1
-extern "C" int regda_stem_im2col_bf16(const void *x, void *a, int n, int h, int w, void *stream) {
+static int stem_im2col(const void *x, bool f32_nchw, void *a, int n, int h, int w, void *stream) {
     if (!x || !a || n < 1 || h < 1 || w < 1) return fail(REGDA_ERR_INVALID_ARG, "stem_im2col: bad arguments");
     if (reinterpret_cast<uintptr_t>(a) & 15) return fail(REGDA_ERR_INVALID_ARG, "stem_im2col: output must be 16-byte aligned");
     const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
     const int segs = (ow + kStemSeg - 1) / kStemSeg;
     const long long blocks = static_cast<long long>(n) * oh * segs;
     if (blocks > 0x7fffffffll) return fail(REGDA_ERR_UNSUPPORTED, "stem_im2col: too many output rows for one launch");
-    stem_im2col_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16 *>(x), static_cast<__nv_bfloat16 *>(a), n, h, w, oh, ow, segs);
+    if (f32_nchw)
+        stem_im2col_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16 *>(a), n, h, w, oh, ow, segs);
+    else
+        stem_im2col_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16 *>(a), n, h, w, oh, ow, segs);
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
+}
+
+// x bf16 [n][h][w][3] (channels-last image), a bf16 [n][oh][ow][192] with oh = (h-1)/2+1, ow = (w-1)/2+1
+extern "C" int regda_stem_im2col_bf16(const void *x, void *a, int n, int h, int w, void *stream) {
+    return stem_im2col(x, false, a, n, h, w, stream);
+}
+
+// x float32 [n][3][h][w] (the loader's NCHW image), rounded to bf16 on the way: same patch matrix as the bf16 form of bf16(x)
+extern "C" int regda_stem_im2col_f32nchw(const float *x, void *a, int n, int h, int w, void *stream) {
+    return stem_im2col(x, true, a, n, h, w, stream);
 }

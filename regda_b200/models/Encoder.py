@@ -168,12 +168,15 @@ class ResNet(nn.Module):
                 inplanes = planes * 4
             setattr(self, f"layer{li}", nn.Sequential(*blocks))
 
-    def forward(self, x):
+    def forward(self, x, compute_dtype=None):
+        """x: the image in the compute dtype, or -- compute_dtype = bf16 -- still the loader's float32 NCHW tensor (the stem's
+        patch kernel rounds it on the way, saving the layout / dtype conversion pass)"""
+        cdt = compute_dtype or x.dtype
         if conv_ops.ENGINE != "cudnn" and fstem.supported(self.conv1, x):
             # the 3-channel stem as an explicit patch matrix + 1x1 tcgen05 convolution (float32 parity mode: split-operand patch
             # matrices on the same kernels); in bf16 training the BatchNorm statistics come from its epilogue
-            stats = FUSED and self.training and x.dtype == torch.bfloat16 and fnorm.supported(x.new_empty((1, 64, 1, 1)), self.bn1)
-            y, st = fstem.stem_conv(x, self.conv1.weight, _GROUPS if stats else None)
+            stats = FUSED and self.training and cdt == torch.bfloat16 and fnorm.supported(x.new_empty((1, 64, 1, 1), dtype=cdt), self.bn1)
+            y, st = fstem.stem_conv(x, self.conv1.weight, _GROUPS if stats else None, cdt)
             x = fnorm.bn_act(y, self.bn1, relu=True, groups=_GROUPS, stats=st) if stats else _bn(y, self.bn1, relu=True)
         else:
             x = self.conv1(x)             # the library baseline (conv_ops.ENGINE == "cudnn"); anything else raises in Conv2d
@@ -196,8 +199,8 @@ class ResNetEncoder(nn.Module):
             raise ValueError("only output_stride=16 is on the self-training path")
         self.resnet = ResNet(rt)
 
-    def forward(self, x):
-        return self.resnet(x)
+    def forward(self, x, compute_dtype=None):
+        return self.resnet(x, compute_dtype)
 
 
 class PPMBilinear(nn.Module):
@@ -294,8 +297,12 @@ class Deeplabv2(nn.Module):
         """feat_dtype: dtype of the returned feature map in train mode (default float32, as the reference returns it; the trainer
         asks for the bf16 tensor the InstanceNorm kernel wrote -- its Aligner kernels read bf16 rows -- which saves a 200 MB
         float32 copy per step)"""
-        xin = x.to(self.compute_dtype).contiguous(memory_format=torch.channels_last)
-        feat = self.encoder(xin)
+        if (self.compute_dtype == torch.bfloat16 and x.dtype == torch.float32 and x.is_cuda and conv_ops.ENGINE != "cudnn"
+                and fstem.supported(self.encoder.resnet.conv1, x)):
+            feat = self.encoder(x, torch.bfloat16)           # the stem reads the float32 NCHW image directly
+        else:
+            xin = x.to(self.compute_dtype).contiguous(memory_format=torch.channels_last)
+            feat = self.encoder(xin)
         if self._cfg.is_ins_norm and FUSED and (self.training or not torch.is_grad_enabled()) and fnorm.instance_norm_supported(feat):
             # hand-written path: per-image statistics groups of the BatchNorm kernels, bf16 in / bf16 out; the Aligner's
             # float32 feature view is one conversion of the result

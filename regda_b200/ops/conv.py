@@ -76,6 +76,13 @@ def _tc():
     return tc
 
 
+def _reached(param):
+    """tell the trainer's gradient buckets that the backward pass has arrived at `param` (regda_b200/parallel.py GradBuckets)"""
+    arena = getattr(param, "_arena", None)
+    if arena is not None:
+        arena.backward_reached(param)
+
+
 class _ConvFn(torch.autograd.Function):
     """x: channels-last bf16 [N,C,H,W]; weight: float32 master [O,I,kh,kw] (channels-last memory).
     The weight gradient is ACCUMULATED into weight.grad by the wgrad kernel (no autograd add)."""
@@ -117,6 +124,7 @@ class _ConvFn(torch.autograd.Function):
         tc = _tc()
         x, w16 = ctx.saved_tensors
         weight = ctx.weight
+        _reached(weight)
         stride, padding, dilation = ctx.geom
         g_tap = rest[-1] if ctx.tap else None
         if gy is None:                           # only the tap branch carried a gradient
@@ -181,6 +189,7 @@ class _ConvF32Fn(torch.autograd.Function):
         tc = _tc()
         (x,) = ctx.saved_tensors
         weight = ctx.weight
+        _reached(weight)
         stride, padding, dilation = ctx.geom
         gy = gy.contiguous(memory_format=torch.channels_last)
         gx = None

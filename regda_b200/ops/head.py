@@ -73,6 +73,9 @@ class _DropoutClassifierFn(torch.autograd.Function):
     def backward(ctx, dout):
         y, keep = ctx.saved_tensors
         weight, bias = ctx.weight, ctx.bias
+        arena = getattr(weight, "_arena", None)
+        if arena is not None:
+            arena.backward_reached(weight)
         b, cin, h, w = y.shape
         ncls = weight.shape[0]
         dout = dout.float().contiguous()

@@ -102,6 +102,9 @@ class _BnActFn(torch.autograd.Function):
         dout = _cl(dout)
         dy = torch.empty_like(y)
         gamma, beta = ctx.gamma, ctx.beta
+        arena = getattr(gamma, "_arena", None)
+        if arena is not None:
+            arena.backward_reached(gamma)          # gradient buckets of the data-parallel trainer (parallel.GradBuckets)
         dgamma = _grad_buffer(gamma) if gamma.requires_grad else None
         dbeta = _grad_buffer(beta) if beta.requires_grad else None
         hd = ctx.handle

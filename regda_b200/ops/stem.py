@@ -24,12 +24,17 @@ def supported(conv, x) -> bool:
 class _StemConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, groups):
+        """x: bf16 (channels-last image), or the loader's float32 NCHW image (rounded to bf16 inside the patch kernel)"""
         n, _, h, w = x.shape
         cout = weight.shape[0]
         oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
-        x = x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
         a = torch.empty((n, K_PAD, oh, ow), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
-        capi.call("regda_stem_im2col_bf16", capi.ptr_any(x), capi.ptr_any(a), n, h, w, capi.stream())
+        if x.dtype == torch.float32:
+            x = x.contiguous()
+            capi.call("regda_stem_im2col_f32nchw", capi.ptr(x), capi.ptr_any(a), n, h, w, capi.stream())
+        else:
+            x = x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
+            capi.call("regda_stem_im2col_bf16", capi.ptr_any(x), capi.ptr_any(a), n, h, w, capi.stream())
         w16 = tc.weight_shadow(weight)                       # bf16 [64,3,7,7] channels-last = OHWI rows of 147
         wp = torch.zeros((cout, K_PAD, 1, 1), dtype=torch.bfloat16, device=x.device).contiguous(memory_format=torch.channels_last)
         wp.view(cout, K_PAD)[:, :147] = w16.permute(0, 2, 3, 1).reshape(cout, 147)
@@ -105,9 +110,11 @@ class _StemConvF32Fn(torch.autograd.Function):
         return None, None
 
 
-def stem_conv(x, weight, groups):
-    """(y, bn_stats): y = conv7x7/2(x, weight) channels-last, bn_stats float32 [groups][2][cout] (bf16 input), or
-    (y float32, None) for a float32 input (parity mode: statistics are taken by the BatchNorm that follows)"""
-    if x.dtype == torch.float32:
-        return _StemConvF32Fn.apply(x, weight), None
+def stem_conv(x, weight, groups, compute_dtype=None):
+    """(y, bn_stats): y = conv7x7/2(x, weight) channels-last, bn_stats float32 [groups][2][cout] (bf16 compute), or
+    (y float32, None) in the float32 parity mode (statistics are taken by the BatchNorm that follows).
+    compute_dtype (default: x.dtype): bf16 compute accepts the float32 NCHW image of the data loader directly."""
+    compute_dtype = compute_dtype or x.dtype
+    if compute_dtype == torch.float32:
+        return _StemConvF32Fn.apply(x.float(), weight), None
     return _StemConvFn.apply(x, weight, groups)

@@ -10,6 +10,12 @@ only exchanges are
     same EMA update and keeps identical prototypes (49 KB),
 plus a one-off broadcast of rank 0's parameters at construction.  Backend: NCCL over NVLink on the
 GPU box, gloo in the CPU tests (tests/test_ddp_gloo.py).
+
+The gradient all-reduce is BUCKETED and OVERLAPPED with the backward pass (GradBuckets): the arena is cut at a few
+module boundaries (PPM heads | layer4 | layer3 | the rest); the backward pass walks the arena from its end to its start,
+and as soon as it enters a parameter below a boundary the bucket above it is complete and its all-reduce is launched
+asynchronously (NCCL's own stream, ordered after the weight-gradient side stream) while the data-gradient chain of the
+earlier layers keeps running.  Only the last, smallest bucket is exposed after the backward pass.
 """
 from __future__ import annotations
 
@@ -62,3 +68,59 @@ def max_over_ranks(value: float, device="cpu") -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class GradBuckets:
+    """Bucketed all-reduce of one flat gradient buffer, launched from inside the backward pass.
+
+    `boundaries`: ascending element offsets that cut `grad` into buckets [0,b0) [b0,b1) ... [bk,n).  The backward pass
+    reports every parameter it ENTERS (`reached(offset)`, offsets decrease as backward proceeds towards the input); a bucket
+    is launched the first time an offset below its lower boundary is reported -- by construction of the boundaries (module
+    boundaries of a sequential network) every gradient of that bucket has been produced, or at least enqueued on the streams
+    `order_after` names, by then.  `finish()` launches whatever is left and makes the current stream wait for all of them."""
+
+    def __init__(self, grad: torch.Tensor, boundaries, order_after=None):
+        n = grad.numel()
+        cuts = sorted({int(b) for b in boundaries if 0 < int(b) < n})
+        self.grad = grad
+        self.edges = [0] + cuts + [n]                    # bucket i = [edges[i], edges[i+1])
+        self.order_after = order_after                   # callable -> (stream to launch on or None): see trainer
+        self.next = len(self.edges) - 2                  # highest bucket not yet launched
+        self.works = []
+        self.active = False
+
+    def begin(self):
+        self.next = len(self.edges) - 2
+        self.works = []
+        self.active = world_info()[1] > 1
+
+    def _launch(self, i):
+        lo, hi = self.edges[i], self.edges[i + 1]
+        if hi <= lo:
+            return
+        seg = self.grad[lo:hi]
+        if self.order_after is not None and self.grad.is_cuda:
+            side = self.order_after()                    # the collective must see the weight gradients of the side stream
+            with torch.cuda.stream(side):
+                self.works.append(dist.all_reduce(seg, op=dist.ReduceOp.SUM, async_op=True))
+        else:
+            self.works.append(dist.all_reduce(seg, op=dist.ReduceOp.SUM, async_op=True))
+
+    def reached(self, offset: int):
+        """the backward pass is about to produce the gradient of the parameter at `offset`"""
+        if not self.active:
+            return
+        while self.next >= 1 and offset < self.edges[self.next]:
+            self._launch(self.next)
+            self.next -= 1
+
+    def finish(self):
+        if not self.active:
+            return
+        while self.next >= 0:
+            self._launch(self.next)
+            self.next -= 1
+        for w in self.works:
+            w.wait()                                     # CUDA: the current stream waits; gloo: blocks the host
+        self.works = []
+        self.active = False

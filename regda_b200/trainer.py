@@ -64,16 +64,34 @@ class ParamArena:
             p.grad = view(self.grad)
             p._bf16 = view(self.param_bf16)            # what the tcgen05 convolutions read (ops/tc.py weight_shadow)
             p._arena = self                            # writers of p.data outside the SGD kernel call p._arena.sync_shadow()
+            p._arena_off = o                           # the backward ops report it to the gradient buckets (parallel.GradBuckets)
         self.param_bf16.copy_(self.param)
         # load_state_dict() (resume, reload-best, evaluate(ckpt)) writes the fp32 arena behind the SGD kernel's back:
         # refresh the bf16 shadow the convolutions read
         module.register_load_state_dict_post_hook(lambda _m, _incompatible: self.sync_shadow())
         self.first_step = True
+        self.offset_of = {n: p._arena_off for n, p in module.named_parameters() if hasattr(p, "_arena_off")}
+        self.buckets = None                            # parallel.GradBuckets when data-parallel (set by the trainer)
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.lr_device = torch.zeros(1, dtype=torch.float32, device=dev)
 
     def zero_grad(self):
         self.grad.zero_()
+
+    def bucket_boundaries(self, prefixes=("layer5.", "encoder.resnet.layer4.", "encoder.resnet.layer3.")):
+        """element offsets of the first parameter of each named sub-module: where the backward pass of a sequential network
+        has finished everything behind it (the two PPM heads, layer5 / layer6, are parallel branches and form ONE bucket)"""
+        cuts = []
+        for pre in prefixes:
+            offs = [o for n, o in self.offset_of.items() if n.startswith(pre)]
+            if offs:
+                cuts.append(min(offs))
+        return cuts
+
+    def backward_reached(self, p):
+        """called by the backward ops (ops/conv.py, ops/norm.py, ops/head.py, ops/stem.py) when they enter parameter p"""
+        if self.buckets is not None:
+            self.buckets.reached(p._arena_off)
 
     def sync_shadow(self):
         """refresh the bf16 shadow after the fp32 parameters were written from outside the SGD kernel
@@ -123,6 +141,18 @@ class SelfTrainingStep:
             self.arena.sync_shadow()
             for buf in model.buffers():
                 parallel.broadcast_parameters(buf)
+            # gradient all-reduce in buckets launched from inside the backward pass, ordered after the weight-gradient
+            # side stream (ops/conv.py) so that the collective sees those kernels' results
+            dev = self.arena.grad.device
+
+            def order_after():
+                key, side = conv_ops._wgrad_stream(dev)
+                side.wait_stream(torch.cuda.current_stream())      # BatchNorm / bias gradients are produced on the main stream
+                conv_ops._side_used.add(key)
+                return side
+
+            self.arena.buckets = parallel.GradBuckets(self.arena.grad, self.arena.bucket_boundaries(),
+                                                      order_after if dev.type == "cuda" else None)
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
         self._static = None
@@ -143,6 +173,18 @@ class SelfTrainingStep:
     def _reduce_proto(self, sums, counts):
         if self.world_size > 1:
             parallel.allreduce_sum_(sums, counts)
+
+    def _backward(self, loss):
+        """loss.backward() with the weight gradients on a side stream (joined at the end) and, data-parallel, the gradient
+        arena all-reduced bucket by bucket while the backward pass is still running (sum; the mean is the SGD kernel's
+        grad_scale = 1 / world)"""
+        bk = self.arena.buckets
+        if bk is not None:
+            bk.begin()
+        with conv_ops.wgrad_side_stream():
+            loss.backward()
+            if bk is not None:
+                bk.finish()                    # remaining bucket(s) + the current stream waits for every collective
 
     def _step_impl(self, images_s, label_s, images_t, soft_t, regs_t):
         m = self.model
@@ -168,10 +210,7 @@ class SelfTrainingStep:
         loss_source = loss_calc([pred_s1, pred_s2], label_s, loss_fn=self.loss_fn_s, multi=True)   # :228
         loss_target = loss_calc([pred_t1, pred_t2], hard, loss_fn=self.loss_fn_t, multi=True)      # :233
         loss = loss_source + loss_target
-        with conv_ops.wgrad_side_stream():                                         # weight gradients run on a side stream, joined here
-            loss.backward()                                                        # :238
-        if self.world_size > 1:
-            parallel.allreduce_sum_(self.arena.grad)                               # mean over ranks via grad_scale
+        self._backward(loss)                                                       # :238 (+ the bucketed gradient all-reduce)
         self.arena.clip_and_sgd(self.max_norm, self.momentum, self.weight_decay, 1.0 / self.world_size)   # :239-241
         capi.zero_pool.disarm()
         return loss.detach(), loss_source.detach(), loss_target.detach(), hard
@@ -230,10 +269,7 @@ class AlignStep(SelfTrainingStep):
             loss_domain = self.aligner.align_domain(feat_s, feat_t, precise=precise)
             self.loss_domain = loss_domain.detach()
             loss = loss + loss_domain
-        with conv_ops.wgrad_side_stream():
-            loss.backward()                                                        # :193
-        if self.world_size > 1:
-            parallel.allreduce_sum_(self.arena.grad)
+        self._backward(loss)                                                       # :193
         self.arena.clip_and_sgd(self.max_norm, self.momentum, self.weight_decay, 1.0 / self.world_size)   # :194-196
         capi.zero_pool.disarm()
         return loss.detach(), loss_seg.detach(), loss_align.detach(), hard

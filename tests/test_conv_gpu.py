@@ -275,6 +275,11 @@ def test_stem_conv_patch_matrix_path_matches_float32_reference(shape):
     y.backward(gy)
     ref.backward(gy.float())
     assert float((conv.weight.grad - wr.grad).abs().max()) <= 5e-3 * float(wr.grad.abs().max())
+    # the loader's float32 NCHW image goes in directly (rounded to bf16 inside the patch kernel): same bits out
+    xf = torch.randn(n, 3, h, w, device="cuda")
+    y16, st16 = stem.stem_conv(xf.bfloat16().contiguous(memory_format=torch.channels_last), conv.weight, groups)
+    y32, st32 = stem.stem_conv(xf, conv.weight, groups, torch.bfloat16)
+    assert torch.equal(y16, y32)
 
 
 @pytest.mark.parametrize("with_bnred", [False, True])

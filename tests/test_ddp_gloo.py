@@ -54,7 +54,34 @@ def _worker(rank, world, port, q):
         arena.zero_grad()
         ((model(x[lo:hi]) - y[lo:hi]) ** 2).mean().backward()
         assert all(p.grad.data_ptr() >= arena.grad.data_ptr() for p in model.parameters())      # grads live in the arena
-        parallel.allreduce_sum_(arena.grad)
+        # the bucketed, backward-overlapped form the trainer uses: cut at the second conv, report parameters in backward order
+        local = arena.grad.clone()
+        bk = parallel.GradBuckets(arena.grad, arena.bucket_boundaries(("2.",)))
+        assert bk.edges == [0, arena.offset_of["2.weight"], arena.numel]
+        bk.begin()
+        for name in ("2.bias", "2.weight"):
+            bk.reached(arena.offset_of[name])
+        assert len(bk.works) == 0                              # still inside the last bucket: nothing launched yet
+        bk.reached(arena.offset_of["0.bias"])
+        assert len(bk.works) == 1                              # the bucket behind the boundary went out
+        bk.reached(arena.offset_of["0.weight"])
+        bk.finish()
+        assert bk.works == [] and not bk.active
+        # every element reduced exactly once
+        check = local.clone()
+        dist.all_reduce(check)
+        assert torch.equal(arena.grad, check)
+        # random cuts / arrival patterns: still exactly one reduction per element
+        g = torch.Generator().manual_seed(11)
+        for trial in range(5):
+            buf = local.clone()
+            cuts = sorted(set(int(v) for v in torch.randint(1, arena.numel, (3,), generator=g)))
+            b2 = parallel.GradBuckets(buf, cuts)
+            b2.begin()
+            for off in sorted((int(v) for v in torch.randint(0, arena.numel, (6,), generator=g)), reverse=True):
+                b2.reached(off)
+            b2.finish()
+            assert torch.equal(buf, check), trial
         got = arena.grad * parallel.grad_scale()
         ((ref(x) - y) ** 2).mean().backward()
         want = torch.cat([torch.cat([p.grad.reshape(-1), torch.zeros((-p.numel()) % 8)]) for p in ref.parameters()])
