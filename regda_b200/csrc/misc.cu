@@ -150,7 +150,7 @@ classifier_bwd_kernel(const T *__restrict__ y, const float *__restrict__ w, cons
     for (int k = 0; k < kMaxClasses; ++k)
 #pragma unroll
         for (int j = 0; j < 8; ++j) { wk[k][j] = k < ncls ? w[k * cin + o * 8 + j] * kp[j] : 0.f; gw[k][j] = 0.f; }
-    if (grp < groups) {
+    {
         const T *yi = y + (static_cast<size_t>(img) * hw + px0) * cin + o * 8;
         T *dyi = dy + (static_cast<size_t>(img) * hw + px0) * cin + o * 8;
         for (int p = grp; p < npx; p += groups) {
@@ -166,14 +166,29 @@ classifier_bwd_kernel(const T *__restrict__ y, const float *__restrict__ w, cons
             }
             store8(dyi + static_cast<size_t>(p) * cin, g);
         }
-        for (int k = 0; k < ncls; ++k)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(dw + k * cin + o * 8 + j, gw[k][j] * kp[j]);
     }
+    __syncthreads();
     if (dbias != nullptr && threadIdx.x < ncls) {
-        float s = 0.f;
-        for (int p = 0; p < npx; ++p) s += sd[p * kMaxClasses + threadIdx.x];
-        atomicAdd(dbias + threadIdx.x, s);
+        float t = 0.f;
+        for (int p = 0; p < npx; ++p) t += sd[p * kMaxClasses + threadIdx.x];
+        atomicAdd(dbias + threadIdx.x, t);
+    }
+    // weight gradient: the block's `groups` row groups hold partial sums for the same (class, channel) -- fold them in shared
+    // memory first (the staged dout slice is dead by now), then ONE global atomic per (class, channel) per block
+    __syncthreads();
+    float *sg = sm;                                     // [groups][ncls][cin] would not fit: fold class by class
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) {
+        if (k >= ncls) break;                           // (block-uniform: the barriers below stay convergent)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sg[grp * cin + o * 8 + j] = gw[k][j] * kp[j];
+        __syncthreads();
+        for (int c = threadIdx.x; c < cin; c += kClsThreads) {
+            float t = 0.f;
+            for (int gi = 0; gi < groups; ++gi) t += sg[gi * cin + c];
+            atomicAdd(dw + k * cin + c, t);
+        }
+        __syncthreads();
     }
 }
 
@@ -235,7 +250,7 @@ extern "C" int regda_classifier_bwd(const void *y, int y_is_f32, const float *w,
     if (!cls_args_ok(y, w, b, hw, cin, ncls) || !dout || !dy || !dw) return fail(REGDA_ERR_INVALID_ARG, "classifier_bwd: bad arguments");
     const int px_per_block = 128;
     const int per_img = (hw + px_per_block - 1) / px_per_block;
-    const size_t smem = static_cast<size_t>(px_per_block) * kMaxClasses * sizeof(float);
+    const size_t smem = std::max(static_cast<size_t>(px_per_block) * kMaxClasses, static_cast<size_t>(kClsThreads / (cin / 8)) * cin) * sizeof(float);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (y_is_f32)
         classifier_bwd_kernel<float><<<dim3(per_img, b), kClsThreads, smem, st>>>(static_cast<const float *>(y), w, keep, dout, static_cast<float *>(dy), dw,

@@ -129,13 +129,11 @@ class Bottleneck(nn.Module):
         if (FUSED and self.training and x.is_cuda and x.dtype == torch.bfloat16) or _GROUPS > 1 or (not self.training and _inference(x)):
             # fnorm.arm(t, k): t (a BatchNorm+ReLU output) has exactly k consumers, all of them the Conv2d calls below, so
             # their data-gradient epilogues may carry the first half of that BatchNorm's backward (ops/norm.py BnHandle)
-            if self.downsample is None:
-                fnorm.arm(x, 1)
-                out, identity = _conv_bn(self.conv1, self.bn1, x, relu=True, tap=True)
-            else:
-                fnorm.arm(x, 2)
-                out = _conv_bn(self.conv1, self.bn1, x, relu=True)
-                identity = _conv_bn(self.downsample[0], self.downsample[1], x)
+            # x is read twice (conv1 and the residual branch): the second reader goes through the tap conv1 hands back, so that
+            # its gradient arrives in conv1's backward and is added inside the data-gradient epilogue instead of an autograd add
+            fnorm.arm(x, 1)
+            out, x_tap = _conv_bn(self.conv1, self.bn1, x, relu=True, tap=True)
+            identity = x_tap if self.downsample is None else _conv_bn(self.downsample[0], self.downsample[1], x_tap)
             fnorm.arm(out, 1)
             out = _conv_bn(self.conv2, self.bn2, out, relu=True)
             fnorm.arm(out, 1)
