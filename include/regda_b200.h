@@ -224,6 +224,22 @@ int regda_conv_wgrad_bf16(const void *dy, const void *x, float *dw, int n, int h
  * (the dY operand of a stride-2 convolution's data gradient: regda/_resnets.py:92-112, layer2.0 / layer3.0). */
 int regda_zero_insert2_bf16(const void *src, void *dst, int n, int oh, int ow, int OH, int OW, int c, void *stream);
 
+/* ---- folded PPM fuse convolution: layout glue (regda/models/Encoder.py:43-52; see csrc/ppm.cu) ------------------
+ * The upsampled pyramid branches enter the 3x3 fuse convolution through two small GEMMs (run as 1x1 convolutions on the
+ * tcgen05 kernels) instead of 2048 materialised channels; these kernels split / merge the OHWI weight and re-lay the
+ * intermediate G between the two GEMMs. */
+int regda_ppm_gather_weights(const void *w, void *wmain, void *wb0, void *wb1, void *wb2, void *wb3, int O, int T, int ct,
+                             int cf, int cb, int nb, void *stream);
+int regda_ppm_scatter_wgrad(const float *gmain, const float *g0, const float *g1, const float *g2, const float *g3, float *gw,
+                            int O, int T, int ct, int cf, int cb, int nb, void *stream);
+int regda_ppm_g_pack(void *g0, void *g1, void *g2, void *g3, void *gt, int b, int O, int T, int kp, const int *scales_host,
+                     int nscales, int pack, void *stream);
+int regda_transpose_bf16(const void *src, void *dst, int batch, int rows, int cols, void *stream);
+/* forward convolution + BatchNorm statistics (bn_stats may be NULL: none) with an epilogue addend bf16 [n][oh][ow][cout] */
+int regda_conv_fprop_addend_bf16(const void *x, const void *wgt, void *y, int n, int h, int w, int cin, int cout,
+                                 int r, int s, int stride, int pad, int dil, const void *addend, float *bn_stats, int groups,
+                                 int stats_zeroed, void *stream);
+
 /* ---- PPM head tail: Dropout2d + classifier (regda/models/Encoder.py:39-40) ----------------------------
  * regda_dropout2d_mask: keep_scale float32 [n] = 0 with probability p, else 1/(1-p), n = images * channels; the generator
  *   state (uint64 {seed, draw counter}) lives in DEVICE memory and is advanced by the kernel, so a replayed CUDA graph

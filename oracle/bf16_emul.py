@@ -13,7 +13,8 @@ Rounding points (regda_b200 file that rounds):
   image -> bf16 (models/Encoder.py Deeplabv2.forward); conv weights -> bf16 (ops/tc.py weight_shadow / optim.cu shadow);
   conv output -> bf16 (csrc/conv_tc.cu epilogue); BatchNorm statistics from the ROUNDED conv output (same epilogue);
   BatchNorm(+residual)(+ReLU) output -> bf16 (csrc/norm.cu bn_apply_kernel); InstanceNorm output -> bf16 (same kernel);
-  pooled pyramid maps -> bf16 (models/Encoder.py PPMBilinear.forward); upsampled branch maps -> bf16 (csrc/ppm.cu upcat);
+  pooled pyramid maps -> bf16 (models/Encoder.py PPMBilinear.forward); the folded fuse convolution (ops/ppm_fold.py): branch
+  GEMM G -> bf16, interpolation weights A -> bf16, their product y_ppm -> bf16 before it joins the 3x3 convolution's accumulator;
   the classifier reads the fp32 master weights and writes fp32 logits (csrc/misc.cu) -- no rounding.
 """
 from __future__ import annotations
@@ -72,13 +73,33 @@ def _instance_norm(x, eps):
 
 
 def _head(head, fin, groups):
-    size = fin.shape[-2:]
-    cat = [fin]
+    """PPM head as regda_b200/ops/ppm_fold.py evaluates it: the 3x3 fuse convolution over cat(fin, up(p_1..4)) split by linearity
+    into conv3x3(fin, W[:, :2048]) + sum_(cell, tap) A[px][(cell, tap)] G[(cell, tap)][o], G_k = p_k . W_k (bf16), A = the bilinear
+    interpolation weights of the pyramid cells at the tap-shifted pixels (bf16), the second term rounded to bf16 before it joins
+    the accumulator.  With ROUND off this is exactly cat + conv (the reference, Encoder.py:43-52)."""
+    b, cf, h, w = fin.shape
+    conv = head.conv_last[0]
+    W = r16(conv.weight.detach())                                   # [O, 4096, 3, 3]
+    O = W.shape[0]
+    yppm = torch.zeros(b, O, h, w, dtype=torch.float64)
+    off = cf
     for br in head.ppm:
         pooled = r16(br[0](fin))                                   # AdaptiveAvgPool2d in exact arithmetic, then the bf16 cast
-        t = _bn_train(_conv(pooled, br[1]), br[2], True, groups=groups)
-        cat.append(r16(F.interpolate(t, size, mode="bilinear", align_corners=False)))
-    y = _bn_train(_conv(torch.cat(cat, 1), head.conv_last[0]), head.conv_last[1], True, groups=groups)
+        p = _bn_train(_conv(pooled, br[1]), br[2], True, groups=groups)          # [b, 512, s, s]
+        s2, cb = p.shape[2] * p.shape[3], p.shape[1]
+        Wk = W[:, off:off + cb]                                                  # [O, cb, 3, 3]
+        off += cb
+        G = r16(torch.einsum("bcj,ocrs->bjrso", p.reshape(b, cb, s2), Wk))       # [b, cell, r, s, O]
+        eye = torch.eye(s2, dtype=torch.float64).view(s2, 1, p.shape[2], p.shape[3])
+        up = F.interpolate(eye, (h, w), mode="bilinear", align_corners=False)[:, 0]          # B[cell][y][x]
+        pad = F.pad(up, (1, 1, 1, 1))
+        for r in range(3):
+            for c in range(3):
+                A = r16(pad[:, r:r + h, c:c + w])                                # basis weight at the tap-shifted pixel (zero padded)
+                yppm = yppm + torch.einsum("jyx,bjo->boyx", A, G[:, :, r, c])
+    yppm = r16(yppm)
+    main = F.conv2d(fin, W[:, :cf], None, 1, 1, 1)
+    y = _bn_train(r16(main + yppm), head.conv_last[1], True, groups=groups)
     cls = head.conv_last[4]                                        # Dropout2d is the identity in the parity runs (p = 0)
     return F.conv2d(y, cls.weight.detach().double(), cls.bias.detach().double())
 

@@ -664,6 +664,26 @@ extern "C" int regda_conv_fprop_stats_bf16(const void *x, const void *wgt, void 
     return launch_conv<false>(x, wgt, y, g, r * s, st, bn_stats, n / groups);
 }
 
+// Forward convolution whose epilogue adds `addend` (bf16, the output's shape) before rounding / taking the statistics;
+// bn_stats == NULL: no statistics.  (The folded PPM fuse convolution hands the pyramid branches' contribution in this way.)
+extern "C" int regda_conv_fprop_addend_bf16(const void *x, const void *wgt, void *y, int n, int h, int w, int cin, int cout,
+                                            int r, int s, int stride, int pad, int dil, const void *addend, float *bn_stats, int groups,
+                                            int stats_zeroed, void *stream) {
+    if (!regda_conv_fprop_supported(n, h, w, cin, cout, r, s, stride, pad, dil))
+        return fail(REGDA_ERR_UNSUPPORTED, "conv_fprop_addend: shape not covered by the tcgen05 kernel");
+    if (bn_stats && !regda_conv_fprop_stats_supported(n, h, w, cin, cout, r, s, stride, pad, dil, groups))
+        return fail(REGDA_ERR_UNSUPPORTED, "conv_fprop_addend: statistics groups not covered by the tcgen05 kernel");
+    if (!x || !wgt || !y) return fail(REGDA_ERR_INVALID_ARG, "conv_fprop_addend: null pointer");
+    if (!aligned16(x, wgt, y) || (addend && (reinterpret_cast<uintptr_t>(addend) & 15)))
+        return fail(REGDA_ERR_INVALID_ARG, "conv_fprop_addend: tensors must be 16-byte aligned");
+    ConvGeom g;
+    geom_init(g, n, h, w, cin, cout, r, s, stride, pad, dil);
+    ensure_context(x);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (bn_stats && !stats_zeroed) REGDA_CUDA_CHECK(cudaMemsetAsync(bn_stats, 0, static_cast<size_t>(groups) * 2 * cout * sizeof(float), st));
+    return launch_conv<false>(x, wgt, y, g, r * s, st, bn_stats, bn_stats ? n / groups : 1, addend);
+}
+
 // Data gradient of a STRIDE-1 convolution, reading the forward weights IN PLACE:
 //   dx[n][h][w][cin] = sum_{r,s,co} dy[n][y + pad - r*dil][x + pad - s*dil][co] * wgt[co][r][s][cin]
 // dy bf16 [n][oh][ow][cout], wgt bf16 [cout][r][s][cin] (OHWI), dx bf16 [n][h][w][cin].

@@ -278,17 +278,9 @@ __device__ __forceinline__ void flush_acc(unsigned bins_s, unsigned region, unsi
     }
 }
 
-// HASHED (large region tables: 1000 .. 20000 ids per tile): the per-CTA bins are not indexed by region id -- a [region_bound]
-// table of packed counters would not leave room for two CTAs per SM -- but kept in a small open-addressing table
-// (`slots` entries of {region id, CW packed words}, slot = id & (slots-1), linear probing, claimed with a shared-memory CAS):
-// a CTA's slice of the image only touches the few hundred regions that cross it.  An insertion that does not find a slot
-// within kHashProbes probes adds its counts straight into the owner CTA's cluster-wide table with remote shared-memory
-// atomics (always correct, just slower), so no table size is ever "too small".
-constexpr int kHashProbes = 8;
-
-template <int CW, typename AccT, int HIST, bool HASHED = false>
+template <int CW, typename AccT, int HIST>
 __global__ void __launch_bounds__(512, 2)
-lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters, const int prefetch_iters, const int slots) {
+lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters, const int prefetch_iters) {
     extern __shared__ __align__(16) unsigned char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned CL = cluster.num_blocks();
@@ -296,11 +288,10 @@ lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters, const i
     const int cluster_id = blockIdx.x / CL;
     const int tid = threadIdx.x, nthreads = blockDim.x;
 
-    const int nwords = (HASHED ? slots : a.region_bound) * CW;
+    const int nwords = a.region_bound * CW;
     const int rpc = ((a.region_bound + static_cast<int>(CL) - 1) / static_cast<int>(CL) + 15) & ~15;
     unsigned *bins = reinterpret_cast<unsigned *>(smem);
-    unsigned *keys = bins + nwords;                                            // HASHED: region id owning each slot (0 = free)
-    const size_t win_off = (static_cast<size_t>(nwords + (HASHED ? slots : 0)) * 4 + 15) & ~static_cast<size_t>(15);
+    const size_t win_off = (static_cast<size_t>(nwords) * 4 + 15) & ~static_cast<size_t>(15);
     unsigned char *win = smem + win_off;                                       // winner code of EVERY region (rpc * CL bytes)
     unsigned *acc = reinterpret_cast<unsigned *>(smem + win_off + static_cast<size_t>(rpc) * CL);   // cluster-wide counts of OWN regions
     const size_t tile_off = win_off + static_cast<size_t>(rpc) * CL + static_cast<size_t>(rpc) * (2 * CW) * 4;
@@ -313,41 +304,12 @@ lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters, const i
     const int r_lo = min(a.region_bound, static_cast<int>(rank) * rpc);
     const int r_hi = min(a.region_bound, r_lo + rpc);
     for (int i = tid; i < rpc * 2 * CW; i += nthreads) acc[i] = 0u;          // re-zeroed by the owner after every use
-    for (int i = tid; i < nwords + (HASHED ? slots : 0); i += nthreads) bins[i] = 0u;   // (+ keys) re-zeroed by the push phase
+    for (int i = tid; i < nwords; i += nthreads) bins[i] = 0u;                // re-zeroed by the push phase
     cluster.sync();                                                            // nobody pushes into an un-zeroed table
     const unsigned max_code = static_cast<unsigned>(a.class_num) + 1u;
     const unsigned bound = static_cast<unsigned>(a.region_bound);
     const unsigned bins_s = static_cast<unsigned>(__cvta_generic_to_shared(bins));
-    const unsigned smask = static_cast<unsigned>(slots - 1);
     bool bad_label = false, bad_region = false;
-
-    // add the nibble accumulator `v` (nibble 0: ignored pixels, nibble k+1: class k) of region r to this CTA's bins
-    auto flush = [&](unsigned r, AccT v) {
-        if (!HASHED) {
-            flush_acc<CW>(bins_s, r, v);
-            return;
-        }
-        unsigned h = r & smask;
-#pragma unroll 1
-        for (int probe = 0; probe < kHashProbes; ++probe) {
-            unsigned k = *reinterpret_cast<volatile unsigned *>(keys + h);
-            if (k == 0u) k = atomicCAS(keys + h, 0u, r);                      // claim a free slot (0 returned: it is ours now)
-            if (k == r || k == 0u) {
-                flush_acc<CW>(bins_s, h, v);
-                return;
-            }
-            h = (h + 1u) & smask;
-        }
-        // table crowded around this id: count directly in the owner CTA's cluster-wide table (it is idle until the first
-        // cluster barrier of this image: every owner re-zeroed it before the last barrier of the previous image)
-        const int owner = static_cast<int>(r) / rpc;
-        unsigned *dst = cluster.map_shared_rank(acc, owner) + (static_cast<int>(r) - owner * rpc) * (2 * CW);
-#pragma unroll
-        for (int c = 0; c < 2 * CW; ++c) {
-            const unsigned cnt = static_cast<unsigned>(v >> (4 * (c + 1))) & 0xFu;
-            if (cnt) atomicAdd(dst + c, cnt);
-        }
-    };
 
     for (int img = cluster_id; img < a.b; img += nclusters) {
         // (bins are zero here: zeroed before the loop and again by the push phase of the previous image, and every
@@ -410,7 +372,7 @@ lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters, const i
                         m |= e ? (1u << k) : 0u;
                         acc += e ? oh[k] : static_cast<AccT>(0);
                     }
-                    if (r != 0u) flush(r, acc);
+                    if (r != 0u) flush_acc<CW>(bins_s, r, acc);
                     rem &= ~m;
                     unsigned nr = rr[7];
 #pragma unroll
@@ -438,8 +400,8 @@ lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters, const i
                 }
                 const unsigned rest = ~(in_a | in_b) & 0xFFu;
                 if (rest == 0u) {
-                    if (ra != 0u) flush(ra, acc_a);
-                    if (rb != 0u && in_b != 0u) flush(rb, acc_b);
+                    if (ra != 0u) flush_acc<CW>(bins_s, ra, acc_a);
+                    if (rb != 0u && in_b != 0u) flush_acc<CW>(bins_s, rb, acc_b);
                 } else {
                     unsigned rm = rr[6];                       // first pixel that is in neither run (pixels 0 and 7 never are)
 #pragma unroll
@@ -448,13 +410,13 @@ lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters, const i
 #pragma unroll
                     for (int k = 1; k < kGroupPx - 1; ++k) in_m |= (rr[k] == rm) ? (1u << k) : 0u;
                     if ((rest & ~in_m) == 0u) {
-                        if (ra != 0u) flush(ra, acc_a);
-                        if (rb != 0u && in_b != 0u) flush(rb, acc_b);
-                        if (rm != 0u) flush(rm, static_cast<AccT>(acc_all - acc_a - acc_b));
+                        if (ra != 0u) flush_acc<CW>(bins_s, ra, acc_a);
+                        if (rb != 0u && in_b != 0u) flush_acc<CW>(bins_s, rb, acc_b);
+                        if (rm != 0u) flush_acc<CW>(bins_s, rm, static_cast<AccT>(acc_all - acc_a - acc_b));
                     } else {
 #pragma unroll
                         for (int k = 0; k < kGroupPx; ++k)
-                            if (rr[k] != 0u) flush(rr[k], static_cast<AccT>(static_cast<AccT>(1) << (4 * cc[k])));
+                            if (rr[k] != 0u) flush_acc<CW>(bins_s, rr[k], static_cast<AccT>(static_cast<AccT>(1) << (4 * cc[k])));
                     }
                 }
             }
@@ -464,33 +426,15 @@ lrh_cluster_fast(const LrhArgs a, const int px_cta, const int nclusters, const i
         // ---- merge: PUSH.  Every CTA adds its non-zero packed bins to the owner CTA's 32-bit table with remote
         // shared-memory reductions (fire and forget: no DSMEM load round trips on the critical path), the owner
         // applies the exact float32 test locally and pushes 16-byte slices of winner codes to all CTAs. ----------
-        if (HASHED) {
-            for (int h = tid; h < slots; h += nthreads) {
-                const unsigned r = keys[h];
-                if (r == 0u) continue;
-                keys[h] = 0u;                                                // slot free for the next image
-                const int owner = static_cast<int>(r) / rpc;
-                unsigned *dst = cluster.map_shared_rank(acc, owner) + (static_cast<int>(r) - owner * rpc) * (2 * CW);
-#pragma unroll
-                for (int w = 0; w < CW; ++w) {
-                    const unsigned v = bins[h * CW + w];
-                    if (v == 0u) continue;
-                    bins[h * CW + w] = 0u;
-                    if (v & 0xFFFFu) atomicAdd(dst + 2 * w, v & 0xFFFFu);
-                    if (v >> 16) atomicAdd(dst + 2 * w + 1, v >> 16);
-                }
-            }
-        } else {
-            for (int i = tid; i < nwords; i += nthreads) {
-                const unsigned v = bins[i];
-                if (v == 0u) continue;
-                bins[i] = 0u;                                                // ready for the next image
-                const int r = i / CW, w = i - r * CW;
-                const int owner = r / rpc;
-                unsigned *dst = cluster.map_shared_rank(acc, owner) + (r - owner * rpc) * (2 * CW) + 2 * w;
-                if (v & 0xFFFFu) atomicAdd(dst, v & 0xFFFFu);
-                if (v >> 16) atomicAdd(dst + 1, v >> 16);
-            }
+        for (int i = tid; i < nwords; i += nthreads) {
+            const unsigned v = bins[i];
+            if (v == 0u) continue;
+            bins[i] = 0u;                                                    // ready for the next image
+            const int r = i / CW, w = i - r * CW;
+            const int owner = r / rpc;
+            unsigned *dst = cluster.map_shared_rank(acc, owner) + (r - owner * rpc) * (2 * CW) + 2 * w;
+            if (v & 0xFFFFu) atomicAdd(dst, v & 0xFFFFu);
+            if (v >> 16) atomicAdd(dst + 1, v >> 16);
         }
         {   // keep HBM busy across the two cluster barriers: pull the head of the next image's slice into L2
             const int nimg = img + nclusters;
@@ -564,7 +508,6 @@ struct ClusterPlan {
     int cw = 0;
     int threads = 0;
     int prefetch = 0;
-    int slots = 0;         // > 0: hashed local bins with this many slots (power of two)
     size_t smem = 0;
 };
 
@@ -573,9 +516,8 @@ int env_int(const char *name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-size_t cluster_smem_bytes(int region_bound, int cw, int px_cta, int cl, int slots = 0) {
-    const size_t bins = slots > 0 ? ((static_cast<size_t>(slots) * (cw + 1) * 4 + 15) & ~static_cast<size_t>(15))
-                                  : ((static_cast<size_t>(region_bound) * cw * 4 + 15) & ~static_cast<size_t>(15));
+size_t cluster_smem_bytes(int region_bound, int cw, int px_cta, int cl) {
+    const size_t bins = (static_cast<size_t>(region_bound) * cw * 4 + 15) & ~static_cast<size_t>(15);
     const size_t rpc = static_cast<size_t>(((region_bound + cl - 1) / cl + 15) & ~15);
     // packed local bins + winner bytes of all regions + 32-bit cluster-wide counts of the owned regions + 3 B/px tile
     return bins + rpc * cl + rpc * (2 * cw) * 4 + static_cast<size_t>(px_cta) * 3;
@@ -598,32 +540,15 @@ ClusterPlan plan_cluster(int b, int64_t hw, int class_num, int64_t region_bound,
     int ncand = allow_single ? 5 : 3;
     const int fc = env_int("REGDA_LRH_CLUSTER", 0), fp = env_int("REGDA_LRH_PER_SM", 0);
     if (fc > 0 && fp > 0) { order[0][0] = fc; order[0][1] = fp; ncand = 1; }
-    // Pass A: bins indexed by region id (fastest while they leave room for >= 2 CTAs per SM); pass B: hashed bins at 2 CTAs
-    // per SM for the large tables (only the fast kernel -- ignore_label == -1, <= 6 classes -- has the hashed form).
-    const bool can_hash = class_num <= 6 && env_int("REGDA_LRH_HASH", 1) != 0;
-    for (int i = 0; i < ncand + (can_hash ? 2 : 0); ++i) {
-        const bool hashed = i >= ncand;
-        const int cl = hashed ? (i == ncand ? 16 : 8) : order[i][0], per_sm = hashed ? 2 : order[i][1];
-        if (!hashed && per_sm == 1 && can_hash && !(fc > 0 && fp > 0)) continue;      // one CTA per SM loses to the hashed form
+    for (int i = 0; i < ncand; ++i) {
+        const int cl = order[i][0], per_sm = order[i][1];
         int px = static_cast<int>((hw + cl - 1) / cl);
         px = (px + kGroupPx - 1) / kGroupPx * kGroupPx;
         if (px > 65535) continue;                              // u16 per-CTA counters
-        int slots = 0;
-        size_t s = 0;
-        if (hashed) {
-            for (slots = 4096; slots >= 512; slots >>= 1) {
-                s = cluster_smem_bytes(static_cast<int>(region_bound), p.cw, px, cl, slots);
-                if (s <= (limit + 1024) / per_sm - 1024) break;
-            }
-            if (slots < 512) continue;
-            slots = env_int("REGDA_LRH_SLOTS", slots);
-            s = cluster_smem_bytes(static_cast<int>(region_bound), p.cw, px, cl, slots);
-        } else {
-            s = cluster_smem_bytes(static_cast<int>(region_bound), p.cw, px, cl);
-        }
+        const size_t s = cluster_smem_bytes(static_cast<int>(region_bound), p.cw, px, cl);
         if (s > (limit + 1024) / per_sm - 1024) continue;      // per_sm CTAs per SM (1 KB reserved each)
         const int groups = px / kGroupPx;
-        p.ok = true; p.cluster = cl; p.px_cta = px; p.smem = s; p.slots = slots;
+        p.ok = true; p.cluster = cl; p.px_cta = px; p.smem = s;
         // 64 registers/thread: 1024 threads per SM fill the register file
         p.threads = per_sm == 3 ? 256 : (groups >= 512 ? 512 : 256);
         p.threads = env_int("REGDA_LRH_THREADS", p.threads);
@@ -668,15 +593,12 @@ int launch_cluster(const LrhArgs &a, const ClusterPlan &p, cudaStream_t st, bool
     if (a.ignore_label == -1 && p.threads <= 512) {
         if constexpr (CW <= 3) {
             if (a.class_num <= 6) {
-                if (p.slots > 0) return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned, 0, true>, a, p, st, launched, p.prefetch, p.slots);
-                if (g_path_mode == 3) return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned, 1>, a, p, st, launched, p.prefetch, 1);
-                return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned, 0>, a, p, st, launched, p.prefetch, 1);
+                if (g_path_mode == 3) return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned, 1>, a, p, st, launched, p.prefetch);
+                return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned, 0>, a, p, st, launched, p.prefetch);
             }
         }
-        if (p.slots == 0 && a.class_num <= 14)
-            return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned long long, 1>, a, p, st, launched, p.prefetch, 1);
+        if (a.class_num <= 14) return launch_cluster_kernel(lrh_cluster_fast<CW, unsigned long long, 1>, a, p, st, launched, p.prefetch);
     }
-    if (p.slots > 0) return REGDA_OK;                          // hashed plan but not the fast kernel's domain: caller falls back
     return launch_cluster_kernel(lrh_cluster_kernel<CW>, a, p, st, launched);
 }
 

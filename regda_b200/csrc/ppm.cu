@@ -331,3 +331,180 @@ extern "C" int regda_ppm_upcat_bwd(const void *dcat, float *dbr0, float *dbr1, f
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
 }
+
+// =========================================================================================================
+// Folded PPM fuse convolution (regda/models/Encoder.py:43-52 + the 3x3 conv of :33-34).
+//
+// The reference concatenates the feature map with four bilinearly UPSAMPLED s x s branch maps (s = 1, 2, 3, 6) and runs a 3x3
+// convolution over all 4096 channels: 42.7 % of the model's multiply-adds, half of them over channels that carry only
+// 1 + 4 + 9 + 36 = 50 distinct values per image.  Upsampling and convolution are both linear, so for the branch channels
+//     conv(up(p_k))[px, o] = sum_tap sum_j B_k[px + tap, j] * G_k[j, tap, o],      G_k[j, tap, o] = sum_c p_k[j, c] W[o, tap, c_k + c]
+// (B_k = bilinear interpolation weights, zero outside the map = the convolution's zero padding).  G is a tiny GEMM (50 cells per
+// image), and the sum over (tap, cell) a [pixels x 450] . [450 x 512] GEMM per image with a CONSTANT left factor: both run on
+// the tcgen05 convolution kernels as 1x1 convolutions (host side: regda_b200/ops/ppm_fold.py), the result is handed to the
+// 3x3 convolution over the 2048 feature channels as its epilogue addend.  The kernels below are the layout glue:
+//   regda_ppm_gather_weights   bf16 OHWI weight -> the dense feature-part weight and the four branch weights [(tap, o)][c]
+//   regda_ppm_scatter_wgrad    their float32 gradients -> added into the OHWI gradient
+//   regda_ppm_g_pack / unpack  G_k [(img, cell)][(tap, o)]  <->  GT [img][o][(cell, tap)] (K-major operand of the second GEMM)
+//   regda_transpose_bf16       batched [r][c] -> [c][r]
+// =========================================================================================================
+namespace regda {
+namespace {
+
+struct GPtrs { __nv_bfloat16 *p[kMaxScales]; };
+
+// grid (taps * o, 1 + nb): row (o, tap) of the OHWI weight -> segment 0: wmain[o][tap][0..cf), segment 1+k: wb[k][tap*O + o][0..cb)
+__global__ void __launch_bounds__(256)
+ppm_gather_weights_kernel(const __nv_bfloat16 *__restrict__ w, __nv_bfloat16 *__restrict__ wmain, const GPtrs wb, int O, int T, int ct, int cf, int cb) {
+    const int row = blockIdx.x;                        // o * T + tap
+    const int o = row / T, tap = row - o * T;
+    const __nv_bfloat16 *src = w + static_cast<size_t>(row) * ct;
+    if (blockIdx.y == 0) {
+        __nv_bfloat16 *dst = wmain + static_cast<size_t>(row) * cf;
+        for (int c = threadIdx.x * 8; c < cf; c += blockDim.x * 8) *reinterpret_cast<uint4 *>(dst + c) = *reinterpret_cast<const uint4 *>(src + c);
+    } else {
+        const int k = blockIdx.y - 1;
+        __nv_bfloat16 *dst = wb.p[k] + (static_cast<size_t>(tap) * O + o) * cb;
+        const __nv_bfloat16 *s2 = src + cf + static_cast<size_t>(k) * cb;
+        for (int c = threadIdx.x * 8; c < cb; c += blockDim.x * 8) *reinterpret_cast<uint4 *>(dst + c) = *reinterpret_cast<const uint4 *>(s2 + c);
+    }
+}
+
+struct FPtrs { const float *p[kMaxScales]; };
+
+__global__ void __launch_bounds__(256)
+ppm_scatter_wgrad_kernel(const float *__restrict__ gmain, const FPtrs gwb, float *__restrict__ gw, int O, int T, int ct, int cf, int cb) {
+    const int row = blockIdx.x;
+    const int o = row / T, tap = row - o * T;
+    float *dst = gw + static_cast<size_t>(row) * ct;
+    if (blockIdx.y == 0) {
+        const float *src = gmain + static_cast<size_t>(row) * cf;
+        for (int c = threadIdx.x * 4; c < cf; c += blockDim.x * 4) {
+            float4 d = *reinterpret_cast<float4 *>(dst + c);
+            const float4 s4 = *reinterpret_cast<const float4 *>(src + c);
+            d.x += s4.x; d.y += s4.y; d.z += s4.z; d.w += s4.w;
+            *reinterpret_cast<float4 *>(dst + c) = d;
+        }
+    } else {
+        const int k = blockIdx.y - 1;
+        const float *src = gwb.p[k] + (static_cast<size_t>(tap) * O + o) * cb;
+        float *d2 = dst + cf + static_cast<size_t>(k) * cb;
+        for (int c = threadIdx.x * 4; c < cb; c += blockDim.x * 4) {
+            float4 d = *reinterpret_cast<float4 *>(d2 + c);
+            const float4 s4 = *reinterpret_cast<const float4 *>(src + c);
+            d.x += s4.x; d.y += s4.y; d.z += s4.z; d.w += s4.w;
+            *reinterpret_cast<float4 *>(d2 + c) = d;
+        }
+    }
+}
+
+// GT[img][o][kappa], kappa = (cell_global * T + tap) < ncell * T, zero up to kp.  One block per (img, o): the 450 source
+// elements G_k[(img, cell)][tap * O + o] are a strided gather (2 B each, L2-resident: G is ~7 MB), the write is one dense row.
+// PACK: G -> GT;  !PACK: GT -> G (the gradient's way back).
+template <bool PACK>
+__global__ void __launch_bounds__(128)
+ppm_g_pack_kernel(const GPtrs g, __nv_bfloat16 *__restrict__ gt, int O, int T, int kp, const PpmScales sc) {
+    const int o = blockIdx.x, img = blockIdx.y;
+    __nv_bfloat16 *row = gt + (static_cast<size_t>(img) * O + o) * kp;
+    const int nk = sc.ncell * T;
+    for (int kappa = threadIdx.x; kappa < kp; kappa += blockDim.x) {
+        if (kappa >= nk) {
+            if (PACK) row[kappa] = __float2bfloat16(0.f);
+            continue;
+        }
+        const int cell = kappa / T, tap = kappa - cell * T;
+        int k = 0;
+#pragma unroll
+        for (int i = 1; i < kMaxScales; ++i) if (i < sc.n && cell >= sc.off[i]) k = i;
+        const int j = cell - sc.off[k], s2 = sc.s[k] * sc.s[k];
+        __nv_bfloat16 *e = g.p[k] + (static_cast<size_t>(img) * s2 + j) * (static_cast<size_t>(T) * O) + static_cast<size_t>(tap) * O + o;
+        if (PACK) row[kappa] = *e; else *e = row[kappa];
+    }
+}
+
+// dst[b][c][r] = src[b][r][c], 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16 *__restrict__ src, __nv_bfloat16 *__restrict__ dst, int rows, int cols) {
+    __shared__ unsigned short tile[32][33];
+    const size_t boff = static_cast<size_t>(blockIdx.z) * rows * cols;
+    const unsigned short *s = reinterpret_cast<const unsigned short *>(src) + boff;
+    unsigned short *d = reinterpret_cast<unsigned short *>(dst) + boff;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int r = r0 + ty + i, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + i][tx] = s[static_cast<size_t>(r) * cols + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const int c = c0 + ty + i, r = r0 + tx;
+        if (r < rows && c < cols) d[static_cast<size_t>(c) * rows + r] = tile[tx][ty + i];
+    }
+}
+
+}  // namespace
+}  // namespace regda
+
+// w bf16 [O][T][ct] (OHWI), ct = cf + nb*cb -> wmain bf16 [O][T][cf], wb_k bf16 [T*O][cb] (row = tap*O + o), k < nb <= 4
+extern "C" int regda_ppm_gather_weights(const void *w, void *wmain, void *wb0, void *wb1, void *wb2, void *wb3, int O, int T, int ct,
+                                        int cf, int cb, int nb, void *stream) {
+    if (!w || !wmain || O < 1 || T < 1 || nb < 1 || nb > kMaxScales || cf % 8 || cb % 8 || ct != cf + nb * cb)
+        return fail(REGDA_ERR_INVALID_ARG, "ppm_gather_weights: bad arguments");
+    GPtrs p;
+    void *ps[4] = {wb0, wb1, wb2, wb3};
+    for (int k = 0; k < kMaxScales; ++k) {
+        p.p[k] = static_cast<__nv_bfloat16 *>(ps[k]);
+        if (k < nb && !ps[k]) return fail(REGDA_ERR_INVALID_ARG, "ppm_gather_weights: null branch weight");
+    }
+    ppm_gather_weights_kernel<<<dim3(O * T, 1 + nb), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16 *>(w), static_cast<__nv_bfloat16 *>(wmain), p, O, T, ct, cf, cb);
+    REGDA_LAUNCH_CHECK();
+    return REGDA_OK;
+}
+
+// gw float32 [O][T][ct] += (gmain float32 [O][T][cf], gwb_k float32 [T*O][cb])
+extern "C" int regda_ppm_scatter_wgrad(const float *gmain, const float *g0, const float *g1, const float *g2, const float *g3, float *gw,
+                                       int O, int T, int ct, int cf, int cb, int nb, void *stream) {
+    if (!gmain || !gw || O < 1 || T < 1 || nb < 1 || nb > kMaxScales || cf % 4 || cb % 4 || ct != cf + nb * cb)
+        return fail(REGDA_ERR_INVALID_ARG, "ppm_scatter_wgrad: bad arguments");
+    FPtrs p;
+    const float *ps[4] = {g0, g1, g2, g3};
+    for (int k = 0; k < kMaxScales; ++k) {
+        p.p[k] = ps[k];
+        if (k < nb && !ps[k]) return fail(REGDA_ERR_INVALID_ARG, "ppm_scatter_wgrad: null branch gradient");
+    }
+    ppm_scatter_wgrad_kernel<<<dim3(O * T, 1 + nb), 256, 0, static_cast<cudaStream_t>(stream)>>>(gmain, p, gw, O, T, ct, cf, cb);
+    REGDA_LAUNCH_CHECK();
+    return REGDA_OK;
+}
+
+// pack != 0: G_k bf16 [b][s_k*s_k][T*O] -> GT bf16 [b][O][kp] (kappa = cell*T + tap, zero padded);  pack == 0: the reverse
+extern "C" int regda_ppm_g_pack(void *g0, void *g1, void *g2, void *g3, void *gt, int b, int O, int T, int kp, const int *scales_host,
+                                int nscales, int pack, void *stream) {
+    PpmScales sc;
+    const int rc = make_scales(scales_host, nscales, &sc);
+    if (rc) return rc;
+    if (!gt || b < 1 || O < 1 || T < 1 || kp < sc.ncell * T) return fail(REGDA_ERR_INVALID_ARG, "ppm_g_pack: bad arguments");
+    GPtrs p;
+    void *ps[4] = {g0, g1, g2, g3};
+    for (int k = 0; k < kMaxScales; ++k) {
+        p.p[k] = static_cast<__nv_bfloat16 *>(ps[k]);
+        if (k < nscales && !ps[k]) return fail(REGDA_ERR_INVALID_ARG, "ppm_g_pack: null branch pointer");
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pack) ppm_g_pack_kernel<true><<<dim3(O, b), 128, 0, st>>>(p, static_cast<__nv_bfloat16 *>(gt), O, T, kp, sc);
+    else ppm_g_pack_kernel<false><<<dim3(O, b), 128, 0, st>>>(p, static_cast<__nv_bfloat16 *>(gt), O, T, kp, sc);
+    REGDA_LAUNCH_CHECK();
+    return REGDA_OK;
+}
+
+// dst bf16 [batch][cols][rows] = src bf16 [batch][rows][cols]
+extern "C" int regda_transpose_bf16(const void *src, void *dst, int batch, int rows, int cols, void *stream) {
+    if (!src || !dst || batch < 1 || rows < 1 || cols < 1 || batch > 65535) return fail(REGDA_ERR_INVALID_ARG, "transpose: bad arguments");
+    transpose_bf16_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32, batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16 *>(src), static_cast<__nv_bfloat16 *>(dst), rows, cols);
+    REGDA_LAUNCH_CHECK();
+    return REGDA_OK;
+}

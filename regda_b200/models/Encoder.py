@@ -25,6 +25,7 @@ from ..ops import conv as conv_ops
 from ..ops import head as fhead
 from ..ops import norm as fnorm
 from ..ops import ppm as fppm
+from ..ops import ppm_fold as ffold
 from ..ops import stem as fstem
 
 FUSED = os.environ.get("REGDA_FUSED", "1") != "0"     # hand-written BN / PPM kernels for bf16 training forward+backward
@@ -234,8 +235,16 @@ class PPMBilinear(nn.Module):
                 off += s * s
                 # 1x1 conv on the s x s map (several images per tcgen05 M tile) + BatchNorm + ReLU, all hand-written kernels
                 branches.append(_conv_bn(branch[1], branch[2], p, relu=True))
-            cat = fppm.upsample_concat(conv_out, branches, self.pool_scales)
-            y = _conv_bn(self.conv_last[0], self.conv_last[1], cat, relu=True)
+            conv, bn = self.conv_last[0], self.conv_last[1]
+            if ffold.supported(conv_out, branches, conv, self.pool_scales) and (bn.training or fnorm.inference_supported(conv_out, bn)):
+                # the upsampled branches enter the 3x3 convolution through two small GEMMs instead of 2048 materialised channels
+                # (ops/ppm_fold.py): half the reference's K, no concatenated tensor
+                train = bn.training and fnorm.supported(conv_out.new_empty((1, conv.out_channels, 1, 1)), bn)
+                y, st = ffold.fuse_conv(conv_out, branches, conv.weight, self.pool_scales, _GROUPS if train else None)
+                y = fnorm.bn_act(y, bn, relu=True, groups=_GROUPS, stats=st) if train else _bn(y, bn, relu=True)
+            else:
+                cat = fppm.upsample_concat(conv_out, branches, self.pool_scales)
+                y = _conv_bn(conv, bn, cat, relu=True)
             return self._classify(y)
         size = conv_out.shape[-2:]
         outs = [conv_out]
