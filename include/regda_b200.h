@@ -86,6 +86,9 @@ int regda_pseudo_select(const float *soft, int64_t *out, int b, int c, int64_t h
  * [b,c,H,W] tensor; hard_out int64 [b][H][W].
  * workspace: regda_refine_workspace_bytes(b, c, k, h, w) for both. */
 size_t regda_refine_workspace_bytes(int b, int c, int k, int h, int w);
+/* regda_refine_select with this (larger) workspace keeps the refined probabilities between its two passes instead of
+ * recomputing them (same result; +b*c*H*W floats) */
+size_t regda_refine_select_workspace_bytes(int b, int c, int k, int h, int w, int H, int W);
 int regda_label_refine(const float *feat_nhwc, const float *prototypes,
                        const float *pred1, const float *pred2,
                        const float *soft_in, float *soft_out,
@@ -236,9 +239,15 @@ int regda_ppm_g_pack(void *g0, void *g1, void *g2, void *g3, void *gt, int b, in
                      int nscales, int pack, void *stream);
 int regda_transpose_bf16(const void *src, void *dst, int batch, int rows, int cols, void *stream);
 /* forward convolution + BatchNorm statistics (bn_stats may be NULL: none) with an epilogue addend bf16 [n][oh][ow][cout] */
-int regda_conv_fprop_addend_bf16(const void *x, const void *wgt, void *y, int n, int h, int w, int cin, int cout,
+int regda_conv_fprop_addend_bf16(const void *x, const void *wgt, int wct, void *y, int n, int h, int w, int cin, int cout,
                                  int r, int s, int stride, int pad, int dil, const void *addend, float *bn_stats, int groups,
                                  int stats_zeroed, void *stream);
+/* `wct` >= cin: the weight has wct channels per tap ([cout][r][s][wct]) and the convolution runs over its FIRST cin channels, in
+ * place -- forward above, data gradient and weight gradient (dw float32 [cout][r][s][wct], columns [0, cin) of every tap) here. */
+int regda_conv_dgrad_wslice_bf16(const void *dy, const void *wgt, int wct, void *dx, int n, int h, int w, int cin, int cout,
+                                 int r, int s, int stride, int pad, int dil, const void *addend, void *stream);
+int regda_conv_wgrad_wslice_bf16(const void *dy, const void *x, float *dw, int wct, int n, int h, int w, int cin, int cout,
+                                 int r, int s, int stride, int pad, int dil, void *stream);
 
 /* ---- PPM head tail: Dropout2d + classifier (regda/models/Encoder.py:39-40) ----------------------------
  * regda_dropout2d_mask: keep_scale float32 [n] = 0 with probability p, else 1/(1-p), n = images * channels; the generator

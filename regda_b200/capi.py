@@ -112,16 +112,22 @@ def call(name, *args):
 
 
 class Workspace:
-    """Grow-only device scratch buffer owned by the caller side (the library never allocates)."""
+    """Grow-only device scratch buffer owned by the caller side (the library never allocates).  A buffer that has been handed
+    out may already be baked into a captured CUDA graph (its raw pointer is a kernel argument of the captured launches), so a
+    buffer that is outgrown is RETIRED, never freed: replays of older graphs keep reading and writing memory that is still
+    theirs (a freed workspace would be silently reused by the caching allocator under such a graph)."""
 
     def __init__(self):
         self._buf = {}
+        self._retired = []
 
     def get(self, nbytes: int, device):
         nbytes = max(int(nbytes), 256)
         key = torch.device(device).index or 0
         b = self._buf.get(key)
         if b is None or b.numel() < nbytes:
+            if b is not None:
+                self._retired.append(b)
             b = torch.empty(nbytes, dtype=torch.uint8, device=device)
             self._buf[key] = b
         return b

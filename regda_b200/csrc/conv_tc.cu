@@ -47,6 +47,8 @@ struct ConvGeom {
     int bh, bw, bn;                  // M tile = bn images x (bh x bw) output pixels, bn*bh*bw == 128
     int tiles_h, tiles_w, tiles_img; // patches per image, image blocks (ceil(n / bn))
     int kc;                          // cin / 64
+    int wct;                         // channels per tap of the WEIGHT tensor (>= the channels this GEMM touches: a convolution over
+                                     // the first channels of a wider OHWI weight reads / differentiates it in place)
 };
 
 struct TileCoord { int n_blk, tw, th, img0; };
@@ -169,7 +171,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                         for (int i = 0; i < BLOCK_N / 64; ++i)
                             tma_load_3d(sb + i * 8192, &tmap_w, full_bar + stage, n_blk * BLOCK_N + i * 64, wtap, c0);
                     } else {
-                        tma_load_2d(sb, &tmap_w, full_bar + stage, tap * g.cin + c0, n_blk * BLOCK_N);
+                        tma_load_2d(sb, &tmap_w, full_bar + stage, tap * g.wct + c0, n_blk * BLOCK_N);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     c0 += kBlockK;
@@ -470,10 +472,10 @@ int make_tmap_w(CUtensorMap *m, const void *w, int cout, int ktot, int block_n) 
     return REGDA_OK;
 }
 
-// dgrad weights in place: memory [red][taps][out] (the forward conv's OHWI), box {64 out, 1 tap, 64 red}
-int make_tmap_w_mn(CUtensorMap *m, const void *w, int red, int taps, int out) {
+// dgrad weights in place: memory [red][taps][wct >= out] (the forward conv's OHWI), box {64 out, 1 tap, 64 red}
+int make_tmap_w_mn(CUtensorMap *m, const void *w, int red, int taps, int out, int wct) {
     const cuuint64_t dims[3] = {static_cast<cuuint64_t>(out), static_cast<cuuint64_t>(taps), static_cast<cuuint64_t>(red)};
-    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(out) * 2, static_cast<cuuint64_t>(taps) * out * 2};
+    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(wct) * 2, static_cast<cuuint64_t>(taps) * wct * 2};
     const cuuint32_t box[3] = {64, 1, 64};
     const cuuint32_t estr[3] = {1, 1, 1};
     if (!encode_bf16_sw128(m, w, 3, dims, strides, box, estr)) return REGDA_ERR_CUDA;   /* text set by encode_bf16_sw128 (weights, MN) */
@@ -526,7 +528,7 @@ int launch_dgrad_bnred(const void *act, const void *wgt, __nv_bfloat16 *out, con
     int rc = make_tmap_x(&tx, act, g);
     if (rc) return rc;
     const int block_n = pick_block_n(g);
-    rc = make_tmap_w_mn(&tw, wgt, g.cin, taps, g.cout);
+    rc = make_tmap_w_mn(&tw, wgt, g.cin, taps, g.cout, g.wct);
     if (rc) return rc;
     // one pipeline stage fewer than the plain kernel at 256 / 128: the 32 KB of BatchNorm-input boxes take their place
     if (block_n == 256) return launch_persistent_impl<256, 3, true, false, false, true>(tx, tw, out, g, st, red, imgs_per_group, addend, br);
@@ -550,7 +552,7 @@ int launch_conv(const void *act, const void *wgt, void *out, const ConvGeom &g, 
     int rc = make_tmap_x(&tx, act, g);
     if (rc) return rc;
     const int block_n = pick_block_n(g);
-    rc = B_MN ? make_tmap_w_mn(&tw, wgt, g.cin, taps, g.cout) : make_tmap_w(&tw, wgt, g.cout, taps * g.cin, block_n);
+    rc = B_MN ? make_tmap_w_mn(&tw, wgt, g.cin, taps, g.cout, g.wct) : make_tmap_w(&tw, wgt, g.cout, taps * g.wct, block_n);
     if (rc) return rc;
     if (block_n == 256) return launch_persistent<256, 4, B_MN>(tx, tw, out, g, st, stats, imgs_per_group, addend, out_f32);
     if (block_n == 128) return launch_persistent<128, 6, B_MN>(tx, tw, out, g, st, stats, imgs_per_group, addend, out_f32);
@@ -575,6 +577,7 @@ int geom_init(ConvGeom &g, int n, int h, int w, int cin, int cout, int r, int s,
     g.tiles_h = (g.oh + g.bh - 1) / g.bh;
     g.tiles_img = (n + bn - 1) / bn;
     g.kc = cin / kBlockK;
+    g.wct = cin;
     return REGDA_OK;
 }
 
@@ -600,6 +603,7 @@ bool dgrad_geom(ConvGeom &g, int n, int h, int w, int cin, int cout, int r, int 
     const int oh = h + 2 * pad - dil * (r - 1), ow = w + 2 * pad - dil * (s - 1);
     geom_init(g, n, oh, ow, cout, cin, r, s, 1, dil * (r - 1) - pad, dil);
     g.flip = 1;
+    g.wct = cin;                     // MN-major weight rows are the forward convolution's input channels
     return g.oh == h && g.ow == w;
 }
 
@@ -666,9 +670,10 @@ extern "C" int regda_conv_fprop_stats_bf16(const void *x, const void *wgt, void 
 
 // Forward convolution whose epilogue adds `addend` (bf16, the output's shape) before rounding / taking the statistics;
 // bn_stats == NULL: no statistics.  (The folded PPM fuse convolution hands the pyramid branches' contribution in this way.)
-extern "C" int regda_conv_fprop_addend_bf16(const void *x, const void *wgt, void *y, int n, int h, int w, int cin, int cout,
+extern "C" int regda_conv_fprop_addend_bf16(const void *x, const void *wgt, int wct, void *y, int n, int h, int w, int cin, int cout,
                                             int r, int s, int stride, int pad, int dil, const void *addend, float *bn_stats, int groups,
                                             int stats_zeroed, void *stream) {
+    if (wct < cin || wct % 8) return fail(REGDA_ERR_INVALID_ARG, "conv_fprop_addend: weight channel count must be >= cin and a multiple of 8");
     if (!regda_conv_fprop_supported(n, h, w, cin, cout, r, s, stride, pad, dil))
         return fail(REGDA_ERR_UNSUPPORTED, "conv_fprop_addend: shape not covered by the tcgen05 kernel");
     if (bn_stats && !regda_conv_fprop_stats_supported(n, h, w, cin, cout, r, s, stride, pad, dil, groups))
@@ -678,6 +683,7 @@ extern "C" int regda_conv_fprop_addend_bf16(const void *x, const void *wgt, void
         return fail(REGDA_ERR_INVALID_ARG, "conv_fprop_addend: tensors must be 16-byte aligned");
     ConvGeom g;
     geom_init(g, n, h, w, cin, cout, r, s, stride, pad, dil);
+    g.wct = wct;
     ensure_context(x);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (bn_stats && !stats_zeroed) REGDA_CUDA_CHECK(cudaMemsetAsync(bn_stats, 0, static_cast<size_t>(groups) * 2 * cout * sizeof(float), st));
@@ -714,6 +720,22 @@ extern "C" int regda_conv_dgrad_bf16(const void *dy, const void *wgt, void *dx, 
     if (!dgrad_geom(g, n, h, w, cin, cout, r, s, pad, dil)) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad: inconsistent geometry");
     ensure_context(dy);
     if (addend != nullptr && (reinterpret_cast<uintptr_t>(addend) & 15)) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad: addend must be 16-byte aligned");
+    return launch_conv<true>(dy, wgt, dx, g, r * s, static_cast<cudaStream_t>(stream), nullptr, 1, addend);
+}
+
+// Data gradient with respect to the FIRST cin input channels of a convolution whose weight has wct >= cin channels per tap
+// (wgt bf16 [cout][r][s][wct], read in place): dx bf16 [n][h][w][cin].
+extern "C" int regda_conv_dgrad_wslice_bf16(const void *dy, const void *wgt, int wct, void *dx, int n, int h, int w, int cin, int cout,
+                                            int r, int s, int stride, int pad, int dil, const void *addend, void *stream) {
+    if (!regda_conv_dgrad_supported(n, h, w, cin, cout, r, s, stride, pad, dil))
+        return fail(REGDA_ERR_UNSUPPORTED, "conv_dgrad_wslice: shape not covered by the tcgen05 kernel");
+    if (!dy || !wgt || !dx || wct < cin || wct % 8) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_wslice: bad arguments");
+    if (!aligned16(dy, wgt, dx) || (addend && (reinterpret_cast<uintptr_t>(addend) & 15)))
+        return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_wslice: tensors must be 16-byte aligned");
+    ConvGeom g;
+    if (!dgrad_geom(g, n, h, w, cin, cout, r, s, pad, dil)) return fail(REGDA_ERR_INVALID_ARG, "conv_dgrad_wslice: inconsistent geometry");
+    g.wct = wct;
+    ensure_context(dy);
     return launch_conv<true>(dy, wgt, dx, g, r * s, static_cast<cudaStream_t>(stream), nullptr, 1, addend);
 }
 

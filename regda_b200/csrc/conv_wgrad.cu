@@ -38,6 +38,7 @@ struct WgradGeom {
     int ksteps;                      // ceil(n / bn) * tiles_h * tiles_w
     int splits, steps_per_split;
     int n_tiles;                     // ceil(cin / BLOCK_N)
+    int wct;                         // channels per tap of the gradient tensor (>= cin: gradient of the first cin channels of a wider weight)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -182,7 +183,7 @@ conv_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy, const 
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
             const WgItem it = wg_decode(item, g, m_tiles);
             const int row0 = it.m_blk * kWgM + q * 32;                                   // first cout row of this warp's box
-            const int colbase = it.tap * g.cin + it.n_blk * BLOCK_N;                     // column in the [cout][taps*cin] matrix
+            const int colbase = it.tap * g.wct + it.n_blk * BLOCK_N;                     // column in the [cout][taps*wct] matrix
             const bool live = it.k_hi > it.k_lo && row0 < g.cout;
             mbar_wait(tfull_bar + acc, acc_phase);
             tc_fence_after_sync();
@@ -230,7 +231,7 @@ int launch_wgrad_persistent(const CUtensorMap &tdy, const CUtensorMap &tx, float
     const int smem = L::kTotal + 1024;
     static_assert(L::kTotal + 1024 <= 232448, "persistent wgrad kernel: shared memory over the 227 KB limit");
     CUtensorMap tdw;
-    if (!encode_f32_2d_sw128(&tdw, dw, g.cout, static_cast<long long>(g.r) * g.s * g.cin, 32)) return REGDA_ERR_CUDA;
+    if (!encode_f32_2d_sw128(&tdw, dw, g.cout, static_cast<long long>(g.r) * g.s * g.wct, 32)) return REGDA_ERR_CUDA;
     REGDA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int m_tiles = (g.cout + kWgM - 1) / kWgM;
     const int num_items = g.n_tiles * m_tiles * g.r * g.s * g.splits;
@@ -251,9 +252,8 @@ extern "C" int regda_conv_wgrad_supported(int n, int h, int w, int cin, int cout
     return 1;
 }
 
-// dy bf16 [n][oh][ow][cout], x bf16 [n][h][w][cin], dw fp32 [cout][r][s][cin] (ACCUMULATED into)
-extern "C" int regda_conv_wgrad_bf16(const void *dy, const void *x, float *dw, int n, int h, int w, int cin, int cout,
-                                     int r, int s, int stride, int pad, int dil, void *stream) {
+static int wgrad_impl(const void *dy, const void *x, float *dw, int wct, int n, int h, int w, int cin, int cout,
+                      int r, int s, int stride, int pad, int dil, void *stream) {
     if (!regda_conv_wgrad_supported(n, h, w, cin, cout, r, s, stride, pad, dil))
         return fail(REGDA_ERR_UNSUPPORTED, "conv_wgrad: shape not covered by the tcgen05 kernel");
     if (!dy || !x || !dw) return fail(REGDA_ERR_INVALID_ARG, "conv_wgrad: null pointer");
@@ -261,6 +261,7 @@ extern "C" int regda_conv_wgrad_bf16(const void *dy, const void *x, float *dw, i
         return fail(REGDA_ERR_INVALID_ARG, "conv_wgrad: tensors must be 16-byte aligned");
     WgradGeom g;
     g.n = n; g.h = h; g.w = w; g.cin = cin; g.cout = cout; g.r = r; g.s = s; g.pad = pad; g.dil = dil; g.stride = stride;
+    g.wct = wct;
     g.oh = (h + 2 * pad - dil * (r - 1) - 1) / stride + 1;
     g.ow = (w + 2 * pad - dil * (s - 1) - 1) / stride + 1;
     int bw = 1;
@@ -292,4 +293,17 @@ extern "C" int regda_conv_wgrad_bf16(const void *dy, const void *x, float *dw, i
     if (block_n == 256) return launch_wgrad_persistent<256, 4>(tdy, tx, dw, g, st);
     if (block_n == 128) return launch_wgrad_persistent<128, 6>(tdy, tx, dw, g, st);
     return launch_wgrad_persistent<64, 8>(tdy, tx, dw, g, st);
+}
+
+// dy bf16 [n][oh][ow][cout], x bf16 [n][h][w][cin], dw fp32 [cout][r][s][cin] (ACCUMULATED into)
+extern "C" int regda_conv_wgrad_bf16(const void *dy, const void *x, float *dw, int n, int h, int w, int cin, int cout,
+                                     int r, int s, int stride, int pad, int dil, void *stream) {
+    return wgrad_impl(dy, x, dw, cin, n, h, w, cin, cout, r, s, stride, pad, dil, stream);
+}
+
+// gradient of the FIRST cin channels of a weight with wct >= cin channels per tap: dw fp32 [cout][r][s][wct], columns [0, cin) of every tap
+extern "C" int regda_conv_wgrad_wslice_bf16(const void *dy, const void *x, float *dw, int wct, int n, int h, int w, int cin, int cout,
+                                            int r, int s, int stride, int pad, int dil, void *stream) {
+    if (wct < cin || wct % 4) return fail(REGDA_ERR_INVALID_ARG, "conv_wgrad_wslice: weight channel count must be >= cin and a multiple of 4");
+    return wgrad_impl(dy, x, dw, wct, n, h, w, cin, cout, r, s, stride, pad, dil, stream);
 }

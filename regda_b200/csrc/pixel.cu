@@ -451,17 +451,43 @@ static int refine_select_impl(const void *feat_nhwc, bool feat_bf16, const float
     const float top = static_cast<float>(cutoff_top), low = static_cast<float>(cutoff_low);
     // max pass: ~8 blocks per SM over all images, each block walks its image with a grid stride
     const dim3 mgrid(std::min<int>(grid.x, std::max(1, 8 * sm_count() / b)), b);
+    // The selection needs every image's per-class maximum of the REFINED probabilities first.  With room in the workspace for
+    // them (regda_refine_select_workspace_bytes: b*c*H*W floats more) the max pass writes the refined probabilities and the
+    // selection is a plain threshold pass over them (24 B/px written + read, L2-friendly) instead of a second evaluation of the
+    // three soft-maxes and eighteen bilinear taps per pixel; without it the refinement is recomputed (same bits either way).
+    const size_t cache_bytes = static_cast<size_t>(b) * c * H * W * sizeof(float);
+    float *cache = workspace_bytes >= align_up(ws.bytes, 256) + cache_bytes ? reinterpret_cast<float *>(static_cast<char *>(workspace) + align_up(ws.bytes, 256)) : nullptr;
+    const long long HW = static_cast<long long>(H) * W;
+    long long *o = reinterpret_cast<long long *>(hard_out);
     if (c <= 8) {
-        refine_max_kernel<8, false><<<mgrid, kPxThreads, 0, st>>>(a, nullptr, ws.gmax);
-        REGDA_LAUNCH_CHECK();
-        refine_select_kernel<8><<<grid, kPxThreads, 0, st>>>(a, ws.gmax, reinterpret_cast<long long *>(hard_out), top, low, ignore_label);
+        if (cache) {
+            refine_max_kernel<8, true><<<mgrid, kPxThreads, 0, st>>>(a, cache, ws.gmax);
+            REGDA_LAUNCH_CHECK();
+            soft_select_kernel<8><<<mgrid, kPxThreads, 0, st>>>(cache, c, HW, ws.gmax, o, top, low, ignore_label);
+        } else {
+            refine_max_kernel<8, false><<<mgrid, kPxThreads, 0, st>>>(a, nullptr, ws.gmax);
+            REGDA_LAUNCH_CHECK();
+            refine_select_kernel<8><<<grid, kPxThreads, 0, st>>>(a, ws.gmax, o, top, low, ignore_label);
+        }
     } else {
-        refine_max_kernel<16, false><<<mgrid, kPxThreads, 0, st>>>(a, nullptr, ws.gmax);
-        REGDA_LAUNCH_CHECK();
-        refine_select_kernel<16><<<grid, kPxThreads, 0, st>>>(a, ws.gmax, reinterpret_cast<long long *>(hard_out), top, low, ignore_label);
+        if (cache) {
+            refine_max_kernel<16, true><<<mgrid, kPxThreads, 0, st>>>(a, cache, ws.gmax);
+            REGDA_LAUNCH_CHECK();
+            soft_select_kernel<16><<<mgrid, kPxThreads, 0, st>>>(cache, c, HW, ws.gmax, o, top, low, ignore_label);
+        } else {
+            refine_max_kernel<16, false><<<mgrid, kPxThreads, 0, st>>>(a, nullptr, ws.gmax);
+            REGDA_LAUNCH_CHECK();
+            refine_select_kernel<16><<<grid, kPxThreads, 0, st>>>(a, ws.gmax, o, top, low, ignore_label);
+        }
     }
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
+}
+
+// workspace of regda_refine_select[_bf16feat] including the refined-probability cache (see refine_select_impl)
+extern "C" size_t regda_refine_select_workspace_bytes(int b, int c, int k, int h, int w, int H, int W) {
+    if (b < 0 || c < 1 || k < 1 || h < 1 || w < 1 || H < 1 || W < 1) return 0;
+    return align_up(carve_refine_ws(nullptr, b, c, k, h, w).bytes, 256) + static_cast<size_t>(b) * c * H * W * sizeof(float);
 }
 
 extern "C" int regda_refine_select(const float *feat_nhwc, const float *prototypes, const float *pred1, const float *pred2,

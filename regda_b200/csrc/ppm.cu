@@ -360,6 +360,7 @@ ppm_gather_weights_kernel(const __nv_bfloat16 *__restrict__ w, __nv_bfloat16 *__
     const int o = row / T, tap = row - o * T;
     const __nv_bfloat16 *src = w + static_cast<size_t>(row) * ct;
     if (blockIdx.y == 0) {
+        if (wmain == nullptr) return;                   // the feature part is read in place (weight channel stride of the conv kernels)
         __nv_bfloat16 *dst = wmain + static_cast<size_t>(row) * cf;
         for (int c = threadIdx.x * 8; c < cf; c += blockDim.x * 8) *reinterpret_cast<uint4 *>(dst + c) = *reinterpret_cast<const uint4 *>(src + c);
     } else {
@@ -378,6 +379,7 @@ ppm_scatter_wgrad_kernel(const float *__restrict__ gmain, const FPtrs gwb, float
     const int o = row / T, tap = row - o * T;
     float *dst = gw + static_cast<size_t>(row) * ct;
     if (blockIdx.y == 0) {
+        if (gmain == nullptr) return;                   // the feature part was accumulated in place by the weight-gradient kernel
         const float *src = gmain + static_cast<size_t>(row) * cf;
         for (int c = threadIdx.x * 4; c < cf; c += blockDim.x * 4) {
             float4 d = *reinterpret_cast<float4 *>(dst + c);
@@ -447,10 +449,10 @@ transpose_bf16_kernel(const __nv_bfloat16 *__restrict__ src, __nv_bfloat16 *__re
 }  // namespace
 }  // namespace regda
 
-// w bf16 [O][T][ct] (OHWI), ct = cf + nb*cb -> wmain bf16 [O][T][cf], wb_k bf16 [T*O][cb] (row = tap*O + o), k < nb <= 4
+// w bf16 [O][T][ct] (OHWI), ct = cf + nb*cb -> wmain bf16 [O][T][cf] (may be NULL: not wanted), wb_k bf16 [T*O][cb] (row = tap*O + o), k < nb <= 4
 extern "C" int regda_ppm_gather_weights(const void *w, void *wmain, void *wb0, void *wb1, void *wb2, void *wb3, int O, int T, int ct,
                                         int cf, int cb, int nb, void *stream) {
-    if (!w || !wmain || O < 1 || T < 1 || nb < 1 || nb > kMaxScales || cf % 8 || cb % 8 || ct != cf + nb * cb)
+    if (!w || O < 1 || T < 1 || nb < 1 || nb > kMaxScales || cf % 8 || cb % 8 || ct != cf + nb * cb)
         return fail(REGDA_ERR_INVALID_ARG, "ppm_gather_weights: bad arguments");
     GPtrs p;
     void *ps[4] = {wb0, wb1, wb2, wb3};
@@ -464,10 +466,10 @@ extern "C" int regda_ppm_gather_weights(const void *w, void *wmain, void *wb0, v
     return REGDA_OK;
 }
 
-// gw float32 [O][T][ct] += (gmain float32 [O][T][cf], gwb_k float32 [T*O][cb])
+// gw float32 [O][T][ct] += (gmain float32 [O][T][cf] (may be NULL), gwb_k float32 [T*O][cb])
 extern "C" int regda_ppm_scatter_wgrad(const float *gmain, const float *g0, const float *g1, const float *g2, const float *g3, float *gw,
                                        int O, int T, int ct, int cf, int cb, int nb, void *stream) {
-    if (!gmain || !gw || O < 1 || T < 1 || nb < 1 || nb > kMaxScales || cf % 4 || cb % 4 || ct != cf + nb * cb)
+    if (!gw || O < 1 || T < 1 || nb < 1 || nb > kMaxScales || cf % 4 || cb % 4 || ct != cf + nb * cb)
         return fail(REGDA_ERR_INVALID_ARG, "ppm_scatter_wgrad: bad arguments");
     FPtrs p;
     const float *ps[4] = {g0, g1, g2, g3};

@@ -136,7 +136,7 @@ class Aligner:
         capi.call("regda_pearson_dist", capi.ptr(rows), capi.ptr(protos), capi.ptr(out), n, m, k, capi.ptr(ws), ws.numel(), capi.stream())
         return out
 
-    def _refine_inputs(self, feat_t, preds_t, label_t_soft, keep_bf16=False):
+    def _refine_inputs(self, feat_t, preds_t, label_t_soft, keep_bf16=False, select=False):
         b, k, h, w = feat_t.shape
         H, W = label_t_soft.shape[-2:]
         if isinstance(preds_t, (list, tuple)):
@@ -148,7 +148,9 @@ class Aligner:
         soft = label_t_soft.detach().float().contiguous()
         c = soft.shape[1]
         assert c == self.class_num == p1.shape[1]
-        ws = capi.workspace.get(capi.lib().regda_refine_workspace_bytes(b, c, k, h, w), rows.device)
+        nbytes = (capi.lib().regda_refine_select_workspace_bytes(b, c, k, h, w, H, W) if select
+                  else capi.lib().regda_refine_workspace_bytes(b, c, k, h, w))
+        ws = capi.workspace.get(nbytes, rows.device)
         return rows, p1, p2, soft, ws, (b, c, k, h, w, H, W)
 
     def label_refine(self, label_t_sup, feat_t, preds_t, label_t_soft, refine=True, mode='all', temp=2.0):
@@ -168,7 +170,7 @@ class Aligner:
     def refine_select(self, feat_t, preds_t, label_t_soft, temp=2.0, cutoff_top=0.8, cutoff_low=0.6):
         """Fused label_refine -> pseudo_selection (tools/train_ssl_reg.py:214-218): returns the hard
         pseudo label [b,H,W] int64 without materialising the refined probabilities."""
-        rows, p1, p2, soft, ws, (b, c, k, h, w, H, W) = self._refine_inputs(feat_t, preds_t, label_t_soft, keep_bf16=True)
+        rows, p1, p2, soft, ws, (b, c, k, h, w, H, W) = self._refine_inputs(feat_t, preds_t, label_t_soft, keep_bf16=True, select=True)
         out = torch.empty((b, H, W), dtype=torch.int64, device=soft.device)
         capi.call("regda_refine_select_bf16feat" if rows.dtype == torch.bfloat16 else "regda_refine_select", capi.ptr(rows), capi.ptr(self.prototypes), capi.ptr(p1), capi.ptr(p2), capi.ptr(soft),
                   capi.ptr(out), b, c, k, h, w, H, W, float(temp), float(cutoff_top), float(cutoff_low), int(self.ignore_label),

@@ -95,10 +95,9 @@ class _FoldedFuseFn(torch.autograd.Function):
         hw, kp = h * w, _kp(scales)
         dev = fin.device
         bf = dict(dtype=torch.bfloat16, device=dev)
-        w16 = _cl(tc.weight_shadow(weight))
-        wmain = torch.empty((O, cf, 3, 3), memory_format=torch.channels_last, **bf)
+        w16 = _cl(tc.weight_shadow(weight))         # OHWI: the feature part [:, :, :cf] is used in place (channel stride ct)
         wb = [torch.empty((9 * O, cb, 1, 1), memory_format=torch.channels_last, **bf) for _ in range(nb)]
-        capi.call("regda_ppm_gather_weights", capi.ptr_any(w16), capi.ptr_any(wmain), *_ptrs(wb), O, 9, ct, cf, cb, nb, capi.stream())
+        capi.call("regda_ppm_gather_weights", capi.ptr_any(w16), None, *_ptrs(wb), O, 9, ct, cf, cb, nb, capi.stream())
         # G_k = p_k . W_k^T: 1x1 convolutions on the s x s maps (several images per tcgen05 M tile)
         gs = [tc.fprop(p, wk, 1, 0, 1) for p, wk in zip(brs, wb)]                  # [b, 9*O, s, s] channels-last: [(img, cell)][tap*O + o]
         gt = torch.empty((b * O, kp), **bf)                                        # GT[img][o][(cell, tap)]
@@ -114,10 +113,10 @@ class _FoldedFuseFn(torch.autograd.Function):
         zeroed = True
         if groups is not None:
             stats, zeroed = capi.zero_pool.take((groups, 2, O), dev)
-        capi.call("regda_conv_fprop_addend_bf16", capi.ptr_any(fin), capi.ptr_any(wmain), capi.ptr_any(y), b, h, w, cf, O, 3, 3, 1, 1, 1,
+        capi.call("regda_conv_fprop_addend_bf16", capi.ptr_any(fin), capi.ptr_any(w16), ct, capi.ptr_any(y), b, h, w, cf, O, 3, 3, 1, 1, 1,
                   capi.ptr_any(yppm), capi.ptr_any(stats) if stats is not None else None, groups or 1, int(zeroed), capi.stream())
         conv_ops.stats["tcgen05_fprop"] += 1
-        ctx.save_for_backward(fin, wmain, aw, *brs, *wb)
+        ctx.save_for_backward(fin, w16, aw, *brs, *wb)
         ctx.weight, ctx.scales, ctx.nb = weight, tuple(scales), nb
         ctx.set_materialize_grads(False)
         if stats is not None:
@@ -127,7 +126,7 @@ class _FoldedFuseFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy, _gstats=None):
         saved = ctx.saved_tensors
-        fin, wmain, aw = saved[0], saved[1], saved[2]
+        fin, w16, aw = saved[0], saved[1], saved[2]
         nb, scales, weight = ctx.nb, ctx.scales, ctx.weight
         brs, wb = saved[3:3 + nb], saved[3 + nb:3 + 2 * nb]
         conv_ops._reached(weight)
@@ -148,22 +147,29 @@ class _FoldedFuseFn(torch.autograd.Function):
         arr, n = _scales(scales)
         capi.call("regda_ppm_g_pack", *_ptrs(dgs), capi.ptr_any(dgt), b, O, 9, kp, arr, n, 0, capi.stream())
         dps = [tc.dgrad(dg, wk, tuple(p.shape), 1, 0, 1) for dg, wk, p in zip(dgs, wb, brs)] if need_br else [None] * nb
-        dfin = tc.dgrad(gy, wmain, tuple(fin.shape), 1, 1, 1) if need_fin else None
+        dfin = None
+        if need_fin:
+            dfin = torch.empty_like(fin)
+            capi.call("regda_conv_dgrad_wslice_bf16", capi.ptr_any(gy), capi.ptr_any(w16), ct, capi.ptr_any(dfin), b, h, w, cf, O, 3, 3, 1, 1, 1,
+                      None, capi.stream())
         conv_ops.stats["tcgen05_dgrad"] += 1
         # weight gradients (feature part + the four branch parts) and their scatter into the OHWI gradient: off the critical path
         if weight.grad is None:
             weight.grad = torch.zeros_like(weight)
 
+        assert weight.grad.dtype == torch.float32 and weight.grad.is_contiguous(memory_format=torch.channels_last)
+
         def wgrads():
-            gmain = torch.zeros((O, cf, 3, 3), dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last)
-            tc.wgrad_accumulate(gy, fin, gmain, 1, 1, 1)
+            # feature part: accumulated straight into the OHWI gradient (columns [0, cf) of every tap)
+            capi.call("regda_conv_wgrad_wslice_bf16", capi.ptr_any(gy), capi.ptr_any(fin), capi.ptr_any(weight.grad), ct, b, h, w, cf, O, 3, 3,
+                      1, 1, 1, capi.stream())
             gwb = []
             for dg, p in zip(dgs, brs):
                 g = torch.zeros((9 * O, cb, 1, 1), dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last)
                 tc.wgrad_accumulate(dg, p, g, 1, 0, 1)
                 gwb.append(g)
-            capi.call("regda_ppm_scatter_wgrad", capi.ptr_any(gmain), *_ptrs(gwb), capi.ptr_any(weight.grad), O, 9, ct, cf, cb, nb, capi.stream())
-            return [gmain] + gwb
+            capi.call("regda_ppm_scatter_wgrad", None, *_ptrs(gwb), capi.ptr_any(weight.grad), O, 9, ct, cf, cb, nb, capi.stream())
+            return gwb
 
         if conv_ops._side_active:
             key, side = conv_ops._wgrad_stream(dev)
