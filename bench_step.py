@@ -182,6 +182,8 @@ def workload_config(stage, imgs, world, use_graph, engine, config="P"):
 
 def run(args, rank, world, local, pk, ClockSampler, barrier, max_over_ranks):
     dev = torch.device("cuda", local)
+    if os.environ.get("REGDA_TUNE_MIN256"):                 # tile-policy sweeps only (profiles/): never set by the driver
+        capi.check(capi.lib().regda_conv_tune(int(os.environ["REGDA_TUNE_MIN256"])))
     use_graph = os.environ.get("REGDA_GRAPH", "1") != "0"
     calls0 = capi.launch_count
     stage = 2 if getattr(args, "workload", None) == "align" else 3

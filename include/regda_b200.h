@@ -185,6 +185,8 @@ int regda_ema_update(float *shadow, const float *param, int64_t n, double decay,
  * 128 pixels (pyramid-pooling branches: 1x1 .. 6x6) put several images into one 128-row M tile.
  * regda_conv_fprop_supported returns 1 when the shape is covered: cin, cout multiples of 64, stride 1 or 2. */
 int regda_conv_fprop_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil);
+/* tile-policy knob for sweeps (0 = default): minimum count of 128x256 tiles for which the 256-wide tile is chosen over 128 */
+int regda_conv_tune(int min_tiles_256_value);
 int regda_conv_fprop_bf16(const void *x, const void *wgt, void *y, int n, int h, int w, int cin, int cout,
                           int r, int s, int stride, int pad, int dil, void *stream);
 /* same convolution, raw float32 accumulators out: y float32 [n][oh][ow][cout].  With the operands of a float32 convolution

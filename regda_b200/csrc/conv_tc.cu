@@ -511,8 +511,10 @@ int launch_persistent_impl(const CUtensorMap &tx, const CUtensorMap &tw, void *y
     return REGDA_OK;
 }
 
-// 256-wide tiles are taken when they give at least half an SM-count of tiles (otherwise 128-wide tiles fill the machine better)
-int min_tiles_256() { return sm_count() / 2; }
+// 256-wide tiles are taken when they give at least half an SM-count of tiles (otherwise 128-wide tiles fill the machine better);
+// regda_conv_tune() overrides the threshold (tile-policy sweeps: scripts/bench_conv.py --min-tiles-256)
+int g_min_tiles_256 = 0;
+int min_tiles_256() { return g_min_tiles_256 > 0 ? g_min_tiles_256 : sm_count() / 2; }
 
 int pick_block_n(const ConvGeom &g) {
     const long long m_tiles = static_cast<long long>(g.tiles_img) * g.tiles_h * g.tiles_w;
@@ -611,6 +613,12 @@ bool dgrad_geom(ConvGeom &g, int n, int h, int w, int cin, int cout, int r, int 
 }  // namespace regda
 
 using namespace regda;
+
+// tile-policy knob for sweeps: minimum number of 128 x 256 tiles for the 256-wide tile to be chosen (0 = default, SM count / 2)
+extern "C" int regda_conv_tune(int min_tiles_256_value) {
+    g_min_tiles_256 = min_tiles_256_value > 0 ? min_tiles_256_value : 0;
+    return REGDA_OK;
+}
 
 // 1 if (shape, alignment) is covered by the tcgen05 kernel: channel counts multiples of 64, stride 1 or 2, any map size
 extern "C" int regda_conv_fprop_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil) {

@@ -26,6 +26,24 @@ from .gast.balance import CrossEntropy
 from .utils.tools import loss_calc
 
 
+class _Range:
+    """NVTX range around one phase of the step (the reference has no profiler hooks).  Host-side markers:
+    visible in an nsys / ncu timeline of the eager step; inside a replayed CUDA graph the whole step is one launch."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if torch.cuda.is_available():
+            torch.cuda.nvtx.range_push("regda/" + self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if torch.cuda.is_available():
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def _is_channels_last_4d(p):
     return p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous()
 
@@ -190,14 +208,15 @@ class SelfTrainingStep:
         m = self.model
         self.arena.zero_grad()
         capi.zero_pool.reset(self.arena.param.device)      # one memset for every small accumulator of the step
-        if self.pair_forward and images_s.shape == images_t.shape:
-            # both domain batches through the network as one tensor, BatchNorm statistics per domain (models/Encoder.py)
-            # (features stay bf16: the Aligner kernels of this step read bf16 rows and nothing differentiates through them)
-            (pred_s1, pred_s2, feat_s), (pred_t1, pred_t2, feat_t) = m.forward_pair(images_s, images_t, feat_dtype=torch.bfloat16)   # :210-212
-        else:
-            pred_s1, pred_s2, feat_s = m(images_s)                                 # :210
-            pred_t1, pred_t2, feat_t = m(images_t)                                 # :212
-        with torch.no_grad():
+        with _Range("forward"):
+            if self.pair_forward and images_s.shape == images_t.shape:
+                # both domain batches through the network as one tensor, BatchNorm statistics per domain (models/Encoder.py)
+                # (features stay bf16: the Aligner kernels of this step read bf16 rows and nothing differentiates through them)
+                (pred_s1, pred_s2, feat_s), (pred_t1, pred_t2, feat_t) = m.forward_pair(images_s, images_t, feat_dtype=torch.bfloat16)   # :210-212
+            else:
+                pred_s1, pred_s2, feat_s = m(images_s)                             # :210
+                pred_t1, pred_t2, feat_t = m(images_t)                             # :212
+        with torch.no_grad(), _Range("pseudo_labels"):
             if self.refine_label:
                 hard = self.aligner.refine_select(feat_t, [pred_t1, pred_t2], soft_t, self.refine_temp,
                                                   self.cutoff_top, self.cutoff_low)   # :214-218
@@ -207,11 +226,14 @@ class SelfTrainingStep:
             if self.sam_refine:
                 hard = self.homogenizer(hard, regs_t.squeeze(1))                   # :223
             self.aligner.update_prototype(feat_s, label_s, reduce_fn=self._reduce_proto)   # :225
-        loss_source = loss_calc([pred_s1, pred_s2], label_s, loss_fn=self.loss_fn_s, multi=True)   # :228
-        loss_target = loss_calc([pred_t1, pred_t2], hard, loss_fn=self.loss_fn_t, multi=True)      # :233
-        loss = loss_source + loss_target
-        self._backward(loss)                                                       # :238 (+ the bucketed gradient all-reduce)
-        self.arena.clip_and_sgd(self.max_norm, self.momentum, self.weight_decay, 1.0 / self.world_size)   # :239-241
+        with _Range("losses"):
+            loss_source = loss_calc([pred_s1, pred_s2], label_s, loss_fn=self.loss_fn_s, multi=True)   # :228
+            loss_target = loss_calc([pred_t1, pred_t2], hard, loss_fn=self.loss_fn_t, multi=True)      # :233
+            loss = loss_source + loss_target
+        with _Range("backward+allreduce"):
+            self._backward(loss)                                                   # :238 (+ the bucketed gradient all-reduce)
+        with _Range("clip+sgd"):
+            self.arena.clip_and_sgd(self.max_norm, self.momentum, self.weight_decay, 1.0 / self.world_size)   # :239-241
         capi.zero_pool.disarm()
         return loss.detach(), loss_source.detach(), loss_target.detach(), hard
 

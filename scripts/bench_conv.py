@@ -59,7 +59,11 @@ def main():
     ap.add_argument("--dgrad", action="store_true", help="time the data-gradient kernel instead of fprop")
     ap.add_argument("--stats", action="store_true", help="fprop with the fused BatchNorm statistics epilogue (2 groups), as the step runs it")
     ap.add_argument("--graph", type=int, default=0, help="time N launches replayed from one CUDA graph")
+    ap.add_argument("--min-tiles-256", type=int, default=0, help="tile policy: minimum number of 128x256 tiles for the 256-wide tile (0 = default)")
     a = ap.parse_args()
+    if a.min_tiles_256:
+        from regda_b200 import capi
+        capi.check(capi.lib().regda_conv_tune(a.min_tiles_256))
     global GRAPH_INNER
     GRAPH_INNER = a.graph
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
