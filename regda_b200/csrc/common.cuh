@@ -42,16 +42,18 @@ int max_optin_smem();
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// REGDA_PDL: 0 = off, 1 = kernels of level 1 (the tensor-core kernels, which have a real prologue to overlap), 2 = all
+// PDL level: 0 = off, 1 = kernels of level 1 (the tensor-core kernels, which have a real prologue to overlap), 2 = all.
+// Default 1 (measured on the step, round 2: 0 -> 1010.8, 1 -> 1027.2, 2 -> 999.2 images/s with the trigger at the kernel start);
+// REGDA_PDL overrides for sweeps.  (Moving the tensor-core kernels' trigger from their start to "last MMA issued" measured
+// neutral at level 1 -- 1018 vs 1017 images/s -- and did not rescue level 2 -- 999; profiles/pdl_sweep_round2.txt.)
 inline int pdl_level() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("REGDA_PDL");
-        v = e ? atoi(e) : 0;
+        v = e ? atoi(e) : 1;
     }
     return v;
 }
-
 template <int LEVEL = 1, typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
     cudaLaunchConfig_t cfg = {};
