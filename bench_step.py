@@ -69,26 +69,43 @@ def ncu_evidence(key):
         return None
 
 
+def head_conv_launcher():
+    """The dominant kernel of the step by algorithmic FLOPs, launched exactly as the product path launches it
+    (regda_b200/ops/ppm_fold.py): the 3x3 PPM fuse convolution over the 2048 feature channels of the 4096-channel OHWI weight,
+    read in place (channel stride 4096), on the 32x32 feature maps of the 16 images of a step -- implicit GEMM M=16384, N=512,
+    K=18432 -- with the pyramid branches' contribution as the bf16 epilogue addend and the next BatchNorm's statistics (2 groups)
+    fused.  Returns (launch, flop)."""
+    n, cf, ct, hw, cout = 2 * B, 2048, 4096, H // 16, 512
+    cl = torch.channels_last
+    x = torch.randn(n, cf, hw, hw, device="cuda").bfloat16().contiguous(memory_format=cl)
+    w = (torch.randn(cout, ct, 3, 3, device="cuda") / (ct * 9) ** 0.5).bfloat16().contiguous(memory_format=cl)
+    add = torch.randn(n, cout, hw, hw, device="cuda").bfloat16().contiguous(memory_format=cl)
+    y = torch.empty((n, cout, hw, hw), dtype=torch.bfloat16, device="cuda", memory_format=cl)
+    stats = torch.zeros(2, 2, cout, device="cuda")
+
+    def launch():
+        capi.call("regda_conv_fprop_addend_bf16", capi.ptr_any(x), capi.ptr_any(w), ct, capi.ptr_any(y), n, hw, hw, cf, cout, 3, 3, 1, 1, 1,
+                  capi.ptr_any(add), capi.ptr_any(stats), 2, 0, capi.stream())
+
+    launch.keep = (x, w, add, y, stats)
+    return launch, 2.0 * n * hw * hw * cout * cf * 9
+
+
 def top_kernel_roofline(pk, reps=10):
-    """The dominant kernel of the step by algorithmic FLOPs -- the PPM fuse convolution (3x3, 4096 -> 512 channels on the
-    32x32 feature maps of the 16 images of a step: implicit GEMM M=16384, N=512, K=36864, 42.7 % of the model's MACs) --
-    timed alone with CUDA events on the launch stream, L2 flushed between launches (burst peak is the denominator)."""
-    from regda_b200.ops import tc
-    n, cin, hw, cout = 2 * B, 4096, H // 16, 512
-    x = torch.randn(n, cin, hw, hw, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
-    w = (torch.randn(cout, cin, 3, 3, device="cuda") / (cin * 9) ** 0.5).bfloat16().contiguous(memory_format=torch.channels_last)
+    """head_conv_launcher() timed alone with CUDA events on the launch stream, L2 flushed between launches (burst peak is the
+    denominator); DRAM traffic / tensor-pipe figures are read from the committed ncu capture of the same launch."""
+    launch, flop = head_conv_launcher()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for _ in range(3):
-        tc.fprop(x, w, 1, 1, 1)
+        launch()
     ts = []
     for _ in range(reps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); tc.fprop(x, w, 1, 1, 1); e1.record()
+        e0.record(); launch(); e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     ms = sum(ts) / len(ts)
-    flop = 2.0 * n * hw * hw * cout * cin * 9
     ach = flop / (ms * 1e-3) / 1e12
     ev = ncu_evidence("conv_head_fprop") or {}
     return {"bound": "tensor", "achieved": round(ach, 1), "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_burst"], 4),
@@ -96,7 +113,8 @@ def top_kernel_roofline(pk, reps=10):
             "traffic": ev.get("dram_bytes"), "traffic_source": ev.get("source"),
             "ncu_tensor_pipe_active_pct": ev.get("tensor_pipe_active_pct"),
             "peak_source": pk["source"] + " (burst: kernel timed alone)",
-            "kernel": "conv_persistent_kernel<256,4> (tcgen05 128x256 tiles, TMA-store epilogue) on the PPM fuse conv (3x3, 4096->512, 16x32x32 px: M=16384 N=512 K=36864)",
+            "kernel": "conv_persistent_kernel<256,4> (tcgen05 128x256 tiles, TMA-store epilogue with addend + BatchNorm statistics) on the folded PPM "
+                      "fuse conv (3x3 over the 2048 feature channels of the 4096-channel weight, 16x32x32 px: M=16384 N=512 K=18432)",
             "algorithmic_flop_per_launch": flop, "us_per_launch": round(ms * 1e3, 1)}
 
 
