@@ -202,6 +202,10 @@ def run(args, rank, world, local, pk, ClockSampler, barrier, max_over_ranks):
     dev = torch.device("cuda", local)
     if os.environ.get("REGDA_TUNE_MIN256"):                 # tile-policy sweeps only (profiles/): never set by the driver
         capi.check(capi.lib().regda_conv_tune(int(os.environ["REGDA_TUNE_MIN256"])))
+    if os.environ.get("REGDA_TUNE_BN_TRIGGER"):             # PDL sweeps only (profiles/pdl_sweep_*): never set by the driver
+        torch.cuda.set_device(dev)
+        torch.zeros(1, device=dev)
+        capi.check(capi.lib().regda_bn_tune(int(os.environ["REGDA_TUNE_BN_TRIGGER"])))
     use_graph = os.environ.get("REGDA_GRAPH", "1") != "0"
     calls0 = capi.launch_count
     stage = 2 if getattr(args, "workload", None) == "align" else 3

@@ -187,6 +187,12 @@ int regda_ema_update(float *shadow, const float *param, int64_t n, double decay,
 int regda_conv_fprop_supported(int n, int h, int w, int cin, int cout, int r, int s, int stride, int pad, int dil);
 /* tile-policy knob for sweeps (0 = default): minimum count of 128x256 tiles for which the 256-wide tile is chosen over 128 */
 int regda_conv_tune(int min_tiles_256_value);
+/* Hint for the next forward / data-gradient convolution launched by the calling thread: its WEIGHT tensor was last written long
+ * before the kernel preceding the launch in the stream (the optimizer writes the bf16 weight copies once per step), so the kernel
+ * may request its first weight tiles before its programmatic-dependent-launch wait.  Consumed by that launch. */
+int regda_conv_hint_static_weights(void);
+/* sweep knob: whether the BatchNorm kernels release their programmatic-dependent-launch successors at their start (1, default) or at exit (0) */
+int regda_bn_tune(int early_trigger);
 int regda_conv_fprop_bf16(const void *x, const void *wgt, void *y, int n, int h, int w, int cin, int cout,
                           int r, int s, int stride, int pad, int dil, void *stream);
 /* same convolution, raw float32 accumulators out: y float32 [n][oh][ow][cout].  With the operands of a float32 convolution
@@ -319,7 +325,7 @@ int regda_upsample_softmax_mean(const float *x1, const float *x2, float *out, in
                                 void *stream);
 
 /* Patch matrix of the stem convolution (regda/_resnets.py:150: Conv2d(3, 64, 7, stride 2, padding 3)): x bf16 [n][h][w][3]
- * -> a bf16 [n][oh][ow][192], k = (r*7 + s)*3 + c for the 147 taps, zeros above; the stem then runs on the tcgen05 kernels
+ * -> a bf16 [n][oh][ow][192], k = r*24 + s*3 + c (filter row r: 21 taps + 3 zeros; k >= 168 zero); the stem then runs on the tcgen05 kernels
  * as a 1x1 convolution over 192 channels (forward + weight gradient). */
 int regda_stem_im2col_bf16(const void *x, void *a, int n, int h, int w, void *stream);
 /* same patch matrix straight from the loader's float32 [n][3][h][w] image (rounded to bf16 while staged) */
@@ -343,6 +349,14 @@ int regda_ppm_pool_fwd(const void *feat, float *pooled, int b, int h, int w, int
                        void *stream);
 int regda_ppm_pool_bwd(const float *dpooled, void *dfeat, int b, int h, int w, int c, const int *scales_host, int nscales,
                        void *stream);
+/* dfeat = addend + pool_backward(dpooled); addend bf16 [b][h][w][c] or NULL: the gradient the feature map's other readers sent
+ * (autograd's AccumulateGrad add after regda/models/Encoder.py:43-52's AdaptiveAvgPool2d backward, fused) */
+int regda_ppm_pool_bwd_add(const float *dpooled, const void *addend, void *dfeat, int b, int h, int w, int c, const int *scales_host,
+                           int nscales, void *stream);
+/* the pooled cells as the branch convolutions read them (Encoder.py:45-47: ppm[k](AdaptiveAvgPool2d(s_k)(x)) takes the s_k x s_k map):
+ * split != 0: pooled float32 [b][ncell][c] -> p_k bf16 [b][s_k][s_k][c]; split == 0: the gradient's way back (float32 result) */
+int regda_ppm_cells(float *pooled, void *p0, void *p1, void *p2, void *p3, int b, int c, const int *scales_host, int nscales, int split,
+                    void *stream);
 int regda_ppm_upcat_fwd(const void *feat, const void *br0, const void *br1, const void *br2, const void *br3, void *cat,
                         int b, int h, int w, int c, int cb, const int *scales_host, int nscales, void *stream);
 int regda_ppm_upcat_bwd(const void *dcat, float *dbr0, float *dbr1, float *dbr2, float *dbr3, int b, int h, int w, int c,

@@ -49,6 +49,8 @@ struct ConvGeom {
     int kc;                          // cin / 64
     int wct;                         // channels per tap of the WEIGHT tensor (>= the channels this GEMM touches: a convolution over
                                      // the first channels of a wider OHWI weight reads / differentiates it in place)
+    int w_early;                     // the weights were written long before the preceding kernel of the stream: their first pipeline
+                                     // stages may be requested BEFORE the programmatic-dependent-launch wait (regda_conv_hint_static_weights)
 };
 
 struct TileCoord { int n_blk, tw, th, img0; };
@@ -105,12 +107,32 @@ struct PersistSmem {
 // tensor is dz = dout * [out > 0], which is also the residual branch's gradient), TMA-loads the matching box of the
 // BatchNorm INPUT y, and accumulates sum(dz) and sum(dz * y) per channel and statistics group into `stats` -- the two
 // reductions of bn_bwd_reduce_kernel, which then does not run at all (norm.cu, regda_bn_backward_bf16 dz_ready = 1).
+// REGDA_CONV_TRACE (scripts/conv_trace.cu only; never defined in the library build): per-CTA phase time stamps of a launch
+#ifdef REGDA_CONV_TRACE
+constexpr int kTraceSlots = 32, kTraceCtas = 160, kTraceLaunches = 64;
+__device__ unsigned long long g_conv_trace[kTraceLaunches * kTraceCtas * kTraceSlots * 2];
+#define CONV_TRACE(slot)                                                                                          \
+    do {                                                                                                          \
+        unsigned long long gt_;                                                                                   \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                                   \
+        unsigned long long *tp_ = g_conv_trace + ((static_cast<size_t>(trace_id) * kTraceCtas + blockIdx.x) * kTraceSlots + (slot)) * 2; \
+        tp_[0] = gt_;                                                                                             \
+        tp_[1] = static_cast<unsigned long long>(clock64());                                                     \
+    } while (0)
+#else
+#define CONV_TRACE(slot)
+#endif
+
 template <int BLOCK_N, int STAGES, bool B_MN, bool STATS, bool OUT_F32, bool BNRED>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                        const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_bn,
                        __nv_bfloat16 *__restrict__ y, const ConvGeom g, const int n_tiles_n, const int num_tiles,
+#ifdef REGDA_CONV_TRACE
+                       float *__restrict__ stats, const int imgs_per_group_, const __nv_bfloat16 *__restrict__ addend,
+#else
                        float *__restrict__ stats, const int imgs_per_group, const __nv_bfloat16 *__restrict__ addend,
+#endif
                        const unsigned char *__restrict__ relu_mask) {
     static_assert(!BNRED || (!OUT_F32 && !STATS), "BNRED rides on the TMA-store epilogue and shares the statistics registers");
     static_assert(!OUT_F32 || !STATS, "the float32-output epilogue carries no BatchNorm statistics");
@@ -127,6 +149,11 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_k = g.r * g.s * g.kc;
+#ifdef REGDA_CONV_TRACE
+    const int trace_id = (imgs_per_group_ >> 16) % kTraceLaunches;
+    const int imgs_per_group = imgs_per_group_ & 0xffff;
+    if (threadIdx.x == 0) CONV_TRACE(0);
+#endif
 
     pdl_trigger();          // the next kernel's prologue may overlap this kernel (it blocks in its own pdl_wait)
     if (warp == 0 && lane == 0) {
@@ -147,13 +174,40 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();             // everything above touched only shared / tensor memory; global memory from here on
+    if (threadIdx.x == 0) CONV_TRACE(1);
+    // B operand (weights) of k-block (tap, c0) of channel block n_blk into pipeline stage buffer sb
+    auto load_b = [&](uint8_t *sb, uint64_t *bar, int n_blk, int tap, int c0) {
+        if (B_MN) {
+            const int wtap = g.flip ? g.r * g.s - 1 - tap : tap;
+#pragma unroll
+            for (int i = 0; i < BLOCK_N / 64; ++i) tma_load_3d(sb + i * 8192, &tmap_w, bar, n_blk * BLOCK_N + i * 64, wtap, c0);
+        } else {
+            tma_load_2d(sb, &tmap_w, bar, tap * g.wct + c0, n_blk * BLOCK_N);
+        }
+    };
+    // Static weights (g.w_early): the weight halves of this CTA's first pipeline stages do not depend on the kernel this launch
+    // waits for -- request them now, so that their DRAM latency overlaps the wait; the activation halves follow after it.
+    const int pre = g.w_early ? min(STAGES, num_k) : 0;
+    if (pre > 0 && warp == 0 && elect_one()) {
+        const int n_blk = decode_tile(blockIdx.x, n_tiles_n, g).n_blk;
+        int tap = 0, c0 = 0;
+        for (int kb = 0; kb < pre; ++kb) {
+            mbar_arrive_expect_tx(full_bar + kb, L::kStageBytes);
+            load_b(smem + kb * L::kStageBytes + L::kABytes, full_bar + kb, n_blk, tap, c0);
+            c0 += kBlockK;
+            if (c0 == g.cin) { c0 = 0; ++tap; }
+        }
+    }
+    pdl_wait();             // everything above touched only shared / tensor memory and static weights; fresh global memory from here on
+    if (threadIdx.x == 0) CONV_TRACE(2);
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
+            CONV_TRACE(12);
             int stage = 0;
             uint32_t phase = 0;
+            int early = pre;                 // k-blocks whose barrier is armed and whose weight half is already on its way
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 const TileCoord tc_ = decode_tile(t, n_tiles_n, g);
                 const int n_blk = tc_.n_blk, img = tc_.img0;
@@ -162,22 +216,19 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(empty_bar + stage, phase ^ 1);
                     uint8_t *sa = smem + stage * L::kStageBytes;
-                    uint8_t *sb = sa + L::kABytes;
-                    mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes);
-                    tma_load_4d(sa, &tmap_x, full_bar + stage, c0, ix0 + fs * g.dil, iy0 + fr * g.dil, img);
-                    if (B_MN) {
-                        const int wtap = g.flip ? g.r * g.s - 1 - tap : tap;
-#pragma unroll
-                        for (int i = 0; i < BLOCK_N / 64; ++i)
-                            tma_load_3d(sb + i * 8192, &tmap_w, full_bar + stage, n_blk * BLOCK_N + i * 64, wtap, c0);
+                    if (early > 0) {
+                        --early;
                     } else {
-                        tma_load_2d(sb, &tmap_w, full_bar + stage, tap * g.wct + c0, n_blk * BLOCK_N);
+                        mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes);
+                        load_b(sa + L::kABytes, full_bar + stage, n_blk, tap, c0);
                     }
+                    tma_load_4d(sa, &tmap_x, full_bar + stage, c0, ix0 + fs * g.dil, iy0 + fr * g.dil, img);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     c0 += kBlockK;
                     if (c0 == g.cin) { c0 = 0; ++tap; if (++fs == g.s) { fs = 0; ++fr; } }
                 }
             }
+            CONV_TRACE(13);
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
@@ -194,6 +245,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(full_bar + stage, phase);
                     tc_fence_after_sync();
+                    if (kb == 0 && t == static_cast<int>(blockIdx.x)) CONV_TRACE(3);
                     const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
                     const uint32_t sb = sa + L::kABytes;
                     const uint64_t adesc = make_smem_desc(sa, 0, 1024);
@@ -206,6 +258,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(tfull_bar + acc);
+                CONV_TRACE(4);          // (overwritten per tile: the last tile's commit stays)
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -228,31 +281,81 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             const uint32_t ybuf_s = smem_u32(ybuf);
             uint32_t yphase = 0;
             // BatchNorm statistics stay in registers across the tiles of this CTA for as long as (channel block, statistics
-            // group) does not change -- with a tile stride of gridDim.x that is most of the walk -- and are flushed with
-            // one coalesced fp32 reduction per 32 channels; per-tile atomics on the same few hundred addresses from every
-            // CTA would serialise in L2.
+            // group) does not change -- with a tile stride of gridDim.x that is most of the walk.  Lane L accumulates the 8
+            // channels of 16-byte chunk (L & 7) of every 64-channel chunk over rows (L >> 3) + 4 i of its warp's 32, as packed
+            // float32 pairs (FADD2 / FFMA2).  The four row groups, the four warps that share a column range and finally the
+            // CTAs are folded at flush time only: one fp32 reduction per channel and quantity per CTA (per-tile or per-warp
+            // atomics on the same few hundred addresses from every CTA serialise in L2 and hold back the grid's completion).
             constexpr int kChunks = kCols / 64;
-            float sacc[kChunks][4];
+            constexpr int kEpiThreads = L::kEpiWarps * 32;
+            const uint32_t lch = static_cast<uint32_t>(lane & 7), lr = static_cast<uint32_t>(lane >> 3);
+            uint64_t sacc[kChunks][8];              // [0..3]: first quantity of the chunk's channel pairs, [4..7]: second quantity
 #pragma unroll
-            for (int i = 0; i < kChunks; ++i) sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f;
+            for (int i = 0; i < kChunks; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sacc[i][j] = 0ull;
             int stat_key = -1;
-            auto flush_stats = [&](int key) {
-                float *base = stats + static_cast<size_t>(key & 0xffff) * 2 * g.cout + static_cast<size_t>(key >> 16) * BLOCK_N + col_lo;
+            auto flush_stats = [&](int key, bool final) {
+                float *base = stats + static_cast<size_t>(key & 0xffff) * 2 * g.cout + static_cast<size_t>(key >> 16) * BLOCK_N;
+                if (final) {
+                    // scratch = the warp's own staging buffer as float [2 quantities][kCols]: its last TMA store must have read it
+                    if (lane == 0) bulk_wait_read0();
+                    __syncwarp();
+                }
 #pragma unroll
                 for (int i = 0; i < kChunks; ++i) {
-                    // lane L holds channels 2L, 2L+1 of the chunk; hand lane L channels L and 32 + L instead
-                    const int src = lane >> 1;
-                    const bool odd = (lane & 1) != 0;
+                    float2 keep_s = make_float2(0.f, 0.f), keep_q = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int qn = 0; qn < 2; ++qn) {
-                        const float e = sacc[i][2 * qn], o = sacc[i][2 * qn + 1];
-                        const float lo_e = __shfl_sync(0xffffffffu, e, src), lo_o = __shfl_sync(0xffffffffu, o, src);
-                        const float hi_e = __shfl_sync(0xffffffffu, e, 16 + src), hi_o = __shfl_sync(0xffffffffu, o, 16 + src);
-                        float *dstp = base + qn * g.cout + i * 64 + lane;
-                        atomicAdd(dstp, odd ? lo_o : lo_e);
-                        atomicAdd(dstp + 32, odd ? hi_o : hi_e);
+                    for (int j = 0; j < 8; ++j) {
+                        float2 v = f32x2_unpack(sacc[i][j]);
+                        v.x += __shfl_xor_sync(0xffffffffu, v.x, 8);  v.y += __shfl_xor_sync(0xffffffffu, v.y, 8);
+                        v.x += __shfl_xor_sync(0xffffffffu, v.x, 16); v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
+                        // all four row groups hold the totals now; lane L keeps channel pair (L >> 3) of its 16-byte chunk
+                        if (static_cast<uint32_t>(j) == lr) keep_s = v;
+                        if (static_cast<uint32_t>(j) == 4 + lr) keep_q = v;
+                        sacc[i][j] = 0ull;
                     }
-                    sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f;
+                    const uint32_t ch = static_cast<uint32_t>(i) * 64u + lch * 8u + 2u * lr;
+                    if (final) {
+                        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(stage_s + ch * 4u), "f"(keep_s.x), "f"(keep_s.y) : "memory");
+                        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(stage_s + (static_cast<uint32_t>(kCols) + ch) * 4u), "f"(keep_q.x), "f"(keep_q.y) : "memory");
+                    } else {
+                        // a flush in the middle of the walk (the CTA moves on to another channel block / statistics group): these are
+                        // spread over the kernel's run time, one reduction per channel, quantity and warp
+                        float *dst = base + col_lo + ch;
+                        atomicAdd(dst, keep_s.x); atomicAdd(dst + 1, keep_s.y);
+                        atomicAdd(dst + g.cout, keep_q.x); atomicAdd(dst + g.cout + 1, keep_q.y);
+                    }
+                }
+                if (!final) return;
+                // the CTA's last flush -- every CTA's arrives in the same microsecond at the end of the grid -- folds the four warps
+                // that share a column range first: one reduction per channel and quantity per CTA
+                named_bar_sync(1, kEpiThreads);
+                const uint32_t store_s = smem_u32(smem + L::kStoreOffset);
+                for (int item = wq * 32 + lane; item < 2 * BLOCK_N; item += kEpiThreads) {
+                    const int qty = item / BLOCK_N, col = item - qty * BLOCK_N;
+                    const int hh = col / kCols, cc = col - hh * kCols;
+                    const uint32_t a = store_s + static_cast<uint32_t>(hh * 4) * 4096u + static_cast<uint32_t>(qty * kCols + cc) * 4u;
+                    const float v = (ld_shared_f32(a) + ld_shared_f32(a + 4096u)) + (ld_shared_f32(a + 8192u) + ld_shared_f32(a + 12288u));
+                    atomicAdd(base + static_cast<size_t>(qty) * g.cout + col, v);
+                }
+            };
+            // bf16 pack of one 32-column accumulator segment of this lane's row (zeros where `keep` has no bit)
+            auto pack32 = [](const uint32_t (&v)[32], uint32_t keep, uint32_t (&pk)[16]) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    __nv_bfloat162 b = __floats2bfloat162_rn(((keep >> j) & 1u) ? __uint_as_float(v[j]) : 0.f,
+                                                             ((keep >> (j + 1)) & 1u) ? __uint_as_float(v[j + 1]) : 0.f);
+                    pk[j >> 1] = *reinterpret_cast<uint32_t *>(&b);
+                }
+            };
+            auto add_bf16x8 = [](uint32_t *v, const uint4 &a) {
+                const uint32_t w4[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w4[e]));
+                    v[2 * e] = __float_as_uint(__uint_as_float(v[2 * e]) + f.x);
+                    v[2 * e + 1] = __float_as_uint(__uint_as_float(v[2 * e + 1]) + f.y);
                 }
             };
             int acc = 0;
@@ -267,14 +370,14 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                     // (the host only selects STATS / BNRED when all images of a tile belong to one statistics group)
                     const int key = (n_blk << 16) | (tc_.img0 / imgs_per_group);
                     if (key != stat_key) {
-                        if (stat_key >= 0) flush_stats(stat_key);
+                        if (stat_key >= 0) flush_stats(stat_key, false);
                         stat_key = key;
                     }
                 }
                 const size_t pix_off = ((static_cast<size_t>(img) * g.oh + oh) * g.ow + ow) * g.cout + static_cast<size_t>(n_blk) * BLOCK_N;
                 const bool has_add = addend != nullptr && valid;
                 const uint4 *ap = reinterpret_cast<const uint4 *>(addend + pix_off + col_lo);
-                uint4 cur[4], nxt[4];
+                uint4 cur[4], nxt[4];                        // the addend of one 32-channel segment of this lane's row, and the next one
                 if (has_add) {
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) cur[q4] = __ldg(ap + q4);
@@ -293,20 +396,21 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                 }
                 mbar_wait(tfull_bar + acc, acc_phase);
                 tc_fence_after_sync();
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+                if (wq == 0 && lane == 0) { if (t == static_cast<int>(blockIdx.x)) CONV_TRACE(5); CONV_TRACE(6); }
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N + col_lo);
 #pragma unroll
                 for (int c64 = 0; c64 < kCols; c64 += 64) {
 #pragma unroll
                     for (int hseg = 0; hseg < 2; ++hseg) {
-                        const int c = col_lo + c64 + hseg * 32;
+                        const int c = c64 + hseg * 32;               // column of this segment inside the warp's range
                         uint32_t v[32];
                         tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
-                        if (has_add && c + 32 < col_lo + kCols) {
+                        if (has_add && c + 32 < kCols) {
 #pragma unroll
-                            for (int q4 = 0; q4 < 4; ++q4) nxt[q4] = __ldg(ap + (c + 32 - col_lo) / 8 + q4);
+                            for (int q4 = 0; q4 < 4; ++q4) nxt[q4] = __ldg(ap + (c + 32) / 8 + q4);
                         }
                         tmem_ld_wait();
-                        if (c + 32 == col_lo + kCols) {
+                        if (c + 32 == kCols) {
                             // the accumulator has been read completely: hand it back to the MMA warp before the stores
                             tc_fence_before_sync();
                             __syncwarp();
@@ -315,32 +419,21 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                         if (has_add) {
 #pragma unroll
                             for (int q4 = 0; q4 < 4; ++q4) {
-                                const uint32_t w4[4] = {cur[q4].x, cur[q4].y, cur[q4].z, cur[q4].w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w4[e]));
-                                    v[q4 * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[q4 * 8 + 2 * e]) + f.x);
-                                    v[q4 * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(v[q4 * 8 + 2 * e + 1]) + f.y);
-                                }
+                                add_bf16x8(v + q4 * 8, cur[q4]);
                                 cur[q4] = nxt[q4];
                             }
                         }
-                        uint32_t pkd[16];
-                        if (BNRED) {
-                            const uint32_t mb = mbits[(c64 + hseg * 32) / 32];       // 0 for rows outside the image
+                        // rows outside the image are stored as zeros (the TMA store clips them; the statistics must not see them)
+                        uint32_t pk[16];
+                        const uint32_t keep = BNRED ? mbits[c / 32] : (valid ? 0xffffffffu : 0u);
+                        if (!BNRED && keep == 0xffffffffu) {       // (a ReLU mask is hardly ever all ones)
 #pragma unroll
                             for (int j = 0; j < 32; j += 2) {
-                                __nv_bfloat162 b = __floats2bfloat162_rn(((mb >> j) & 1u) ? __uint_as_float(v[j]) : 0.f,
-                                                                         ((mb >> (j + 1)) & 1u) ? __uint_as_float(v[j + 1]) : 0.f);
-                                pkd[j >> 1] = *reinterpret_cast<uint32_t *>(&b);
+                                __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                                pk[j >> 1] = *reinterpret_cast<uint32_t *>(&b);
                             }
                         } else {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 2) {
-                                // rows outside the image are stored as zeros (the TMA store clips them; the statistics must not see them)
-                                __nv_bfloat162 b = __floats2bfloat162_rn(valid ? __uint_as_float(v[j]) : 0.f, valid ? __uint_as_float(v[j + 1]) : 0.f);
-                                pkd[j >> 1] = *reinterpret_cast<uint32_t *>(&b);
-                            }
+                            pack32(v, keep, pk);
                         }
                         if (hseg == 0) {
                             // the previous TMA store of this warp must have finished reading the staging buffer
@@ -348,10 +441,8 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                             __syncwarp();
                         }
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t chunk = static_cast<uint32_t>(hseg * 4 + j) ^ sw;       // 128B swizzle: 16-byte chunk ^ (row & 7)
-                            st_shared_v4(my_row_s + (chunk << 4), pkd[4 * j], pkd[4 * j + 1], pkd[4 * j + 2], pkd[4 * j + 3]);
-                        }
+                        for (int j = 0; j < 4; ++j)      // 128B swizzle: 16-byte chunk ^ (row & 7)
+                            st_shared_v4(my_row_s + ((static_cast<uint32_t>(hseg * 4 + j) ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                     }
                     fence_proxy_async();
                     __syncwarp();
@@ -360,46 +451,52 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                         bulk_commit();
                     }
                     if (STATS) {
-                        // lane L sums channels 2L, 2L+1 of this 64-channel chunk over the warp's 32 rows (bf16-rounded values,
-                        // i.e. what BatchNorm will read back); word L of row r sits in 16-byte chunk (L/4) ^ (r & 7)
-                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-                        const uint32_t lchunk = static_cast<uint32_t>(lane >> 2), lword = static_cast<uint32_t>(lane & 3) << 2;
+                        // column sums of the staged tile (bf16-rounded values, i.e. what BatchNorm will read back): 8 x LDS.128 per lane
 #pragma unroll
-                        for (int r = 0; r < 32; ++r) {
-                            const uint32_t wv = ld_shared_u32(stage_s + static_cast<uint32_t>(r) * 128u + ((lchunk ^ static_cast<uint32_t>(r & 7)) << 4) + lword);
-                            const float f0 = __uint_as_float(wv << 16), f1 = __uint_as_float(wv & 0xffff0000u);
-                            s0 += f0; s1 += f1;
-                            q0 = fmaf(f0, f0, q0); q1 = fmaf(f1, f1, q1);
+                        for (int i8 = 0; i8 < 8; ++i8) {
+                            const uint32_t r = lr + 4u * static_cast<uint32_t>(i8);
+                            const uint4 wv = ld_shared_v4(stage_s + r * 128u + ((lch ^ (r & 7u)) << 4));
+                            const uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const uint64_t f = bf16x2_to_f32x2(w4[e]);
+                                f32x2_add(sacc[c64 / 64][e], f);
+                                f32x2_fma(sacc[c64 / 64][4 + e], f, f);
+                            }
                         }
-                        sacc[c64 / 64][0] += s0; sacc[c64 / 64][1] += s1; sacc[c64 / 64][2] += q0; sacc[c64 / 64][3] += q1;
                     }
                     if (BNRED) {
-                        // sum(dz) and sum(dz * y) over the warp's 32 rows for channels 2L, 2L+1: dz from the staged tile, y from
-                        // the TMA-loaded BatchNorm input box (same swizzled layout)
+                        // sum(dz) and sum(dz * y): dz from the staged tile, y from the TMA-loaded BatchNorm input box (same layout)
                         mbar_wait(ybar + wq, yphase);
                         yphase ^= 1;
-                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-                        const uint32_t lchunk = static_cast<uint32_t>(lane >> 2), lword = static_cast<uint32_t>(lane & 3) << 2;
 #pragma unroll
-                        for (int r = 0; r < 32; ++r) {
-                            const uint32_t off = static_cast<uint32_t>(r) * 128u + ((lchunk ^ static_cast<uint32_t>(r & 7)) << 4) + lword;
-                            const uint32_t dv = ld_shared_u32(stage_s + off), yv = ld_shared_u32(ybuf_s + off);
-                            const float d0 = __uint_as_float(dv << 16), d1 = __uint_as_float(dv & 0xffff0000u);
-                            s0 += d0; s1 += d1;
-                            q0 = fmaf(d0, __uint_as_float(yv << 16), q0); q1 = fmaf(d1, __uint_as_float(yv & 0xffff0000u), q1);
+                        for (int i8 = 0; i8 < 8; ++i8) {
+                            const uint32_t r = lr + 4u * static_cast<uint32_t>(i8);
+                            const uint32_t off = r * 128u + ((lch ^ (r & 7u)) << 4);
+                            const uint4 dv = ld_shared_v4(stage_s + off), yv = ld_shared_v4(ybuf_s + off);
+                            const uint32_t d4[4] = {dv.x, dv.y, dv.z, dv.w}, y4[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const uint64_t d = bf16x2_to_f32x2(d4[e]);
+                                f32x2_add(sacc[c64 / 64][e], d);
+                                f32x2_fma(sacc[c64 / 64][4 + e], d, bf16x2_to_f32x2(y4[e]));
+                            }
                         }
-                        sacc[c64 / 64][0] += s0; sacc[c64 / 64][1] += s1; sacc[c64 / 64][2] += q0; sacc[c64 / 64][3] += q1;
                         __syncwarp();                                  // every lane is done with ybuf
                         if (c64 + 64 < kCols && lane == 0) {
                             mbar_arrive_expect_tx(ybar + wq, 4096);
                             tma_load_4d(ybuf, &tmap_bn, ybar + wq, n_blk * BLOCK_N + col_lo + c64 + 64, tw * g.bw + bpw0, th * g.bh + bph0, bimg);
                         }
                     }
+                    if (wq == 0 && lane == 0) CONV_TRACE(16 + (c64 / 64) * 8 + 7);
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if ((STATS || BNRED) && stat_key >= 0) flush_stats(stat_key);
+            if (wq == 0 && lane == 0) CONV_TRACE(7);
+            if ((STATS || BNRED) && stat_key >= 0) flush_stats(stat_key, true);
+            if (wq == 0 && lane == 0) CONV_TRACE(8);
             if (lane == 0) bulk_wait_read0();          // shared memory must outlive the last TMA store's reads
+            if (wq == 0 && lane == 0) CONV_TRACE(9);
         }
     } else {
         // ===== epilogue (OUT_F32): TMEM -> registers (+ float32 addend) -> float32 global (NHWC) =====
@@ -450,9 +547,11 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     }
     tc_fence_before_sync();
     __syncthreads();
+    if (threadIdx.x == 0) CONV_TRACE(10);
     if (warp == 2) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, 2 * BLOCK_N);
+        if (lane == 0) CONV_TRACE(11);
     }
 }
 
@@ -488,9 +587,15 @@ struct BnRed {                       // BNRED launch: the BatchNorm whose output
 };
 
 // `y` / `addend` are bf16, or float32 when OUT_F32
+// regda_conv_hint_static_weights(): consumed by the next convolution this thread launches
+thread_local int t_static_weights = 0;
+
 template <int BLOCK_N, int STAGES, bool B_MN, bool STATS, bool OUT_F32, bool BNRED = false>
-int launch_persistent_impl(const CUtensorMap &tx, const CUtensorMap &tw, void *y, const ConvGeom &g, cudaStream_t st,
+int launch_persistent_impl(const CUtensorMap &tx, const CUtensorMap &tw, void *y, const ConvGeom &g_in, cudaStream_t st,
                            float *stats, int imgs_per_group, const void *addend, const BnRed &br = BnRed()) {
+    ConvGeom g = g_in;
+    g.w_early = (t_static_weights && pdl_level() >= 1) ? 1 : 0;
+    t_static_weights = 0;
     using L = PersistSmem<BLOCK_N, STAGES, BNRED>;
     auto kern = conv_persistent_kernel<BLOCK_N, STAGES, B_MN, STATS, OUT_F32, BNRED>;
     const int smem = L::kTotal + 1024;
@@ -580,6 +685,7 @@ int geom_init(ConvGeom &g, int n, int h, int w, int cin, int cout, int r, int s,
     g.tiles_img = (n + bn - 1) / bn;
     g.kc = cin / kBlockK;
     g.wct = cin;
+    g.w_early = 0;
     return REGDA_OK;
 }
 
@@ -613,6 +719,15 @@ bool dgrad_geom(ConvGeom &g, int n, int h, int w, int cin, int cout, int r, int 
 }  // namespace regda
 
 using namespace regda;
+
+// Hint for the NEXT forward / data-gradient convolution launched by the calling thread: its weight tensor was last written long
+// before the kernel that precedes the launch in its stream (true for the bf16 weight copies of a training step, which the optimizer
+// kernel writes once per step; NOT true for a weight-like operand produced by the kernel just before).  The kernel then requests the
+// weight halves of its first pipeline stages before its programmatic-dependent-launch wait.  Consumed by that launch.
+extern "C" int regda_conv_hint_static_weights(void) {
+    t_static_weights = 1;
+    return REGDA_OK;
+}
 
 // tile-policy knob for sweeps: minimum number of 128 x 256 tiles for the 256-wide tile to be chosen (0 = default, SM count / 2)
 extern "C" int regda_conv_tune(int min_tiles_256_value) {

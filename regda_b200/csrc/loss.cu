@@ -34,7 +34,7 @@ struct CeArgs {
 };
 
 template <int CMAX>
-__global__ void __launch_bounds__(kCeThreads)
+__global__ void __launch_bounds__(kCeThreads, CMAX <= 8 ? 3 : 1)
 ce_bilinear_kernel(const CeArgs a) {
     extern __shared__ float sm[];
     const int img = blockIdx.y;
@@ -60,11 +60,19 @@ ce_bilinear_kernel(const CeArgs a) {
         const int x0 = static_cast<int>(fx);
         const int x1 = x0 + (x0 < a.w - 1 ? 1 : 0);
         const float wx1 = fx - static_cast<float>(x0), wx0 = 1.0f - wx1;
-        float g[3][CMAX];
+        // the column direction of the interpolation does not depend on Y: interpolate the three staged rows once per column
+        float g[3][CMAX], hx[3][CMAX];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int j = 0; j < CMAX; ++j) g[r][j] = 0.f;
+            for (int j = 0; j < CMAX; ++j) {
+                g[r][j] = 0.f;
+                hx[r][j] = 0.f;
+                if (j < a.c) {
+                    const float *p = lo + (r * a.c + j) * a.w;
+                    hx[r][j] = wx0 * p[x0] + wx1 * p[x1];
+                }
+            }
         for (int Y = Y0; Y < Y1; ++Y) {
             const long long l = lab[static_cast<size_t>(Y) * a.W + X];
             if (l == a.ignore_label) continue;
@@ -73,14 +81,15 @@ ce_bilinear_kernel(const CeArgs a) {
             const int y0 = static_cast<int>(fy);
             const int y1 = y0 + (y0 < a.h - 1 ? 1 : 0);
             const float wy1 = fy - static_cast<float>(y0), wy0 = 1.0f - wy1;
-            const int r0 = y0 - ylo, r1 = y1 - ylo;
+            const int r0 = y0 - ylo, r1 = y1 - ylo;       // block-uniform (0..2): the row selects below do not diverge
             float z[CMAX];
             float m = -INFINITY;
 #pragma unroll
             for (int j = 0; j < CMAX; ++j)
                 if (j < a.c) {
-                    const float *p0 = lo + (r0 * a.c + j) * a.w, *p1 = lo + (r1 * a.c + j) * a.w;
-                    z[j] = wy0 * (wx0 * p0[x0] + wx1 * p0[x1]) + wy1 * (wx0 * p1[x0] + wx1 * p1[x1]);
+                    const float h0 = r0 == 0 ? hx[0][j] : (r0 == 1 ? hx[1][j] : hx[2][j]);
+                    const float h1 = r1 == 0 ? hx[0][j] : (r1 == 1 ? hx[1][j] : hx[2][j]);
+                    z[j] = wy0 * h0 + wy1 * h1;
                     m = fmaxf(m, z[j]);
                 }
             float s = 0.f, zl = 0.f;
@@ -94,15 +103,16 @@ ce_bilinear_kernel(const CeArgs a) {
             const float wgt = a.class_weight ? a.class_weight[l] : 1.0f;
             loss_sum += wgt * (logf(s) + m - zl);            // -log_softmax[label]
             const float inv = wgt / s;
+            const float w0 = (r0 == 0 ? wy0 : 0.f) + (r1 == 0 ? wy1 : 0.f);
+            const float w1 = (r0 == 1 ? wy0 : 0.f) + (r1 == 1 ? wy1 : 0.f);
+            const float w2 = (r0 == 2 ? wy0 : 0.f) + (r1 == 2 ? wy1 : 0.f);
 #pragma unroll
             for (int j = 0; j < CMAX; ++j)
                 if (j < a.c) {
                     const float gj = z[j] * inv - (j == static_cast<int>(l) ? wgt : 0.f);
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        const float wr = (r == r0 ? wy0 : 0.f) + (r == r1 ? wy1 : 0.f);
-                        g[r][j] += wr * gj;
-                    }
+                    g[0][j] += w0 * gj;
+                    g[1][j] += w1 * gj;
+                    g[2][j] += w2 * gj;
                 }
         }
         if (a.dpred != nullptr) {
@@ -232,13 +242,18 @@ extern "C" int regda_ce_bilinear(const float *pred, const int64_t *label, float 
     a.gscale = static_cast<float>(grad_scale / npx);
     if (dpred) REGDA_CUDA_CHECK(cudaMemsetAsync(dpred, 0, static_cast<size_t>(b) * c * h * w * 4, st));
     const dim3 grid((H + a.rows_per_block - 1) / a.rows_per_block, b);
-    if (c <= 8) {
-        if (smem > 48 * 1024) REGDA_CUDA_CHECK(cudaFuncSetAttribute(ce_bilinear_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        ce_bilinear_kernel<8><<<grid, kCeThreads, smem, st>>>(a);
-    } else {
-        if (smem > 48 * 1024) REGDA_CUDA_CHECK(cudaFuncSetAttribute(ce_bilinear_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        ce_bilinear_kernel<16><<<grid, kCeThreads, smem, st>>>(a);
-    }
+    // (register arrays are sized by the template argument: the 6- and 7-class configurations of the recipes get their own)
+#define REGDA_CE_LAUNCH(CM)                                                                                                              \
+    do {                                                                                                                                 \
+        if (smem > 48 * 1024)                                                                                                            \
+            REGDA_CUDA_CHECK(cudaFuncSetAttribute(ce_bilinear_kernel<CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+        ce_bilinear_kernel<CM><<<grid, kCeThreads, smem, st>>>(a);                                                                       \
+    } while (0)
+    if (c == 6) REGDA_CE_LAUNCH(6);
+    else if (c == 7) REGDA_CE_LAUNCH(7);
+    else if (c <= 8) REGDA_CE_LAUNCH(8);
+    else REGDA_CE_LAUNCH(16);
+#undef REGDA_CE_LAUNCH
     REGDA_LAUNCH_CHECK();
     ce_finalize_kernel<<<1, 256, 0, st>>>(a.partial, static_cast<int>(grid.x * grid.y), static_cast<float>(1.0 / npx), loss);
     REGDA_LAUNCH_CHECK();

@@ -71,13 +71,18 @@ __device__ __forceinline__ void block_channel_reduce(float (&a)[8], float (&b)[8
     }
 }
 
+// PDL (REGDA_PDL=2 only, where these kernels are launched with programmatic stream serialization): 1 = let the next kernel start
+// its prologue as soon as all of this grid's blocks are resident, 0 = only when this grid's blocks exit (the next kernel is a
+// convolution whose 148 CTAs would otherwise sit on the SMs' registers while this grid's last wave runs).  regda_bn_tune().
+__constant__ int c_bn_early_trigger = 1;
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBnThreads)
 bn_stats_kernel(const __nv_bfloat16 *__restrict__ y, long long total, int c, long long span_per_block,
                 float *__restrict__ gsum, float *__restrict__ gsq) {
-    pdl_trigger();
+    if (c_bn_early_trigger) pdl_trigger();
     pdl_wait();
     // blockIdx.y = statistics group (a contiguous range of `total` elements); group g accumulates into gsum + 2*c*g
     y += static_cast<long long>(blockIdx.y) * total;
@@ -116,7 +121,7 @@ bn_apply_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__rest
                 long long total, int c, const float *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta,
                 float inv_n, float unbias, float eps, float momentum, float *__restrict__ running_mean, float *__restrict__ running_var,
                 long long *__restrict__ num_batches, unsigned char *__restrict__ relu_mask) {
-    pdl_trigger();
+    if (c_bn_early_trigger) pdl_trigger();
     pdl_wait();
     if (blockIdx.x == 0 && blockIdx.y == 0) {
         const int groups = gridDim.y;
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 *__restrict__ out, const __nv_bfloat16 *__restrict__ y,
                      long long total, int c, long long span_per_block, float *__restrict__ gdz, float *__restrict__ gdzy,
                      const float *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta, float inv_n, float eps) {
-    pdl_trigger();
+    if (c_bn_early_trigger) pdl_trigger();
     pdl_wait();
     {
         const long long off = static_cast<long long>(blockIdx.y) * total;
@@ -264,7 +269,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 
                     __nv_bfloat16 *__restrict__ dy, __nv_bfloat16 *__restrict__ dres, long long total, int c,
                     const float *__restrict__ stats, const float *__restrict__ red, const float *__restrict__ gamma, float inv_n, float eps,
                     float *__restrict__ dgamma, float *__restrict__ dbeta, const float *__restrict__ beta) {
-    pdl_trigger();
+    if (c_bn_early_trigger) pdl_trigger();
     pdl_wait();
     if (blockIdx.x == 0 && blockIdx.y == 0 && (dgamma != nullptr || dbeta != nullptr)) {
         const int groups = gridDim.y;
@@ -476,80 +481,80 @@ extern "C" int regda_bn_backward_bf16(const void *dout, const void *out, const v
 namespace regda {
 namespace {
 
+// grid (n * oh, ceil(ow * c/8 / 256)): one output row per blockIdx.x, a thread per (output pixel, 8 channels) -- 32-bit index math
+// only (the flat 64-bit divisions of a 1-D grid-stride loop cost more than the pooling itself)
 __global__ void __launch_bounds__(256)
 maxpool3s2_fwd_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restrict__ y, unsigned char *__restrict__ arg, int n, int h, int w,
                       int c, int oh, int ow) {
-    const int octs = c >> 3;
-    const long long total = static_cast<long long>(n) * oh * ow * octs;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int o = static_cast<int>(i % octs);
-        long long p = i / octs;
-        const int ox = static_cast<int>(p % ow); p /= ow;
-        const int oy = static_cast<int>(p % oh);
-        const int img = static_cast<int>(p / oh);
-        float m[8];
-        unsigned am[8];
+    const unsigned octs = static_cast<unsigned>(c) >> 3;
+    const unsigned e = blockIdx.y * blockDim.x + threadIdx.x;
+    if (e >= static_cast<unsigned>(ow) * octs) return;
+    const int ox = static_cast<int>(e / octs), o = static_cast<int>(e - static_cast<unsigned>(ox) * octs);
+    const int img = static_cast<int>(blockIdx.x / static_cast<unsigned>(oh)), oy = static_cast<int>(blockIdx.x - static_cast<unsigned>(img) * oh);
+    float m[8];
+    unsigned am[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) { m[t] = -INFINITY; am[t] = 0u; }
+    for (int t = 0; t < 8; ++t) { m[t] = -INFINITY; am[t] = 0u; }
+    const __nv_bfloat16 *ximg = x + static_cast<size_t>(img) * h * w * c + o * 8;
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-            const int iy = oy * 2 - 1 + dy;
-            if (iy < 0 || iy >= h) continue;
+    for (int dy = 0; dy < 3; ++dy) {
+        const int iy = oy * 2 - 1 + dy;
+        if (iy < 0 || iy >= h) continue;
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-                const int ix = ox * 2 - 1 + dx;
-                if (ix < 0 || ix >= w) continue;
-                float f[8];
-                unpack(ld8(x + ((static_cast<long long>(img) * h + iy) * w + ix) * c + o * 8), f);
+        for (int dx = 0; dx < 3; ++dx) {
+            const int ix = ox * 2 - 1 + dx;
+            if (ix < 0 || ix >= w) continue;
+            float f[8];
+            unpack(ld8(ximg + (static_cast<size_t>(iy) * w + ix) * c), f);
 #pragma unroll
-                for (int t = 0; t < 8; ++t)
-                    if (f[t] > m[t]) { m[t] = f[t]; am[t] = static_cast<unsigned>(dy * 3 + dx); }      // first maximum wins, as ATen
-            }
+            for (int t = 0; t < 8; ++t)
+                if (f[t] > m[t]) { m[t] = f[t]; am[t] = static_cast<unsigned>(dy * 3 + dx); }      // first maximum wins, as ATen
         }
-        const long long q = ((static_cast<long long>(img) * oh + oy) * ow + ox) * c + o * 8;
-        st8(y + q, pack(m));
-        if (arg != nullptr) {
-            uint2 pk;
-            pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
-            pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
-            *reinterpret_cast<uint2 *>(arg + q) = pk;
-        }
+    }
+    const size_t q = ((static_cast<size_t>(img) * oh + oy) * ow + ox) * c + o * 8;
+    st8(y + q, pack(m));
+    if (arg != nullptr) {
+        uint2 pk;
+        pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+        pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+        *reinterpret_cast<uint2 *>(arg + q) = pk;
     }
 }
 
-// one thread per (input pixel, 8 channels): the <= 4 windows containing the pixel, one byte compare each
+// grid (n * h, ceil(w * c/8 / 256)): one thread per (input pixel, 8 channels): the <= 4 windows containing the pixel, one byte compare each
 __global__ void __launch_bounds__(256)
 maxpool3s2_bwd_kernel(const unsigned char *__restrict__ arg, const __nv_bfloat16 *__restrict__ dy, __nv_bfloat16 *__restrict__ dx, int n, int h,
                       int w, int c, int oh, int ow) {
-    const int octs = c >> 3;
-    const long long total = static_cast<long long>(n) * h * w * octs;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int o = static_cast<int>(i % octs);
-        long long p = i / octs;
-        const int ix = static_cast<int>(p % w); p /= w;
-        const int iy = static_cast<int>(p % h);
-        const int img = static_cast<int>(p / h);
-        float acc[8];
+    const unsigned octs = static_cast<unsigned>(c) >> 3;
+    const unsigned e = blockIdx.y * blockDim.x + threadIdx.x;
+    if (e >= static_cast<unsigned>(w) * octs) return;
+    const int ix = static_cast<int>(e / octs), o = static_cast<int>(e - static_cast<unsigned>(ix) * octs);
+    const int img = static_cast<int>(blockIdx.x / static_cast<unsigned>(h)), iy = static_cast<int>(blockIdx.x - static_cast<unsigned>(img) * h);
+    float acc[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) acc[t] = 0.f;
-        const int oy0 = max(0, iy >> 1), oy1 = min(oh - 1, (iy + 1) >> 1);
-        const int ox0 = max(0, ix >> 1), ox1 = min(ow - 1, (ix + 1) >> 1);
-        for (int oy = oy0; oy <= oy1; ++oy) {
-            for (int ox = ox0; ox <= ox1; ++ox) {
-                const unsigned pos = static_cast<unsigned>((iy - (oy * 2 - 1)) * 3 + (ix - (ox * 2 - 1)));      // my index in that window
-                const long long q = ((static_cast<long long>(img) * oh + oy) * ow + ox) * c + o * 8;
-                const uint2 av = *reinterpret_cast<const uint2 *>(arg + q);
-                float gv[8];
-                unpack(ld8(dy + q), gv);
+    for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+    const int oy0 = max(0, iy >> 1), oy1 = min(oh - 1, (iy + 1) >> 1);
+    const int ox0 = max(0, ix >> 1), ox1 = min(ow - 1, (ix + 1) >> 1);
+    for (int oy = oy0; oy <= oy1; ++oy) {
+        for (int ox = ox0; ox <= ox1; ++ox) {
+            const unsigned pos = static_cast<unsigned>((iy - (oy * 2 - 1)) * 3 + (ix - (ox * 2 - 1)));      // my index in that window
+            const size_t q = ((static_cast<size_t>(img) * oh + oy) * ow + ox) * c + o * 8;
+            const uint2 av = *reinterpret_cast<const uint2 *>(arg + q);
+            const uint4 gv = *reinterpret_cast<const uint4 *>(dy + q);
+            // byte-wise compare of the 8 arg-max codes with my position, widened to the bf16 lanes: the gradient words are masked
+            // as integers (no per-channel extract / compare / select)
+            const unsigned pos4 = pos * 0x01010101u;
+            const unsigned mlo = __vcmpeq4(av.x, pos4), mhi = __vcmpeq4(av.y, pos4);
+            const unsigned w[4] = {gv.x & __byte_perm(mlo, 0u, 0x1100u), gv.y & __byte_perm(mlo, 0u, 0x3322u),
+                                   gv.z & __byte_perm(mhi, 0u, 0x1100u), gv.w & __byte_perm(mhi, 0u, 0x3322u)};
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const unsigned a = ((t < 4 ? av.x : av.y) >> ((t & 3) * 8)) & 0xFFu;
-                    acc[t] += a == pos ? gv[t] : 0.f;
-                }
+            for (int t = 0; t < 4; ++t) {
+                acc[2 * t] += __uint_as_float(w[t] << 16);
+                acc[2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
             }
         }
-        st8(dx + i * 8, pack(acc));
     }
+    st8(dx + ((static_cast<size_t>(img) * h + iy) * w + ix) * c + o * 8, pack(acc));
 }
 
 }  // namespace
@@ -558,8 +563,8 @@ maxpool3s2_bwd_kernel(const unsigned char *__restrict__ arg, const __nv_bfloat16
 extern "C" int regda_maxpool3s2_fwd_bf16(const void *x, void *y, void *argmax_u8, int n, int h, int w, int c, void *stream) {
     if (!x || !y || n < 1 || h < 1 || w < 1 || c < 8 || c % 8) return fail(REGDA_ERR_INVALID_ARG, "maxpool_fwd: bad arguments");
     const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
-    const long long total = static_cast<long long>(n) * oh * ow * (c / 8);
-    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 16ll * sm_count()));
+    if (static_cast<long long>(n) * oh > 0x7fffffffll || static_cast<long long>(ow) * (c / 8) > 65535ll * 256) return fail(REGDA_ERR_UNSUPPORTED, "maxpool_fwd: tensor too large");
+    const dim3 blocks(n * oh, (ow * (c / 8) + 255) / 256);
     maxpool3s2_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16 *>(x), static_cast<__nv_bfloat16 *>(y),
                                                                                     static_cast<unsigned char *>(argmax_u8), n, h, w, c, oh, ow);
     REGDA_LAUNCH_CHECK();
@@ -569,11 +574,18 @@ extern "C" int regda_maxpool3s2_fwd_bf16(const void *x, void *y, void *argmax_u8
 extern "C" int regda_maxpool3s2_bwd_bf16(const void *argmax_u8, const void *dy, void *dx, int n, int h, int w, int c, void *stream) {
     if (!argmax_u8 || !dy || !dx || n < 1 || h < 1 || w < 1 || c < 8 || c % 8) return fail(REGDA_ERR_INVALID_ARG, "maxpool_bwd: bad arguments");
     const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
-    const long long total = static_cast<long long>(n) * h * w * (c / 8);
-    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 16ll * sm_count()));
+    if (static_cast<long long>(n) * h > 0x7fffffffll || static_cast<long long>(w) * (c / 8) > 65535ll * 256) return fail(REGDA_ERR_UNSUPPORTED, "maxpool_bwd: tensor too large");
+    const dim3 blocks(n * h, (w * (c / 8) + 255) / 256);
     maxpool3s2_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const unsigned char *>(argmax_u8),
                                                                                     static_cast<const __nv_bfloat16 *>(dy), static_cast<__nv_bfloat16 *>(dx),
                                                                                     n, h, w, c, oh, ow);
     REGDA_LAUNCH_CHECK();
+    return REGDA_OK;
+}
+
+// tuning knob for sweeps: early_trigger != 0 -> the BatchNorm kernels release their PDL dependents at their start (default)
+extern "C" int regda_bn_tune(int early_trigger) {
+    const int v = early_trigger ? 1 : 0;
+    REGDA_CUDA_CHECK(cudaMemcpyToSymbol(c_bn_early_trigger, &v, sizeof(v)));
     return REGDA_OK;
 }

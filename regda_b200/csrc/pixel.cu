@@ -134,7 +134,7 @@ struct RefineArgs {
     const float *pred2;   // may be null
     const float *soft;    // [b][c][H*W]
     int c, h, w, H, W;
-    float temp, sy, sx;   // align_corners=True scales (in-1)/(out-1)
+    float inv_temp, sy, sx;   // 1 / temperature; align_corners=True scales (in-1)/(out-1)
 };
 
 struct Taps {
@@ -167,8 +167,10 @@ __device__ __forceinline__ void softmax_inplace(float (&v)[CMAX], int c) {
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < CMAX; ++j) if (j < c) { v[j] = expf(v[j] - m); s += v[j]; }
+    // one correctly rounded reciprocal + c multiplications (<= 1.5 ulp from the quotient; the refinement is compared at 1e-4)
+    const float inv = __frcp_rn(s);
 #pragma unroll
-    for (int j = 0; j < CMAX; ++j) if (j < c) v[j] = v[j] / s;
+    for (int j = 0; j < CMAX; ++j) if (j < c) v[j] = v[j] * inv;
 }
 
 template <int CMAX>
@@ -176,9 +178,9 @@ __device__ __forceinline__ void peak_normalise(float (&v)[CMAX], int c) {
     float m = -INFINITY;
 #pragma unroll
     for (int j = 0; j < CMAX; ++j) if (j < c) m = fmaxf(m, v[j]);
-    const float d = m + kEps;
+    const float inv = __frcp_rn(m + kEps);
 #pragma unroll
-    for (int j = 0; j < CMAX; ++j) if (j < c) v[j] = v[j] / d;
+    for (int j = 0; j < CMAX; ++j) if (j < c) v[j] = v[j] * inv;
 }
 
 // refined[c] for pixel (img, pos) -- alignment.py:216-236, 263-264
@@ -194,12 +196,12 @@ __device__ __forceinline__ void refine_pixel(const RefineArgs &a, int img, int p
     softmax_inplace<CMAX>(wgt, a.c);                 // _softmax_T(temp=1) (:220)
     peak_normalise<CMAX>(wgt, a.c);                  // (:221-222)
 #pragma unroll
-    for (int j = 0; j < CMAX; ++j) if (j < a.c) p1[j] = interp(a.pred1 + base + static_cast<size_t>(j) * lp, t) / a.temp;
+    for (int j = 0; j < CMAX; ++j) if (j < a.c) p1[j] = interp(a.pred1 + base + static_cast<size_t>(j) * lp, t) * a.inv_temp;
     softmax_inplace<CMAX>(p1, a.c);
     if (a.pred2 != nullptr) {
         float p2[CMAX];
 #pragma unroll
-        for (int j = 0; j < CMAX; ++j) if (j < a.c) p2[j] = interp(a.pred2 + base + static_cast<size_t>(j) * lp, t) / a.temp;
+        for (int j = 0; j < CMAX; ++j) if (j < a.c) p2[j] = interp(a.pred2 + base + static_cast<size_t>(j) * lp, t) * a.inv_temp;
         softmax_inplace<CMAX>(p2, a.c);
 #pragma unroll
         for (int j = 0; j < CMAX; ++j) if (j < a.c) p1[j] = (p1[j] + p2[j]) * 0.5f;   // (:230-231)
@@ -214,9 +216,9 @@ __device__ __forceinline__ void refine_pixel(const RefineArgs &a, int img, int p
             out[j] = (wgt[j] + p1[j]) * __ldg(s + static_cast<size_t>(j) * HW);      // (:263)
             sum += out[j];
         }
-    const float d = sum + kEps;                      // _logits_norm (:295-297)
+    const float inv = __frcp_rn(sum + kEps);         // _logits_norm (:295-297)
 #pragma unroll
-    for (int j = 0; j < CMAX; ++j) if (j < a.c) out[j] = out[j] / d;
+    for (int j = 0; j < CMAX; ++j) if (j < a.c) out[j] = out[j] * inv;
 }
 
 // block-wide per-class max -> one atomicMax per class per block (values are >= 0: the int
@@ -243,7 +245,7 @@ __device__ __forceinline__ void block_class_max(float (&v)[CMAX], int c, unsigne
 // the block-wide reduction and the c atomicMax per block happen once per block, not once per 256 pixels (8192 blocks x 6
 // same-address atomics per image serialise in L2).
 template <int CMAX, bool WRITE>
-__global__ void __launch_bounds__(kPxThreads)
+__global__ void __launch_bounds__(kPxThreads, CMAX <= 8 ? 3 : 1)
 refine_max_kernel(const RefineArgs a, float *__restrict__ soft_out, unsigned *__restrict__ gmax) {
     const int img = blockIdx.y;
     const int HW = a.H * a.W;
@@ -380,7 +382,7 @@ RefineArgs make_refine_args(const float *simi, const float *p1, const float *p2,
     RefineArgs a;
     a.simi = simi; a.pred1 = p1; a.pred2 = p2; a.soft = soft;
     a.c = c; a.h = h; a.w = w; a.H = H; a.W = W;
-    a.temp = static_cast<float>(temp);
+    a.inv_temp = static_cast<float>(1.0 / temp);
     a.sy = H > 1 ? static_cast<float>(h - 1) / static_cast<float>(H - 1) : 0.f;
     a.sx = W > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f;
     return a;

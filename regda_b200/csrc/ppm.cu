@@ -84,56 +84,103 @@ ppm_pool_fwd_kernel(const __nv_bfloat16 *__restrict__ feat, float *__restrict__ 
     }
 }
 
-// grid (h, b, c / kPoolBwdChunk): for one feature-map row y and a 512-channel chunk, phase 1 folds the (at most two) row
-// cells of every scale that contain y into per-column vectors R[column cell][channel] (12 x 512 floats in shared memory,
-// 1/area included), phase 2 writes each pixel as the sum of the <= 2 column vectors per scale that contain x.
+// Fast pooling kernels for pyramids with at most 16 column cells over all scales (1 + 2 + 3 + 6 = 12): the column cells of all
+// scales side by side, cell `col` = column j[col] of scale k[col], covering pixels [lo[col], hi[col]) of a feature-map row.
+constexpr int kMaxColCells = 16;
+struct PpmCols {
+    int n;
+    int k[kMaxColCells], j[kMaxColCells], lo[kMaxColCells], hi[kMaxColCells];
+};
+
+// Backward: dfeat[y][x] = addend[y][x] + sum over the cells containing (y, x) of dpooled[cell] / area(cell).
+// grid (h, b, c / 512): one feature-map row and a 512-channel chunk.  Phase 1 folds, per column cell, the (at most two) row cells
+// of its scale that contain y into R[col][512 channels] in shared memory (every thread 2 channels, all loads independent);
+// phase 2 writes the row: a thread handles 8 (pixel, 8-channel) items -- a warp = 32 consecutive channel octets of ONE pixel, so
+// the column-cell membership test is warp-uniform -- with the optional bf16 addend (the gradient the feature map's other readers
+// sent) prefetched for all 8 items before the first sum.
 constexpr int kPoolBwdChunk = 512;
-constexpr int kMaxColCells = 16;           // sum of the pool scales (1+2+3+6 = 12)
 __global__ void __launch_bounds__(256)
-ppm_pool_bwd_kernel(const float *__restrict__ dpooled, __nv_bfloat16 *__restrict__ dfeat, int h, int w, int c, const PpmScales sc) {
-    __shared__ float R[kMaxColCells][kPoolBwdChunk];
+ppm_pool_bwd_cols_kernel(const float *__restrict__ dpooled, const __nv_bfloat16 *__restrict__ addend, __nv_bfloat16 *__restrict__ dfeat,
+                         int h, int w, int c, const PpmScales sc, const PpmCols cols) {
+    __shared__ __align__(16) float R[kMaxColCells][kPoolBwdChunk];
+    __shared__ int cell_of[kMaxColCells][2];          // the row cells (index into dpooled's cell axis, -1 = none) of column cell col
+    __shared__ float area_of[kMaxColCells][2];
     const int y = blockIdx.x, img = blockIdx.y, c0 = blockIdx.z * kPoolBwdChunk;
     const int cw = min(kPoolBwdChunk, c - c0);
-    const float *pimg = dpooled + static_cast<size_t>(img) * sc.ncell * c + c0;
-    int col = 0;
-    for (int k = 0; k < sc.n; ++k) {
-        const int s = sc.s[k];
-        const int i0 = (y * s) / h;
-        for (int j = 0; j < s; ++j, ++col) {
-            const int x0 = win_lo(j, w, s), x1 = win_hi(j, w, s);
-            for (int ch = threadIdx.x; ch < cw; ch += blockDim.x) {
-                float acc = 0.f;
-                for (int i = max(i0 - 1, 0); i <= min(i0 + 1, s - 1); ++i) {
-                    const int y0 = win_lo(i, h, s), y1 = win_hi(i, h, s);
-                    if (y < y0 || y >= y1) continue;
-                    acc += pimg[static_cast<size_t>(sc.off[k] + i * s + j) * c + ch] / static_cast<float>((y1 - y0) * (x1 - x0));
-                }
-                R[col][ch] = acc;
+    if (threadIdx.x < kMaxColCells) {
+        const int col = threadIdx.x;
+        cell_of[col][0] = cell_of[col][1] = -1;
+        area_of[col][0] = area_of[col][1] = 1.f;
+        if (col < cols.n) {
+            const int k = cols.k[col], s = sc.s[k], i0 = (y * s) / h;
+            int e = 0;
+            for (int i = max(i0 - 1, 0); i <= min(i0 + 1, s - 1); ++i) {
+                const int y0 = win_lo(i, h, s), y1 = win_hi(i, h, s);
+                if (y < y0 || y >= y1 || e == 2) continue;
+                cell_of[col][e] = sc.off[k] + i * s + cols.j[col];
+                area_of[col][e] = static_cast<float>((y1 - y0) * (cols.hi[col] - cols.lo[col]));
+                ++e;
             }
         }
     }
     __syncthreads();
-    __nv_bfloat16 *row = dfeat + (static_cast<size_t>(img) * h + y) * w * c + c0;
-    const int octs = cw >> 3;
-    for (int item = threadIdx.x; item < w * octs; item += blockDim.x) {
-        const int x = item / octs, ch = (item - x * octs) * 8;
-        float acc[8];
+    const float *pimg = dpooled + static_cast<size_t>(img) * sc.ncell * c + c0;
+    for (int ch = threadIdx.x * 2; ch < cw; ch += blockDim.x * 2) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) acc[t] = 0.f;
-        int base = 0;
-        for (int k = 0; k < sc.n; ++k) {
-            const int s = sc.s[k];
-            const int j0 = (x * s) / w;
-            for (int j = max(j0 - 1, 0); j <= min(j0 + 1, s - 1); ++j) {
-                if (x < win_lo(j, w, s) || x >= win_hi(j, w, s)) continue;
-                const float4 a = *reinterpret_cast<const float4 *>(&R[base + j][ch]);
-                const float4 b = *reinterpret_cast<const float4 *>(&R[base + j][ch + 4]);
-                acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-                acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        for (int col = 0; col < kMaxColCells; ++col) {
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int cell = cell_of[col][e];
+                if (cell >= 0) {
+                    const float2 v = __ldg(reinterpret_cast<const float2 *>(pimg + static_cast<size_t>(cell) * c + ch));
+                    acc.x += v.x / area_of[col][e];
+                    acc.y += v.y / area_of[col][e];
+                }
             }
-            base += s;
+            *reinterpret_cast<float2 *>(&R[col][ch]) = acc;
         }
-        *reinterpret_cast<bf16x8 *>(row + static_cast<size_t>(x) * c + ch) = pack(acc);
+    }
+    __syncthreads();
+    const size_t row_off = (static_cast<size_t>(img) * h + y) * w * c + c0;
+    const int octs = cw >> 3, items = w * octs;
+    for (int it0 = threadIdx.x; it0 < items; it0 += blockDim.x * 8) {
+        bf16x8 av[8];
+        if (addend != nullptr) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int item = it0 + u * blockDim.x;
+                if (item < items) {
+                    const int x = item / octs, oc = item - x * octs;
+                    av[u] = *reinterpret_cast<const bf16x8 *>(addend + row_off + static_cast<size_t>(x) * c + oc * 8);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int item = it0 + u * blockDim.x;
+            if (item >= items) break;
+            const int x = item / octs, oc = item - x * octs;
+            float acc[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+#pragma unroll
+            for (int col = 0; col < kMaxColCells; ++col) {
+                if (col < cols.n && x >= cols.lo[col] && x < cols.hi[col]) {
+                    const float4 a = *reinterpret_cast<const float4 *>(&R[col][oc * 8]);
+                    const float4 b2 = *reinterpret_cast<const float4 *>(&R[col][oc * 8 + 4]);
+                    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+                    acc[4] += b2.x; acc[5] += b2.y; acc[6] += b2.z; acc[7] += b2.w;
+                }
+            }
+            if (addend != nullptr) {
+                float f[8];
+                unpack(av[u], f);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) acc[t] += f[t];
+            }
+            *reinterpret_cast<bf16x8 *>(dfeat + row_off + static_cast<size_t>(x) * c + oc * 8) = pack(acc);
+        }
     }
 }
 
@@ -263,6 +310,24 @@ int make_scales(const int *scales, int nscales, PpmScales *out) {
 
 using namespace regda;
 
+// column-cell table of a pyramid on rows of w pixels; false when it has more than kMaxColCells column cells
+static bool make_cols(const PpmScales &sc, int w, PpmCols *out) {
+    int n = 0;
+    for (int k = 0; k < sc.n; ++k) n += sc.s[k];
+    if (n > kMaxColCells) return false;
+    memset(out, 0, sizeof(*out));
+    out->n = n;
+    int col = 0;
+    for (int k = 0; k < sc.n; ++k)
+        for (int j = 0; j < sc.s[k]; ++j, ++col) {
+            out->k[col] = k;
+            out->j[col] = j;
+            out->lo[col] = (j * w) / sc.s[k];
+            out->hi[col] = ((j + 1) * w + sc.s[k] - 1) / sc.s[k];
+        }
+    return true;
+}
+
 extern "C" int regda_ppm_pool_fwd(const void *feat, float *pooled, int b, int h, int w, int c, const int *scales_host, int nscales,
                                   void *stream) {
     PpmScales sc;
@@ -277,19 +342,27 @@ extern "C" int regda_ppm_pool_fwd(const void *feat, float *pooled, int b, int h,
     return REGDA_OK;
 }
 
-extern "C" int regda_ppm_pool_bwd(const float *dpooled, void *dfeat, int b, int h, int w, int c, const int *scales_host, int nscales,
-                                  void *stream) {
+// dfeat = addend + pool_backward(dpooled); addend bf16 [b][h][w][c] or NULL (the gradient the feature map's other consumers sent:
+// the pooling is then the one place where the feature map's gradient is assembled, no separate add kernels)
+extern "C" int regda_ppm_pool_bwd_add(const float *dpooled, const void *addend, void *dfeat, int b, int h, int w, int c,
+                                      const int *scales_host, int nscales, void *stream) {
     PpmScales sc;
     const int rc = make_scales(scales_host, nscales, &sc);
     if (rc) return rc;
     if (!dpooled || !dfeat || b < 1 || h < 1 || w < 1 || c < 8 || c % 8) return fail(REGDA_ERR_INVALID_ARG, "ppm_pool_bwd: bad arguments");
-    int cols = 0;
-    for (int k = 0; k < sc.n; ++k) cols += sc.s[k];
-    if (cols > kMaxColCells) return fail(REGDA_ERR_UNSUPPORTED, "ppm_pool_bwd: pool scales sum to more than 16");
-    ppm_pool_bwd_kernel<<<dim3(h, b, (c + kPoolBwdChunk - 1) / kPoolBwdChunk), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        dpooled, static_cast<__nv_bfloat16 *>(dfeat), h, w, c, sc);
+    if ((reinterpret_cast<uintptr_t>(dpooled) | reinterpret_cast<uintptr_t>(dfeat) | reinterpret_cast<uintptr_t>(addend)) & 15)
+        return fail(REGDA_ERR_INVALID_ARG, "ppm_pool_bwd: tensors must be 16-byte aligned");
+    PpmCols cols;
+    if (!make_cols(sc, w, &cols)) return fail(REGDA_ERR_UNSUPPORTED, "ppm_pool_bwd: pool scales sum to more than 16");
+    ppm_pool_bwd_cols_kernel<<<dim3(h, b, (c + kPoolBwdChunk - 1) / kPoolBwdChunk), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        dpooled, static_cast<const __nv_bfloat16 *>(addend), static_cast<__nv_bfloat16 *>(dfeat), h, w, c, sc, cols);
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
+}
+
+extern "C" int regda_ppm_pool_bwd(const float *dpooled, void *dfeat, int b, int h, int w, int c, const int *scales_host, int nscales,
+                                  void *stream) {
+    return regda_ppm_pool_bwd_add(dpooled, nullptr, dfeat, b, h, w, c, scales_host, nscales, stream);
 }
 
 extern "C" int regda_ppm_upcat_fwd(const void *feat, const void *br0, const void *br1, const void *br2, const void *br3, void *cat,
@@ -400,27 +473,77 @@ ppm_scatter_wgrad_kernel(const float *__restrict__ gmain, const FPtrs gwb, float
     }
 }
 
-// GT[img][o][kappa], kappa = (cell_global * T + tap) < ncell * T, zero up to kp.  One block per (img, o): the 450 source
-// elements G_k[(img, cell)][tap * O + o] are a strided gather (2 B each, L2-resident: G is ~7 MB), the write is one dense row.
-// PACK: G -> GT;  !PACK: GT -> G (the gradient's way back).
+// GT[img][o][kappa], kappa = (cell_global * T + tap) < ncell * T, zero up to kp  <->  G_k[(img, cell)][o * T + tap] (the branch
+// GEMMs run against the OHWI weight in place, so their output columns come in the weight's (o, tap) row order).
+// One block per (image, 32 output channels): for every cell the 32 * T source elements are ONE contiguous run; they pass through a
+// [32][kp] shared-memory tile whose rows are the dense GT rows (16-byte accesses on the GT side).
+// PACK: G -> GT;  !PACK: GT -> G (the gradient's way back).  grid (ceil(O/32), b), dynamic shared memory 32 * kp * 2 bytes.
 template <bool PACK>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 ppm_g_pack_kernel(const GPtrs g, __nv_bfloat16 *__restrict__ gt, int O, int T, int kp, const PpmScales sc) {
-    const int o = blockIdx.x, img = blockIdx.y;
-    __nv_bfloat16 *row = gt + (static_cast<size_t>(img) * O + o) * kp;
-    const int nk = sc.ncell * T;
-    for (int kappa = threadIdx.x; kappa < kp; kappa += blockDim.x) {
-        if (kappa >= nk) {
-            if (PACK) row[kappa] = __float2bfloat16(0.f);
-            continue;
+    extern __shared__ __align__(16) unsigned short gtile[];        // [32][kp]
+    const int o0 = blockIdx.x * 32, img = blockIdx.y;
+    const int no = min(32, O - o0);
+    const int nk = sc.ncell * T, run = no * T;
+    unsigned short *gtu = reinterpret_cast<unsigned short *>(gt) + (static_cast<size_t>(img) * O + o0) * kp;
+    const int row_q = kp >> 3;                                     // 16-byte chunks per GT row (kp is a multiple of 8)
+    if (PACK) {
+        for (int i = threadIdx.x; i < no * (kp - nk); i += blockDim.x) {
+            const int oo = i / (kp - nk), kappa = nk + i - oo * (kp - nk);
+            gtile[oo * kp + kappa] = 0;
         }
-        const int cell = kappa / T, tap = kappa - cell * T;
+    } else {
+        for (int i = threadIdx.x; i < no * row_q; i += blockDim.x) {
+            const int oo = i / row_q, q = i - oo * row_q;
+            *reinterpret_cast<uint4 *>(gtile + oo * kp + q * 8) = *reinterpret_cast<const uint4 *>(gtu + static_cast<size_t>(oo) * kp + q * 8);
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < sc.ncell * run; i += blockDim.x) {
+        const int cell = i / run, e = i - cell * run;
+        const int oo = e / T, tap = e - oo * T;
         int k = 0;
 #pragma unroll
-        for (int i = 1; i < kMaxScales; ++i) if (i < sc.n && cell >= sc.off[i]) k = i;
+        for (int q = 1; q < kMaxScales; ++q) if (q < sc.n && cell >= sc.off[q]) k = q;
         const int j = cell - sc.off[k], s2 = sc.s[k] * sc.s[k];
-        __nv_bfloat16 *e = g.p[k] + (static_cast<size_t>(img) * s2 + j) * (static_cast<size_t>(T) * O) + static_cast<size_t>(tap) * O + o;
-        if (PACK) row[kappa] = *e; else *e = row[kappa];
+        unsigned short *src = reinterpret_cast<unsigned short *>(g.p[k]) + (static_cast<size_t>(img) * s2 + j) * (static_cast<size_t>(T) * O) +
+                              static_cast<size_t>(o0) * T + e;
+        if (PACK) gtile[oo * kp + cell * T + tap] = *src;
+        else *src = gtile[oo * kp + cell * T + tap];
+    }
+    if (PACK) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < no * row_q; i += blockDim.x) {
+            const int oo = i / row_q, q = i - oo * row_q;
+            *reinterpret_cast<uint4 *>(gtu + static_cast<size_t>(oo) * kp + q * 8) = *reinterpret_cast<const uint4 *>(gtile + oo * kp + q * 8);
+        }
+    }
+}
+
+// pooled f32 [b][ncell][c] <-> the per-scale branch inputs p_k bf16 [b][s_k][s_k][c] (dense NHWC, what the branch convolutions read).
+// SPLIT: p_k[img][j][:] = bf16(pooled[img][off_k + j][:]);   !SPLIT (the gradient's way back): dpooled[img][off_k + j][:] = dp_k[img][j][:]
+// grid (ncell, b), a thread moves 8 channels.
+template <bool SPLIT>
+__global__ void __launch_bounds__(256)
+ppm_cells_kernel(float *__restrict__ pooled, const GPtrs p, int c, const PpmScales sc) {
+    const int cell = blockIdx.x, img = blockIdx.y;
+    int k = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxScales; ++i) if (i < sc.n && cell >= sc.off[i]) k = i;
+    const int j = cell - sc.off[k], s2 = sc.s[k] * sc.s[k];
+    float *src = pooled + (static_cast<size_t>(img) * sc.ncell + cell) * c;
+    __nv_bfloat16 *dst = p.p[k] + (static_cast<size_t>(img) * s2 + j) * c;
+    for (int ch = threadIdx.x * 8; ch < c; ch += blockDim.x * 8) {
+        if (SPLIT) {
+            const float4 a = *reinterpret_cast<const float4 *>(src + ch), b2 = *reinterpret_cast<const float4 *>(src + ch + 4);
+            const float f[8] = {a.x, a.y, a.z, a.w, b2.x, b2.y, b2.z, b2.w};
+            *reinterpret_cast<bf16x8 *>(dst + ch) = pack(f);
+        } else {
+            float f[8];
+            unpack(*reinterpret_cast<const bf16x8 *>(dst + ch), f);
+            *reinterpret_cast<float4 *>(src + ch) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4 *>(src + ch + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        }
     }
 }
 
@@ -482,13 +605,13 @@ extern "C" int regda_ppm_scatter_wgrad(const float *gmain, const float *g0, cons
     return REGDA_OK;
 }
 
-// pack != 0: G_k bf16 [b][s_k*s_k][T*O] -> GT bf16 [b][O][kp] (kappa = cell*T + tap, zero padded);  pack == 0: the reverse
+// pack != 0: G_k bf16 [b][s_k*s_k][O*T] (column = o*T + tap) -> GT bf16 [b][O][kp] (kappa = cell*T + tap, zero padded);  pack == 0: the reverse
 extern "C" int regda_ppm_g_pack(void *g0, void *g1, void *g2, void *g3, void *gt, int b, int O, int T, int kp, const int *scales_host,
                                 int nscales, int pack, void *stream) {
     PpmScales sc;
     const int rc = make_scales(scales_host, nscales, &sc);
     if (rc) return rc;
-    if (!gt || b < 1 || O < 1 || T < 1 || kp < sc.ncell * T) return fail(REGDA_ERR_INVALID_ARG, "ppm_g_pack: bad arguments");
+    if (!gt || b < 1 || b > 65535 || O < 1 || O > 65535 * 32 || T < 1 || kp < sc.ncell * T) return fail(REGDA_ERR_INVALID_ARG, "ppm_g_pack: bad arguments");
     GPtrs p;
     void *ps[4] = {g0, g1, g2, g3};
     for (int k = 0; k < kMaxScales; ++k) {
@@ -496,8 +619,40 @@ extern "C" int regda_ppm_g_pack(void *g0, void *g1, void *g2, void *g3, void *gt
         if (k < nscales && !ps[k]) return fail(REGDA_ERR_INVALID_ARG, "ppm_g_pack: null branch pointer");
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (pack) ppm_g_pack_kernel<true><<<dim3(O, b), 128, 0, st>>>(p, static_cast<__nv_bfloat16 *>(gt), O, T, kp, sc);
-    else ppm_g_pack_kernel<false><<<dim3(O, b), 128, 0, st>>>(p, static_cast<__nv_bfloat16 *>(gt), O, T, kp, sc);
+    if (kp % 8 || (reinterpret_cast<uintptr_t>(gt) & 15)) return fail(REGDA_ERR_INVALID_ARG, "ppm_g_pack: kp must be a multiple of 8 and GT 16-byte aligned");
+    const size_t smem = static_cast<size_t>(32) * kp * 2;
+    if (smem > 160 * 1024) return fail(REGDA_ERR_UNSUPPORTED, "ppm_g_pack: kp too large for the shared-memory tile");
+    const dim3 grid((O + 31) / 32, b);
+    if (pack) {
+        if (smem > 48 * 1024) REGDA_CUDA_CHECK(cudaFuncSetAttribute(ppm_g_pack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        ppm_g_pack_kernel<true><<<grid, 256, smem, st>>>(p, static_cast<__nv_bfloat16 *>(gt), O, T, kp, sc);
+    } else {
+        if (smem > 48 * 1024) REGDA_CUDA_CHECK(cudaFuncSetAttribute(ppm_g_pack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        ppm_g_pack_kernel<false><<<grid, 256, smem, st>>>(p, static_cast<__nv_bfloat16 *>(gt), O, T, kp, sc);
+    }
+    REGDA_LAUNCH_CHECK();
+    return REGDA_OK;
+}
+
+// split != 0: pooled float32 [b][ncell][c] -> p_k bf16 [b][s_k][s_k][c] for every scale (the branch convolutions' inputs);
+// split == 0: the reverse with a float32 result (the gradient of the pooled cells from the branch inputs' gradients)
+extern "C" int regda_ppm_cells(float *pooled, void *p0, void *p1, void *p2, void *p3, int b, int c, const int *scales_host, int nscales,
+                               int split, void *stream) {
+    PpmScales sc;
+    const int rc = make_scales(scales_host, nscales, &sc);
+    if (rc) return rc;
+    if (!pooled || b < 1 || b > 65535 || c < 8 || c % 8) return fail(REGDA_ERR_INVALID_ARG, "ppm_cells: bad arguments");
+    GPtrs p;
+    void *ps[4] = {p0, p1, p2, p3};
+    for (int k = 0; k < kMaxScales; ++k) {
+        p.p[k] = static_cast<__nv_bfloat16 *>(ps[k]);
+        if (k < nscales && (!ps[k] || (reinterpret_cast<uintptr_t>(ps[k]) & 15))) return fail(REGDA_ERR_INVALID_ARG, "ppm_cells: null / unaligned branch pointer");
+    }
+    if (reinterpret_cast<uintptr_t>(pooled) & 15) return fail(REGDA_ERR_INVALID_ARG, "ppm_cells: pooled must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int threads = std::min(256, c / 8);
+    if (split) ppm_cells_kernel<true><<<dim3(sc.ncell, b), threads, 0, st>>>(pooled, p, c, sc);
+    else ppm_cells_kernel<false><<<dim3(sc.ncell, b), threads, 0, st>>>(pooled, p, c, sc);
     REGDA_LAUNCH_CHECK();
     return REGDA_OK;
 }

@@ -1,8 +1,8 @@
 // Stem convolution support (regda/_resnets.py:150-153: Conv2d(3, 64, 7, stride 2, padding 3)).
 //
 // Three input channels cannot feed the implicit-GEMM kernel directly (its K-blocks are 64 channels of one filter tap), so
-// the stem is lowered to a GEMM explicitly: this kernel writes the patch matrix A [n*oh*ow][192] (k = (r*7 + s)*3 + c for
-// the 147 real taps, zero up to 192 = 3 K-blocks) and the tcgen05 kernels then run it as a 1x1 convolution with 192 input
+// the stem is lowered to a GEMM explicitly: this kernel writes the patch matrix A [n*oh*ow][192] (k = r*24 + s*3 + c: every
+// filter row r padded from 21 to 24 taps, zero up to 192 = 3 K-blocks) and the tcgen05 kernels then run it as a 1x1 convolution with 192 input
 // channels -- forward (with the fused BatchNorm statistics) and weight gradient; the image needs no data gradient.
 // HBM-bound: 384 B written per output pixel; the 3-channel image is read through L1/L2 (each element is used ~12 times).
 #include <cuda_bf16.h>
@@ -14,31 +14,26 @@
 namespace regda {
 namespace {
 
-constexpr int kStemK = 192, kStemTaps = 147;
+constexpr int kStemK = 192;
 
 constexpr int kStemSeg = 64;                       // output pixels per block
 constexpr int kStemRow = (2 * kStemSeg + 5) * 3 + 1; // staged input elements per filter row: 133 pixels x 3 channels (+1 pad)
 
 // One block = 64 consecutive output pixels of one output row: the 7 input rows x 133 input pixels they read are staged in
 // shared memory with coalesced loads (zero outside the image), then every thread emits 16-byte chunks of the patch matrix
-// (fully coalesced 384-byte rows); tap k of pixel p reads staged element tab[k] + 6*p.
+// (fully coalesced 384-byte rows); tap (r, j) of pixel p is staged element r * kStemRow + j + 6*p.
 // F32_NCHW: the image is the float32 [n][3][h][w] tensor the data loader delivers (regda/datasets: CHW float images); it is
 // rounded to bf16 while it is staged, so the separate NCHW float32 -> NHWC bf16 conversion pass over the batch disappears.
 template <bool F32_NCHW>
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const void *__restrict__ xv, __nv_bfloat16 *__restrict__ a, int n, int h, int w, int oh, int ow, int segs) {
-    __shared__ unsigned short sin[7 * kStemRow];
-    __shared__ unsigned short tab[kStemK];
+    __shared__ __align__(16) unsigned short sin[7 * kStemRow + 8];      // (+8: the masked tail of the last chunk is still read)
     int b = blockIdx.x;
     const int seg = b % segs; b /= segs;
     const int oy = b % oh;
     const int img = b / oh;
     const int ox0 = seg * kStemSeg;
     const int ix_start = 2 * ox0 - 3;
-    for (int k = threadIdx.x; k < kStemK; k += 256) {
-        const int r = k / 21, jj = k - r * 21;
-        tab[k] = static_cast<unsigned short>(k < kStemTaps ? r * kStemRow + jj : 7 * kStemRow - 1);   // padding taps read a zeroed slot
-    }
     if (F32_NCHW) {
         // one plane row at a time (coalesced float loads): element (r, ch, px) -> staged slot r*kStemRow + px*3 + ch
         const float *xi = static_cast<const float *>(xv) + static_cast<long long>(img) * 3 * h * w;
@@ -65,20 +60,20 @@ stem_im2col_kernel(const void *__restrict__ xv, __nv_bfloat16 *__restrict__ a, i
         }
     }
     __syncthreads();
+    // Patch row = 8 groups of 24 taps: group r < 7 holds filter row r as (s, c) = 21 real taps + 3 zeros, group 7 is zero.  A
+    // 16-byte chunk is 8 consecutive staged elements of one filter row (4 aligned 32-bit shared loads: every index below is even).
     const int npx = min(kStemSeg, ow - ox0);
     __nv_bfloat16 *arow = a + ((static_cast<long long>(img) * oh + oy) * ow + ox0) * kStemK;
     for (int q = threadIdx.x; q < npx * (kStemK / 8); q += 256) {
         const int p = q / (kStemK / 8), c = q - p * (kStemK / 8);
-        const int base = 6 * p;
-        unsigned short v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int t = tab[c * 8 + j];
-            v[j] = sin[t + (t == 7 * kStemRow - 1 ? 0 : base)];
+        const int r = c / 3, part = c - r * 3;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (r < 7) {
+            const unsigned *src = reinterpret_cast<const unsigned *>(sin + r * kStemRow + part * 8 + 6 * p);
+            o.x = src[0]; o.y = src[1];
+            if (part < 2) { o.z = src[2]; o.w = src[3]; }
+            else o.z = src[2] & 0xffffu;                       // taps 16..20 of the row; 21..23 are padding
         }
-        uint4 o;
-        o.x = v[0] | (static_cast<unsigned>(v[1]) << 16); o.y = v[2] | (static_cast<unsigned>(v[3]) << 16);
-        o.z = v[4] | (static_cast<unsigned>(v[5]) << 16); o.w = v[6] | (static_cast<unsigned>(v[7]) << 16);
         *reinterpret_cast<uint4 *>(arow + static_cast<long long>(q) * 8) = o;
     }
 }

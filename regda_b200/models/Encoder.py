@@ -222,30 +222,34 @@ class PPMBilinear(nn.Module):
                 and len(self.pool_scales) <= 4
                 and conv_out.shape[1] % 8 == 0 and self.ppm[0][1].out_channels % 8 == 0)
 
-    def forward(self, conv_out, pooled=None):
+    def forward(self, conv_out, pooled=None, tap=False):
+        """tap=True (folded fuse convolution only) returns (logits, conv_out_tap): the handle the NEXT reader of the feature map
+        should use, so that its gradient is added inside this head's data-gradient kernel (ops/ppm_fold.py)"""
+        if tap:
+            assert self.fused_ok(conv_out) and pooled is not None
         if self.fused_ok(conv_out):
             # one-pass pyramid pooling (shared by both heads when the caller passes `pooled`), tiny per-branch
             # 1x1 conv + BN + ReLU on the pooled maps, fused bilinear-upsample + concat, tcgen05 3x3 conv.
             if pooled is None:
                 pooled = fppm.pool(conv_out, self.pool_scales)
-            b, c = conv_out.shape[:2]
-            branches, off = [], 0
-            for s, branch in zip(self.pool_scales, self.ppm):
-                p = pooled[:, off:off + s * s, :].reshape(b, s, s, c).permute(0, 3, 1, 2).to(conv_out.dtype)
-                off += s * s
-                # 1x1 conv on the s x s map (several images per tcgen05 M tile) + BatchNorm + ReLU, all hand-written kernels
-                branches.append(_conv_bn(branch[1], branch[2], p, relu=True))
+            # the s x s pooled maps as bf16 NHWC tensors (one launch; shared by both heads when the caller passes them as a list)
+            cells = pooled if isinstance(pooled, (list, tuple)) else fppm.cells(pooled, self.pool_scales)
+            # 1x1 conv on the s x s map (several images per tcgen05 M tile) + BatchNorm + ReLU, all hand-written kernels
+            branches = [_conv_bn(branch[1], branch[2], p, relu=True) for p, branch in zip(cells, self.ppm)]
             conv, bn = self.conv_last[0], self.conv_last[1]
             if ffold.supported(conv_out, branches, conv, self.pool_scales) and (bn.training or fnorm.inference_supported(conv_out, bn)):
                 # the upsampled branches enter the 3x3 convolution through two small GEMMs instead of 2048 materialised channels
                 # (ops/ppm_fold.py): half the reference's K, no concatenated tensor
                 train = bn.training and fnorm.supported(conv_out.new_empty((1, conv.out_channels, 1, 1)), bn)
-                y, st = ffold.fuse_conv(conv_out, branches, conv.weight, self.pool_scales, _GROUPS if train else None)
+                res = ffold.fuse_conv(conv_out, branches, conv.weight, self.pool_scales, _GROUPS if train else None, tap)
+                y, st = res[0], res[1]
                 y = fnorm.bn_act(y, bn, relu=True, groups=_GROUPS, stats=st) if train else _bn(y, bn, relu=True)
+                if tap:
+                    return self._classify(y), res[2]
             else:
                 cat = fppm.upsample_concat(conv_out, branches, self.pool_scales)
                 y = _conv_bn(conv, bn, cat, relu=True)
-            return self._classify(y)
+            return (self._classify(y), conv_out) if tap else self._classify(y)
         size = conv_out.shape[-2:]
         outs = [conv_out]
         for branch in self.ppm:
@@ -314,8 +318,7 @@ class Deeplabv2(nn.Module):
             # hand-written path: per-image statistics groups of the BatchNorm kernels, bf16 in / bf16 out; the Aligner's
             # float32 feature view is one conversion of the result
             fin = fnorm.instance_norm(feat, self.instance_norm.eps)
-            # (the float32 copy is made on the dense NHWC view: a contiguous, vectorised cast instead of a strided one)
-            feat = fin if (feat_dtype == torch.bfloat16 and self.training) else fin.permute(0, 2, 3, 1).float().permute(0, 3, 1, 2)
+            feat = None                                       # made from fin (or from its last tap) after the heads
         else:
             if self._cfg.is_ins_norm:
                 feat = self.instance_norm(feat.float())      # float32 statistics and output (feeds the Aligner)
@@ -323,12 +326,25 @@ class Deeplabv2(nn.Module):
                 feat = feat.float()
             fin = feat.to(self.compute_dtype)
         if self.layer5.fused_ok(fin) and self.layer5.pool_scales == self.layer6.pool_scales:
-            pooled = fppm.pool(fin, self.layer5.pool_scales)          # both heads pool the same feature map
-            x1 = self.layer5(fin, pooled).float()
-            x2 = self.layer6(fin, pooled).float()
+            if self.training and feat is None and torch.is_grad_enabled():
+                # the feature map has four readers (pooling, the two heads' fuse convolutions, the caller's Aligner losses): chain
+                # them through taps -- pooling <- head 5 <- head 6 <- caller -- so that every reader's gradient is added inside the
+                # next one's backward kernel instead of by three autograd adds over the 67 MB map
+                pooled, fin5 = fppm.pool(fin, self.layer5.pool_scales, tap=True)
+                pooled = fppm.cells(pooled, self.layer5.pool_scales)
+                x1, fin6 = self.layer5(fin5, pooled, tap=True)
+                x2, fin = self.layer6(fin6, pooled, tap=True)
+                x1, x2 = x1.float(), x2.float()
+            else:
+                pooled = fppm.cells(fppm.pool(fin, self.layer5.pool_scales), self.layer5.pool_scales)    # both heads pool the same feature map
+                x1 = self.layer5(fin, pooled).float()
+                x2 = self.layer6(fin, pooled).float()
         else:
             x1 = self.layer5(fin).float()
             x2 = self.layer6(fin).float()
+        if feat is None:
+            # (the float32 copy is made on the dense NHWC view: a contiguous, vectorised cast instead of a strided one)
+            feat = fin if (feat_dtype == torch.bfloat16 and self.training) else fin.permute(0, 2, 3, 1).float().permute(0, 3, 1, 2)
         if self.training:
             return x1, x2, feat
         if FUSED and x1.is_cuda and not torch.is_grad_enabled() and x1.shape[1] <= 16:

@@ -109,6 +109,7 @@ class _ConvFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)        # no zero-filled gradient tensors for the statistics / unused tap outputs
         stats["tcgen05_fprop"] += 1
         outs = []
+        tc.hint_static(weight)
         if stats_groups is None:
             outs.append(tc.fprop(x, w16, stride, padding, dilation))
         else:
@@ -138,6 +139,7 @@ class _ConvFn(torch.autograd.Function):
             stats["tcgen05_dgrad"] += 1
             fuse = g_tap is not None and g_tap.dtype == torch.bfloat16 and FUSE_BN_STATS
             hd = ctx.bn_handle
+            tc.hint_static(weight)
             if hd is not None and hd.fused:
                 assert g_tap is None or fuse
                 if hd.red is None:

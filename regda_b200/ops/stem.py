@@ -1,7 +1,7 @@
 """Stem convolution Conv2d(3, 64, 7, stride 2, padding 3) (regda/_resnets.py:150) on the tcgen05 kernels.
 
 Three input channels cannot form the 64-channel K-blocks of the implicit-GEMM kernel, so the stem is lowered explicitly:
-`regda_stem_im2col_bf16` writes the patch matrix [n, oh, ow, 192] (147 taps + zero padding) and the forward / weight-gradient
+`regda_stem_im2col_bf16` writes the patch matrix [n, oh, ow, 192] (7 filter rows of 21 taps, each padded to 24, + 24 zeros) and the forward / weight-gradient
 kernels run it as a 1x1 convolution over 192 channels, with the BatchNorm statistics from the forward epilogue like every
 other convolution of the network.  The image needs no data gradient.  (Replaces the library call this layer used to be.)
 """
@@ -12,7 +12,12 @@ import torch
 from .. import capi
 from . import tc
 
-K_PAD = 192
+K_PAD = 192          # the patch row: 8 groups of 24 = filter row r as 21 real (s, c) taps + 3 zeros; group 7 all zero (csrc/stem.cu)
+
+
+def _rows(t, cout):
+    """the [cout, 7, 21] real-tap view of a [cout, 192(,1,1)] patch-ordered weight / weight-gradient tensor"""
+    return t.view(cout, 8, 24)[:, :7, :21]
 
 
 def supported(conv, x) -> bool:
@@ -37,7 +42,7 @@ class _StemConvFn(torch.autograd.Function):
             capi.call("regda_stem_im2col_bf16", capi.ptr_any(x), capi.ptr_any(a), n, h, w, capi.stream())
         w16 = tc.weight_shadow(weight)                       # bf16 [64,3,7,7] channels-last = OHWI rows of 147
         wp = torch.zeros((cout, K_PAD, 1, 1), dtype=torch.bfloat16, device=x.device).contiguous(memory_format=torch.channels_last)
-        wp.view(cout, K_PAD)[:, :147] = w16.permute(0, 2, 3, 1).reshape(cout, 147)
+        _rows(wp, cout).copy_(w16.permute(0, 2, 3, 1).reshape(cout, 7, 21))
         ctx.save_for_backward(a)
         ctx.weight = weight
         ctx.set_materialize_grads(False)
@@ -59,10 +64,10 @@ class _StemConvFn(torch.autograd.Function):
         tc.wgrad_accumulate(gy, a, gw, 1, 0, 1)
         if weight.grad is None:
             weight.grad = torch.zeros_like(weight)
-        # weight.grad is OHWI memory: rows of 147 = (r, s, c), the patch matrix's k order
-        gview = weight.grad.permute(0, 2, 3, 1).reshape(cout, 147)
+        # weight.grad is OHWI memory: 7 filter rows of 21 = (s, c) taps, the patch matrix's 24-padded row groups
+        gview = weight.grad.permute(0, 2, 3, 1).reshape(cout, 7, 21)
         assert gview.data_ptr() == weight.grad.data_ptr(), "stem weight gradient must live in channels-last (OHWI) memory"
-        gview.add_(gw.view(cout, K_PAD)[:, :147])
+        gview.add_(_rows(gw, cout))
         return None, None, None
 
 
@@ -84,7 +89,7 @@ class _StemConvF32Fn(torch.autograd.Function):
         cout = weight.shape[0]
         ap = [_im2col(t) for t in tc.split_bf16(x)]
         wp = torch.zeros((cout, K_PAD), dtype=torch.float32, device=x.device)
-        wp[:, :147] = weight.detach().permute(0, 2, 3, 1).reshape(cout, 147)
+        _rows(wp, cout).copy_(weight.detach().permute(0, 2, 3, 1).reshape(cout, 7, 21))
         wps = tc.split_bf16(wp.view(cout, K_PAD, 1, 1))
         y = (tc.fprop(ap[0], tc._cat_cl([wps[0]], 1), 1, 0, 1, out_f32=True) +
              tc.fprop(tc._cat_cl([ap[i] for i in tc._A_PARTS], 1), tc._cat_cl([wps[i] for i in tc._W_PARTS], 1), 1, 0, 1, out_f32=True))
@@ -104,9 +109,9 @@ class _StemConvF32Fn(torch.autograd.Function):
             tc.wgrad_accumulate(gp[i], ap[j], gw, 1, 0, 1)
         if weight.grad is None:
             weight.grad = torch.zeros_like(weight)
-        gview = weight.grad.permute(0, 2, 3, 1).reshape(cout, 147)
+        gview = weight.grad.permute(0, 2, 3, 1).reshape(cout, 7, 21)
         assert gview.data_ptr() == weight.grad.data_ptr(), "stem weight gradient must live in channels-last (OHWI) memory"
-        gview.add_(gw.view(cout, K_PAD)[:, :147])
+        gview.add_(_rows(gw, cout))
         return None, None
 
 

@@ -76,6 +76,14 @@ def weight_shadow(weight):
     return ent[1]
 
 
+def hint_static(weight):
+    """tell the next forward / data-gradient convolution launched from this thread that its weight operand is the bf16 copy of an
+    arena parameter -- written once per step by the optimizer kernel (or by ParamArena.sync_shadow, which fences it), never by the
+    kernel that precedes the convolution -- so the kernel may request its first weight tiles before its PDL wait (conv_tc.cu)"""
+    if getattr(weight, "_bf16", None) is not None:
+        capi.lib().regda_conv_hint_static_weights()
+
+
 def _nhwc(t):
     """the tensor in channels-last memory (a copy only when the producer left it in another stride order)"""
     if not t.is_contiguous(memory_format=torch.channels_last):

@@ -83,7 +83,8 @@ class ParamArena:
             p._bf16 = view(self.param_bf16)            # what the tcgen05 convolutions read (ops/tc.py weight_shadow)
             p._arena = self                            # writers of p.data outside the SGD kernel call p._arena.sync_shadow()
             p._arena_off = o                           # the backward ops report it to the gradient buckets (parallel.GradBuckets)
-        self.param_bf16.copy_(self.param)
+        self.lr_device = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.sync_shadow()
         # load_state_dict() (resume, reload-best, evaluate(ckpt)) writes the fp32 arena behind the SGD kernel's back:
         # refresh the bf16 shadow the convolutions read
         module.register_load_state_dict_post_hook(lambda _m, _incompatible: self.sync_shadow())
@@ -91,7 +92,6 @@ class ParamArena:
         self.offset_of = {n: p._arena_off for n, p in module.named_parameters() if hasattr(p, "_arena_off")}
         self.buckets = None                            # parallel.GradBuckets when data-parallel (set by the trainer)
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.lr_device = torch.zeros(1, dtype=torch.float32, device=dev)
 
     def zero_grad(self):
         self.grad.zero_()
@@ -115,6 +115,9 @@ class ParamArena:
         """refresh the bf16 shadow after the fp32 parameters were written from outside the SGD kernel
         (load_state_dict, broadcast)"""
         self.param_bf16.copy_(self.param)
+        # a plainly launched kernel after the copy: convolutions prefetch these weights ahead of their programmatic-dependent-launch
+        # wait (regda_conv_hint_static_weights), which orders them only after the kernels BEFORE their immediate predecessor
+        self.lr_device.add_(0.0)
 
     def set_lr(self, lr):
         """host float -> the device scalar the SGD kernel reads (graph-replay safe)."""

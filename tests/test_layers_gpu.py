@@ -90,6 +90,82 @@ def test_ppm_pool_forward_backward(shape):
     _close(x.grad, xr.grad, 1e-2)
 
 
+@pytest.mark.parametrize("shape", [(2, 2048, 32, 32), (1, 64, 20, 13), (2, 640, 16, 16)], ids=str)
+def test_ppm_pool_tap_adds_the_other_readers_gradient(shape):
+    """the feature map's second reader goes through the tap: its gradient is added inside the pooling backward kernel"""
+    from regda_b200.ops import ppm
+    scales = (1, 2, 3, 6)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = _cl(torch.randn(shape, device="cuda", generator=g).bfloat16()).requires_grad_(True)
+    pooled, x_tap = ppm.pool(x, scales, tap=True)
+    assert x_tap.data_ptr() == x.data_ptr()
+    xr = x.detach().float().requires_grad_(True)
+    ref = torch.cat([F.adaptive_avg_pool2d(xr, s).flatten(2).transpose(1, 2) for s in scales], 1)
+    gp = torch.randn(ref.shape, device="cuda", generator=g)
+    gt = _cl(torch.randn(shape, device="cuda", generator=g).bfloat16())
+    torch.autograd.backward([pooled, x_tap], [gp, gt])
+    torch.autograd.backward([ref, xr * 1.0], [gp, gt.float()])
+    _close(x.grad, xr.grad, 1e-2)
+    # only the tap carries a gradient
+    x2 = x.detach().clone().requires_grad_(True)
+    _, t2 = ppm.pool(x2, scales, tap=True)
+    t2.backward(gt)
+    assert torch.equal(x2.grad, gt)
+
+
+def test_folded_fuse_conv_matches_concat_conv_and_adds_tap_gradient():
+    """ops/ppm_fold.py against the reference formulation (Encoder.py:43-52: conv3x3 over cat(feat, up(branch_k))), float32 torch; with
+    tap=True the next reader's gradient is added inside the data-gradient kernel"""
+    from regda_b200.ops import ppm_fold
+    scales = (1, 2, 3, 6)
+    b, cf, cb, h, w, O = 4, 256, 64, 16, 16, 128
+    g = torch.Generator(device="cuda").manual_seed(12)
+    fin = _cl((torch.randn(b, cf, h, w, device="cuda", generator=g)).bfloat16()).requires_grad_(True)
+    brs = [_cl(torch.randn(b, cb, s, s, device="cuda", generator=g).bfloat16()).requires_grad_(True) for s in scales]
+    wt = (torch.randn(O, cf + 4 * cb, 3, 3, device="cuda", generator=g) / (9 * (cf + 4 * cb)) ** 0.5).contiguous(memory_format=torch.channels_last)
+    wt = torch.nn.Parameter(wt)
+    y, st, fin_tap = ppm_fold.fuse_conv(fin, brs, wt, scales, 2, tap=True)
+    finr = fin.detach().float().requires_grad_(True)
+    brr = [t.detach().float().requires_grad_(True) for t in brs]
+    wr = wt.detach().bfloat16().float().requires_grad_(True)
+    cat = torch.cat([finr] + [F.interpolate(t, (h, w), mode="bilinear", align_corners=False) for t in brr], 1)
+    ref = F.conv2d(cat, wr, padding=1)
+    _close(y, ref, 1.5e-2)
+    yf = y.detach().float().view(2, b // 2, O, h * w)
+    _close(st[:, 0], yf.sum((1, 3)), 1e-2)
+    _close(st[:, 1], (yf * yf).sum((1, 3)), 1e-2)
+    gy = _cl(torch.randn(ref.shape, device="cuda", generator=g).bfloat16())
+    gt = _cl(torch.randn(fin.shape, device="cuda", generator=g).bfloat16())
+    torch.autograd.backward([y, fin_tap], [gy, gt])
+    torch.cuda.synchronize()
+    from regda_b200.ops import conv as C
+    C.join_wgrad_stream()
+    torch.autograd.backward([ref, finr * 1.0], [gy.float(), gt.float()])
+    _close(fin.grad, finr.grad, 1.5e-2)
+    for t, tr in zip(brs, brr):
+        _close(t.grad, tr.grad, 2e-2)
+    _close(wt.grad, wr.grad, 1.5e-2)
+
+
+def test_ppm_cells_split_and_gradient():
+    from regda_b200.ops import ppm
+    scales = (1, 2, 3, 6)
+    b, c = 3, 256
+    g = torch.Generator(device="cuda").manual_seed(10)
+    pooled = torch.randn(b, 50, c, device="cuda", generator=g).requires_grad_(True)
+    ps = ppm.cells(pooled, scales)
+    off = 0
+    gs = []
+    for p, s in zip(ps, scales):
+        want = pooled.detach()[:, off:off + s * s, :].reshape(b, s, s, c).permute(0, 3, 1, 2).bfloat16()
+        assert p.shape == want.shape and p.is_contiguous(memory_format=torch.channels_last) and torch.equal(p, want)
+        gs.append(torch.randn(want.shape, device="cuda", generator=g).bfloat16())
+        off += s * s
+    torch.autograd.backward(list(ps), gs)
+    want = torch.cat([t.permute(0, 2, 3, 1).reshape(b, -1, c) for t in gs], 1).float()
+    assert torch.equal(pooled.grad, want)
+
+
 @pytest.mark.parametrize("shape", [(2, 2048, 32, 32, 512), (2, 64, 8, 8, 32), (1, 128, 20, 13, 64)], ids=str)
 def test_ppm_upsample_concat_forward_backward(shape):
     from regda_b200.ops import ppm
