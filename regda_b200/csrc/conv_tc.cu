@@ -49,16 +49,27 @@ struct ConvGeom {
     int kc;                          // cin / 64
     int wct;                         // channels per tap of the WEIGHT tensor (>= the channels this GEMM touches: a convolution over
                                      // the first channels of a wider OHWI weight reads / differentiates it in place)
+    int contig;                      // tile walk: 0 = strided, channel block fastest; 1 = contiguous ranges, channel block slowest
     int w_early;                     // the weights were written long before the preceding kernel of the stream: their first pipeline
                                      // stages may be requested BEFORE the programmatic-dependent-launch wait (regda_conv_hint_static_weights)
 };
 
 struct TileCoord { int n_blk, tw, th, img0; };
 
+// tile t -> (channel block, M tile).  Default: channel block fastest -- the CTAs that run side by side share an activation patch
+// in L2 and, walking the list with a stride of gridDim.x, keep their channel block whenever it divides the grid size.  g.contig
+// (channel-block count does not divide the grid): M tile fastest, channel block slowest, each CTA a contiguous range.
 __device__ __forceinline__ TileCoord decode_tile(int t, int n_tiles_n, const ConvGeom &g) {
     TileCoord c;
-    c.n_blk = t % n_tiles_n;
-    int m = t / n_tiles_n;
+    int m;
+    if (g.contig) {
+        const int m_tiles = g.tiles_img * g.tiles_h * g.tiles_w;
+        c.n_blk = t / m_tiles;
+        m = t - c.n_blk * m_tiles;
+    } else {
+        c.n_blk = t % n_tiles_n;
+        m = t / n_tiles_n;
+    }
     c.tw = m % g.tiles_w; m /= g.tiles_w;
     c.th = m % g.tiles_h;
     c.img0 = (m / g.tiles_h) * g.bn;
@@ -66,7 +77,7 @@ __device__ __forceinline__ TileCoord decode_tile(int t, int n_tiles_n, const Con
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Persistent variant: one CTA per SM walks the tile list (N tile fastest, so CTAs running side by side share the
+// Persistent variant: one CTA per SM walks the tile list (decode_tile: N tile fastest, so CTAs running side by side share the
 // activation patch in L2); the TMA / MMA / epilogue warps each loop over the tiles on their own, coupled only by
 // mbarriers: the shared-memory ring keeps streaming across tile boundaries and TWO accumulators in tensor memory
 // (2 x BLOCK_N columns) let the epilogue of tile i drain while the MMAs of tile i+1 run.  Barrier / TMEM /
@@ -149,6 +160,12 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_k = g.r * g.s * g.kc;
+    // this CTA's tiles: every gridDim.x-th tile, or (g.contig) a contiguous range of the list (sizes differ by at most one) -- either
+    // way the channel block and the BatchNorm statistics group change at most once each on the way (the fused statistics are
+    // flushed when they do; a channel block that alternated from tile to tile would flush at every tile)
+    const int tile_lo = g.contig ? static_cast<int>(static_cast<long long>(blockIdx.x) * num_tiles / gridDim.x) : static_cast<int>(blockIdx.x);
+    const int tile_hi = g.contig ? static_cast<int>(static_cast<long long>(blockIdx.x + 1) * num_tiles / gridDim.x) : num_tiles;
+    const int tile_step = g.contig ? 1 : static_cast<int>(gridDim.x);
 #ifdef REGDA_CONV_TRACE
     const int trace_id = (imgs_per_group_ >> 16) % kTraceLaunches;
     const int imgs_per_group = imgs_per_group_ & 0xffff;
@@ -189,7 +206,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     // waits for -- request them now, so that their DRAM latency overlaps the wait; the activation halves follow after it.
     const int pre = g.w_early ? min(STAGES, num_k) : 0;
     if (pre > 0 && warp == 0 && elect_one()) {
-        const int n_blk = decode_tile(blockIdx.x, n_tiles_n, g).n_blk;
+        const int n_blk = decode_tile(tile_lo, n_tiles_n, g).n_blk;
         int tap = 0, c0 = 0;
         for (int kb = 0; kb < pre; ++kb) {
             mbar_arrive_expect_tx(full_bar + kb, L::kStageBytes);
@@ -208,7 +225,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             int stage = 0;
             uint32_t phase = 0;
             int early = pre;                 // k-blocks whose barrier is armed and whose weight half is already on its way
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = tile_lo; t < tile_hi; t += tile_step) {
                 const TileCoord tc_ = decode_tile(t, n_tiles_n, g);
                 const int n_blk = tc_.n_blk, img = tc_.img0;
                 const int ix0 = tc_.tw * g.bw * g.stride - g.pad, iy0 = tc_.th * g.bh * g.stride - g.pad;
@@ -216,13 +233,11 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(empty_bar + stage, phase ^ 1);
                     uint8_t *sa = smem + stage * L::kStageBytes;
-                    if (early > 0) {
-                        --early;
-                    } else {
-                        mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes);
-                        load_b(sa + L::kABytes, full_bar + stage, n_blk, tap, c0);
-                    }
+                    const bool armed = early > 0;       // barrier armed and weight half requested before the PDL wait
+                    if (armed) --early;
+                    else mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes);
                     tma_load_4d(sa, &tmap_x, full_bar + stage, c0, ix0 + fs * g.dil, iy0 + fr * g.dil, img);
+                    if (!armed) load_b(sa + L::kABytes, full_bar + stage, n_blk, tap, c0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     c0 += kBlockK;
                     if (c0 == g.cin) { c0 = 0; ++tap; if (++fs == g.s) { fs = 0; ++fr; } }
@@ -238,14 +253,14 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = tile_lo; t < tile_hi; t += tile_step) {
                 mbar_wait(tempty_bar + acc, acc_phase ^ 1);           // epilogue has drained this accumulator
                 tc_fence_after_sync();
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(full_bar + stage, phase);
                     tc_fence_after_sync();
-                    if (kb == 0 && t == static_cast<int>(blockIdx.x)) CONV_TRACE(3);
+                    if (kb == 0 && t == tile_lo) CONV_TRACE(3);
                     const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
                     const uint32_t sb = sa + L::kABytes;
                     const uint64_t adesc = make_smem_desc(sa, 0, 1024);
@@ -281,7 +296,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             const uint32_t ybuf_s = smem_u32(ybuf);
             uint32_t yphase = 0;
             // BatchNorm statistics stay in registers across the tiles of this CTA for as long as (channel block, statistics
-            // group) does not change -- with a tile stride of gridDim.x that is most of the walk.  Lane L accumulates the 8
+            // group) does not change -- each changes at most once over the CTA's tiles.  Lane L accumulates the 8
             // channels of 16-byte chunk (L & 7) of every 64-channel chunk over rows (L >> 3) + 4 i of its warp's 32, as packed
             // float32 pairs (FADD2 / FFMA2).  The four row groups, the four warps that share a column range and finally the
             // CTAs are folded at flush time only: one fp32 reduction per channel and quantity per CTA (per-tile or per-warp
@@ -297,11 +312,9 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             int stat_key = -1;
             auto flush_stats = [&](int key, bool final) {
                 float *base = stats + static_cast<size_t>(key & 0xffff) * 2 * g.cout + static_cast<size_t>(key >> 16) * BLOCK_N;
-                if (final) {
-                    // scratch = the warp's own staging buffer as float [2 quantities][kCols]: its last TMA store must have read it
-                    if (lane == 0) bulk_wait_read0();
-                    __syncwarp();
-                }
+                // scratch = the warp's own staging buffer as float [2 quantities][kCols]: its last TMA store must have read it
+                if (lane == 0) bulk_wait_read0();
+                __syncwarp();
 #pragma unroll
                 for (int i = 0; i < kChunks; ++i) {
                     float2 keep_s = make_float2(0.f, 0.f), keep_q = make_float2(0.f, 0.f);
@@ -316,20 +329,10 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                         sacc[i][j] = 0ull;
                     }
                     const uint32_t ch = static_cast<uint32_t>(i) * 64u + lch * 8u + 2u * lr;
-                    if (final) {
-                        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(stage_s + ch * 4u), "f"(keep_s.x), "f"(keep_s.y) : "memory");
-                        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(stage_s + (static_cast<uint32_t>(kCols) + ch) * 4u), "f"(keep_q.x), "f"(keep_q.y) : "memory");
-                    } else {
-                        // a flush in the middle of the walk (the CTA moves on to another channel block / statistics group): these are
-                        // spread over the kernel's run time, one reduction per channel, quantity and warp
-                        float *dst = base + col_lo + ch;
-                        atomicAdd(dst, keep_s.x); atomicAdd(dst + 1, keep_s.y);
-                        atomicAdd(dst + g.cout, keep_q.x); atomicAdd(dst + g.cout + 1, keep_q.y);
-                    }
+                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(stage_s + ch * 4u), "f"(keep_s.x), "f"(keep_s.y) : "memory");
+                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(stage_s + (static_cast<uint32_t>(kCols) + ch) * 4u), "f"(keep_q.x), "f"(keep_q.y) : "memory");
                 }
-                if (!final) return;
-                // the CTA's last flush -- every CTA's arrives in the same microsecond at the end of the grid -- folds the four warps
-                // that share a column range first: one reduction per channel and quantity per CTA
+                // fold the four warps that share a column range: one (coalesced) reduction per channel and quantity per CTA
                 named_bar_sync(1, kEpiThreads);
                 const uint32_t store_s = smem_u32(smem + L::kStoreOffset);
                 for (int item = wq * 32 + lane; item < 2 * BLOCK_N; item += kEpiThreads) {
@@ -339,6 +342,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                     const float v = (ld_shared_f32(a) + ld_shared_f32(a + 4096u)) + (ld_shared_f32(a + 8192u) + ld_shared_f32(a + 12288u));
                     atomicAdd(base + static_cast<size_t>(qty) * g.cout + col, v);
                 }
+                if (!final) named_bar_sync(1, kEpiThreads);      // the scratch is staging memory again
             };
             // bf16 pack of one 32-column accumulator segment of this lane's row (zeros where `keep` has no bit)
             auto pack32 = [](const uint32_t (&v)[32], uint32_t keep, uint32_t (&pk)[16]) {
@@ -360,7 +364,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
             };
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = tile_lo; t < tile_hi; t += tile_step) {
                 const TileCoord tc_ = decode_tile(t, n_tiles_n, g);
                 const int n_blk = tc_.n_blk, tw = tc_.tw, th = tc_.th;
                 const int img = tc_.img0 + pn, bimg = tc_.img0 + bpn0;
@@ -396,7 +400,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                 }
                 mbar_wait(tfull_bar + acc, acc_phase);
                 tc_fence_after_sync();
-                if (wq == 0 && lane == 0) { if (t == static_cast<int>(blockIdx.x)) CONV_TRACE(5); CONV_TRACE(6); }
+                if (wq == 0 && lane == 0) { if (t == tile_lo) CONV_TRACE(5); CONV_TRACE(6); }
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N + col_lo);
 #pragma unroll
                 for (int c64 = 0; c64 < kCols; c64 += 64) {
@@ -508,7 +512,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         const int pw = row % g.bw, ph = (row / g.bw) % g.bh, pn = row / (g.bw * g.bh);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int t = tile_lo; t < tile_hi; t += tile_step) {
             const TileCoord tc_ = decode_tile(t, n_tiles_n, g);
             const int img = tc_.img0 + pn;
             const int oh = tc_.th * g.bh + ph, ow = tc_.tw * g.bw + pw;
@@ -596,6 +600,10 @@ int launch_persistent_impl(const CUtensorMap &tx, const CUtensorMap &tw, void *y
     ConvGeom g = g_in;
     g.w_early = (t_static_weights && pdl_level() >= 1) ? 1 : 0;
     t_static_weights = 0;
+    {
+        const int nn = g.cout / BLOCK_N, nt = nn * g.tiles_img * g.tiles_h * g.tiles_w;
+        g.contig = (std::min(nt, sm_count()) % nn) != 0 ? 1 : 0;
+    }
     using L = PersistSmem<BLOCK_N, STAGES, BNRED>;
     auto kern = conv_persistent_kernel<BLOCK_N, STAGES, B_MN, STATS, OUT_F32, BNRED>;
     const int smem = L::kTotal + 1024;
@@ -686,6 +694,7 @@ int geom_init(ConvGeom &g, int n, int h, int w, int cin, int cout, int r, int s,
     g.kc = cin / kBlockK;
     g.wct = cin;
     g.w_early = 0;
+    g.contig = 0;
     return REGDA_OK;
 }
 

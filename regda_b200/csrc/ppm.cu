@@ -99,18 +99,20 @@ struct PpmCols {
 // the column-cell membership test is warp-uniform -- with the optional bf16 addend (the gradient the feature map's other readers
 // sent) prefetched for all 8 items before the first sum.
 constexpr int kPoolBwdChunk = 512;
-__global__ void __launch_bounds__(256)
+constexpr int kPoolMaxW = 512;            // widest feature-map row of the fast backward kernel
+__global__ void __launch_bounds__(256, 3)
 ppm_pool_bwd_cols_kernel(const float *__restrict__ dpooled, const __nv_bfloat16 *__restrict__ addend, __nv_bfloat16 *__restrict__ dfeat,
                          int h, int w, int c, const PpmScales sc, const PpmCols cols) {
     __shared__ __align__(16) float R[kMaxColCells][kPoolBwdChunk];
-    __shared__ int cell_of[kMaxColCells][2];          // the row cells (index into dpooled's cell axis, -1 = none) of column cell col
-    __shared__ float area_of[kMaxColCells][2];
+    __shared__ int cell_of[kMaxColCells][2];          // the row cells (index into dpooled's cell axis) of column cell col that contain y
+    __shared__ float winv[kMaxColCells][2];           // 1 / area of that cell; 0 for an unused slot (which then points at cell 0)
+    __shared__ unsigned colmask[kPoolMaxW];           // bit col = pixel x lies in column cell col
     const int y = blockIdx.x, img = blockIdx.y, c0 = blockIdx.z * kPoolBwdChunk;
     const int cw = min(kPoolBwdChunk, c - c0);
     if (threadIdx.x < kMaxColCells) {
         const int col = threadIdx.x;
-        cell_of[col][0] = cell_of[col][1] = -1;
-        area_of[col][0] = area_of[col][1] = 1.f;
+        cell_of[col][0] = cell_of[col][1] = 0;
+        winv[col][0] = winv[col][1] = 0.f;
         if (col < cols.n) {
             const int k = cols.k[col], s = sc.s[k], i0 = (y * s) / h;
             int e = 0;
@@ -118,37 +120,40 @@ ppm_pool_bwd_cols_kernel(const float *__restrict__ dpooled, const __nv_bfloat16 
                 const int y0 = win_lo(i, h, s), y1 = win_hi(i, h, s);
                 if (y < y0 || y >= y1 || e == 2) continue;
                 cell_of[col][e] = sc.off[k] + i * s + cols.j[col];
-                area_of[col][e] = static_cast<float>((y1 - y0) * (cols.hi[col] - cols.lo[col]));
+                winv[col][e] = 1.0f / static_cast<float>((y1 - y0) * (cols.hi[col] - cols.lo[col]));
                 ++e;
             }
         }
     }
+    for (int x = threadIdx.x; x < w; x += blockDim.x) {
+        unsigned m = 0u;
+#pragma unroll
+        for (int col = 0; col < kMaxColCells; ++col)
+            if (col < cols.n && x >= cols.lo[col] && x < cols.hi[col]) m |= 1u << col;
+        colmask[x] = m;
+    }
     __syncthreads();
     const float *pimg = dpooled + static_cast<size_t>(img) * sc.ncell * c + c0;
     for (int ch = threadIdx.x * 2; ch < cw; ch += blockDim.x * 2) {
+        float2 v[kMaxColCells][2];
+#pragma unroll
+        for (int col = 0; col < kMaxColCells; ++col)          // 32 independent loads (unused slots read cell 0 with weight 0)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) v[col][e] = __ldg(reinterpret_cast<const float2 *>(pimg + static_cast<size_t>(cell_of[col][e]) * c + ch));
 #pragma unroll
         for (int col = 0; col < kMaxColCells; ++col) {
-            float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int cell = cell_of[col][e];
-                if (cell >= 0) {
-                    const float2 v = __ldg(reinterpret_cast<const float2 *>(pimg + static_cast<size_t>(cell) * c + ch));
-                    acc.x += v.x / area_of[col][e];
-                    acc.y += v.y / area_of[col][e];
-                }
-            }
-            *reinterpret_cast<float2 *>(&R[col][ch]) = acc;
+            const float w0 = winv[col][0], w1 = winv[col][1];
+            *reinterpret_cast<float2 *>(&R[col][ch]) = make_float2(v[col][0].x * w0 + v[col][1].x * w1, v[col][0].y * w0 + v[col][1].y * w1);
         }
     }
     __syncthreads();
     const size_t row_off = (static_cast<size_t>(img) * h + y) * w * c + c0;
     const int octs = cw >> 3, items = w * octs;
-    for (int it0 = threadIdx.x; it0 < items; it0 += blockDim.x * 8) {
-        bf16x8 av[8];
+    for (int it0 = threadIdx.x; it0 < items; it0 += blockDim.x * 4) {
+        bf16x8 av[4];
         if (addend != nullptr) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < 4; ++u) {
                 const int item = it0 + u * blockDim.x;
                 if (item < items) {
                     const int x = item / octs, oc = item - x * octs;
@@ -157,16 +162,17 @@ ppm_pool_bwd_cols_kernel(const float *__restrict__ dpooled, const __nv_bfloat16 
             }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 4; ++u) {
             const int item = it0 + u * blockDim.x;
             if (item >= items) break;
             const int x = item / octs, oc = item - x * octs;
+            const unsigned m = colmask[x];                     // warp-uniform: a warp is 32 channel octets of one pixel
             float acc[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) acc[t] = 0.f;
 #pragma unroll
             for (int col = 0; col < kMaxColCells; ++col) {
-                if (col < cols.n && x >= cols.lo[col] && x < cols.hi[col]) {
+                if (m & (1u << col)) {
                     const float4 a = *reinterpret_cast<const float4 *>(&R[col][oc * 8]);
                     const float4 b2 = *reinterpret_cast<const float4 *>(&R[col][oc * 8 + 4]);
                     acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
@@ -354,6 +360,7 @@ extern "C" int regda_ppm_pool_bwd_add(const float *dpooled, const void *addend, 
         return fail(REGDA_ERR_INVALID_ARG, "ppm_pool_bwd: tensors must be 16-byte aligned");
     PpmCols cols;
     if (!make_cols(sc, w, &cols)) return fail(REGDA_ERR_UNSUPPORTED, "ppm_pool_bwd: pool scales sum to more than 16");
+    if (w > kPoolMaxW) return fail(REGDA_ERR_UNSUPPORTED, "ppm_pool_bwd: feature-map rows wider than 512 pixels");
     ppm_pool_bwd_cols_kernel<<<dim3(h, b, (c + kPoolBwdChunk - 1) / kPoolBwdChunk), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         dpooled, static_cast<const __nv_bfloat16 *>(addend), static_cast<__nv_bfloat16 *>(dfeat), h, w, c, sc, cols);
     REGDA_LAUNCH_CHECK();

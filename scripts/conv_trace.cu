@@ -37,7 +37,7 @@ int run(const Shape &sh, int launches, int grid_override) {
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     const bool early = getenv("REGDA_TRACE_EARLY") && atoi(getenv("REGDA_TRACE_EARLY")) != 0;
     auto launch = [&](int id) {
-        const int ipg = (sh.n / 2) | (id << 16);
+        const int ipg = (getenv("REGDA_TRACE_ONE_GROUP") ? sh.n : sh.n / 2) | (id << 16);
         if (early) regda_conv_hint_static_weights();
         if (block_n == 256) return launch_persistent_impl<256, 4, false, STATS, false>(tx, tw, y, g, st, stats, ipg, nullptr);
         if (block_n == 128) return launch_persistent_impl<128, 6, false, STATS, false>(tx, tw, y, g, st, stats, ipg, nullptr);
