@@ -31,7 +31,8 @@
 extern "C" {
 #endif
 
-#define REGDA_ABI_VERSION 2   /* 2: bn_forward relu_mask, bn_backward beta + dz_ready; new entry points (dgrad_bnred, stem, inference, pcl) */
+#define REGDA_ABI_VERSION 3   /* 2: bn_forward relu_mask, bn_backward beta + dz_ready; new entry points (dgrad_bnred, stem, inference, pcl)
+                               * 3: stem patch rows padded per filter row, G_k in (o, tap) column order, ppm gather / scatter removed (weights in place) */
 
 #define REGDA_OK 0
 #define REGDA_ERR_INVALID_ARG 1
@@ -237,12 +238,8 @@ int regda_zero_insert2_bf16(const void *src, void *dst, int n, int oh, int ow, i
 
 /* ---- folded PPM fuse convolution: layout glue (regda/models/Encoder.py:43-52; see csrc/ppm.cu) ------------------
  * The upsampled pyramid branches enter the 3x3 fuse convolution through two small GEMMs (run as 1x1 convolutions on the
- * tcgen05 kernels) instead of 2048 materialised channels; these kernels split / merge the OHWI weight and re-lay the
- * intermediate G between the two GEMMs. */
-int regda_ppm_gather_weights(const void *w, void *wmain, void *wb0, void *wb1, void *wb2, void *wb3, int O, int T, int ct,
-                             int cf, int cb, int nb, void *stream);
-int regda_ppm_scatter_wgrad(const float *gmain, const float *g0, const float *g1, const float *g2, const float *g3, float *gw,
-                            int O, int T, int ct, int cf, int cb, int nb, void *stream);
+ * tcgen05 kernels) instead of 2048 materialised channels; every GEMM uses its channel block of the OHWI weight in place (weight
+ * channel stride of the convolution entry points), these kernels re-lay the intermediate G between the two GEMMs. */
 int regda_ppm_g_pack(void *g0, void *g1, void *g2, void *g3, void *gt, int b, int O, int T, int kp, const int *scales_host,
                      int nscales, int pack, void *stream);
 int regda_transpose_bf16(const void *src, void *dst, int batch, int rows, int cols, void *stream);

@@ -72,7 +72,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError here = header/library mismatch
             fn.restype = restype
             fn.argtypes = argtypes
-        if L.regda_abi_version() != 2:
+        if L.regda_abi_version() != 3:
             raise RuntimeError("regda_b200 ABI version mismatch")
         _lib = L
     return _lib

@@ -422,63 +422,16 @@ extern "C" int regda_ppm_upcat_bwd(const void *dcat, float *dbr0, float *dbr1, f
 // (B_k = bilinear interpolation weights, zero outside the map = the convolution's zero padding).  G is a tiny GEMM (50 cells per
 // image), and the sum over (tap, cell) a [pixels x 450] . [450 x 512] GEMM per image with a CONSTANT left factor: both run on
 // the tcgen05 convolution kernels as 1x1 convolutions (host side: regda_b200/ops/ppm_fold.py), the result is handed to the
-// 3x3 convolution over the 2048 feature channels as its epilogue addend.  The kernels below are the layout glue:
-//   regda_ppm_gather_weights   bf16 OHWI weight -> the dense feature-part weight and the four branch weights [(tap, o)][c]
-//   regda_ppm_scatter_wgrad    their float32 gradients -> added into the OHWI gradient
-//   regda_ppm_g_pack / unpack  G_k [(img, cell)][(tap, o)]  <->  GT [img][o][(cell, tap)] (K-major operand of the second GEMM)
+// 3x3 convolution over the 2048 feature channels as its epilogue addend.  Every GEMM reads (and differentiates) its part of the
+// OHWI weight IN PLACE through the convolution kernels' weight channel stride; the kernels below are the remaining layout glue:
+//   regda_ppm_g_pack / unpack  G_k [(img, cell)][(o, tap)]  <->  GT [img][o][(cell, tap)] (K-major operand of the second GEMM)
+//   regda_ppm_cells            pooled float32 cells <-> the bf16 s x s branch inputs
 //   regda_transpose_bf16       batched [r][c] -> [c][r]
 // =========================================================================================================
 namespace regda {
 namespace {
 
 struct GPtrs { __nv_bfloat16 *p[kMaxScales]; };
-
-// grid (taps * o, 1 + nb): row (o, tap) of the OHWI weight -> segment 0: wmain[o][tap][0..cf), segment 1+k: wb[k][tap*O + o][0..cb)
-__global__ void __launch_bounds__(256)
-ppm_gather_weights_kernel(const __nv_bfloat16 *__restrict__ w, __nv_bfloat16 *__restrict__ wmain, const GPtrs wb, int O, int T, int ct, int cf, int cb) {
-    const int row = blockIdx.x;                        // o * T + tap
-    const int o = row / T, tap = row - o * T;
-    const __nv_bfloat16 *src = w + static_cast<size_t>(row) * ct;
-    if (blockIdx.y == 0) {
-        if (wmain == nullptr) return;                   // the feature part is read in place (weight channel stride of the conv kernels)
-        __nv_bfloat16 *dst = wmain + static_cast<size_t>(row) * cf;
-        for (int c = threadIdx.x * 8; c < cf; c += blockDim.x * 8) *reinterpret_cast<uint4 *>(dst + c) = *reinterpret_cast<const uint4 *>(src + c);
-    } else {
-        const int k = blockIdx.y - 1;
-        __nv_bfloat16 *dst = wb.p[k] + (static_cast<size_t>(tap) * O + o) * cb;
-        const __nv_bfloat16 *s2 = src + cf + static_cast<size_t>(k) * cb;
-        for (int c = threadIdx.x * 8; c < cb; c += blockDim.x * 8) *reinterpret_cast<uint4 *>(dst + c) = *reinterpret_cast<const uint4 *>(s2 + c);
-    }
-}
-
-struct FPtrs { const float *p[kMaxScales]; };
-
-__global__ void __launch_bounds__(256)
-ppm_scatter_wgrad_kernel(const float *__restrict__ gmain, const FPtrs gwb, float *__restrict__ gw, int O, int T, int ct, int cf, int cb) {
-    const int row = blockIdx.x;
-    const int o = row / T, tap = row - o * T;
-    float *dst = gw + static_cast<size_t>(row) * ct;
-    if (blockIdx.y == 0) {
-        if (gmain == nullptr) return;                   // the feature part was accumulated in place by the weight-gradient kernel
-        const float *src = gmain + static_cast<size_t>(row) * cf;
-        for (int c = threadIdx.x * 4; c < cf; c += blockDim.x * 4) {
-            float4 d = *reinterpret_cast<float4 *>(dst + c);
-            const float4 s4 = *reinterpret_cast<const float4 *>(src + c);
-            d.x += s4.x; d.y += s4.y; d.z += s4.z; d.w += s4.w;
-            *reinterpret_cast<float4 *>(dst + c) = d;
-        }
-    } else {
-        const int k = blockIdx.y - 1;
-        const float *src = gwb.p[k] + (static_cast<size_t>(tap) * O + o) * cb;
-        float *d2 = dst + cf + static_cast<size_t>(k) * cb;
-        for (int c = threadIdx.x * 4; c < cb; c += blockDim.x * 4) {
-            float4 d = *reinterpret_cast<float4 *>(d2 + c);
-            const float4 s4 = *reinterpret_cast<const float4 *>(src + c);
-            d.x += s4.x; d.y += s4.y; d.z += s4.z; d.w += s4.w;
-            *reinterpret_cast<float4 *>(d2 + c) = d;
-        }
-    }
-}
 
 // GT[img][o][kappa], kappa = (cell_global * T + tap) < ncell * T, zero up to kp  <->  G_k[(img, cell)][o * T + tap] (the branch
 // GEMMs run against the OHWI weight in place, so their output columns come in the weight's (o, tap) row order).
@@ -578,39 +531,6 @@ transpose_bf16_kernel(const __nv_bfloat16 *__restrict__ src, __nv_bfloat16 *__re
 
 }  // namespace
 }  // namespace regda
-
-// w bf16 [O][T][ct] (OHWI), ct = cf + nb*cb -> wmain bf16 [O][T][cf] (may be NULL: not wanted), wb_k bf16 [T*O][cb] (row = tap*O + o), k < nb <= 4
-extern "C" int regda_ppm_gather_weights(const void *w, void *wmain, void *wb0, void *wb1, void *wb2, void *wb3, int O, int T, int ct,
-                                        int cf, int cb, int nb, void *stream) {
-    if (!w || O < 1 || T < 1 || nb < 1 || nb > kMaxScales || cf % 8 || cb % 8 || ct != cf + nb * cb)
-        return fail(REGDA_ERR_INVALID_ARG, "ppm_gather_weights: bad arguments");
-    GPtrs p;
-    void *ps[4] = {wb0, wb1, wb2, wb3};
-    for (int k = 0; k < kMaxScales; ++k) {
-        p.p[k] = static_cast<__nv_bfloat16 *>(ps[k]);
-        if (k < nb && !ps[k]) return fail(REGDA_ERR_INVALID_ARG, "ppm_gather_weights: null branch weight");
-    }
-    ppm_gather_weights_kernel<<<dim3(O * T, 1 + nb), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16 *>(w), static_cast<__nv_bfloat16 *>(wmain), p, O, T, ct, cf, cb);
-    REGDA_LAUNCH_CHECK();
-    return REGDA_OK;
-}
-
-// gw float32 [O][T][ct] += (gmain float32 [O][T][cf] (may be NULL), gwb_k float32 [T*O][cb])
-extern "C" int regda_ppm_scatter_wgrad(const float *gmain, const float *g0, const float *g1, const float *g2, const float *g3, float *gw,
-                                       int O, int T, int ct, int cf, int cb, int nb, void *stream) {
-    if (!gw || O < 1 || T < 1 || nb < 1 || nb > kMaxScales || cf % 4 || cb % 4 || ct != cf + nb * cb)
-        return fail(REGDA_ERR_INVALID_ARG, "ppm_scatter_wgrad: bad arguments");
-    FPtrs p;
-    const float *ps[4] = {g0, g1, g2, g3};
-    for (int k = 0; k < kMaxScales; ++k) {
-        p.p[k] = ps[k];
-        if (k < nb && !ps[k]) return fail(REGDA_ERR_INVALID_ARG, "ppm_scatter_wgrad: null branch gradient");
-    }
-    ppm_scatter_wgrad_kernel<<<dim3(O * T, 1 + nb), 256, 0, static_cast<cudaStream_t>(stream)>>>(gmain, p, gw, O, T, ct, cf, cb);
-    REGDA_LAUNCH_CHECK();
-    return REGDA_OK;
-}
 
 // pack != 0: G_k bf16 [b][s_k*s_k][O*T] (column = o*T + tap) -> GT bf16 [b][O][kp] (kappa = cell*T + tap, zero padded);  pack == 0: the reverse
 extern "C" int regda_ppm_g_pack(void *g0, void *g1, void *g2, void *g3, void *gt, int b, int O, int T, int kp, const int *scales_host,

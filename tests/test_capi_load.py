@@ -16,7 +16,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/regda_b200.h but not exported"
     L.regda_abi_version.restype = ctypes.c_int
-    assert L.regda_abi_version() == 2
+    assert L.regda_abi_version() == 3
 
 
 def test_sass_is_sm100a_only():
