@@ -35,16 +35,34 @@ stem_im2col_kernel(const void *__restrict__ xv, __nv_bfloat16 *__restrict__ a, i
     const int ox0 = seg * kStemSeg;
     const int ix_start = 2 * ox0 - 3;
     if (F32_NCHW) {
-        // one plane row at a time (coalesced float loads): element (r, ch, px) -> staged slot r*kStemRow + px*3 + ch
+        // one plane row (r, ch) at a time, 16 bytes per load: the run starts one pixel left of the first staged pixel, where the row is
+        // 16-byte aligned (ix_start - 1 = 2 * (ox0 - 2), ox0 a multiple of 64, w a multiple of 4); element (r, ch, px) -> staged slot
+        // r*kStemRow + px*3 + ch
         const float *xi = static_cast<const float *>(xv) + static_cast<long long>(img) * 3 * h * w;
-        constexpr int kPx = (kStemRow - 1) / 3;
-        for (int e = threadIdx.x; e < 7 * 3 * kPx; e += 256) {
-            const int r = e / (3 * kPx), rem = e - r * (3 * kPx);
-            const int ch = rem / kPx, px = rem - ch * kPx;
-            const int iy = 2 * oy - 3 + r, ix = ix_start + px;
-            float v = 0.f;
-            if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(xi + (static_cast<long long>(ch) * h + iy) * w + ix);
-            sin[r * kStemRow + px * 3 + ch] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+        constexpr int kPx = (kStemRow - 1) / 3;                       // 133 staged pixels per row
+        constexpr int kQuads = (kPx + 1 + 3) / 4;                     // float4 loads per plane row (pixels -1 .. 4*kQuads-2)
+        const bool vec_ok = (w & 3) == 0 && (reinterpret_cast<uintptr_t>(xv) & 15) == 0;
+        for (int e = threadIdx.x; e < 7 * 3 * kQuads; e += 256) {
+            const int rc = e / kQuads, qd = e - rc * kQuads;
+            const int r = rc / 3, ch = rc - r * 3;
+            const int iy = 2 * oy - 3 + r, ix0 = ix_start - 1 + 4 * qd;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (iy >= 0 && iy < h) {
+                const float *rowp = xi + (static_cast<long long>(ch) * h + iy) * w;
+                if (vec_ok && ix0 >= 0 && ix0 + 3 < w) {
+                    const float4 f = __ldg(reinterpret_cast<const float4 *>(rowp + ix0));
+                    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (ix0 + t >= 0 && ix0 + t < w) v[t] = __ldg(rowp + ix0 + t);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int px = 4 * qd - 1 + t;
+                if (px >= 0 && px < kPx) sin[r * kStemRow + px * 3 + ch] = __bfloat16_as_ushort(__float2bfloat16_rn(v[t]));
+            }
         }
         if (threadIdx.x < 7) sin[threadIdx.x * kStemRow + kStemRow - 1] = 0;
     } else {
