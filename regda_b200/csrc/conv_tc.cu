@@ -389,7 +389,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                 uint32_t mbits[kCols / 32];                  // BNRED: ReLU mask of this lane's pixel, one bit per channel
                 if (BNRED) {
                     // the BatchNorm input box of the first 64-channel chunk (the buffer is free: the previous tile's column
-                    // sums ended with __syncwarp) and the mask words do not depend on the accumulator: request them first
+                    // sums ended with a proxy fence + __syncwarp) and the mask words do not depend on the accumulator: request them first
                     if (lane == 0) {
                         mbar_arrive_expect_tx(ybar + wq, 4096);
                         tma_load_4d(ybuf, &tmap_bn, ybar + wq, n_blk * BLOCK_N + col_lo, tw * g.bw + bpw0, th * g.bh + bph0, bimg);
@@ -486,6 +486,12 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                                 f32x2_fma(sacc[c64 / 64][4 + e], d, bf16x2_to_f32x2(y4[e]));
                             }
                         }
+                        // Every lane must HOLD its y values before the buffer is handed back to the TMA unit (async proxy): the shared
+                        // loads above are only ISSUED at this point and ptxas schedules the products that consume them after the next
+                        // box has been requested.  Observed with the addend path keeping the load/store pipe busy and the next box
+                        // coming from L2: the box overtook the last loads of the previous one.  The proxy fence (MEMBAR + FENCE.VIEW.ASYNC)
+                        // completes this thread's outstanding shared-memory reads and orders them before the async-proxy write.
+                        fence_proxy_async();
                         __syncwarp();                                  // every lane is done with ybuf
                         if (c64 + 64 < kCols && lane == 0) {
                             mbar_arrive_expect_tx(ybar + wq, 4096);
@@ -602,7 +608,8 @@ int launch_persistent_impl(const CUtensorMap &tx, const CUtensorMap &tw, void *y
     t_static_weights = 0;
     {
         const int nn = g.cout / BLOCK_N, nt = nn * g.tiles_img * g.tiles_h * g.tiles_w;
-        g.contig = (std::min(nt, sm_count()) % nn) != 0 ? 1 : 0;
+        static const int force = getenv("REGDA_CONV_CONTIG") ? atoi(getenv("REGDA_CONV_CONTIG")) : -1;      // sweeps / debugging only
+        g.contig = force >= 0 ? (force != 0) : ((std::min(nt, sm_count()) % nn) != 0 ? 1 : 0);
     }
     using L = PersistSmem<BLOCK_N, STAGES, BNRED>;
     auto kern = conv_persistent_kernel<BLOCK_N, STAGES, B_MN, STATS, OUT_F32, BNRED>;

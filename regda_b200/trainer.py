@@ -17,6 +17,8 @@ and prototype sums all-reduced (sum) so every rank keeps identical weights and p
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -154,6 +156,8 @@ class SelfTrainingStep:
         # convolution algorithms the golden vectors were produced with
         if pair_forward is None:
             pair_forward = getattr(model, "compute_dtype", None) == torch.bfloat16
+        if os.environ.get("REGDA_PAIR_FORWARD") == "0":      # A/B measurements only
+            pair_forward = False
         self.pair_forward = bool(pair_forward) and hasattr(model, "forward_pair")
         self.arena = ParamArena(model)
         if world_size > 1:

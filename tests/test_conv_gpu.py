@@ -187,7 +187,10 @@ def test_conv_tap_adds_the_residual_gradient_in_the_dgrad_epilogue():
 
 @pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[2], SHAPES[4], SHAPES[8], SHAPES[11], (4, 256, 32, 32, 1024, 1, 0, 1),
                                    (2, 128, 5, 40, 128, 3, 1, 1), (16, 2048, 6, 6, 512, 1, 0, 1), (4, 512, 8, 8, 256, 3, 1, 1),
-                                   (2, 256, 6, 6, 256, 3, 1, 1)], ids=str)
+                                   (2, 256, 6, 6, 256, 3, 1, 1),
+                                   # 8 channel blocks of 256 do not divide the 148-CTA grid: contiguous tile ranges, several
+                                   # statistics flushes per CTA (layer4 conv3 / downsample, ResNet width 2048)
+                                   (16, 512, 32, 32, 2048, 1, 0, 1), (6, 256, 24, 40, 2048, 1, 0, 1)], ids=str)
 def test_fused_bn_statistics_and_float32_epilogue(shape):
     """The conv epilogue's per-group per-channel (sum, sum of squares) equal those of the bf16 output it wrote; the
     float32-output epilogue returns the same accumulators un-rounded (their bf16 rounding is the bf16 output, bit for bit)."""
@@ -219,7 +222,8 @@ def test_fused_bn_statistics_and_float32_epilogue(shape):
 
 @pytest.mark.parametrize("with_addend", [False, True])
 @pytest.mark.parametrize("shape", [SHAPES[1], SHAPES[2], SHAPES[4], SHAPES[5], SHAPES[8], SHAPES[11], (4, 1024, 32, 32, 256, 1, 0, 1),
-                                   (16, 256, 6, 6, 256, 3, 1, 1), (4, 512, 8, 8, 128, 1, 0, 1)], ids=str)
+                                   (16, 256, 6, 6, 256, 3, 1, 1), (4, 512, 8, 8, 128, 1, 0, 1),
+                                   (16, 2048, 32, 32, 512, 1, 0, 1)], ids=str)        # 8 channel blocks: contiguous tile ranges
 def test_dgrad_bnred_matches_masked_dgrad_and_reductions(shape, with_addend):
     """regda_conv_dgrad_bnred_bf16: dz == bf16((dgrad + addend) * mask) bit for bit against the plain dgrad kernel's unrounded
     sum (checked at bf16 resolution), and red == (sum dz, sum dz * bn_y) per statistics group and channel in float32."""
