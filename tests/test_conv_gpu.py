@@ -220,6 +220,30 @@ def test_fused_bn_statistics_and_float32_epilogue(shape):
     assert torch.allclose(st[:, 1], want_sq, rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("shape", [(16, 256, 32, 32, 1024, 1, 0, 1), (4, 128, 24, 24, 128, 3, 1, 1), (16, 2048, 6, 6, 512, 1, 0, 1)], ids=str)
+def test_static_weight_hint_changes_nothing_but_the_order_of_the_first_loads(shape):
+    """regda_conv_hint_static_weights: the next convolution requests the weight halves of its first pipeline stages before its
+    programmatic-dependent-launch wait -- same bits out, forward and data gradient, and the hint is consumed by one launch"""
+    from regda_b200 import capi
+    from regda_b200.ops import tc
+    n, cin, h, w, cout, k, pad, dil = shape
+    g = torch.Generator(device="cuda").manual_seed(5)
+    cl = torch.channels_last
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g).bfloat16().contiguous(memory_format=cl)
+    wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5).bfloat16().contiguous(memory_format=cl)
+    y0, st0 = tc.fprop(x, wt, 1, pad, dil, 2)
+    for _ in range(3):
+        capi.check(capi.lib().regda_conv_hint_static_weights())
+        y1, st1 = tc.fprop(x, wt, 1, pad, dil, 2)
+        assert torch.equal(y0, y1) and torch.allclose(st0, st1, rtol=1e-5, atol=1e-3)
+    gy = torch.randn_like(y0)
+    d0 = tc.dgrad(gy, wt, x.shape, 1, pad, dil)
+    capi.check(capi.lib().regda_conv_hint_static_weights())
+    d1 = tc.dgrad(gy, wt, x.shape, 1, pad, dil)
+    assert torch.equal(d0, d1)
+    assert torch.equal(tc.dgrad(gy, wt, x.shape, 1, pad, dil), d0)          # (hint consumed: a plain launch again)
+
+
 @pytest.mark.parametrize("with_addend", [False, True])
 @pytest.mark.parametrize("shape", [SHAPES[1], SHAPES[2], SHAPES[4], SHAPES[5], SHAPES[8], SHAPES[11], (4, 1024, 32, 32, 256, 1, 0, 1),
                                    (16, 256, 6, 6, 256, 3, 1, 1), (4, 512, 8, 8, 128, 1, 0, 1),
