@@ -111,6 +111,36 @@ __device__ __forceinline__ void bn_moments(const float *__restrict__ st, int c, 
     rstd = rsqrtf(var + eps);
 }
 
+// REGDA_BN_TRACE (scripts/bn_trace.cu only; never defined in the library build): per-block phase time stamps of the apply kernel
+#ifdef REGDA_BN_TRACE
+constexpr int kBnTraceSlots = 8, kBnTraceBlocks = 1024;
+__device__ unsigned long long g_bn_trace[kBnTraceBlocks * kBnTraceSlots];
+#define BN_TRACE(slot)                                                                                              \
+    do {                                                                                                            \
+        if (threadIdx.x == 0) {                                                                                     \
+            unsigned long long gt_;                                                                                 \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                                 \
+            g_bn_trace[((blockIdx.y * gridDim.x + blockIdx.x) % kBnTraceBlocks) * kBnTraceSlots + (slot)] = gt_;    \
+        }                                                                                                           \
+    } while (0)
+#else
+#define BN_TRACE(slot)
+#endif
+
+// 8 consecutive per-channel floats.  Two 16-byte loads: a warp then reads whole lines; eight scalar loads at a lane stride of 32
+// bytes touch 32 sectors each, and the 32-48 of them per thread that the apply kernels' prologues used to issue kept the load pipe
+// busy for 2.7 us of an 8 MB tensor's 5.4 us (scripts/bn_trace.cu).  `vec`: p + ch is 16-byte aligned (kernel-uniform).
+__device__ __forceinline__ void load8f(const float *__restrict__ p, int ch, bool vec, float (&v)[8]) {
+    if (vec) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(p + ch)), b = __ldg(reinterpret_cast<const float4 *>(p + ch) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = p[ch + i];
+    }
+}
+__device__ __forceinline__ bool aligned16f(const float *p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // out = relu?(gamma*(y-mean)*rstd + beta + res).  stats [groups][2][c] are the per-group sums / sums of squares (from the
 // producing convolution's epilogue or from bn_stats_kernel); every thread derives the constants of its 8 channels itself
 // (no separate "finalize" launch), and block (0,0) updates the running statistics once per group, in group order
@@ -121,6 +151,7 @@ bn_apply_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__rest
                 long long total, int c, const float *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta,
                 float inv_n, float unbias, float eps, float momentum, float *__restrict__ running_mean, float *__restrict__ running_var,
                 long long *__restrict__ num_batches, unsigned char *__restrict__ relu_mask) {
+    BN_TRACE(0);
     if (c_bn_early_trigger) pdl_trigger();
     pdl_wait();
     if (blockIdx.x == 0 && blockIdx.y == 0) {
@@ -151,28 +182,46 @@ bn_apply_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__rest
     long long e = static_cast<long long>(blockIdx.x) * kBnSpan + static_cast<long long>(threadIdx.x) * 8;
     if (e >= total) return;
     const int ch = static_cast<int>(e % c);   // invariant: stride % c == 0
-    float sc[8], sh[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float mean, rstd, var;
-        bn_moments(stats, c, ch + i, inv_n, eps, mean, rstd, var);
-        const float g = gamma ? gamma[ch + i] : 1.f, b = beta ? beta[ch + i] : 0.f;
-        sc[i] = g * rstd;
-        sh[i] = fmaf(-mean, sc[i], b);
-    }
-    // U grid-stride positions per iteration, all loads issued first (bytes in flight per SM = blocks x 256 threads x U x 16-32 B)
-    for (; e < total; e += U * stride) {
-        bf16x8 yv[U], rv[U];
-        bool ok[U];
+    // U grid-stride positions per batch, all loads issued first (bytes in flight per SM = blocks x 256 threads x U x 16-32 B).
+    // The FIRST batch is requested before the per-channel constants are derived: most tensors of the step are one or two batches
+    // long, and the statistics' load latency would otherwise sit in front of the data's.
+    bf16x8 yv[U], rv[U];
+    bool ok[U];
+    auto issue = [&](long long e0) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long pos = e + u * stride;
+            const long long pos = e0 + u * stride;
             ok[u] = pos < total;
             if (ok[u]) {
                 yv[u] = ld8_stream(y + pos);
                 if (RES) rv[u] = ld8_stream(res + pos);
             }
         }
+    };
+    issue(e);
+    float sc[8], sh[8];
+    {
+        const bool vec = aligned16f(stats) && aligned16f(gamma) && aligned16f(beta) && (c & 3) == 0;
+        float s1[8], s2[8], gm[8], bt[8];
+        load8f(stats, ch, vec, s1);
+        load8f(stats + c, ch, vec, s2);
+        if (gamma) load8f(gamma, ch, vec, gm);
+        if (beta) load8f(beta, ch, vec, bt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float mean = s1[i] * inv_n;                                  // (bn_moments)
+            const float var = fmaxf(fmaf(-mean, mean, s2[i] * inv_n), 0.f);
+            const float rstd = rsqrtf(var + eps);
+            sc[i] = (gamma ? gm[i] : 1.f) * rstd;
+            sh[i] = fmaf(-mean, sc[i], beta ? bt[i] : 0.f);
+        }
+    }
+#ifdef REGDA_BN_TRACE
+    if (sc[0] == 12345.678f) return;      // (forces the constants before the stamp)
+    BN_TRACE(1);
+    int trace_it = 0;
+#endif
+    for (;;) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (!ok[u]) break;
@@ -201,7 +250,15 @@ bn_apply_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__rest
             }
             st8(out + pos, pack(f));
         }
+#ifdef REGDA_BN_TRACE
+        if (trace_it < 2) BN_TRACE(2 + trace_it);
+        ++trace_it;
+#endif
+        e += U * stride;
+        if (e >= total) break;
+        issue(e);
     }
+    BN_TRACE(4);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -231,13 +288,19 @@ bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16
     float sc[8], sh[8];
     if (RELU == 2) {
         const int ch = static_cast<int>((lo + static_cast<long long>(threadIdx.x) * 8) % c);      // invariant: kBnSpan % c == 0
+        const bool vec = aligned16f(stats) && aligned16f(gamma) && aligned16f(beta) && (c & 3) == 0;
+        float s1[8], s2[8], gm[8], bt[8];
+        load8f(stats, ch, vec, s1);
+        load8f(stats + c, ch, vec, s2);
+        if (gamma) load8f(gamma, ch, vec, gm);
+        if (beta) load8f(beta, ch, vec, bt);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            float mean, rstd, var;
-            bn_moments(stats, c, ch + i, inv_n, eps, mean, rstd, var);
-            const float g = gamma ? gamma[ch + i] : 1.f, b = beta ? beta[ch + i] : 0.f;
-            sc[i] = g * rstd;
-            sh[i] = fmaf(-mean, sc[i], b);
+            const float mean = s1[i] * inv_n;                                  // (bn_moments)
+            const float var = fmaxf(fmaf(-mean, mean, s2[i] * inv_n), 0.f);
+            const float rstd = rsqrtf(var + eps);
+            sc[i] = (gamma ? gm[i] : 1.f) * rstd;
+            sh[i] = fmaf(-mean, sc[i], beta ? bt[i] : 0.f);
         }
     }
 #pragma unroll 2
@@ -298,16 +361,27 @@ bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dout, const __nv_bfloat16 
     if (e >= total) return;
     const int ch = static_cast<int>(e % c);
     float a[8], k1[8], k2[8], mu[8], sh[8];
+    {
+        const bool vec = aligned16f(stats) && aligned16f(red) && aligned16f(gamma) && aligned16f(beta) && (c & 3) == 0;
+        float s1[8], s2[8], r1[8], r2[8], gm[8], bt[8];
+        load8f(stats, ch, vec, s1);
+        load8f(stats + c, ch, vec, s2);
+        load8f(red, ch, vec, r1);
+        load8f(red + c, ch, vec, r2);
+        if (gamma) load8f(gamma, ch, vec, gm);
+        if (RELU == 2 && beta) load8f(beta, ch, vec, bt);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float rstd, var;
-        bn_moments(stats, c, ch + i, inv_n, eps, mu[i], rstd, var);
-        const float sdz = red[ch + i];
-        const float sdzx = (red[c + ch + i] - mu[i] * sdz) * rstd;        // sum dz * xhat
-        a[i] = (gamma ? gamma[ch + i] : 1.f) * rstd;
-        k1[i] = sdz * inv_n;
-        k2[i] = sdzx * inv_n * rstd;
-        sh[i] = RELU == 2 ? fmaf(-mu[i], a[i], beta ? beta[ch + i] : 0.f) : 0.f;     // forward shift (a = forward scale)
+        for (int i = 0; i < 8; ++i) {
+            mu[i] = s1[i] * inv_n;                                             // (bn_moments)
+            const float var = fmaxf(fmaf(-mu[i], mu[i], s2[i] * inv_n), 0.f);
+            const float rstd = rsqrtf(var + eps);
+            const float sdz = r1[i];
+            const float sdzx = (r2[i] - mu[i] * sdz) * rstd;                   // sum dz * xhat
+            a[i] = (gamma ? gm[i] : 1.f) * rstd;
+            k1[i] = sdz * inv_n;
+            k2[i] = sdzx * inv_n * rstd;
+            sh[i] = RELU == 2 ? fmaf(-mu[i], a[i], beta ? bt[i] : 0.f) : 0.f;  // forward shift (a = forward scale)
+        }
     }
     for (; e < total; e += U * stride) {
         bf16x8 dv[U], vv[U], ov[U];
