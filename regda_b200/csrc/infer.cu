@@ -26,12 +26,28 @@ bn_inference_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__
     long long e = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8;
     if (e >= total) return;
     const int ch = static_cast<int>(e % c);           // invariant: stride % c == 0 (c divides 2048)
-    float sc[8], sh[8];
+    // per-channel constants of this thread's 8 channels: 16-byte loads where the pointers allow (a warp then reads whole lines; the
+    // scalar form touches 32 sectors per instruction -- csrc/norm.cu load8f has the measurement)
+    const bool vec = ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(rmean) |
+                       reinterpret_cast<uintptr_t>(rvar)) & 15) == 0 && (c & 3) == 0;
+    auto load8 = [&](const float *p, float (&v)[8]) {
+        if (vec) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(p + ch)), b = __ldg(reinterpret_cast<const float4 *>(p + ch) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = p[ch + i];
+        }
+    };
+    float sc[8], sh[8], gm[8], bt[8], mu[8], vr[8];
+    if (gamma) load8(gamma, gm);
+    if (beta) load8(beta, bt);
+    load8(rmean, mu);
+    load8(rvar, vr);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const float g = gamma ? gamma[ch + i] : 1.f, b = beta ? beta[ch + i] : 0.f;
-        sc[i] = g * rsqrtf(rvar[ch + i] + eps);
-        sh[i] = fmaf(-rmean[ch + i], sc[i], b);
+        sc[i] = (gamma ? gm[i] : 1.f) * rsqrtf(vr[i] + eps);
+        sh[i] = fmaf(-mu[i], sc[i], beta ? bt[i] : 0.f);
     }
     for (; e < total; e += stride) {
         const bf16x8i yv = *reinterpret_cast<const bf16x8i *>(y + e);
