@@ -144,12 +144,32 @@ classifier_bwd_kernel(const T *__restrict__ y, const float *__restrict__ w, cons
     const int groups = kClsThreads / octs;              // pixel rows in flight
     const int o = threadIdx.x % octs, grp = threadIdx.x / octs;
     float wk[kMaxClasses][8], kp[8], gw[kMaxClasses][8];
+    {
+        // this thread's 8 channels of the dropout factors and of every class's weight row: 16-byte loads (cin is a multiple of 8 and
+        // the tensors come 16-byte aligned; the scalar form issues 72 loads per thread at a lane stride of 32 bytes)
+        const bool vec = ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(keep)) & 15) == 0;
+        auto load8w = [&](const float *p, float (&v)[8]) {
+            if (vec) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b4 = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
+            } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) kp[j] = keep != nullptr ? keep[static_cast<size_t>(img) * cin + o * 8 + j] : 1.f;
+                for (int j = 0; j < 8; ++j) v[j] = p[j];
+            }
+        };
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k)
+        for (int j = 0; j < 8; ++j) kp[j] = 1.f;
+        if (keep != nullptr) load8w(keep + static_cast<size_t>(img) * cin + o * 8, kp);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { wk[k][j] = k < ncls ? w[k * cin + o * 8 + j] * kp[j] : 0.f; gw[k][j] = 0.f; }
+        for (int k = 0; k < kMaxClasses; ++k) {
+            float wr[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wr[j] = 0.f;
+            if (k < ncls) load8w(w + static_cast<size_t>(k) * cin + o * 8, wr);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { wk[k][j] = wr[j] * kp[j]; gw[k][j] = 0.f; }
+        }
+    }
     {
         const T *yi = y + (static_cast<size_t>(img) * hw + px0) * cin + o * 8;
         T *dyi = dy + (static_cast<size_t>(img) * hw + px0) * cin + o * 8;
@@ -233,7 +253,9 @@ int cls_args_ok(const void *y, const float *w, int b, int hw, int cin, int ncls)
 extern "C" int regda_classifier_fwd(const void *y, int y_is_f32, const float *w, const float *bias, const float *keep, float *out, int b,
                                     int hw, int cin, int ncls, void *stream) {
     if (!cls_args_ok(y, w, b, hw, cin, ncls) || !out) return fail(REGDA_ERR_INVALID_ARG, "classifier_fwd: bad arguments (cin / 8 must divide 256, <= 8 classes)");
-    const int per_img = std::max(1, std::min((hw + 7) / 8, 2 * sm_count() / b + 1));
+    // ~8 resident blocks per SM: a block's prologue (weights x dropout factors into shared memory) is a chain of global-load latencies,
+    // and a warp then walks its pixels one after the other -- many short blocks hide both (2 blocks per SM: 27 us per head)
+    const int per_img = std::max(1, std::min((hw + 7) / 8, 8 * sm_count() / b + 1));
     const size_t smem = static_cast<size_t>(ncls) * cin * sizeof(float);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (y_is_f32)
@@ -248,7 +270,7 @@ extern "C" int regda_classifier_fwd(const void *y, int y_is_f32, const float *w,
 extern "C" int regda_classifier_bwd(const void *y, int y_is_f32, const float *w, const float *keep, const float *dout, void *dy, float *dw,
                                     float *dbias, int b, int hw, int cin, int ncls, void *stream) {
     if (!cls_args_ok(y, w, b, hw, cin, ncls) || !dout || !dy || !dw) return fail(REGDA_ERR_INVALID_ARG, "classifier_bwd: bad arguments");
-    const int px_per_block = 128;
+    const int px_per_block = 128;         // (measured: 32 pixels per block -- 512 blocks instead of 128 -- is slower, 42 vs 31 us: four times the weight-gradient atomics)
     const int per_img = (hw + px_per_block - 1) / px_per_block;
     const size_t smem = std::max(static_cast<size_t>(px_per_block) * kMaxClasses, static_cast<size_t>(kClsThreads / (cin / 8)) * cin) * sizeof(float);
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -73,13 +73,34 @@ class_sums_partial_kernel(const T *__restrict__ feat, const long long *__restric
 #pragma unroll
     for (int j = 0; j < CMAX; ++j) { acc[j] = make_float4(0.f, 0.f, 0.f, 0.f); cnt[j] = 0.f; }
     if (col < k) {
-        for (long long r = r0; r < r1; ++r) {
-            const long long l = lab[r];
-            if (l == ignore_label || l < 0 || l >= c) continue;             // (:442-452) ignored rows add nothing
-            const float4 v = load_feat4(feat + r * k + col);
+        // 8 rows per trip: the labels, then the feature loads of the rows that count, are all in flight before the first add (one
+        // row per trip was a chain of 64 dependent load latencies); rows are added in row order, as before
+        constexpr int kU = 8;
+        for (long long rb = r0; rb < r1; rb += kU) {
+            int cls[kU];
+            float4 v[kU];
 #pragma unroll
-            for (int j = 0; j < CMAX; ++j)
-                if (j == static_cast<int>(l)) { acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w; cnt[j] += 1.f; }
+            for (int u = 0; u < kU; ++u) {
+                const long long l = rb + u < r1 ? lab[rb + u] : ignore_label;
+                cls[u] = (l == ignore_label || l < 0 || l >= c) ? -1 : static_cast<int>(l);      // (:442-452) ignored rows add nothing
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cls[u] >= 0) v[u] = load_feat4(feat + (rb + u) * k + col);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                // (multiply-by-mask keeps the per-class accumulators in registers: the compare-and-add form is turned into a
+                // dynamically indexed local-memory array; x + 0 * v is exact, so the sums are the same bits)
+#pragma unroll
+                for (int j = 0; j < CMAX; ++j) {
+                    const float m = j == cls[u] ? 1.f : 0.f;
+                    acc[j].x = fmaf(m, v[u].x, acc[j].x); acc[j].y = fmaf(m, v[u].y, acc[j].y);
+                    acc[j].z = fmaf(m, v[u].z, acc[j].z); acc[j].w = fmaf(m, v[u].w, acc[j].w);
+                    cnt[j] += m;
+                }
+            }
         }
 #pragma unroll
         for (int j = 0; j < CMAX; ++j)
