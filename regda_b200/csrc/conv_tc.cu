@@ -394,9 +394,16 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
                         mbar_arrive_expect_tx(ybar + wq, 4096);
                         tma_load_4d(ybuf, &tmap_bn, ybar + wq, n_blk * BLOCK_N + col_lo, tw * g.bw + bpw0, th * g.bh + bph0, bimg);
                     }
-                    const uint32_t *mp = reinterpret_cast<const uint32_t *>(relu_mask + ((pix_off + col_lo) >> 3));
-#pragma unroll
-                    for (int i = 0; i < kCols / 32; ++i) mbits[i] = valid ? __ldg(mp + i) : 0u;
+                    // this lane's kCols mask bits are 16 (8) consecutive, equally aligned bytes: ONE load (four scalar ones at a lane stride
+                    // of a pixel row quadruple the sector requests of the load pipe)
+                    const unsigned char *mp = relu_mask + ((pix_off + col_lo) >> 3);
+                    if (kCols == 128) {
+                        const uint4 m4 = valid ? __ldg(reinterpret_cast<const uint4 *>(mp)) : make_uint4(0u, 0u, 0u, 0u);
+                        mbits[0] = m4.x; mbits[1] = m4.y; mbits[kCols / 32 - 2] = m4.z; mbits[kCols / 32 - 1] = m4.w;
+                    } else {
+                        const uint2 m2 = valid ? __ldg(reinterpret_cast<const uint2 *>(mp)) : make_uint2(0u, 0u);
+                        mbits[0] = m2.x; mbits[kCols / 32 - 1] = m2.y;
+                    }
                 }
                 mbar_wait(tfull_bar + acc, acc_phase);
                 tc_fence_after_sync();
