@@ -353,7 +353,9 @@ def reference(args, rank, world):
         "impl": "reference", "metric": "train images/sec (512x512, 6-class)", "value": r["value"], "unit": "images/s",
         "n_gpus": world, "steps": steps, "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "st.regda.2potsdam self-training step: ResNet-101 DeepLab, 512x512 tiles, CPU port"},
+        # the same workload as our arm (same label), timed per step on a bounded sample of it: see cpu_baseline.sample
+        "config": {"workload": workload_config(3, 16, 1, False, "cpu")["workload"], "global_batch": 16, "parallelism": "host cpu",
+                   "sample": r["sample"], "engine": "torch fp32 CPU port of the reference's inner step (oracle/step_oracle.py)"},
         "cpu_baseline": {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)

@@ -35,3 +35,19 @@ def test_reference_arm_line_shape():
     assert r.returncode == 0, r.stderr[-1500:]
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_step_reference_arm_names_our_workload(monkeypatch, capsys):
+    """the CPU arm reports the SAME metric / workload label as our arm (the driver compares the two lines), the bounded sample stated beside it"""
+    import json
+    import types
+    monkeypatch.setattr(bench_step, "cpu_step_baseline",
+                        lambda reps=2, batch=2: dict(value=2.5, unit="images/s", cores=4, kind="port", sample="2+2 tiles", ms_per_step=1600.0))
+    bench_step.reference(types.SimpleNamespace(steps=2, warmup=1), 0, 1)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    ours = bench_step.workload_config(3, 16, 1, True, "tcgen05")
+    assert line["impl"] == "reference" and line["metric"] == "train images/sec (512x512, 6-class)" and line["unit"] == "images/s"
+    assert line["config"]["workload"] == ours["workload"] and line["config"]["sample"] == "2+2 tiles"
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"] == {"value": 2.5, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    bench_step.reference(types.SimpleNamespace(steps=2, warmup=1), 1, 2)          # other ranks: no work, no line
+    assert capsys.readouterr().out == ""
